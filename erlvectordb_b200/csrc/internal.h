@@ -1,0 +1,120 @@
+// internal.h -- store layout and kernel launchers shared by the .cu files.
+#pragma once
+#include "common.cuh"
+
+namespace evdb {
+
+// per-query scalars produced by prep_queries and consumed by the scans
+struct QStat {
+    float inv_norm;  // 1/||q|| (0 when ||q|| == 0)
+    float sum;       // sum(q)   (quantized scans: of the fixed-point query)
+    float fx;        // 2^-e: value of one fixed-point unit (quantized scans)
+    float norm_sq;   // ||q||^2
+};
+
+constexpr int kMaxKP = 1024;   // widest candidate window the scan/select path carries
+constexpr int kMinKP = 16;
+constexpr int kScanWarps = 8;  // warps per scan CTA
+constexpr int kProfMax = 512;
+
+}  // namespace evdb
+
+// Device-resident store.  One owner thread at a time (the store's gen_server).
+struct evdb_store {
+    int device = 0;
+    int dtype = EVDB_F32;
+    int dim = 0;    // 0 = undefined (reference: dimension :: undefined)
+    int dpad = 0;   // elements per row incl. zero padding (row = nch 16-byte chunks)
+    int nch = 0;    // 16-byte chunks per row of the main column
+    size_t row_bytes = 0;
+    int sm_count = 148;
+    int plan = EVDB_PLAN_AUTO;
+    int gemm_shadow = 0;
+    uint64_t count = 0, capacity = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    // ---- columns (all [capacity]) ----
+    uint8_t *rows = nullptr;       // F32: f32[dpad]; BF16: bf16[dpad]; U8: u8[dpad]; U4: u8[dpad/2]
+    double *norm64 = nullptr;      // exact reference vector_norm of the stored row
+    float *inv_norm = nullptr;     // (float)(1/norm64), 0 for a zero row
+    float *norm_sq = nullptr;      // (float)(norm64^2)   (GEMM euclidean)
+    float2 *qcoef = nullptr;       // U8/U4: {scale/||y||, min/||y||}
+    double2 *qms64 = nullptr;      // U8/U4: {min, scale} fp64 (exact re-rank, read-back)
+    __nv_bfloat16 *shadow = nullptr; // F32 + gemm_shadow: bf16 copy for the tcgen05 path
+    uint64_t shadow_valid = 0;     // rows [0, shadow_valid) of the shadow are current
+
+    // ---- workspace (grown on demand) ----
+    double *w_q64 = nullptr;   size_t w_q64_cap = 0;    // [B][dim]
+    float *w_q32 = nullptr;    size_t w_q32_cap = 0;    // [B][dpad32]
+    uint8_t *w_qdig = nullptr; size_t w_qdig_cap = 0;   // [B][3][dpad] digit planes
+    evdb::QStat *w_qstat = nullptr; size_t w_qstat_cap = 0;
+    uint64_t *w_partial = nullptr; size_t w_partial_cap = 0; // [B][G][KP]
+    uint64_t *w_ids = nullptr;  size_t w_ids_cap = 0;   // [B][k]
+    double *w_dists = nullptr;  size_t w_dists_cap = 0; // [B][k]
+    int32_t *w_counts = nullptr; size_t w_counts_cap = 0; // [B] counts + [B] flags
+    void *w_tmp = nullptr;      size_t w_tmp_cap = 0;   // ingest staging / exact plan
+    void *h_pin = nullptr;      size_t h_pin_cap = 0;   // pinned host staging
+
+    // ---- dominant-kernel profiling (evdb_store_profile) ----
+    int prof_on = 0, prof_n = 0;
+    cudaEvent_t *prof_ev = nullptr;  // [2 * kProfMax]
+    cudaStream_t prof_stream = nullptr;
+
+    // ---- counters ----
+    uint64_t n_searches = 0, n_rows_scanned = 0, n_escalations = 0, n_launches = 0;
+    int last_plan = 0;
+    double last_search_ms = 0.0;
+};
+
+namespace evdb {
+
+struct ScanArgs {
+    const uint8_t *rows;
+    size_t row_bytes;
+    int nch;                 // 16-byte chunks per row
+    uint64_t n;
+    const float *inv_norm;   // F32/BF16 cosine
+    const float2 *qcoef;     // U8/U4 cosine
+    const float *q32;        // [B][q32_stride]
+    int q32_stride;
+    const uint8_t *qdig;     // [B][3][qdig_stride]
+    int qdig_stride;
+    const QStat *qstat;      // [B]
+    uint64_t *partial;       // [B][G][KP]
+    int KP;
+    int G;
+    int B;
+};
+
+// ---- launchers (each returns EVDB_OK or an error; all async on `st`) ----
+int launch_prep_queries(evdb_store *s, const double *d_q64, int B, cudaStream_t st);
+int scan_grid_size(evdb_store *s, int metric, int KP, int *G_out);
+int launch_scan(evdb_store *s, int metric, const ScanArgs &a, cudaStream_t st);
+int launch_select(evdb_store *s, const double *d_q64, const uint64_t *partial, int lists_per_query,
+                  int KP, int B, int kk, int kstride, int metric, float eps_abs, float eps_rel,
+                  uint64_t slot_base, uint64_t *d_out_ids, double *d_out_dists,
+                  int32_t *d_out_counts, int32_t *d_out_flags, cudaStream_t st);
+int launch_finalize_rows(evdb_store *s, uint64_t slot0, uint64_t n, cudaStream_t st);
+int launch_fill_synthetic(evdb_store *s, uint64_t seed, uint64_t row0, uint64_t n, cudaStream_t st);
+int launch_quantize_rows(int dtype, const double *d_rows64, const float *d_rows32, uint64_t n,
+                         int d, uint8_t *codes, size_t code_row_bytes, double2 *ms64,
+                         double *maxs, uint8_t *ok, cudaStream_t st);
+int launch_dequantize_rows(int dtype, const uint8_t *codes, size_t code_row_bytes,
+                           const double2 *ms64, uint64_t n, int d, double *out, cudaStream_t st);
+int exact_plan_search(evdb_store *s, const double *d_q64, int B, int kk, int kstride, int metric,
+                      uint64_t slot_base, uint64_t *d_out_ids, double *d_out_dists,
+                      int32_t *d_out_counts, int32_t *d_out_flags, cudaStream_t st);
+int launch_merge_topk(const uint64_t *ids, const double *dists, const int32_t *counts, int G, int B,
+                      int k, uint64_t *out_ids, double *out_dists, int32_t *out_counts,
+                      cudaStream_t st);
+// tcgen05 path (gemm_tcgen05.cu)
+bool gemm_plan_supported(evdb_store *s, int metric, int B, int KP);
+int launch_gemm_topk(evdb_store *s, int metric, int B, int KP, uint64_t *partial,
+                     int *lists_per_query, cudaStream_t st);
+
+int ensure_bytes(void **p, size_t *cap, size_t need, bool pinned = false);
+void prof_begin(evdb_store *s, cudaStream_t st);
+void prof_end(evdb_store *s, cudaStream_t st);
+
+}  // namespace evdb

@@ -1,0 +1,466 @@
+// scan.cu -- HBM-bound distance scans with fused partial top-k (family A).
+//
+// Replaces the maps:fold over all N entries in perform_search/3
+// (reference src/vector_store.erl:227-231) and the per-row cosine_distance /
+// dot_product / vector_norm passes (:238-252) for small query batches, the
+// manhattan/euclidean forms of src/vector_utils.erl:38-43, and the scan over
+// quantization_8bit / quantization_4bit codes (src/vector_compression.erl:166-204).
+//
+// Layout: rows are dense, row-major, padded to 16-byte chunks.  A group of TPR
+// lanes owns a row; each lane streams 128-bit chunks of R rows at a time
+// (ld.global.nc.L1::no_allocate), the query sits in shared memory, partial
+// sums are combined with warp shuffles, and each warp keeps its KP best
+// (score, slot) keys in a sorted shared-memory list guarded by a register
+// threshold.  The CTA bitonic-merges its warps' lists and writes KP keys; the
+// select kernel (select.cu) merges CTAs and re-ranks exactly in fp64.
+#include "internal.h"
+#include "topk.cuh"
+
+namespace evdb {
+
+// ----------------------------------------------------------------------------
+// query preparation
+// ----------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T block_reduce(T v, T *red, bool is_max) {
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int o = 16; o > 0; o >>= 1) {
+        T u = __shfl_xor_sync(0xffffffffu, v, o);
+        v = is_max ? (u > v ? u : v) : (v + u);
+    }
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    T r = red[0];
+    for (int i = 1; i < nw; ++i) r = is_max ? (red[i] > r ? red[i] : r) : (r + red[i]);
+    __syncthreads();
+    return r;
+}
+
+// One CTA per query: narrow to fp32 (zero padded), norms, and -- for quantized
+// stores -- the 24-bit fixed-point query split into three 8-bit digit planes so
+// that sum(Q_i * c_i) is an exact integer computed with dp4a.
+__global__ void __launch_bounds__(256) prep_queries_kernel(const double *__restrict__ q64, int d,
+                                                           float *__restrict__ q32, int q32_stride,
+                                                           uint8_t *__restrict__ qdig,
+                                                           int qdig_stride, int dtype,
+                                                           QStat *__restrict__ qstat) {
+    __shared__ double redd[8];
+    __shared__ long long redl[8];
+    const int b = blockIdx.x;
+    const double *q = q64 + (size_t)b * d;
+    double ss = 0.0, sm = 0.0, mx = 0.0;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) {
+        double v = q[i];
+        ss += v * v;
+        sm += v;
+        mx = fmax(mx, fabs(v));
+    }
+    ss = block_reduce<double>(ss, redd, false);
+    sm = block_reduce<double>(sm, redd, false);
+    if (q32) {
+        float *o = q32 + (size_t)b * q32_stride;
+        for (int i = threadIdx.x; i < q32_stride; i += blockDim.x) o[i] = i < d ? (float)q[i] : 0.0f;
+    }
+    QStat st;
+    st.norm_sq = (float)ss;
+    st.inv_norm = ss > 0.0 ? (float)(1.0 / sqrt(ss)) : 0.0f;
+    st.sum = (float)sm;
+    st.fx = 0.0f;
+    if (dtype == EVDB_U8 || dtype == EVDB_U4) {
+        mx = block_reduce<double>(mx, redd, true);
+        int e = 0;
+        if (mx > 0.0) {
+            int x;
+            frexp(mx, &x);  // mx = m * 2^x, m in [0.5,1)  =>  |q| * 2^(23-x) < 2^23
+            e = 23 - x;
+        }
+        double sc = ldexp(1.0, e);
+        uint8_t *p0 = qdig + (size_t)b * 3 * qdig_stride;
+        uint8_t *p1 = p0 + qdig_stride, *p2 = p1 + qdig_stride;
+        long long qsum = 0;
+        for (int i = threadIdx.x; i < qdig_stride; i += blockDim.x) {
+            int Q = 0;
+            if (i < d) {
+                double t = rint(q[i] * sc);
+                t = fmin(fmax(t, -8388608.0), 8388607.0);
+                Q = (int)t;
+            }
+            qsum += Q;
+            int pos = i;
+            if (dtype == EVDB_U4) {
+                // codes: byte j = (elem 2j << 4) | elem 2j+1.  (w >> 4) & 0x0F0F0F0F yields the
+                // even elements of a word, w & 0x0F0F0F0F the odd ones: lay the digits out to match.
+                int c = i >> 5, r = i & 31, w = r >> 3, e8 = r & 7;
+                pos = c * 32 + ((e8 & 1) ? 16 : 0) + w * 4 + (e8 >> 1);
+            }
+            p0[pos] = (uint8_t)((Q >> 16) & 0xFF);  // signed high digit
+            p1[pos] = (uint8_t)((Q >> 8) & 0xFF);
+            p2[pos] = (uint8_t)(Q & 0xFF);
+        }
+        qsum = block_reduce<long long>(qsum, redl, false);
+        st.fx = (float)ldexp(1.0, -e);
+        st.sum = (float)((double)qsum * ldexp(1.0, -e));
+    }
+    if (threadIdx.x == 0) qstat[b] = st;
+}
+
+int launch_prep_queries(evdb_store *s, const double *d_q64, int B, cudaStream_t st) {
+    bool quant = s->dtype == EVDB_U8 || s->dtype == EVDB_U4;
+    int q32_stride = quant ? 0 : s->dpad;
+    int qdig_stride = quant ? s->dpad : 0;
+    if (!quant) EVDB_TRY(ensure_bytes((void **)&s->w_q32, &s->w_q32_cap, sizeof(float) * (size_t)B * q32_stride));
+    else EVDB_TRY(ensure_bytes((void **)&s->w_qdig, &s->w_qdig_cap, (size_t)B * 3 * qdig_stride));
+    EVDB_TRY(ensure_bytes((void **)&s->w_qstat, &s->w_qstat_cap, sizeof(QStat) * (size_t)B));
+    prep_queries_kernel<<<B, 256, 0, st>>>(d_q64, s->dim, quant ? nullptr : s->w_q32, q32_stride,
+                                           s->w_qdig, qdig_stride, s->dtype, s->w_qstat);
+    s->n_launches++;
+    EVDB_CUDA(cudaGetLastError());
+    return EVDB_OK;
+}
+
+// ----------------------------------------------------------------------------
+// per-chunk accumulation
+// ----------------------------------------------------------------------------
+template <int METRIC>
+__device__ __forceinline__ void acc_f4(float4 &a, const float4 v, const float4 q) {
+    if (METRIC == EVDB_COSINE) {
+        a.x = fmaf(v.x, q.x, a.x); a.y = fmaf(v.y, q.y, a.y);
+        a.z = fmaf(v.z, q.z, a.z); a.w = fmaf(v.w, q.w, a.w);
+    } else if (METRIC == EVDB_EUCLIDEAN) {
+        float t0 = v.x - q.x, t1 = v.y - q.y, t2 = v.z - q.z, t3 = v.w - q.w;
+        a.x = fmaf(t0, t0, a.x); a.y = fmaf(t1, t1, a.y);
+        a.z = fmaf(t2, t2, a.z); a.w = fmaf(t3, t3, a.w);
+    } else {
+        a.x += fabsf(v.x - q.x); a.y += fabsf(v.y - q.y);
+        a.z += fabsf(v.z - q.z); a.w += fabsf(v.w - q.w);
+    }
+}
+
+__device__ __forceinline__ float4 bf16x4_lo(const uint4 w) {  // elements 0..3 of 8 bf16
+    return make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xFFFF0000u),
+                       __uint_as_float(w.y << 16), __uint_as_float(w.y & 0xFFFF0000u));
+}
+__device__ __forceinline__ float4 bf16x4_hi(const uint4 w) {  // elements 4..7
+    return make_float4(__uint_as_float(w.z << 16), __uint_as_float(w.z & 0xFFFF0000u),
+                       __uint_as_float(w.w << 16), __uint_as_float(w.w & 0xFFFF0000u));
+}
+
+// ----------------------------------------------------------------------------
+// shared epilogue: threshold test, warp-list insertion, CTA merge
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void offer(uint64_t key, uint64_t &thr, uint64_t *mylist, int KP,
+                                      int lane) {
+    unsigned m = __ballot_sync(0xffffffffu, key < thr);
+    while (m) {
+        int src = __ffs(m) - 1;
+        m &= m - 1;
+        uint64_t k2 = __shfl_sync(0xffffffffu, key, src);
+        if (k2 < thr) thr = warp_list_insert(mylist, KP, k2, lane);
+    }
+}
+
+__device__ __forceinline__ void cta_merge_and_store(uint64_t *lists, int KP, uint64_t *out) {
+    __syncthreads();
+    block_bitonic_sort(lists, kScanWarps * KP);
+    for (int i = threadIdx.x; i < KP; i += blockDim.x) out[i] = lists[i];
+}
+
+// ----------------------------------------------------------------------------
+// fp32 / bf16 rows: cosine, euclidean, manhattan
+// ----------------------------------------------------------------------------
+template <int METRIC, int DTYPE, int TPR, int R>
+__global__ void __launch_bounds__(kScanWarps * 32)
+scan_float_kernel(const ScanArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr int QPC = (DTYPE == EVDB_F32) ? 1 : 2;  // query float4s per 16-byte row chunk
+    constexpr int GPW = 32 / TPR;                      // row groups per warp
+    const int nch = a.nch, KP = a.KP;
+    float4 *sq = reinterpret_cast<float4 *>(smem);
+    uint64_t *lists = reinterpret_cast<uint64_t *>(smem + (size_t)nch * QPC * 16);
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    const float4 *qsrc = reinterpret_cast<const float4 *>(a.q32 + (size_t)b * a.q32_stride);
+    for (int i = threadIdx.x; i < nch * QPC; i += blockDim.x) sq[i] = qsrc[i];
+    for (int i = threadIdx.x; i < kScanWarps * KP; i += blockDim.x) lists[i] = kKeyMax;
+    __syncthreads();
+    const float q_inv = a.qstat[b].inv_norm;
+    uint64_t *mylist = lists + warp * KP;
+    uint64_t thr = kKeyMax;
+
+    const int g = lane / TPR, gl = lane % TPR;
+    const uint64_t rows_per_wi = (uint64_t)GPW * R;
+    const uint64_t total_wi = (a.n + rows_per_wi - 1) / rows_per_wi;
+    for (uint64_t wi = (uint64_t)blockIdx.x * kScanWarps + warp; wi < total_wi;
+         wi += (uint64_t)gridDim.x * kScanWarps) {
+        const uint64_t base = wi * rows_per_wi;
+        const uint4 *rp[R];
+        uint64_t rix[R];
+        bool valid[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            uint64_t r = base + (uint64_t)j * GPW + g;
+            valid[j] = r < a.n;
+            rix[j] = r;
+            rp[j] = reinterpret_cast<const uint4 *>(a.rows + (valid[j] ? r : a.n - 1) * a.row_bytes);
+        }
+        float4 acc[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+        for (int c = gl; c < nch; c += TPR) {
+            uint4 v[R];
+#pragma unroll
+            for (int j = 0; j < R; ++j) v[j] = ldg_stream_u4(rp[j] + c);
+            if (DTYPE == EVDB_F32) {
+                const float4 q0 = sq[c];
+#pragma unroll
+                for (int j = 0; j < R; ++j)
+                    acc_f4<METRIC>(acc[j],
+                                   make_float4(__uint_as_float(v[j].x), __uint_as_float(v[j].y),
+                                               __uint_as_float(v[j].z), __uint_as_float(v[j].w)),
+                                   q0);
+            } else {
+                const float4 q0 = sq[2 * c], q1 = sq[2 * c + 1];
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    acc_f4<METRIC>(acc[j], bf16x4_lo(v[j]), q0);
+                    acc_f4<METRIC>(acc[j], bf16x4_hi(v[j]), q1);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            float sacc = (acc[j].x + acc[j].y) + (acc[j].z + acc[j].w);
+#pragma unroll
+            for (int o = TPR / 2; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+            float score;
+            if (METRIC == EVDB_COSINE) {
+                float inv = (valid[j] && gl == 0) ? __ldg(a.inv_norm + rix[j]) : 0.f;
+                score = (inv == 0.f || q_inv == 0.f) ? 1.0f : 1.0f - sacc * inv * q_inv;
+            } else if (METRIC == EVDB_EUCLIDEAN) {
+                score = sqrtf(sacc);
+            } else {
+                score = sacc;
+            }
+            uint64_t key = (valid[j] && gl == 0) ? make_key(score, (uint32_t)rix[j]) : kKeyMax;
+            offer(key, thr, mylist, KP, lane);
+        }
+    }
+    cta_merge_and_store(lists, KP, a.partial + ((size_t)b * a.G + blockIdx.x) * KP);
+}
+
+// ----------------------------------------------------------------------------
+// u8 / packed-u4 codes: cosine of an unquantised query against Min + c*Scale
+//   q.y = Min*sum(q) + Scale*sum(q_i c_i);  sum(Q_i c_i) is an exact integer:
+//   Q = a*2^16 + b*2^8 + c (a signed, b,c unsigned digits), three dp4a per word.
+// ----------------------------------------------------------------------------
+template <int DTYPE, int TPR, int R>
+__global__ void __launch_bounds__(kScanWarps * 32)
+scan_quant_kernel(const ScanArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr int GPW = 32 / TPR;
+    constexpr int UPC = (DTYPE == EVDB_U8) ? 1 : 2;  // uint4 of digits per plane per row chunk
+    const int nch = a.nch, KP = a.KP;
+    const int plane_u4 = nch * UPC;                  // uint4 per plane
+    uint4 *sd = reinterpret_cast<uint4 *>(smem);     // [3][plane_u4]
+    uint64_t *lists = reinterpret_cast<uint64_t *>(smem + (size_t)3 * plane_u4 * 16);
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    const uint4 *dsrc = reinterpret_cast<const uint4 *>(a.qdig + (size_t)b * 3 * a.qdig_stride);
+    for (int i = threadIdx.x; i < 3 * plane_u4; i += blockDim.x) sd[i] = dsrc[i];
+    for (int i = threadIdx.x; i < kScanWarps * KP; i += blockDim.x) lists[i] = kKeyMax;
+    __syncthreads();
+    const QStat qs = a.qstat[b];
+    uint64_t *mylist = lists + warp * KP;
+    uint64_t thr = kKeyMax;
+
+    const int g = lane / TPR, gl = lane % TPR;
+    const uint64_t rows_per_wi = (uint64_t)GPW * R;
+    const uint64_t total_wi = (a.n + rows_per_wi - 1) / rows_per_wi;
+    for (uint64_t wi = (uint64_t)blockIdx.x * kScanWarps + warp; wi < total_wi;
+         wi += (uint64_t)gridDim.x * kScanWarps) {
+        const uint64_t base = wi * rows_per_wi;
+        const uint4 *rp[R];
+        uint64_t rix[R];
+        bool valid[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            uint64_t r = base + (uint64_t)j * GPW + g;
+            valid[j] = r < a.n;
+            rix[j] = r;
+            rp[j] = reinterpret_cast<const uint4 *>(a.rows + (valid[j] ? r : a.n - 1) * a.row_bytes);
+        }
+        int A[R], Bm[R], Cl[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) A[j] = Bm[j] = Cl[j] = 0;
+#pragma unroll 2
+        for (int c = gl; c < nch; c += TPR) {
+            uint4 v[R];
+#pragma unroll
+            for (int j = 0; j < R; ++j) v[j] = ldg_stream_u4(rp[j] + c);
+            if (DTYPE == EVDB_U8) {
+                const uint4 d0 = sd[c], d1 = sd[plane_u4 + c], d2 = sd[2 * plane_u4 + c];
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    A[j] = dp4a_su((int)d0.x, v[j].x, A[j]); A[j] = dp4a_su((int)d0.y, v[j].y, A[j]);
+                    A[j] = dp4a_su((int)d0.z, v[j].z, A[j]); A[j] = dp4a_su((int)d0.w, v[j].w, A[j]);
+                    Bm[j] = (int)dp4a_uu(d1.x, v[j].x, (uint32_t)Bm[j]); Bm[j] = (int)dp4a_uu(d1.y, v[j].y, (uint32_t)Bm[j]);
+                    Bm[j] = (int)dp4a_uu(d1.z, v[j].z, (uint32_t)Bm[j]); Bm[j] = (int)dp4a_uu(d1.w, v[j].w, (uint32_t)Bm[j]);
+                    Cl[j] = (int)dp4a_uu(d2.x, v[j].x, (uint32_t)Cl[j]); Cl[j] = (int)dp4a_uu(d2.y, v[j].y, (uint32_t)Cl[j]);
+                    Cl[j] = (int)dp4a_uu(d2.z, v[j].z, (uint32_t)Cl[j]); Cl[j] = (int)dp4a_uu(d2.w, v[j].w, (uint32_t)Cl[j]);
+                }
+            } else {
+                const uint4 e0 = sd[2 * c], o0 = sd[2 * c + 1];
+                const uint4 e1 = sd[plane_u4 + 2 * c], o1 = sd[plane_u4 + 2 * c + 1];
+                const uint4 e2 = sd[2 * plane_u4 + 2 * c], o2 = sd[2 * plane_u4 + 2 * c + 1];
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+                    const uint32_t E0[4] = {e0.x, e0.y, e0.z, e0.w}, O0[4] = {o0.x, o0.y, o0.z, o0.w};
+                    const uint32_t E1[4] = {e1.x, e1.y, e1.z, e1.w}, O1[4] = {o1.x, o1.y, o1.z, o1.w};
+                    const uint32_t E2[4] = {e2.x, e2.y, e2.z, e2.w}, O2[4] = {o2.x, o2.y, o2.z, o2.w};
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        uint32_t hi = (w[t] >> 4) & 0x0F0F0F0Fu, lo = w[t] & 0x0F0F0F0Fu;
+                        A[j] = dp4a_su((int)E0[t], hi, A[j]); A[j] = dp4a_su((int)O0[t], lo, A[j]);
+                        Bm[j] = (int)dp4a_uu(E1[t], hi, (uint32_t)Bm[j]); Bm[j] = (int)dp4a_uu(O1[t], lo, (uint32_t)Bm[j]);
+                        Cl[j] = (int)dp4a_uu(E2[t], hi, (uint32_t)Cl[j]); Cl[j] = (int)dp4a_uu(O2[t], lo, (uint32_t)Cl[j]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            int sa = A[j], sb = Bm[j], sc = Cl[j];
+#pragma unroll
+            for (int o = TPR / 2; o > 0; o >>= 1) {
+                sa += __shfl_xor_sync(0xffffffffu, sa, o);
+                sb += __shfl_xor_sync(0xffffffffu, sb, o);
+                sc += __shfl_xor_sync(0xffffffffu, sc, o);
+            }
+            uint64_t key = kKeyMax;
+            if (valid[j] && gl == 0) {
+                long long S = ((long long)sa << 16) + ((long long)sb << 8) + (long long)sc;
+                float2 co = __ldg(a.qcoef + rix[j]);  // {scale/||y||, min/||y||}
+                float dotn = fmaf(co.x, __ll2float_rn(S) * qs.fx, co.y * qs.sum);
+                bool zero = (co.x == 0.f && co.y == 0.f) || qs.inv_norm == 0.f;
+                float score = zero ? 1.0f : 1.0f - dotn * qs.inv_norm;
+                key = make_key(score, (uint32_t)rix[j]);
+            }
+            offer(key, thr, mylist, KP, lane);
+        }
+    }
+    cta_merge_and_store(lists, KP, a.partial + ((size_t)b * a.G + blockIdx.x) * KP);
+}
+
+// ----------------------------------------------------------------------------
+// dispatch
+// ----------------------------------------------------------------------------
+typedef void (*scan_fn_t)(const ScanArgs);
+
+static int pick_tpr(int nch) {
+    int t = 1;
+    while (t < 32 && t * 2 <= nch / 2) t <<= 1;
+    return t;
+}
+
+template <int METRIC, int DTYPE>
+static scan_fn_t pick_float(int tpr) {
+    switch (tpr) {
+        case 1: return scan_float_kernel<METRIC, DTYPE, 1, 4>;
+        case 2: return scan_float_kernel<METRIC, DTYPE, 2, 4>;
+        case 4: return scan_float_kernel<METRIC, DTYPE, 4, 4>;
+        case 8: return scan_float_kernel<METRIC, DTYPE, 8, 4>;
+        case 16: return scan_float_kernel<METRIC, DTYPE, 16, 4>;
+        default: return scan_float_kernel<METRIC, DTYPE, 32, 4>;
+    }
+}
+template <int DTYPE>
+static scan_fn_t pick_quant(int tpr) {
+    switch (tpr) {
+        case 1: return scan_quant_kernel<DTYPE, 1, 4>;
+        case 2: return scan_quant_kernel<DTYPE, 2, 4>;
+        case 4: return scan_quant_kernel<DTYPE, 4, 4>;
+        case 8: return scan_quant_kernel<DTYPE, 8, 4>;
+        case 16: return scan_quant_kernel<DTYPE, 16, 4>;
+        default: return scan_quant_kernel<DTYPE, 32, 2>;
+    }
+}
+
+struct ScanPlan {
+    scan_fn_t fn;
+    size_t smem;
+    int tpr, rows_per_wi;
+};
+
+static int make_scan_plan(evdb_store *s, int metric, int KP, ScanPlan *p) {
+    int tpr = pick_tpr(s->nch);
+    p->tpr = tpr;
+    int R = 4;
+    size_t qbytes;
+    switch (s->dtype) {
+        case EVDB_F32:
+            p->fn = metric == EVDB_COSINE ? pick_float<EVDB_COSINE, EVDB_F32>(tpr)
+                  : metric == EVDB_EUCLIDEAN ? pick_float<EVDB_EUCLIDEAN, EVDB_F32>(tpr)
+                                             : pick_float<EVDB_MANHATTAN, EVDB_F32>(tpr);
+            qbytes = (size_t)s->nch * 16;
+            break;
+        case EVDB_BF16:
+            p->fn = metric == EVDB_COSINE ? pick_float<EVDB_COSINE, EVDB_BF16>(tpr)
+                  : metric == EVDB_EUCLIDEAN ? pick_float<EVDB_EUCLIDEAN, EVDB_BF16>(tpr)
+                                             : pick_float<EVDB_MANHATTAN, EVDB_BF16>(tpr);
+            qbytes = (size_t)s->nch * 32;
+            break;
+        case EVDB_U8:
+            if (metric != EVDB_COSINE) return EVDB_E_UNSUPPORTED;
+            p->fn = pick_quant<EVDB_U8>(tpr);
+            qbytes = (size_t)s->nch * 16 * 3;
+            if (tpr == 32) R = 2;
+            break;
+        case EVDB_U4:
+            if (metric != EVDB_COSINE) return EVDB_E_UNSUPPORTED;
+            p->fn = pick_quant<EVDB_U4>(tpr);
+            qbytes = (size_t)s->nch * 32 * 3;
+            if (tpr == 32) R = 2;
+            break;
+        default:
+            return EVDB_E_BAD_ARG;
+    }
+    p->rows_per_wi = (32 / tpr) * R;
+    p->smem = qbytes + (size_t)kScanWarps * KP * sizeof(uint64_t);
+    if (p->smem > 200 * 1024) return EVDB_E_UNSUPPORTED;
+    return EVDB_OK;
+}
+
+int scan_grid_size(evdb_store *s, int metric, int KP, int *G_out) {
+    ScanPlan p;
+    EVDB_TRY(make_scan_plan(s, metric, KP, &p));
+    if (p.smem > 48 * 1024)
+        EVDB_CUDA(cudaFuncSetAttribute((const void *)p.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    int occ = 1;
+    EVDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)p.fn, kScanWarps * 32, p.smem));
+    if (occ < 1) occ = 1;
+    if (occ > 4) occ = 4;
+    uint64_t total_wi = (s->count + p.rows_per_wi - 1) / p.rows_per_wi;
+    // at least 4 warp-iterations per warp, so the warp-list warm-up amortises
+    uint64_t want = (total_wi + (uint64_t)kScanWarps * 4 - 1) / ((uint64_t)kScanWarps * 4);
+    uint64_t cap = (uint64_t)s->sm_count * occ;
+    uint64_t G = want < cap ? want : cap;
+    if (G < 1) G = 1;
+    *G_out = (int)G;
+    return EVDB_OK;
+}
+
+int launch_scan(evdb_store *s, int metric, const ScanArgs &a, cudaStream_t st) {
+    ScanPlan p;
+    EVDB_TRY(make_scan_plan(s, metric, a.KP, &p));
+    dim3 grid(a.G, a.B);
+    p.fn<<<grid, kScanWarps * 32, p.smem, st>>>(a);
+    s->n_launches++;
+    EVDB_CUDA(cudaGetLastError());
+    return EVDB_OK;
+}
+
+}  // namespace evdb

@@ -1,0 +1,322 @@
+// select.cu -- per-query candidate merge, exact fp64 re-rank and final top-k.
+//
+// Replaces lists:sort/1 + lists:sublist/2 of perform_search/3 (reference
+// src/vector_store.erl:233-236).  One CTA per query:
+//   1. bitonic-merge the per-CTA candidate lists of the scan / GEMM stage into
+//      the KP best approximate (score, slot) keys;
+//   2. one warp per candidate recomputes the distance in fp64 in the
+//      reference's exact operation order (exact.cuh);
+//   3. sort by (exact distance, slot), emit the first k, and PROVE the window
+//      complete: every row outside it has approximate score >= the window's
+//      last key, hence exact distance >= bound - eps; if the k-th exact
+//      distance is not strictly below that, flag the query for escalation.
+// Also: the exhaustive fp64 plan (every row, then a stable radix sort) that
+// backs k > kMaxKP, metrics without a fast scan, and failed escalations; and
+// the G-way merge that follows the cross-GPU allgather.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "exact.cuh"
+#include "internal.h"
+#include "topk.cuh"
+
+namespace evdb {
+
+constexpr int kSelThreads = 1024;
+constexpr int kSelWarps = kSelThreads / 32;
+constexpr int kSelSort = 4096;  // keys sorted per merge round
+
+struct SelectArgs {
+    const uint8_t *rows;
+    size_t row_bytes;
+    const double *norm64;
+    const double2 *qms64;
+    uint64_t n;
+    int d;
+    const double *q64;        // [B][d]
+    const uint64_t *partial;  // [B][L][KP]
+    int L, KP, kk, kstride, metric;
+    float eps_abs, eps_rel;
+    uint64_t slot_base;
+    uint64_t *out_ids;
+    double *out_dists;
+    int32_t *out_counts;
+    int32_t *out_flags;
+};
+
+template <int DTYPE>
+__global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint64_t *buf = reinterpret_cast<uint64_t *>(smem);                       // [kSelSort]
+    double *sp_all = reinterpret_cast<double *>(smem + sizeof(uint64_t) * kSelSort);  // [warps][2*chunk]
+    uint64_t *dkey = reinterpret_cast<uint64_t *>(sp_all + kSelWarps * 2 * kExactChunk);  // [kMaxKP]
+    uint64_t *dslot = dkey + kMaxKP;                                          // [kMaxKP]
+    __shared__ int s_ncand;
+    __shared__ float s_bound;
+
+    const int b = blockIdx.x;
+    const int KP = a.KP;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // ---- 1. merge L lists of KP keys into the KP smallest ----
+    const uint64_t *src = a.partial + (size_t)b * a.L * KP;
+    const size_t total = (size_t)a.L * KP;
+    size_t pos = 0;
+    int carried = 0;
+    while (true) {
+        size_t room = (size_t)kSelSort - carried;
+        size_t take = total - pos < room ? total - pos : room;
+        int filled = carried + (int)take;
+        int nsort = KP;
+        while (nsort < filled) nsort <<= 1;
+        for (int i = threadIdx.x; i < nsort - carried; i += blockDim.x)
+            buf[carried + i] = (size_t)i < take ? src[pos + i] : kKeyMax;
+        __syncthreads();
+        block_bitonic_sort(buf, nsort);
+        pos += take;
+        carried = KP;
+        if (pos >= total) break;
+    }
+    // ---- count valid candidates (keys are ascending; kKeyMax pads) ----
+    if (threadIdx.x == 0) s_ncand = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < KP; i += blockDim.x)
+        if (buf[i] != kKeyMax && (i + 1 == KP || buf[i + 1] == kKeyMax)) {
+            s_ncand = i + 1;
+            s_bound = key_score(buf[i]);
+        }
+    __syncthreads();
+    const int ncand = s_ncand;
+    const float bound = s_bound;
+
+    // ---- 2. exact fp64 distance per candidate, one warp each ----
+    const double *q = a.q64 + (size_t)b * a.d;
+    double *sp = sp_all + warp * 2 * kExactChunk;
+    for (int j = warp; j < KP; j += kSelWarps) {
+        if (j < ncand) {
+            uint32_t slot = key_slot(buf[j]);
+            const uint8_t *row = a.rows + (size_t)slot * a.row_bytes;
+            double mn = 0.0, sc = 0.0;
+            if (DTYPE == EVDB_U8 || DTYPE == EVDB_U4) {
+                double2 ms = a.qms64[slot];
+                mn = ms.x;
+                sc = ms.y;
+            }
+            double dist = exact_distance_warp<DTYPE>(row, mn, sc, q, a.d, a.metric,
+                                                     a.norm64[slot], sp, lane);
+            if (lane == 0) {
+                dkey[j] = f64_orderable(dist);
+                dslot[j] = slot;
+            }
+        } else if (lane == 0) {
+            dkey[j] = kKeyMax;
+            dslot[j] = kKeyMax;
+        }
+    }
+    __syncthreads();
+
+    // ---- 3. final order by (exact distance, slot); emit k; completeness proof ----
+    block_bitonic_sort_pairs(dkey, dslot, KP);
+    const int kout = a.kk < ncand ? a.kk : ncand;
+    for (int i = threadIdx.x; i < a.kstride; i += blockDim.x) {
+        size_t o = (size_t)b * a.kstride + i;
+        if (i < kout) {
+            uint64_t ob = dkey[i];
+            uint64_t bits = ob ^ ((ob >> 63) ? 0x8000000000000000ull : 0xFFFFFFFFFFFFFFFFull);
+            a.out_dists[o] = __longlong_as_double((long long)bits);
+            a.out_ids[o] = a.slot_base + dslot[i];
+        } else {
+            a.out_dists[o] = 0.0;
+            a.out_ids[o] = kKeyMax;
+        }
+    }
+    if (threadIdx.x == 0) {
+        a.out_counts[b] = kout;
+        int flag = 0;
+        if (kout > 0 && (uint64_t)ncand < a.n) {  // rows exist outside the window
+            uint64_t ob = dkey[kout - 1];
+            uint64_t bits = ob ^ ((ob >> 63) ? 0x8000000000000000ull : 0xFFFFFFFFFFFFFFFFull);
+            double dk = __longlong_as_double((long long)bits);
+            double lim = (double)bound - (double)a.eps_abs - (double)a.eps_rel * fabs((double)bound);
+            flag = !(dk < lim);
+        }
+        if (a.out_flags) a.out_flags[b] = flag;
+    }
+}
+
+static size_t select_smem() {
+    return sizeof(uint64_t) * kSelSort + sizeof(double) * kSelWarps * 2 * kExactChunk +
+           sizeof(uint64_t) * 2 * kMaxKP;
+}
+
+int launch_select(evdb_store *s, const double *d_q64, const uint64_t *partial, int L, int KP, int B,
+                  int kk, int kstride, int metric, float eps_abs, float eps_rel, uint64_t slot_base,
+                  uint64_t *d_out_ids, double *d_out_dists, int32_t *d_out_counts,
+                  int32_t *d_out_flags, cudaStream_t st) {
+    SelectArgs a;
+    a.rows = s->rows; a.row_bytes = s->row_bytes; a.norm64 = s->norm64; a.qms64 = s->qms64;
+    a.n = s->count; a.d = s->dim; a.q64 = d_q64; a.partial = partial; a.L = L; a.KP = KP;
+    a.kk = kk; a.kstride = kstride; a.metric = metric; a.eps_abs = eps_abs; a.eps_rel = eps_rel;
+    a.slot_base = slot_base; a.out_ids = d_out_ids; a.out_dists = d_out_dists;
+    a.out_counts = d_out_counts; a.out_flags = d_out_flags;
+    size_t smem = select_smem();
+    void (*fn)(const SelectArgs) = nullptr;
+    switch (s->dtype) {
+        case EVDB_F32: fn = select_kernel<EVDB_F32>; break;
+        case EVDB_BF16: fn = select_kernel<EVDB_BF16>; break;
+        case EVDB_U8: fn = select_kernel<EVDB_U8>; break;
+        default: fn = select_kernel<EVDB_U4>; break;
+    }
+    EVDB_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fn<<<B, kSelThreads, smem, st>>>(a);
+    s->n_launches++;
+    EVDB_CUDA(cudaGetLastError());
+    return EVDB_OK;
+}
+
+// ----------------------------------------------------------------------------
+// exhaustive fp64 plan
+// ----------------------------------------------------------------------------
+template <int DTYPE>
+__global__ void __launch_bounds__(256) exact_all_kernel(const uint8_t *__restrict__ rows,
+                                                        size_t row_bytes,
+                                                        const double *__restrict__ norm64,
+                                                        const double2 *__restrict__ qms64,
+                                                        uint64_t n, int d, const double *__restrict__ q,
+                                                        int metric, uint64_t *__restrict__ keys,
+                                                        uint32_t *__restrict__ slots) {
+    __shared__ double sp_all[8 * 2 * kExactChunk];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *sp = sp_all + warp * 2 * kExactChunk;
+    for (uint64_t r = (uint64_t)blockIdx.x * 8 + warp; r < n; r += (uint64_t)gridDim.x * 8) {
+        double mn = 0.0, sc = 0.0;
+        if (DTYPE == EVDB_U8 || DTYPE == EVDB_U4) {
+            double2 ms = qms64[r];
+            mn = ms.x;
+            sc = ms.y;
+        }
+        double dist = exact_distance_warp<DTYPE>(rows + r * row_bytes, mn, sc, q, d, metric,
+                                                 norm64[r], sp, lane);
+        if (lane == 0) {
+            keys[r] = f64_orderable(dist);
+            slots[r] = (uint32_t)r;
+        }
+    }
+}
+
+__global__ void emit_sorted_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ slots,
+                                   int kout, int kstride, uint64_t slot_base, uint64_t *out_ids,
+                                   double *out_dists, int32_t *out_count, int32_t *out_flag) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kstride; i += gridDim.x * blockDim.x) {
+        if (i < kout) {
+            uint64_t ob = keys[i];
+            uint64_t bits = ob ^ ((ob >> 63) ? 0x8000000000000000ull : 0xFFFFFFFFFFFFFFFFull);
+            out_dists[i] = __longlong_as_double((long long)bits);
+            out_ids[i] = slot_base + slots[i];
+        } else {
+            out_dists[i] = 0.0;
+            out_ids[i] = kKeyMax;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *out_count = kout;
+        if (out_flag) *out_flag = 0;
+    }
+}
+
+int exact_plan_search(evdb_store *s, const double *d_q64, int B, int kk, int kstride, int metric,
+                      uint64_t slot_base, uint64_t *d_out_ids, double *d_out_dists,
+                      int32_t *d_out_counts, int32_t *d_out_flags, cudaStream_t st) {
+    const uint64_t n = s->count;
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (uint64_t *)nullptr, (uint64_t *)nullptr,
+                                    (uint32_t *)nullptr, (uint32_t *)nullptr, (int64_t)n, 0, 64, st);
+    size_t kb = round_up64(n * sizeof(uint64_t), 256), sb = round_up64(n * sizeof(uint32_t), 256);
+    size_t need = 2 * kb + 2 * sb + cub_bytes;
+    EVDB_TRY(ensure_bytes(&s->w_tmp, &s->w_tmp_cap, need));
+    uint8_t *p = (uint8_t *)s->w_tmp;
+    uint64_t *k0 = (uint64_t *)p, *k1 = (uint64_t *)(p + kb);
+    uint32_t *s0 = (uint32_t *)(p + 2 * kb), *s1 = (uint32_t *)(p + 2 * kb + sb);
+    void *cub_tmp = p + 2 * kb + 2 * sb;
+    int grid = s->sm_count * 8;
+    int kout = (uint64_t)kk < n ? kk : (int)n;
+    for (int b = 0; b < B; ++b) {
+        const double *q = d_q64 + (size_t)b * s->dim;
+        switch (s->dtype) {
+            case EVDB_F32: exact_all_kernel<EVDB_F32><<<grid, 256, 0, st>>>(s->rows, s->row_bytes, s->norm64, s->qms64, n, s->dim, q, metric, k0, s0); break;
+            case EVDB_BF16: exact_all_kernel<EVDB_BF16><<<grid, 256, 0, st>>>(s->rows, s->row_bytes, s->norm64, s->qms64, n, s->dim, q, metric, k0, s0); break;
+            case EVDB_U8: exact_all_kernel<EVDB_U8><<<grid, 256, 0, st>>>(s->rows, s->row_bytes, s->norm64, s->qms64, n, s->dim, q, metric, k0, s0); break;
+            default: exact_all_kernel<EVDB_U4><<<grid, 256, 0, st>>>(s->rows, s->row_bytes, s->norm64, s->qms64, n, s->dim, q, metric, k0, s0); break;
+        }
+        EVDB_CUDA(cudaGetLastError());
+        // LSD radix sort is stable: equal distances keep ascending slot order
+        EVDB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, k0, k1, s0, s1, (int64_t)n, 0, 64, st));
+        emit_sorted_kernel<<<(kstride + 255) / 256 > 0 ? (kstride + 255) / 256 : 1, 256, 0, st>>>(
+            k1, s1, kout, kstride, slot_base, d_out_ids + (size_t)b * kstride,
+            d_out_dists + (size_t)b * kstride, d_out_counts + b, d_out_flags ? d_out_flags + b : nullptr);
+        EVDB_CUDA(cudaGetLastError());
+        s->n_launches += 3;
+    }
+    return EVDB_OK;
+}
+
+// ----------------------------------------------------------------------------
+// G-way merge of per-shard (distance, id) lists after the allgather
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) merge_topk_kernel(const uint64_t *__restrict__ ids,
+                                                          const double *__restrict__ dists,
+                                                          const int32_t *__restrict__ counts, int G,
+                                                          int B, int k, int nsort,
+                                                          uint64_t *__restrict__ out_ids,
+                                                          double *__restrict__ out_dists,
+                                                          int32_t *__restrict__ out_counts) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint64_t *dk = reinterpret_cast<uint64_t *>(smem);
+    uint64_t *di = dk + nsort;
+    const int b = blockIdx.x;
+    int total = 0;
+    for (int g = 0; g < G; ++g) total += counts[(size_t)g * B + b];
+    for (int i = threadIdx.x; i < nsort; i += blockDim.x) {
+        uint64_t key = kKeyMax, id = kKeyMax;
+        if (i < G * k) {
+            int g = i / k, j = i % k;
+            if (j < counts[(size_t)g * B + b]) {
+                size_t o = ((size_t)g * B + b) * k + j;
+                key = f64_orderable(dists[o]);
+                id = ids[o];
+            }
+        }
+        dk[i] = key;
+        di[i] = id;
+    }
+    __syncthreads();
+    block_bitonic_sort_pairs(dk, di, nsort);
+    int kout = total < k ? total : k;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        size_t o = (size_t)b * k + i;
+        if (i < kout) {
+            uint64_t ob = dk[i];
+            uint64_t bits = ob ^ ((ob >> 63) ? 0x8000000000000000ull : 0xFFFFFFFFFFFFFFFFull);
+            out_dists[o] = __longlong_as_double((long long)bits);
+            out_ids[o] = di[i];
+        } else {
+            out_dists[o] = 0.0;
+            out_ids[o] = kKeyMax;
+        }
+    }
+    if (threadIdx.x == 0) out_counts[b] = kout;
+}
+
+int launch_merge_topk(const uint64_t *ids, const double *dists, const int32_t *counts, int G, int B,
+                      int k, uint64_t *out_ids, double *out_dists, int32_t *out_counts,
+                      cudaStream_t st) {
+    if (G <= 0 || B <= 0 || k <= 0) return EVDB_E_BAD_ARG;
+    int nsort = next_pow2(G * k);
+    size_t smem = (size_t)nsort * 16;
+    if (smem > 200 * 1024) return EVDB_E_UNSUPPORTED;
+    EVDB_CUDA(cudaFuncSetAttribute((const void *)merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    merge_topk_kernel<<<B, 1024, smem, st>>>(ids, dists, counts, G, B, k, nsort, out_ids, out_dists, out_counts);
+    EVDB_CUDA(cudaGetLastError());
+    return EVDB_OK;
+}
+
+}  // namespace evdb

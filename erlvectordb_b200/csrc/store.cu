@@ -1,0 +1,804 @@
+// store.cu -- device-resident store, search orchestration and the C ABI.
+//
+// The store is what a vector_store gen_server (reference
+// src/vector_store.erl:21-35,60-207) keeps in its `vectors` map, re-laid-out as
+// packed device columns.  See include/evdb.h for the entry-point <-> reference
+// mapping.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+
+#include "internal.h"
+
+namespace evdb {
+
+static thread_local char g_cuda_err[256] = "";
+
+void set_cuda_error(cudaError_t e, const char *file, int line) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s (%s) at %s:%d", cudaGetErrorName(e),
+             cudaGetErrorString(e), file, line);
+    cudaGetLastError();  // clear the sticky-less error state
+}
+
+int ensure_bytes(void **p, size_t *cap, size_t need, bool pinned) {
+    if (need <= *cap && *p) return EVDB_OK;
+    size_t ncap = *cap ? *cap : 4096;
+    while (ncap < need) ncap *= 2;
+    if (*p) {
+        if (pinned) cudaFreeHost(*p); else cudaFree(*p);
+        *p = nullptr;
+        *cap = 0;
+    }
+    if (pinned) EVDB_CUDA(cudaMallocHost(p, ncap));
+    else EVDB_CUDA(cudaMalloc(p, ncap));
+    *cap = ncap;
+    return EVDB_OK;
+}
+
+void prof_begin(evdb_store *s, cudaStream_t st) {
+    if (!s->prof_on || s->prof_n >= kProfMax) return;
+    cudaEventRecord(s->prof_ev[2 * s->prof_n], st);
+    s->prof_stream = st;
+}
+void prof_end(evdb_store *s, cudaStream_t st) {
+    if (!s->prof_on || s->prof_n >= kProfMax) return;
+    cudaEventRecord(s->prof_ev[2 * s->prof_n + 1], st);
+    s->prof_n++;
+}
+
+static bool is_quant(const evdb_store *s) { return s->dtype == EVDB_U8 || s->dtype == EVDB_U4; }
+
+static int set_device(const evdb_store *s) {
+    EVDB_CUDA(cudaSetDevice(s->device));
+    return EVDB_OK;
+}
+
+static void set_dim(evdb_store *s, int d) {
+    s->dim = d;
+    switch (s->dtype) {
+        case EVDB_F32: s->dpad = round_up(d, 4); s->nch = s->dpad / 4; s->row_bytes = (size_t)s->dpad * 4; break;
+        case EVDB_BF16: s->dpad = round_up(d, 8); s->nch = s->dpad / 8; s->row_bytes = (size_t)s->dpad * 2; break;
+        case EVDB_U8: s->dpad = round_up(d, 16); s->nch = s->dpad / 16; s->row_bytes = (size_t)s->dpad; break;
+        default: s->dpad = round_up(d, 32); s->nch = s->dpad / 32; s->row_bytes = (size_t)s->dpad / 2; break;
+    }
+}
+
+template <typename T>
+static int regrow(T **p, uint64_t old_rows, uint64_t new_rows, size_t per_row, cudaStream_t st) {
+    T *np = nullptr;
+    EVDB_CUDA(cudaMalloc((void **)&np, new_rows * per_row));
+    if (*p && old_rows) EVDB_CUDA(cudaMemcpyAsync(np, *p, old_rows * per_row, cudaMemcpyDeviceToDevice, st));
+    if (*p) {
+        EVDB_CUDA(cudaStreamSynchronize(st));
+        cudaFree(*p);
+    }
+    *p = np;
+    return EVDB_OK;
+}
+
+static int ensure_capacity(evdb_store *s, uint64_t need) {
+    if (need <= s->capacity) return EVDB_OK;
+    uint64_t ncap = s->capacity ? s->capacity * 2 : 1024;
+    if (ncap < need) ncap = need;
+    uint64_t live = s->count;
+    EVDB_TRY(regrow(&s->rows, live, ncap, s->row_bytes, s->stream));
+    EVDB_TRY(regrow(&s->norm64, live, ncap, sizeof(double), s->stream));
+    EVDB_TRY(regrow(&s->inv_norm, live, ncap, sizeof(float), s->stream));
+    EVDB_TRY(regrow(&s->norm_sq, live, ncap, sizeof(float), s->stream));
+    if (is_quant(s)) {
+        EVDB_TRY(regrow(&s->qcoef, live, ncap, sizeof(float2), s->stream));
+        EVDB_TRY(regrow(&s->qms64, live, ncap, sizeof(double2), s->stream));
+    }
+    if (s->dtype == EVDB_F32 && s->gemm_shadow)
+        EVDB_TRY(regrow(&s->shadow, live, ncap, (size_t)s->dpad * sizeof(__nv_bfloat16), s->stream));
+    s->capacity = ncap;
+    return EVDB_OK;
+}
+
+static uint64_t device_bytes(const evdb_store *s) {
+    uint64_t per = s->row_bytes + sizeof(double) + 2 * sizeof(float);
+    if (is_quant(s)) per += sizeof(float2) + sizeof(double2);
+    if (s->shadow) per += (uint64_t)s->dpad * 2;
+    return per * s->capacity + s->w_q64_cap + s->w_q32_cap + s->w_qdig_cap + s->w_qstat_cap +
+           s->w_partial_cap + s->w_ids_cap + s->w_dists_cap + s->w_counts_cap + s->w_tmp_cap;
+}
+
+// ----------------------------------------------------------------------------
+// search orchestration (device side, asynchronous on `st`)
+// ----------------------------------------------------------------------------
+static int choose_kp(int kk, int kp_min) {
+    int slack = kk / 4 > 6 ? kk / 4 : 6;
+    int want = kk + slack;
+    if (want < kp_min) want = kp_min;
+    if (want < kMinKP) want = kMinKP;
+    return next_pow2(want);
+}
+
+// d_q64: [B][dim] fp64 on the device.  Outputs [B][kstride].
+static int search_core(evdb_store *s, const double *d_q64, int B, int k, int kstride, int metric,
+                       int kp_min, int plan, uint64_t slot_base, uint64_t *d_ids, double *d_dists,
+                       int32_t *d_counts, int32_t *d_flags, cudaStream_t st) {
+    const int kk = (uint64_t)k < s->count ? k : (int)s->count;
+    if (plan == EVDB_PLAN_AUTO) plan = s->plan;
+    int KP = choose_kp(kk, kp_min);
+    bool fast_ok = KP <= kMaxKP && !(is_quant(s) && metric != EVDB_COSINE);
+    if (plan == EVDB_PLAN_EXACT || !fast_ok) {
+        s->last_plan = EVDB_PLAN_EXACT;
+        return exact_plan_search(s, d_q64, B, kk, kstride, metric, slot_base, d_ids, d_dists,
+                                 d_counts, d_flags, st);
+    }
+    if ((uint64_t)KP > s->count) {
+        // the whole store fits in the window: keep KP a power of two, lists pad with kKeyMax
+    }
+    const double u = 5.9604644775390625e-08;  // 2^-24
+    float eps_abs = 0.f, eps_rel = 0.f;
+    int lists = 0;
+    bool use_gemm = false;
+    if (plan == EVDB_PLAN_GEMM || (plan == EVDB_PLAN_AUTO && B >= 16))
+        use_gemm = gemm_plan_supported(s, metric, B, KP);
+    if (plan == EVDB_PLAN_GEMM && !use_gemm) return EVDB_E_UNSUPPORTED;
+
+    EVDB_TRY(launch_prep_queries(s, d_q64, B, st));
+    if (use_gemm) {
+        s->last_plan = EVDB_PLAN_GEMM;
+        prof_begin(s, st);
+        EVDB_TRY(launch_gemm_topk(s, metric, B, KP, nullptr, &lists, st));
+        prof_end(s, st);
+        // bf16 operands (2^-9 each, round-to-nearest) + fp32 accumulation in the tensor core
+        eps_abs = (float)(0.00390625 * 1.02 + (double)s->dim * 4.0 * u);
+        if (metric != EVDB_COSINE) return EVDB_E_UNSUPPORTED;
+    } else {
+        s->last_plan = EVDB_PLAN_SCAN;
+        int G = 0;
+        int rc = scan_grid_size(s, metric, KP, &G);
+        if (rc == EVDB_E_UNSUPPORTED) {
+            s->last_plan = EVDB_PLAN_EXACT;
+            return exact_plan_search(s, d_q64, B, kk, kstride, metric, slot_base, d_ids, d_dists,
+                                     d_counts, d_flags, st);
+        }
+        EVDB_TRY(rc);
+        EVDB_TRY(ensure_bytes((void **)&s->w_partial, &s->w_partial_cap,
+                              sizeof(uint64_t) * (size_t)B * G * KP));
+        ScanArgs a;
+        a.rows = s->rows; a.row_bytes = s->row_bytes; a.nch = s->nch; a.n = s->count;
+        a.inv_norm = s->inv_norm; a.qcoef = s->qcoef;
+        a.q32 = s->w_q32; a.q32_stride = s->dpad;
+        a.qdig = s->w_qdig; a.qdig_stride = s->dpad;
+        a.qstat = s->w_qstat; a.partial = s->w_partial; a.KP = KP; a.G = G; a.B = B;
+        prof_begin(s, st);
+        EVDB_TRY(launch_scan(s, metric, a, st));
+        prof_end(s, st);
+        lists = G;
+        double depth = (double)s->dim / 64.0 + 24.0;
+        if (is_quant(s)) eps_abs = (float)((2.0 * sqrt((double)s->dim) + 24.0) * u);
+        else if (metric == EVDB_COSINE) eps_abs = (float)(depth * u);
+        else { eps_rel = (float)(depth * u); eps_abs = 1e-37f; }
+    }
+    EVDB_TRY(launch_select(s, d_q64, s->w_partial, lists, KP, B, kk, kstride, metric, eps_abs,
+                           eps_rel, slot_base, d_ids, d_dists, d_counts, d_flags, st));
+    s->n_rows_scanned += (uint64_t)B * s->count;
+    return EVDB_OK;
+}
+
+__global__ void widen_kernel(const float *__restrict__ in, double *__restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = (double)in[i];
+}
+
+static int ensure_out(evdb_store *s, int B, int kstride) {
+    size_t nk = (size_t)B * (kstride > 0 ? kstride : 1);
+    EVDB_TRY(ensure_bytes((void **)&s->w_ids, &s->w_ids_cap, nk * sizeof(uint64_t)));
+    EVDB_TRY(ensure_bytes((void **)&s->w_dists, &s->w_dists_cap, nk * sizeof(double)));
+    EVDB_TRY(ensure_bytes((void **)&s->w_counts, &s->w_counts_cap, sizeof(int32_t) * 2 * (size_t)B));
+    return EVDB_OK;
+}
+
+// Host-facing search: H2D queries, search, D2H results, escalate flagged queries.
+static int search_host(evdb_store *s, const void *queries, bool is_f64, int B, int d, int k,
+                       int metric, uint32_t *out_slots, double *out_dists, int32_t *out_counts) {
+    if (!s || B < 0 || k < 0 || (B > 0 && !queries) || metric < 0 || metric > 2) return EVDB_E_BAD_ARG;
+    if (B == 0) return EVDB_OK;
+    if (!out_counts || (k > 0 && (!out_slots || !out_dists))) return EVDB_E_BAD_ARG;
+    // validate_vector(Q, undefined) accepts any length on an empty store -> {ok, []}
+    if (s->dim == 0 || s->count == 0) {
+        if (s->dim != 0 && d != s->dim) return EVDB_E_DIM_MISMATCH;
+        for (int b = 0; b < B; ++b) out_counts[b] = 0;
+        return EVDB_OK;
+    }
+    if (d != s->dim) return EVDB_E_DIM_MISMATCH;
+    size_t nq = (size_t)B * d;
+    if (is_f64) {
+        const double *q = (const double *)queries;
+        for (size_t i = 0; i < nq; ++i) if (!isfinite(q[i])) return EVDB_E_BAD_VECTOR;
+    } else {
+        const float *q = (const float *)queries;
+        for (size_t i = 0; i < nq; ++i) if (!isfinite(q[i])) return EVDB_E_BAD_VECTOR;
+    }
+    EVDB_TRY(set_device(s));
+    if (k == 0) {
+        for (int b = 0; b < B; ++b) out_counts[b] = 0;
+        return EVDB_OK;
+    }
+    cudaStream_t st = s->stream;
+    const int kk = (uint64_t)k < s->count ? k : (int)s->count;
+    const int kstride = kk;
+    EVDB_TRY(ensure_bytes((void **)&s->w_q64, &s->w_q64_cap, nq * sizeof(double)));
+    EVDB_TRY(ensure_out(s, B, kstride));
+    EVDB_CUDA(cudaEventRecord(s->ev0, st));
+    if (is_f64) {
+        EVDB_CUDA(cudaMemcpyAsync(s->w_q64, queries, nq * sizeof(double), cudaMemcpyHostToDevice, st));
+    } else {
+        EVDB_TRY(ensure_bytes(&s->w_tmp, &s->w_tmp_cap, nq * sizeof(float)));
+        EVDB_CUDA(cudaMemcpyAsync(s->w_tmp, queries, nq * sizeof(float), cudaMemcpyHostToDevice, st));
+        widen_kernel<<<(int)((nq + 255) / 256 < 1024 ? (nq + 255) / 256 : 1024), 256, 0, st>>>(
+            (const float *)s->w_tmp, s->w_q64, nq);
+        s->n_launches++;
+        EVDB_CUDA(cudaGetLastError());
+    }
+    int32_t *d_counts = s->w_counts, *d_flags = s->w_counts + B;
+    EVDB_TRY(search_core(s, s->w_q64, B, k, kstride, metric, 0, EVDB_PLAN_AUTO, 0, s->w_ids,
+                         s->w_dists, d_counts, d_flags, st));
+    size_t nk = (size_t)B * kstride;
+    size_t pin_need = nk * (sizeof(uint64_t) + sizeof(double)) + sizeof(int32_t) * 2 * (size_t)B;
+    EVDB_TRY(ensure_bytes(&s->h_pin, &s->h_pin_cap, pin_need, true));
+    uint64_t *h_ids = (uint64_t *)s->h_pin;
+    double *h_d = (double *)(h_ids + nk);
+    int32_t *h_c = (int32_t *)(h_d + nk);
+    EVDB_CUDA(cudaMemcpyAsync(h_ids, s->w_ids, nk * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    EVDB_CUDA(cudaMemcpyAsync(h_d, s->w_dists, nk * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EVDB_CUDA(cudaMemcpyAsync(h_c, s->w_counts, sizeof(int32_t) * 2 * (size_t)B, cudaMemcpyDeviceToHost, st));
+    EVDB_CUDA(cudaEventRecord(s->ev1, st));
+    EVDB_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, s->ev0, s->ev1);
+    s->last_search_ms = ms;
+    s->n_searches += (uint64_t)B;
+
+    // escalate queries whose candidate window could not be proven complete
+    int first_plan = s->last_plan;
+    for (int b = 0; b < B; ++b) {
+        if (!h_c[B + b]) continue;
+        s->n_escalations++;
+        int kp_min = 256;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            int plan = attempt == 0 ? EVDB_PLAN_SCAN : EVDB_PLAN_EXACT;
+            if (attempt == 0 && (choose_kp(kk, kp_min) > kMaxKP)) continue;
+            const double *dq = s->w_q64 + (size_t)b * d;
+            EVDB_TRY(search_core(s, dq, 1, k, kstride, metric, kp_min, plan, 0,
+                                 s->w_ids + (size_t)b * kstride, s->w_dists + (size_t)b * kstride,
+                                 d_counts + b, d_flags + b, st));
+            EVDB_CUDA(cudaMemcpyAsync(h_ids + (size_t)b * kstride, s->w_ids + (size_t)b * kstride,
+                                      kstride * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+            EVDB_CUDA(cudaMemcpyAsync(h_d + (size_t)b * kstride, s->w_dists + (size_t)b * kstride,
+                                      kstride * sizeof(double), cudaMemcpyDeviceToHost, st));
+            EVDB_CUDA(cudaMemcpyAsync(h_c + b, d_counts + b, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            EVDB_CUDA(cudaMemcpyAsync(h_c + B + b, d_flags + b, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            EVDB_CUDA(cudaStreamSynchronize(st));
+            if (!h_c[B + b]) break;
+        }
+    }
+    s->last_plan = first_plan;
+    for (int b = 0; b < B; ++b) {
+        out_counts[b] = h_c[b];
+        for (int j = 0; j < k; ++j) {
+            size_t o = (size_t)b * k + j;
+            if (j < h_c[b]) {
+                out_slots[o] = (uint32_t)h_ids[(size_t)b * kstride + j];
+                out_dists[o] = h_d[(size_t)b * kstride + j];
+            } else {
+                out_slots[o] = 0xFFFFFFFFu;
+                out_dists[o] = 0.0;
+            }
+        }
+    }
+    return EVDB_OK;
+}
+
+// ----------------------------------------------------------------------------
+// ingest helpers
+// ----------------------------------------------------------------------------
+static int check_dim(evdb_store *s, int d) {
+    if (d <= 0) return EVDB_E_BAD_VECTOR;
+    if (s->dim == 0) {
+        set_dim(s, d);
+        return EVDB_OK;
+    }
+    return d == s->dim ? EVDB_OK : EVDB_E_DIM_MISMATCH;
+}
+
+int launch_narrow_rows(evdb_store *s, uint64_t dst0, const void *src, bool is_f64, uint64_t n,
+                       cudaStream_t st);
+
+// rows: n x d host values (fp64 or fp32) -> slots [slot0, slot0+n)
+static int ingest_rows(evdb_store *s, uint64_t slot0, const void *rows, bool is_f64, uint64_t n) {
+    const int d = s->dim;
+    cudaStream_t st = s->stream;
+    const size_t esz = is_f64 ? sizeof(double) : sizeof(float);
+    // chunk so that staging stays <= 256 MiB
+    uint64_t chunk = (256ull << 20) / ((size_t)d * esz);
+    if (chunk < 1) chunk = 1;
+    for (uint64_t r0 = 0; r0 < n; r0 += chunk) {
+        uint64_t cnt = n - r0 < chunk ? n - r0 : chunk;
+        const uint8_t *src = (const uint8_t *)rows + r0 * (size_t)d * esz;
+        uint64_t dst0 = slot0 + r0;
+        if (s->dtype == EVDB_F32 && !is_f64) {
+            EVDB_CUDA(cudaMemcpy2DAsync(s->rows + dst0 * s->row_bytes, s->row_bytes, src, (size_t)d * 4,
+                                        (size_t)d * 4, cnt, cudaMemcpyHostToDevice, st));
+            if (s->dpad != d)
+                EVDB_CUDA(cudaMemset2DAsync(s->rows + dst0 * s->row_bytes + (size_t)d * 4, s->row_bytes, 0,
+                                            (size_t)(s->dpad - d) * 4, cnt, st));
+        } else {
+            size_t bytes = cnt * (size_t)d * esz;
+            EVDB_TRY(ensure_bytes(&s->w_tmp, &s->w_tmp_cap, bytes));
+            EVDB_CUDA(cudaMemcpyAsync(s->w_tmp, src, bytes, cudaMemcpyHostToDevice, st));
+            if (is_quant(s)) {
+                EVDB_TRY(launch_quantize_rows(s->dtype, is_f64 ? (const double *)s->w_tmp : nullptr,
+                                              is_f64 ? nullptr : (const float *)s->w_tmp, cnt, d,
+                                              s->rows + dst0 * s->row_bytes, s->row_bytes,
+                                              s->qms64 + dst0, nullptr, nullptr, st));
+            } else {
+                EVDB_TRY(launch_narrow_rows(s, dst0, s->w_tmp, is_f64, cnt, st));
+            }
+            s->n_launches++;
+        }
+        EVDB_TRY(launch_finalize_rows(s, dst0, cnt, st));
+        EVDB_CUDA(cudaStreamSynchronize(st));
+    }
+    return EVDB_OK;
+}
+
+template <typename SRC, int DTYPE>
+__global__ void narrow_rows_kernel(const SRC *__restrict__ src, uint8_t *__restrict__ rows,
+                                   size_t row_bytes, int d, int dpad, uint64_t n) {
+    uint64_t total = n * (uint64_t)dpad;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t r = i / dpad;
+        int c = (int)(i % dpad);
+        float v = c < d ? (float)src[r * (uint64_t)d + c] : 0.0f;
+        if (DTYPE == EVDB_F32) reinterpret_cast<float *>(rows + r * row_bytes)[c] = v;
+        else reinterpret_cast<__nv_bfloat16 *>(rows + r * row_bytes)[c] = __float2bfloat16_rn(v);
+    }
+}
+
+int launch_narrow_rows(evdb_store *s, uint64_t dst0, const void *src, bool is_f64, uint64_t n,
+                       cudaStream_t st) {
+    uint64_t blocks = (n * (uint64_t)s->dpad + 255) / 256;
+    int grid = (int)(blocks < (uint64_t)s->sm_count * 16 ? blocks : (uint64_t)s->sm_count * 16);
+    uint8_t *dst = s->rows + dst0 * s->row_bytes;
+    if (s->dtype == EVDB_F32) {
+        if (is_f64) narrow_rows_kernel<double, EVDB_F32><<<grid, 256, 0, st>>>((const double *)src, dst, s->row_bytes, s->dim, s->dpad, n);
+        else narrow_rows_kernel<float, EVDB_F32><<<grid, 256, 0, st>>>((const float *)src, dst, s->row_bytes, s->dim, s->dpad, n);
+    } else {
+        if (is_f64) narrow_rows_kernel<double, EVDB_BF16><<<grid, 256, 0, st>>>((const double *)src, dst, s->row_bytes, s->dim, s->dpad, n);
+        else narrow_rows_kernel<float, EVDB_BF16><<<grid, 256, 0, st>>>((const float *)src, dst, s->row_bytes, s->dim, s->dpad, n);
+    }
+    EVDB_CUDA(cudaGetLastError());
+    return EVDB_OK;
+}
+
+template <typename T>
+static int upsert_any(evdb_store *s, uint32_t slot, const T *vec, int d, bool is_f64) {
+    if (!s || !vec) return EVDB_E_BAD_ARG;
+    EVDB_TRY(check_dim(s, d));
+    for (int i = 0; i < d; ++i) if (!isfinite((double)vec[i])) return EVDB_E_BAD_VECTOR;
+    if ((uint64_t)slot > s->count) return EVDB_E_BAD_ARG;
+    EVDB_TRY(set_device(s));
+    EVDB_TRY(ensure_capacity(s, (uint64_t)slot + 1));
+    EVDB_TRY(ingest_rows(s, slot, vec, is_f64, 1));
+    if ((uint64_t)slot == s->count) s->count++;
+    return EVDB_OK;
+}
+
+template <typename T>
+static int bulk_any(evdb_store *s, const T *rows, uint64_t n, int d, bool is_f64) {
+    if (!s || (n > 0 && !rows)) return EVDB_E_BAD_ARG;
+    if (n == 0) { s->count = 0; s->shadow_valid = 0; return EVDB_OK; }
+    EVDB_TRY(check_dim(s, d));
+    if (n > 0xFFFFFFF0ull) return EVDB_E_BAD_ARG;
+    EVDB_TRY(set_device(s));
+    EVDB_TRY(ensure_capacity(s, n));
+    s->count = 0;
+    s->shadow_valid = 0;
+    EVDB_TRY(ingest_rows(s, 0, rows, is_f64, n));
+    s->count = n;
+    return EVDB_OK;
+}
+
+}  // namespace evdb
+
+using namespace evdb;
+
+// ============================================================================
+// C ABI
+// ============================================================================
+extern "C" {
+
+int evdb_abi_version(void) { return EVDB_ABI_VERSION; }
+
+const char *evdb_strerror(int code) {
+    switch (code) {
+        case EVDB_OK: return "ok";
+        case EVDB_E_DIM_MISMATCH: return "dimension_mismatch";
+        case EVDB_E_BAD_VECTOR: return "invalid_vector_format";
+        case EVDB_E_OOM: return "out_of_device_memory";
+        case EVDB_E_CUDA: return "cuda_error";
+        case EVDB_E_NCCL: return "nccl_error";
+        case EVDB_E_BAD_ARG: return "badarg";
+        case EVDB_E_NO_DEVICE: return "no_sm100_device";
+        case EVDB_E_UNSUPPORTED: return "unsupported";
+        case EVDB_E_BADARITH: return "badarith";
+        default: return "unknown_error";
+    }
+}
+
+const char *evdb_last_cuda_error(void) { return g_cuda_err; }
+
+static int check_device(int dev) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); return EVDB_E_NO_DEVICE; }
+    if (dev < 0 || dev >= n) return EVDB_E_NO_DEVICE;
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) { cudaGetLastError(); return EVDB_E_NO_DEVICE; }
+    if (p.major != 10) return EVDB_E_NO_DEVICE;  // sm_100a SASS only: no fallback
+    return EVDB_OK;
+}
+
+int evdb_init(const int *devices, int n_dev) {
+    if (!devices || n_dev <= 0) return check_device(0);
+    for (int i = 0; i < n_dev; ++i) EVDB_TRY(check_device(devices[i]));
+    return EVDB_OK;
+}
+
+int evdb_store_create(const evdb_opts *opts, evdb_store **out) {
+    if (!opts || !out) return EVDB_E_BAD_ARG;
+    *out = nullptr;
+    if (opts->dtype < EVDB_F32 || opts->dtype > EVDB_U4 || opts->dim < 0) return EVDB_E_BAD_ARG;
+    EVDB_TRY(check_device(opts->device));
+    evdb_store *s = new (std::nothrow) evdb_store();
+    if (!s) return EVDB_E_OOM;
+    s->device = opts->device;
+    s->dtype = opts->dtype;
+    s->gemm_shadow = opts->gemm_shadow;
+    int rc = EVDB_OK;
+    do {
+        if (cudaSetDevice(s->device) != cudaSuccess) { rc = EVDB_E_CUDA; break; }
+        cudaDeviceProp p;
+        cudaGetDeviceProperties(&p, s->device);
+        s->sm_count = p.multiProcessorCount;
+        if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = EVDB_E_CUDA; break; }
+        if (cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess) { rc = EVDB_E_CUDA; break; }
+        if (opts->dim > 0) {
+            set_dim(s, opts->dim);
+            if (opts->capacity_hint) rc = ensure_capacity(s, opts->capacity_hint);
+        }
+    } while (0);
+    if (rc != EVDB_OK) { evdb_store_destroy(s); return rc; }
+    *out = s;
+    return EVDB_OK;
+}
+
+void evdb_store_destroy(evdb_store *s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    cudaFree(s->rows); cudaFree(s->norm64); cudaFree(s->inv_norm); cudaFree(s->norm_sq);
+    cudaFree(s->qcoef); cudaFree(s->qms64); cudaFree(s->shadow);
+    cudaFree(s->w_q64); cudaFree(s->w_q32); cudaFree(s->w_qdig); cudaFree(s->w_qstat);
+    cudaFree(s->w_partial); cudaFree(s->w_ids); cudaFree(s->w_dists); cudaFree(s->w_counts);
+    cudaFree(s->w_tmp);
+    if (s->h_pin) cudaFreeHost(s->h_pin);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->prof_ev) {
+        for (int i = 0; i < 2 * kProfMax; ++i) if (s->prof_ev[i]) cudaEventDestroy(s->prof_ev[i]);
+        free(s->prof_ev);
+    }
+    if (s->stream) cudaStreamDestroy(s->stream);
+    cudaGetLastError();
+    delete s;
+}
+
+int evdb_store_stats(evdb_store *s, evdb_stats *out) {
+    if (!s || !out) return EVDB_E_BAD_ARG;
+    memset(out, 0, sizeof(*out));
+    out->count = s->count;
+    out->dimension = s->dim;
+    out->dtype = s->dtype;
+    out->device = s->device;
+    out->last_plan = s->last_plan;
+    out->capacity = s->capacity;
+    out->device_bytes = device_bytes(s);
+    out->searches = s->n_searches;
+    out->rows_scanned = s->n_rows_scanned;
+    out->escalations = s->n_escalations;
+    out->kernel_launches = s->n_launches;
+    out->last_search_ms = s->last_search_ms;
+    return EVDB_OK;
+}
+
+int evdb_store_set_plan(evdb_store *s, int plan) {
+    if (!s || plan < EVDB_PLAN_AUTO || plan > EVDB_PLAN_EXACT) return EVDB_E_BAD_ARG;
+    s->plan = plan;
+    return EVDB_OK;
+}
+
+int evdb_store_profile(evdb_store *s, int enable) {
+    if (!s) return EVDB_E_BAD_ARG;
+    EVDB_TRY(set_device(s));
+    if (enable && !s->prof_ev) {
+        s->prof_ev = (cudaEvent_t *)calloc(2 * kProfMax, sizeof(cudaEvent_t));
+        if (!s->prof_ev) return EVDB_E_OOM;
+        for (int i = 0; i < 2 * kProfMax; ++i) EVDB_CUDA(cudaEventCreate(&s->prof_ev[i]));
+    }
+    s->prof_on = enable ? 1 : 0;
+    s->prof_n = 0;
+    return EVDB_OK;
+}
+
+int evdb_store_profile_read(evdb_store *s, int32_t *n_samples, double *total_ms) {
+    if (!s || !n_samples || !total_ms) return EVDB_E_BAD_ARG;
+    *n_samples = 0;
+    *total_ms = 0.0;
+    if (!s->prof_ev || s->prof_n == 0) return EVDB_OK;
+    EVDB_TRY(set_device(s));
+    EVDB_CUDA(cudaEventSynchronize(s->prof_ev[2 * s->prof_n - 1]));
+    double tot = 0.0;
+    for (int i = 0; i < s->prof_n; ++i) {
+        float ms = 0.f;
+        EVDB_CUDA(cudaEventElapsedTime(&ms, s->prof_ev[2 * i], s->prof_ev[2 * i + 1]));
+        tot += ms;
+    }
+    *n_samples = s->prof_n;
+    *total_ms = tot;
+    s->prof_n = 0;
+    return EVDB_OK;
+}
+
+int evdb_store_upsert_f64(evdb_store *s, uint32_t slot, const double *vec, int d) {
+    return upsert_any<double>(s, slot, vec, d, true);
+}
+int evdb_store_upsert_f32(evdb_store *s, uint32_t slot, const float *vec, int d) {
+    return upsert_any<float>(s, slot, vec, d, false);
+}
+int evdb_store_bulk_load_f32(evdb_store *s, const float *rows, uint64_t n, int d) {
+    return bulk_any<float>(s, rows, n, d, false);
+}
+int evdb_store_bulk_load_f64(evdb_store *s, const double *rows, uint64_t n, int d) {
+    return bulk_any<double>(s, rows, n, d, true);
+}
+
+int evdb_store_bulk_load_codes(evdb_store *s, const uint8_t *codes, const double *mins,
+                               const double *scales, uint64_t n, int d) {
+    if (!s || !is_quant(s)) return EVDB_E_BAD_ARG;
+    if (n == 0) { s->count = 0; return EVDB_OK; }
+    if (!codes || !mins || !scales) return EVDB_E_BAD_ARG;
+    EVDB_TRY(check_dim(s, d));
+    if (n > 0xFFFFFFF0ull) return EVDB_E_BAD_ARG;
+    EVDB_TRY(set_device(s));
+    EVDB_TRY(ensure_capacity(s, n));
+    s->count = 0;
+    cudaStream_t st = s->stream;
+    size_t src_row = s->dtype == EVDB_U8 ? (size_t)d : (size_t)(d + 1) / 2;
+    EVDB_CUDA(cudaMemset2DAsync(s->rows, s->row_bytes, 0, s->row_bytes, n, st));
+    EVDB_CUDA(cudaMemcpy2DAsync(s->rows, s->row_bytes, codes, src_row, src_row, n, cudaMemcpyHostToDevice, st));
+    // interleave {min, scale} on the host (n pairs), one H2D
+    EVDB_TRY(ensure_bytes(&s->h_pin, &s->h_pin_cap, n * sizeof(double2), true));
+    double2 *hp = (double2 *)s->h_pin;
+    for (uint64_t i = 0; i < n; ++i) { hp[i].x = mins[i]; hp[i].y = scales[i]; }
+    EVDB_CUDA(cudaMemcpyAsync(s->qms64, hp, n * sizeof(double2), cudaMemcpyHostToDevice, st));
+    EVDB_TRY(launch_finalize_rows(s, 0, n, st));
+    EVDB_CUDA(cudaStreamSynchronize(st));
+    s->count = n;
+    return EVDB_OK;
+}
+
+int evdb_store_delete(evdb_store *s, uint32_t slot, int64_t *moved_from) {
+    if (!s) return EVDB_E_BAD_ARG;
+    if (moved_from) *moved_from = -1;
+    if ((uint64_t)slot >= s->count) return EVDB_E_BAD_ARG;
+    EVDB_TRY(set_device(s));
+    uint64_t last = s->count - 1;
+    cudaStream_t st = s->stream;
+    if ((uint64_t)slot != last) {
+        EVDB_CUDA(cudaMemcpyAsync(s->rows + (size_t)slot * s->row_bytes, s->rows + last * s->row_bytes, s->row_bytes, cudaMemcpyDeviceToDevice, st));
+        EVDB_CUDA(cudaMemcpyAsync(s->norm64 + slot, s->norm64 + last, sizeof(double), cudaMemcpyDeviceToDevice, st));
+        EVDB_CUDA(cudaMemcpyAsync(s->inv_norm + slot, s->inv_norm + last, sizeof(float), cudaMemcpyDeviceToDevice, st));
+        EVDB_CUDA(cudaMemcpyAsync(s->norm_sq + slot, s->norm_sq + last, sizeof(float), cudaMemcpyDeviceToDevice, st));
+        if (is_quant(s)) {
+            EVDB_CUDA(cudaMemcpyAsync(s->qcoef + slot, s->qcoef + last, sizeof(float2), cudaMemcpyDeviceToDevice, st));
+            EVDB_CUDA(cudaMemcpyAsync(s->qms64 + slot, s->qms64 + last, sizeof(double2), cudaMemcpyDeviceToDevice, st));
+        }
+        if (s->shadow)
+            EVDB_CUDA(cudaMemcpyAsync(s->shadow + (size_t)slot * s->dpad, s->shadow + last * (size_t)s->dpad, (size_t)s->dpad * 2, cudaMemcpyDeviceToDevice, st));
+        EVDB_CUDA(cudaStreamSynchronize(st));
+        if (moved_from) *moved_from = (int64_t)last;
+    }
+    s->count = last;
+    if (s->shadow_valid > s->count) s->shadow_valid = s->count;
+    return EVDB_OK;
+}
+
+int evdb_store_get_f64(evdb_store *s, uint32_t slot, double *out, int d) {
+    if (!s || !out) return EVDB_E_BAD_ARG;
+    if ((uint64_t)slot >= s->count) return EVDB_E_BAD_ARG;
+    if (d != s->dim) return EVDB_E_DIM_MISMATCH;
+    EVDB_TRY(set_device(s));
+    cudaStream_t st = s->stream;
+    EVDB_TRY(ensure_bytes(&s->h_pin, &s->h_pin_cap, s->row_bytes + sizeof(double2) + (size_t)d * sizeof(double), true));
+    uint8_t *h = (uint8_t *)s->h_pin;
+    if (is_quant(s)) {
+        EVDB_TRY(ensure_bytes(&s->w_tmp, &s->w_tmp_cap, (size_t)d * sizeof(double)));
+        EVDB_TRY(launch_dequantize_rows(s->dtype, s->rows + (size_t)slot * s->row_bytes, s->row_bytes,
+                                        s->qms64 + slot, 1, d, (double *)s->w_tmp, st));
+        EVDB_CUDA(cudaMemcpyAsync(out, s->w_tmp, (size_t)d * sizeof(double), cudaMemcpyDeviceToHost, st));
+        EVDB_CUDA(cudaStreamSynchronize(st));
+        return EVDB_OK;
+    }
+    EVDB_CUDA(cudaMemcpyAsync(h, s->rows + (size_t)slot * s->row_bytes, s->row_bytes, cudaMemcpyDeviceToHost, st));
+    EVDB_CUDA(cudaStreamSynchronize(st));
+    if (s->dtype == EVDB_F32) {
+        const float *f = (const float *)h;
+        for (int i = 0; i < d; ++i) out[i] = (double)f[i];
+    } else {
+        const uint16_t *u = (const uint16_t *)h;
+        for (int i = 0; i < d; ++i) {
+            union { uint32_t u; float f; } cv;
+            cv.u = (uint32_t)u[i] << 16;
+            out[i] = (double)cv.f;
+        }
+    }
+    return EVDB_OK;
+}
+
+int evdb_store_get_codes(evdb_store *s, uint32_t slot, uint8_t *codes, double *mn, double *scale) {
+    if (!s || !codes || !is_quant(s)) return EVDB_E_BAD_ARG;
+    if ((uint64_t)slot >= s->count) return EVDB_E_BAD_ARG;
+    EVDB_TRY(set_device(s));
+    size_t nb = s->dtype == EVDB_U8 ? (size_t)s->dim : (size_t)(s->dim + 1) / 2;
+    double2 ms;
+    EVDB_CUDA(cudaMemcpyAsync(codes, s->rows + (size_t)slot * s->row_bytes, nb, cudaMemcpyDeviceToHost, s->stream));
+    EVDB_CUDA(cudaMemcpyAsync(&ms, s->qms64 + slot, sizeof(ms), cudaMemcpyDeviceToHost, s->stream));
+    EVDB_CUDA(cudaStreamSynchronize(s->stream));
+    if (mn) *mn = ms.x;
+    if (scale) *scale = ms.y;
+    return EVDB_OK;
+}
+
+int evdb_store_fill_synthetic(evdb_store *s, uint64_t seed, uint64_t row0, uint64_t n, int d) {
+    if (!s) return EVDB_E_BAD_ARG;
+    EVDB_TRY(check_dim(s, d));
+    if (n > 0xFFFFFFF0ull) return EVDB_E_BAD_ARG;
+    EVDB_TRY(set_device(s));
+    EVDB_TRY(ensure_capacity(s, n));
+    s->count = 0;
+    s->shadow_valid = 0;
+    EVDB_TRY(launch_fill_synthetic(s, seed, row0, n, s->stream));
+    EVDB_TRY(launch_finalize_rows(s, 0, n, s->stream));
+    EVDB_CUDA(cudaStreamSynchronize(s->stream));
+    s->count = n;
+    return EVDB_OK;
+}
+
+int evdb_store_search_f64(evdb_store *s, const double *queries, int B, int d, int k, int metric,
+                          uint32_t *out_slots, double *out_dists, int32_t *out_counts) {
+    return search_host(s, queries, true, B, d, k, metric, out_slots, out_dists, out_counts);
+}
+int evdb_store_search_f32(evdb_store *s, const float *queries, int B, int d, int k, int metric,
+                          uint32_t *out_slots, double *out_dists, int32_t *out_counts) {
+    return search_host(s, queries, false, B, d, k, metric, out_slots, out_dists, out_counts);
+}
+
+int evdb_store_search_dev(evdb_store *s, const void *d_queries_f64, int B, int d, int k, int metric,
+                          uint64_t slot_base, void *d_out_ids_u64, void *d_out_dists_f64,
+                          void *d_out_counts_i32, void *d_out_flags_i32, void *stream) {
+    if (!s || !d_queries_f64 || B <= 0 || k <= 0 || metric < 0 || metric > 2) return EVDB_E_BAD_ARG;
+    if (!d_out_ids_u64 || !d_out_dists_f64 || !d_out_counts_i32) return EVDB_E_BAD_ARG;
+    if (s->dim == 0 || s->count == 0) return EVDB_E_BAD_ARG;
+    if (d != s->dim) return EVDB_E_DIM_MISMATCH;
+    EVDB_TRY(set_device(s));
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    EVDB_TRY(search_core(s, (const double *)d_queries_f64, B, k, k, metric, 0, EVDB_PLAN_AUTO,
+                         slot_base, (uint64_t *)d_out_ids_u64, (double *)d_out_dists_f64,
+                         (int32_t *)d_out_counts_i32, (int32_t *)d_out_flags_i32, st));
+    s->n_searches += (uint64_t)B;
+    return EVDB_OK;
+}
+
+int evdb_merge_topk_dev(int device, const void *d_ids_u64, const void *d_dists_f64,
+                        const void *d_counts_i32, int G, int B, int k, void *d_out_ids_u64,
+                        void *d_out_dists_f64, void *d_out_counts_i32, void *stream) {
+    if (!d_ids_u64 || !d_dists_f64 || !d_counts_i32 || !d_out_ids_u64 || !d_out_dists_f64 || !d_out_counts_i32)
+        return EVDB_E_BAD_ARG;
+    EVDB_TRY(check_device(device));
+    EVDB_CUDA(cudaSetDevice(device));
+    return launch_merge_topk((const uint64_t *)d_ids_u64, (const double *)d_dists_f64,
+                             (const int32_t *)d_counts_i32, G, B, k, (uint64_t *)d_out_ids_u64,
+                             (double *)d_out_dists_f64, (int32_t *)d_out_counts_i32, (cudaStream_t)stream);
+}
+
+// ---- standalone codecs ------------------------------------------------------
+static int codec_quantize(int device, int dtype, const double *rows, uint64_t n, int d, uint8_t *codes,
+                          double *mins, double *maxs, double *scales, uint8_t *ok) {
+    if (!rows || !codes || !mins || !scales || d <= 0) return EVDB_E_BAD_ARG;
+    if (n == 0) return EVDB_OK;
+    EVDB_TRY(check_device(device));
+    EVDB_CUDA(cudaSetDevice(device));
+    size_t crb = dtype == EVDB_U8 ? (size_t)d : (size_t)(d + 1) / 2;
+    double *d_rows = nullptr, *d_max = nullptr;
+    uint8_t *d_codes = nullptr, *d_ok = nullptr;
+    double2 *d_ms = nullptr;
+    int rc = EVDB_OK;
+    double2 *h_ms = (double2 *)malloc(n * sizeof(double2));
+    if (!h_ms) return EVDB_E_OOM;
+#define CQ(expr) do { if ((expr) != cudaSuccess) { set_cuda_error(cudaGetLastError(), __FILE__, __LINE__); rc = EVDB_E_CUDA; goto done; } } while (0)
+    CQ(cudaMalloc((void **)&d_rows, n * (size_t)d * sizeof(double)));
+    CQ(cudaMalloc((void **)&d_codes, n * crb));
+    CQ(cudaMalloc((void **)&d_ms, n * sizeof(double2)));
+    CQ(cudaMalloc((void **)&d_max, n * sizeof(double)));
+    CQ(cudaMalloc((void **)&d_ok, n));
+    CQ(cudaMemcpy(d_rows, rows, n * (size_t)d * sizeof(double), cudaMemcpyHostToDevice));
+    rc = launch_quantize_rows(dtype, d_rows, nullptr, n, d, d_codes, crb, d_ms, d_max, d_ok, 0);
+    if (rc != EVDB_OK) goto done;
+    CQ(cudaMemcpy(codes, d_codes, n * crb, cudaMemcpyDeviceToHost));
+    CQ(cudaMemcpy(h_ms, d_ms, n * sizeof(double2), cudaMemcpyDeviceToHost));
+    if (maxs) CQ(cudaMemcpy(maxs, d_max, n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (ok) CQ(cudaMemcpy(ok, d_ok, n, cudaMemcpyDeviceToHost));
+    for (uint64_t i = 0; i < n; ++i) { mins[i] = h_ms[i].x; scales[i] = h_ms[i].y; }
+done:
+#undef CQ
+    cudaFree(d_rows); cudaFree(d_codes); cudaFree(d_ms); cudaFree(d_max); cudaFree(d_ok);
+    free(h_ms);
+    return rc;
+}
+
+static int codec_dequantize(int device, int dtype, const uint8_t *codes, const double *mins,
+                            const double *scales, uint64_t n, int d, double *out) {
+    if (!codes || !mins || !scales || !out || d <= 0) return EVDB_E_BAD_ARG;
+    if (n == 0) return EVDB_OK;
+    EVDB_TRY(check_device(device));
+    EVDB_CUDA(cudaSetDevice(device));
+    size_t crb = dtype == EVDB_U8 ? (size_t)d : (size_t)(d + 1) / 2;
+    uint8_t *d_codes = nullptr;
+    double2 *d_ms = nullptr;
+    double *d_out = nullptr;
+    int rc = EVDB_OK;
+    double2 *h_ms = (double2 *)malloc(n * sizeof(double2));
+    if (!h_ms) return EVDB_E_OOM;
+    for (uint64_t i = 0; i < n; ++i) { h_ms[i].x = mins[i]; h_ms[i].y = scales[i]; }
+#define CQ(expr) do { if ((expr) != cudaSuccess) { set_cuda_error(cudaGetLastError(), __FILE__, __LINE__); rc = EVDB_E_CUDA; goto done; } } while (0)
+    CQ(cudaMalloc((void **)&d_codes, n * crb));
+    CQ(cudaMalloc((void **)&d_ms, n * sizeof(double2)));
+    CQ(cudaMalloc((void **)&d_out, n * (size_t)d * sizeof(double)));
+    CQ(cudaMemcpy(d_codes, codes, n * crb, cudaMemcpyHostToDevice));
+    CQ(cudaMemcpy(d_ms, h_ms, n * sizeof(double2), cudaMemcpyHostToDevice));
+    rc = launch_dequantize_rows(dtype, d_codes, crb, d_ms, n, d, d_out, 0);
+    if (rc != EVDB_OK) goto done;
+    CQ(cudaMemcpy(out, d_out, n * (size_t)d * sizeof(double), cudaMemcpyDeviceToHost));
+done:
+#undef CQ
+    cudaFree(d_codes); cudaFree(d_ms); cudaFree(d_out);
+    free(h_ms);
+    return rc;
+}
+
+int evdb_quantize_8bit(int device, const double *rows, uint64_t n, int d, uint8_t *codes,
+                       double *mins, double *maxs, double *scales, uint8_t *ok) {
+    return codec_quantize(device, EVDB_U8, rows, n, d, codes, mins, maxs, scales, ok);
+}
+int evdb_quantize_4bit(int device, const double *rows, uint64_t n, int d, uint8_t *packed,
+                       double *mins, double *maxs, double *scales, uint8_t *ok) {
+    return codec_quantize(device, EVDB_U4, rows, n, d, packed, mins, maxs, scales, ok);
+}
+int evdb_dequantize_8bit(int device, const uint8_t *codes, const double *mins, const double *scales,
+                         uint64_t n, int d, double *out) {
+    return codec_dequantize(device, EVDB_U8, codes, mins, scales, n, d, out);
+}
+int evdb_dequantize_4bit(int device, const uint8_t *packed, const double *mins, const double *scales,
+                         uint64_t n, int d, double *out) {
+    return codec_dequantize(device, EVDB_U4, packed, mins, scales, n, d, out);
+}
+
+}  // extern "C"

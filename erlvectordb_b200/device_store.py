@@ -1,0 +1,160 @@
+"""DeviceStore: numpy-facing wrapper of one evdb_store handle (one GPU, one store).
+
+This is the level the Erlang NIF shim (erlang/c_src/evdb_nif.c) exposes to the
+vector_store gen_server: slots in, (slot, distance) out.  Ids and metadata live
+one level up (vector_store.py), exactly as they stay in Erlang state.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+
+
+def _p(a, ct):
+    return a.ctypes.data_as(C.POINTER(ct))
+
+
+class DeviceStore:
+    def __init__(self, dtype="f32", dim=0, device=0, capacity_hint=0, gemm_shadow=True):
+        L = N.lib()
+        self._h = C.c_void_p()
+        opts = N.Opts(device=device, dtype=N.DTYPES.get(dtype, dtype), dim=dim,
+                      gemm_shadow=1 if gemm_shadow else 0, capacity_hint=capacity_hint)
+        N.check(L.evdb_store_create(C.byref(opts), C.byref(self._h)), "evdb_store_create")
+        self.device = device
+        self.dtype = N.DTYPES.get(dtype, dtype)
+
+    # -- lifecycle ---------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            N.lib().evdb_store_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def stats(self) -> dict:
+        st = N.Stats()
+        N.check(N.lib().evdb_store_stats(self._h, C.byref(st)), "evdb_store_stats")
+        return {f: getattr(st, f) for f, _ in N.Stats._fields_}
+
+    def set_plan(self, plan):
+        N.check(N.lib().evdb_store_set_plan(self._h, N.PLANS.get(plan, plan)), "evdb_store_set_plan")
+
+    def profile(self, enable=True):
+        N.check(N.lib().evdb_store_profile(self._h, 1 if enable else 0), "evdb_store_profile")
+
+    def profile_read(self):
+        """(samples, total_ms) of the dominant kernel since the last read."""
+        n, ms = C.c_int32(0), C.c_double(0.0)
+        N.check(N.lib().evdb_store_profile_read(self._h, C.byref(n), C.byref(ms)), "evdb_store_profile_read")
+        return n.value, ms.value
+
+    @property
+    def count(self) -> int:
+        return self.stats()["count"]
+
+    @property
+    def dim(self) -> int:
+        return self.stats()["dimension"]
+
+    # -- ingest --------------------------------------------------------------
+    def upsert(self, slot: int, vec) -> int:
+        """Returns the raw status code for DIM_MISMATCH / BAD_VECTOR (the caller maps them
+        to the reference's error atoms); raises on anything else."""
+        v = np.ascontiguousarray(vec, dtype=np.float64)
+        rc = N.lib().evdb_store_upsert_f64(self._h, slot, _p(v, C.c_double), v.shape[0])
+        if rc in (N.OK, N.E_DIM_MISMATCH, N.E_BAD_VECTOR):
+            return rc
+        raise N.EvdbError(rc, "evdb_store_upsert_f64")
+
+    def bulk_load(self, rows):
+        rows = np.asarray(rows)
+        if rows.ndim != 2:
+            raise ValueError("rows must be (n, d)")
+        n, d = rows.shape
+        if rows.dtype == np.float32:
+            r = np.ascontiguousarray(rows)
+            N.check(N.lib().evdb_store_bulk_load_f32(self._h, _p(r, C.c_float), n, d), "bulk_load_f32")
+        else:
+            r = np.ascontiguousarray(rows, dtype=np.float64)
+            N.check(N.lib().evdb_store_bulk_load_f64(self._h, _p(r, C.c_double), n, d), "bulk_load_f64")
+
+    def bulk_load_codes(self, codes, mins, scales, d):
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        mins = np.ascontiguousarray(mins, dtype=np.float64)
+        scales = np.ascontiguousarray(scales, dtype=np.float64)
+        n = mins.shape[0]
+        N.check(N.lib().evdb_store_bulk_load_codes(self._h, _p(codes, C.c_uint8), _p(mins, C.c_double),
+                                                   _p(scales, C.c_double), n, d), "bulk_load_codes")
+
+    def fill_synthetic(self, seed, n, d, row0=0):
+        N.check(N.lib().evdb_store_fill_synthetic(self._h, seed, row0, n, d), "fill_synthetic")
+
+    def delete(self, slot: int) -> int:
+        moved = C.c_int64(-1)
+        N.check(N.lib().evdb_store_delete(self._h, slot, C.byref(moved)), "evdb_store_delete")
+        return moved.value
+
+    def get(self, slot: int) -> np.ndarray:
+        d = self.dim
+        out = np.empty(d, dtype=np.float64)
+        N.check(N.lib().evdb_store_get_f64(self._h, slot, _p(out, C.c_double), d), "evdb_store_get_f64")
+        return out
+
+    def get_codes(self, slot: int):
+        d = self.dim
+        nb = d if self.dtype == N.U8 else (d + 1) // 2
+        codes = np.empty(nb, dtype=np.uint8)
+        mn, sc = C.c_double(), C.c_double()
+        N.check(N.lib().evdb_store_get_codes(self._h, slot, _p(codes, C.c_uint8), C.byref(mn), C.byref(sc)),
+                "evdb_store_get_codes")
+        return codes, mn.value, sc.value
+
+    # -- search --------------------------------------------------------------
+    def search(self, queries, k: int, metric="cosine"):
+        """queries: (B, d) or (d,).  Returns (slots (B,k) u32, dists (B,k) f64, counts (B,))
+        or a negative status code for DIM_MISMATCH / BAD_VECTOR."""
+        q = np.asarray(queries)
+        single = q.ndim == 1
+        if single:
+            q = q[None, :]
+        B, d = q.shape
+        m = N.METRICS.get(metric, metric)
+        slots = np.empty((B, max(k, 0)), dtype=np.uint32)
+        dists = np.empty((B, max(k, 0)), dtype=np.float64)
+        counts = np.zeros(B, dtype=np.int32)
+        if q.dtype == np.float32:
+            q = np.ascontiguousarray(q)
+            rc = N.lib().evdb_store_search_f32(self._h, _p(q, C.c_float), B, d, k, m, _p(slots, C.c_uint32),
+                                               _p(dists, C.c_double), _p(counts, C.c_int32))
+        else:
+            q = np.ascontiguousarray(q, dtype=np.float64)
+            rc = N.lib().evdb_store_search_f64(self._h, _p(q, C.c_double), B, d, k, m, _p(slots, C.c_uint32),
+                                               _p(dists, C.c_double), _p(counts, C.c_int32))
+        if rc in (N.E_DIM_MISMATCH, N.E_BAD_VECTOR):
+            return rc
+        N.check(rc, "evdb_store_search")
+        return slots, dists, counts
+
+    def search_dev(self, d_queries_ptr, B, d, k, metric, slot_base, d_ids, d_dists, d_counts, d_flags,
+                   stream=0):
+        """Raw device-pointer search (enqueue only, no sync)."""
+        N.check(N.lib().evdb_store_search_dev(self._h, d_queries_ptr, B, d, k, N.METRICS.get(metric, metric),
+                                              slot_base, d_ids, d_dists, d_counts, d_flags, stream),
+                "evdb_store_search_dev")
+
+
+def merge_topk_dev(device, d_ids, d_dists, d_counts, G, B, k, d_out_ids, d_out_dists, d_out_counts, stream=0):
+    N.check(N.lib().evdb_merge_topk_dev(device, d_ids, d_dists, d_counts, G, B, k, d_out_ids, d_out_dists,
+                                        d_out_counts, stream), "evdb_merge_topk_dev")

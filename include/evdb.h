@@ -1,0 +1,191 @@
+/*
+ * evdb.h -- C ABI of libevdb_b200: a B200 (sm_100a) brute-force kNN engine that
+ * drops in behind ErlVectorDB's search hot path.
+ *
+ * The reference (pure Erlang) has no FFI; the seam this ABI replaces is the
+ * body of the vector_store gen_server (reference src/vector_store.erl:60-207):
+ *
+ *   init/1 bulk load            src/vector_store.erl:60-111  -> evdb_store_create + evdb_store_bulk_load_*
+ *   handle_call({insert,..})    src/vector_store.erl:113-141 -> evdb_store_upsert_f64/_f32
+ *   handle_call({search,..})    src/vector_store.erl:143-150,227-252 -> evdb_store_search_f64/_f32
+ *   handle_call({delete,..})    src/vector_store.erl:152-164 -> evdb_store_delete
+ *   handle_call(get_stats)      src/vector_store.erl:166-173 -> evdb_store_stats
+ *   handle_call(get_all_vectors)src/vector_store.erl:184-190 -> evdb_store_get_f64
+ *   terminate/2                 src/vector_store.erl:201-207 -> evdb_store_destroy
+ *   vector_utils distances      src/vector_utils.erl:28-43   -> `metric` argument of search
+ *   8/4-bit codecs              src/vector_compression.erl:166-204,306-329
+ *                                                            -> evdb_quantize_{8,4}bit, evdb_dequantize_{8,4}bit,
+ *                                                               evdb_store_bulk_load_codes
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; the caller owns every in/out
+ *     buffer, the library owns device memory behind the opaque handle.
+ *   - Every function returns EVDB_OK (0) or a negative EVDB_E_* code; nothing
+ *     throws across the boundary.  EVDB_E_DIM_MISMATCH / EVDB_E_BAD_VECTOR map
+ *     to the reference atoms dimension_mismatch / invalid_vector_format.
+ *   - A handle is used by one caller at a time (the store's gen_server
+ *     guarantees it); distinct handles are fully concurrent.
+ *   - There is NO CPU fallback: without a usable sm_100 device every entry
+ *     point that touches a store fails with EVDB_E_NO_DEVICE.
+ *   - Rows live in dense slots [0, count).  Id <-> slot and metadata stay with
+ *     the caller (Erlang state).  Results order by (distance, slot); the caller
+ *     re-applies the reference's {Distance, Id} term order among exact ties.
+ */
+#ifndef EVDB_H
+#define EVDB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EVDB_ABI_VERSION 1
+
+typedef struct evdb_store evdb_store;
+
+/* element type of the device-resident columns */
+enum { EVDB_F32 = 0, EVDB_BF16 = 1, EVDB_U8 = 2, EVDB_U4 = 3 };
+/* distance (src/vector_store.erl:238-246, src/vector_utils.erl:38-43) */
+enum { EVDB_COSINE = 0, EVDB_EUCLIDEAN = 1, EVDB_MANHATTAN = 2 };
+/* search plan override (evdb_store_set_plan); AUTO picks by batch size */
+enum { EVDB_PLAN_AUTO = 0, EVDB_PLAN_SCAN = 1, EVDB_PLAN_GEMM = 2, EVDB_PLAN_EXACT = 3 };
+
+enum {
+    EVDB_OK = 0,
+    EVDB_E_DIM_MISMATCH = -1, /* {error, dimension_mismatch}     */
+    EVDB_E_BAD_VECTOR = -2,   /* {error, invalid_vector_format}  */
+    EVDB_E_OOM = -3,
+    EVDB_E_CUDA = -4,
+    EVDB_E_NCCL = -5,
+    EVDB_E_BAD_ARG = -6,
+    EVDB_E_NO_DEVICE = -7,
+    EVDB_E_UNSUPPORTED = -8,
+    EVDB_E_BADARITH = -9 /* Max == Min in a quantizer (reference: badarith) */
+};
+
+typedef struct evdb_opts {
+    int32_t device;         /* CUDA device ordinal */
+    int32_t dtype;          /* EVDB_F32 | EVDB_BF16 | EVDB_U8 | EVDB_U4 */
+    int32_t dim;            /* 0 = fixed by the first upsert/bulk load (reference :213-217) */
+    int32_t gemm_shadow;    /* F32 stores: keep a bf16 shadow column for the tcgen05 path */
+    uint64_t capacity_hint; /* rows to reserve up front (0 = grow by doubling) */
+} evdb_opts;
+
+typedef struct evdb_stats {
+    uint64_t count;          /* maps:size(Vectors)                       */
+    int32_t dimension;       /* 0 == undefined                           */
+    int32_t dtype;
+    int32_t device;
+    int32_t last_plan;       /* EVDB_PLAN_* actually used by the last search */
+    uint64_t capacity;
+    uint64_t device_bytes;   /* HBM held by this store                   */
+    uint64_t searches;       /* queries answered                         */
+    uint64_t rows_scanned;   /* sum over queries of rows visited         */
+    uint64_t escalations;    /* candidate windows that had to be widened */
+    uint64_t kernel_launches;/* CUDA kernels launched by this store      */
+    double last_search_ms;   /* device time of the last search call      */
+} evdb_stats;
+
+/* ---- process / device ---------------------------------------------------- */
+int evdb_abi_version(void);
+/* Probe the devices a deployment intends to use; EVDB_E_NO_DEVICE unless each
+ * is a compute-capability 10.x GPU.  devices == NULL -> device 0.           */
+int evdb_init(const int *devices, int n_dev);
+const char *evdb_strerror(int code);
+/* last CUDA error text seen by the calling thread ("" if none) */
+const char *evdb_last_cuda_error(void);
+
+/* ---- store lifecycle (vector_store_sup:start_store / stop_store) --------- */
+int evdb_store_create(const evdb_opts *opts, evdb_store **out);
+void evdb_store_destroy(evdb_store *s);
+int evdb_store_stats(evdb_store *s, evdb_stats *out);
+int evdb_store_set_plan(evdb_store *s, int plan);
+/* Measurement aid (bench.py roofline): when enabled, every search brackets its dominant
+ * kernel (the scan or the tcgen05 GEMM) with a CUDA event pair on the launching stream.
+ * _read synchronises that stream, returns the samples taken since the last read and their
+ * summed duration, and resets.  At most 512 samples are kept between reads.           */
+int evdb_store_profile(evdb_store *s, int enable);
+int evdb_store_profile_read(evdb_store *s, int32_t *n_samples, double *total_ms);
+
+/* ---- ingest --------------------------------------------------------------
+ * upsert: slot == count appends, slot < count overwrites (maps:put upsert).
+ * First vector fixes the dimension; d != dimension -> EVDB_E_DIM_MISMATCH.
+ * Non-finite elements -> EVDB_E_BAD_VECTOR (Erlang floats are always finite).
+ * For U8/U4 stores the row is quantized on the device exactly as
+ * compress_{8,4}bit_quantization does (fp64); Max == Min -> EVDB_E_BADARITH. */
+int evdb_store_upsert_f64(evdb_store *s, uint32_t slot, const double *vec, int d);
+int evdb_store_upsert_f32(evdb_store *s, uint32_t slot, const float *vec, int d);
+/* Replace the whole content with n rows (vector_store:init/1 bulk load). */
+int evdb_store_bulk_load_f32(evdb_store *s, const float *rows, uint64_t n, int d);
+int evdb_store_bulk_load_f64(evdb_store *s, const double *rows, uint64_t n, int d);
+/* Compressed records straight to device columns, no decompress-to-list
+ * (vector_persistence:load_vectors + decompress_if_needed, :157-165,:276-284).
+ * codes: n rows of d bytes (U8) or (d+1)/2 bytes (U4, first element in the
+ * high nibble); mins/scales: the records' fp64 metadata.                    */
+int evdb_store_bulk_load_codes(evdb_store *s, const uint8_t *codes, const double *mins,
+                               const double *scales, uint64_t n, int d);
+/* Swap-with-last delete.  *moved_from = slot that now lives in `slot`, or -1. */
+int evdb_store_delete(evdb_store *s, uint32_t slot, int64_t *moved_from);
+/* Read a row back as the reference would see it (fp64; quantized stores give
+ * Min + Q*Scale).                                                           */
+int evdb_store_get_f64(evdb_store *s, uint32_t slot, double *out, int d);
+/* Raw codes + metadata of a quantized row (bit-exact codec checks). */
+int evdb_store_get_codes(evdb_store *s, uint32_t slot, uint8_t *codes, double *mn,
+                         double *scale);
+/* Bench/test only: fill slots [0,n) with the counter-based synthetic corpus
+ *  generated on the device; rows are global rows
+ * [row0, row0+n) of that corpus (row0 > 0 for a shard).                     */
+int evdb_store_fill_synthetic(evdb_store *s, uint64_t seed, uint64_t row0, uint64_t n, int d);
+
+/* ---- search ---------------------------------------------------------------
+ * B queries of d numbers each.  For each query b: out_counts[b] = min(k, count)
+ * results in out_slots[b*k ..], out_dists[b*k ..], ascending by
+ * (distance, slot).  Distances are fp64 and, for F32/U8/U4 stores, bit-equal
+ * to the reference's Erlang arithmetic on the stored rows (same operation
+ * order, no FMA).  k == 0 -> counts 0.  k < 0 -> EVDB_E_BAD_ARG (the reference
+ * crashes with function_clause).  Empty store -> counts 0 for any d.        */
+int evdb_store_search_f64(evdb_store *s, const double *queries, int B, int d, int k,
+                          int metric, uint32_t *out_slots, double *out_dists,
+                          int32_t *out_counts);
+int evdb_store_search_f32(evdb_store *s, const float *queries, int B, int d, int k,
+                          int metric, uint32_t *out_slots, double *out_dists,
+                          int32_t *out_counts);
+
+/* Device-resident variant: d_queries (B x d fp64), d_out_slots (B x k u32),
+ * d_out_dists (B x k fp64), d_out_counts (B i32) are DEVICE pointers on the
+ * store's device; work is enqueued on `stream` (a cudaStream_t; NULL = the
+ * store's own stream) and NOT synchronised.  slot_base is added to every
+ * returned slot (global row ids for a row-sharded corpus).  Escalation of the
+ * candidate window needs a host decision, so this variant reports a query
+ * whose window could not be proven complete in d_out_flags[b] != 0 (may be
+ * NULL) instead of retrying; callers re-issue those through the host path.  */
+int evdb_store_search_dev(evdb_store *s, const void *d_queries_f64, int B, int d, int k,
+                          int metric, uint64_t slot_base, void *d_out_ids_u64,
+                          void *d_out_dists_f64, void *d_out_counts_i32,
+                          void *d_out_flags_i32, void *stream);
+
+/* G-way merge of per-shard results (the step after the NCCL allgather):
+ * in: G lists per query, laid out [G][B][k] (ids u64, dists fp64, counts
+ * [G][B]); out: [B][k] ascending by (distance, id).  Device pointers.        */
+int evdb_merge_topk_dev(int device, const void *d_ids_u64, const void *d_dists_f64,
+                        const void *d_counts_i32, int G, int B, int k, void *d_out_ids_u64,
+                        void *d_out_dists_f64, void *d_out_counts_i32, void *stream);
+
+/* ---- codecs (vector_compression.erl:166-204), computed on the device ------
+ * n rows of d fp64 -> codes (+ per-row fp64 min/max/scale).  ok[i] = 0 for a
+ * row whose Max == Min (reference: badarith, caller stores it raw).          */
+int evdb_quantize_8bit(int device, const double *rows, uint64_t n, int d, uint8_t *codes,
+                       double *mins, double *maxs, double *scales, uint8_t *ok);
+int evdb_quantize_4bit(int device, const double *rows, uint64_t n, int d, uint8_t *packed,
+                       double *mins, double *maxs, double *scales, uint8_t *ok);
+int evdb_dequantize_8bit(int device, const uint8_t *codes, const double *mins,
+                         const double *scales, uint64_t n, int d, double *out);
+int evdb_dequantize_4bit(int device, const uint8_t *packed, const double *mins,
+                         const double *scales, uint64_t n, int d, double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVDB_H */

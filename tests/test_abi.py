@@ -1,0 +1,74 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads, exports every symbol
+include/evdb.h declares, and refuses to work (loudly) without a B200 -- no compute calls."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "evdb.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(evdb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported_and_bound():
+    from erlvectordb_b200 import _native as N
+    L = N.lib()
+    syms = declared_symbols()
+    assert len(syms) >= 24
+    bound = {name for name, _, _ in N.SYMBOLS}
+    for s in syms:
+        assert hasattr(L, s), f"libevdb_b200.so does not export {s}"
+        assert s in bound, f"_native.py does not bind {s}"
+    assert L.evdb_abi_version() == 1
+
+
+def test_error_strings_map_to_reference_atoms():
+    from erlvectordb_b200 import _native as N
+    L = N.lib()
+    assert L.evdb_strerror(N.E_DIM_MISMATCH) == b"dimension_mismatch"   # vector_store.erl:221
+    assert L.evdb_strerror(N.E_BAD_VECTOR) == b"invalid_vector_format"  # vector_store.erl:216,222,225
+    assert L.evdb_strerror(0) == b"ok"
+
+
+def test_no_cpu_fallback():
+    """Without a GPU the product path must fail loudly, never compute on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from erlvectordb_b200 import _native as N
+    from erlvectordb_b200 import vector_store, vector_compression
+    assert N.lib().evdb_init(None, 0) == N.E_NO_DEVICE
+    with pytest.raises(N.EvdbError):
+        vector_store.start_link("no_gpu_store")
+    with pytest.raises(N.EvdbError):
+        vector_compression.compress_vector([1.0, 2.0], "quantization_8bit")
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under the package may import, link or call it."""
+    pkg = os.path.join(ROOT, "erlvectordb_b200")
+    banned = ("import oracle", "from oracle", "libevdb_oracle", "evo_", "oracle.")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".c")):
+                src = open(os.path.join(dirpath, f)).read()
+                for b in banned:
+                    assert b not in src, f"{f} references the oracle ({b!r})"
+
+
+def test_validate_vector_mirror():
+    from erlvectordb_b200.vector_store import validate_vector, term_key
+    assert validate_vector([1.0, 2, 3.5], None) == ("ok", 3)          # ints are numbers
+    assert validate_vector([1.0, 2.0], 3) == ("error", "dimension_mismatch")
+    assert validate_vector([1.0, "a"], 2) == ("error", "invalid_vector_format")
+    assert validate_vector("abc", None) == ("error", "invalid_vector_format")
+    assert validate_vector([True, 1.0], 2) == ("error", "invalid_vector_format")  # atoms are not numbers
+    assert validate_vector(np.zeros(4, dtype=np.float32), 4) == ("ok", 4)
+    # Erlang term order: binaries bytewise then by length; numbers < atoms < binaries
+    assert term_key(b"v1") < term_key(b"v2") < term_key(b"v2a")
+    assert term_key(3) < term_key("atom") < term_key(b"bin")
