@@ -1,13 +1,416 @@
-// gemm_tcgen05.cu -- batched cosine as a tcgen05/TMEM GEMM (family B).  Placeholder until the
-// kernel lands: the planner never selects it.
+// gemm_tcgen05.cu -- batched cosine search as a TMA-fed tcgen05/TMEM GEMM with a fused
+// per-query top-k epilogue (family B).
+//
+// Replaces, for query batches, the same reference text as the scans: the maps:fold of
+// cosine_distance/2 over all rows (reference src/vector_store.erl:227-252) -- here for B
+// queries at once as  D[q][r] = <q_hat_q, v_hat_r>  with q_hat = q/||q||, v_hat = v/||v||
+// held in fp16 (the "shadow" column of an F32 store), fp32 accumulation in tensor memory.
+// The GEMM only GENERATES CANDIDATES: scores carry a rigorous error bound eps (two fp16
+// roundings + fp32 accumulation), the KP best per query go to select.cu, which re-ranks them
+// in exact fp64 and proves the window complete -- returned distances never see fp16.
+//
+// Kernel anatomy (one persistent CTA per SM, 256 threads, no cluster):
+//   warp 0   TMA producer: cp.async.bulk.tensor 2D tiles (128B swizzle) of Q [128 x 64] and
+//            V [256 x 64] into a 3-stage shared-memory ring, mbarrier complete_tx
+//   warp 1   MMA issuer: one elected thread, tcgen05.mma cta_group::1 kind::f16, M=128 N=256
+//            K=16, 4 per stage; tcgen05.commit frees the stage / publishes the accumulator
+//   warp 2   TMEM allocator (512 columns = 2 accumulator stages x 256 fp32 columns)
+//   warps 4-7 epilogue: thread t owns TMEM lane t == query t of the CTA's 128-query block;
+//            tcgen05.ld 32 columns at a time, dist = 1 - acc, compare against the query's
+//            running threshold (register); rare hits are inserted warp-cooperatively into
+//            the query's sorted candidate list in shared memory.
+// A CTA keeps one query block for a whole sweep over its share of the corpus tiles, so the
+// candidate lists never leave shared memory until the final flush.  The 256-row corpus tile
+// is shared by the MB CTAs working on different query blocks at the same time (L2 hits).
+#include <cuda.h>
+#include <cuda_fp16.h>
+
 #include "internal.h"
+#include "topk.cuh"
 
 namespace evdb {
 
-bool gemm_plan_supported(evdb_store *, int, int, int) { return false; }
+constexpr int GM = 128;        // queries per CTA tile (UMMA M)
+constexpr int GN = 256;        // corpus rows per tile (UMMA N)
+constexpr int GK = 64;         // K elements per stage (64 fp16 = one 128-byte swizzle row)
+constexpr int GUK = 16;        // UMMA K
+constexpr int kGemmStages = 3;
+constexpr int kGemmThreads = 256;
+constexpr uint32_t kStageABytes = GM * GK * 2;   // 16 KB
+constexpr uint32_t kStageBBytes = GN * GK * 2;   // 32 KB
+constexpr uint32_t kStageBytes = kStageABytes + kStageBBytes;
+constexpr int kGemmMaxKP = 64;
 
-int launch_gemm_topk(evdb_store *, int, int, int, uint64_t *, int *, cudaStream_t) {
-    return EVDB_E_UNSUPPORTED;
+struct GemmArgs {
+    uint64_t n;          // corpus rows
+    int kblocks;         // ceil(dim / 64)
+    int nt;              // corpus tiles = ceil(n / 256)
+    int MB;              // query blocks processed concurrently
+    int NG;              // CTAs per query block (lists per query)
+    int nchunks;         // sweeps: query blocks [c*MB, (c+1)*MB)
+    int KP;
+    uint64_t *partial;   // [Bpad][NG][KP]
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must trap, never hang the device.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile in shared memory, 128-byte swizzle: rows of 128 bytes, 8-row groups
+// 1024 bytes apart (SBO), descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);       // start address  [0,14)
+    d |= (uint64_t)1 << 16;                       // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset [32,46)
+    d |= (uint64_t)1 << 46;                       // version = 1
+    d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: fp16 x fp16 -> fp32, both K-major, M=128, N=256
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4)                 // c_format = F32
+         | (0u << 7) | (0u << 10)    // a_format = b_format = F16
+         | (0u << 15) | (0u << 16)   // a_major = b_major = K
+         | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- the kernel ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmV,
+                 const GemmArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // dynamic smem is only guaranteed 16-byte aligned: realign to 1024 for the 128B swizzle
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *stage_base = smem;                                            // [stages][A|B]
+    uint64_t *lists = reinterpret_cast<uint64_t *>(smem + kGemmStages * kStageBytes);  // [128][KP]
+    uint64_t *bars = lists + GM * a.KP;                                    // full[S] empty[S] tfull[2] tempty[2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kGemmStages + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int KP = a.KP;
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kGemmStages);
+    const uint32_t tfull0 = smem_u32(bars + 2 * kGemmStages), tempty0 = smem_u32(bars + 2 * kGemmStages + 2);
+
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < kGemmStages; ++i) {
+            mbar_init(full0 + 8 * i, 1);
+            mbar_init(empty0 + 8 * i, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(tfull0 + 8 * i, 1);
+            mbar_init(tempty0 + 8 * i, 4);  // one arrive per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int cta = blockIdx.x;
+    const bool active = cta < a.MB * a.NG;
+    const int mb_local = cta % a.MB, ng = cta / a.MB;
+    int my_tiles = 0;
+    if (active) my_tiles = (a.nt - ng + a.NG - 1) / a.NG;  // tiles ng, ng+NG, ...
+
+    if (active && warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int c = 0; c < a.nchunks; ++c) {
+                const int qrow = (c * a.MB + mb_local) * GM;
+                for (int t = 0; t < my_tiles; ++t) {
+                    const int vrow = (ng + t * a.NG) * GN;
+                    for (int kb = 0; kb < a.kblocks; ++kb) {
+                        mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                        const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
+                        mbar_arrive_expect_tx(full0 + 8 * stage, kStageBytes);
+                        tma_load_2d(sa, &tmQ, full0 + 8 * stage, kb * GK, qrow);
+                        tma_load_2d(sa + kStageABytes, &tmV, full0 + 8 * stage, kb * GK, vrow);
+                        if (++stage == kGemmStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (active && warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(GM, GN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int c = 0; c < a.nchunks; ++c) {
+                for (int t = 0; t < my_tiles; ++t) {
+                    mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);  // epilogue drained this accumulator
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + (uint32_t)acc * GN;
+                    for (int kb = 0; kb < a.kblocks; ++kb) {
+                        mbar_wait(full0 + 8 * stage, phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
+                        const uint64_t adesc = make_sw128_kmajor_desc(sa);
+                        const uint64_t bdesc = make_sw128_kmajor_desc(sa + kStageABytes);
+#pragma unroll
+                        for (int k = 0; k < GK / GUK; ++k) {
+                            // advance 16 fp16 = 32 bytes along K inside the swizzled row: +2 in >>4 units
+                            umma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                     (uint32_t)((kb | k) != 0));
+                        }
+                        umma_commit(empty0 + 8 * stage);  // stage reusable once these MMAs retire
+                        if (++stage == kGemmStages) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit(tfull0 + 8 * acc);        // accumulator complete
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+            }
+        }
+    } else if (active && warp >= 4) {
+        // ===== epilogue: thread <-> TMEM lane <-> query =====
+        const int ew = warp - 4;                 // == warp % 4: TMEM lanes [32*ew, 32*ew+32)
+        const int qloc = ew * 32 + lane;         // query within the CTA's block
+        uint64_t *wlists = lists + (size_t)(ew * 32) * KP;  // this warp's 32 lists
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int c = 0; c < a.nchunks; ++c) {
+            for (int i = lane; i < 32 * KP; i += 32) wlists[i] = kKeyMax;
+            __syncwarp();
+            float thr = __int_as_float(0x7f800000);  // +inf
+            for (int t = 0; t < my_tiles; ++t) {
+                const uint32_t row0 = (uint32_t)(ng + t * a.NG) * GN;
+                const uint32_t valid = a.n - row0 < (uint64_t)GN ? (uint32_t)(a.n - row0) : (uint32_t)GN;
+                mbar_wait(tfull0 + 8 * acc, acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * GN;
+#pragma unroll 1
+                for (int cb = 0; cb < GN / 32; ++cb) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(taddr + cb * 32, v);
+                    tmem_ld_wait();
+                    float dist[32];
+                    float mn = __int_as_float(0x7f800000);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        dist[j] = 1.0f - __uint_as_float(v[j]);
+                        mn = fminf(mn, dist[j]);
+                    }
+                    const uint32_t col0 = cb * 32;
+                    if (col0 + 32 > valid) {  // rows past the end of the store (zero-filled by TMA)
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j >= valid) dist[j] = __int_as_float(0x7f800000);
+                        mn = __int_as_float(0x7f800000);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) mn = fminf(mn, dist[j]);
+                    }
+                    if (__ballot_sync(0xffffffffu, mn < thr)) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            unsigned m = __ballot_sync(0xffffffffu, dist[j] < thr);
+                            while (m) {
+                                const int src = __ffs(m) - 1;
+                                m &= m - 1;
+                                const float dd = __shfl_sync(0xffffffffu, dist[j], src);
+                                const uint64_t key = make_key(dd, row0 + col0 + j);
+                                const uint64_t tail = warp_list_insert(wlists + (size_t)src * KP, KP, key, lane);
+                                if (lane == src) thr = tail == kKeyMax ? __int_as_float(0x7f800000) : key_score(tail);
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+            // flush this sweep's lists: partial[query][ng][KP]
+            __syncwarp();
+            const size_t q0 = (size_t)(c * a.MB + mb_local) * GM + ew * 32;
+            for (int ql = 0; ql < 32; ++ql) {
+                uint64_t *dst = a.partial + ((q0 + ql) * a.NG + ng) * KP;
+                for (int i = lane; i < KP; i += 32) dst[i] = wlists[(size_t)ql * KP + i];
+            }
+            __syncwarp();
+            (void)qloc;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---- query preparation: q_hat = q / ||q|| in fp16, zero padded to [Bpad][kpitch] ------------
+__global__ void __launch_bounds__(256) prep_queries_gemm_kernel(const double *__restrict__ q64, int B,
+                                                                int d, __half *__restrict__ qh, int kpitch) {
+    __shared__ double red[8];
+    const int b = blockIdx.x;
+    __half *o = qh + (size_t)b * kpitch;
+    if (b >= B) {
+        for (int i = threadIdx.x; i < kpitch; i += blockDim.x) o[i] = __float2half_rn(0.f);
+        return;
+    }
+    const double *q = q64 + (size_t)b * d;
+    double ss = 0.0;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) ss += q[i] * q[i];
+    for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    ss = 0.0;
+    for (int i = 0; i < 8; ++i) ss += red[i];
+    const float inv = ss > 0.0 ? (float)(1.0 / sqrt(ss)) : 0.0f;
+    for (int i = threadIdx.x; i < kpitch; i += blockDim.x)
+        o[i] = __float2half_rn(i < d ? (float)q[i] * inv : 0.f);
+}
+
+// ---- host side ------------------------------------------------------------------------------
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+static encode_tiled_fn get_encode() {
+    static encode_tiled_fn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (encode_tiled_fn)p;
+    }
+    return fn;
+}
+
+static int make_map(CUtensorMap *tm, const void *base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
+                    uint32_t box_rows) {
+    encode_tiled_fn enc = get_encode();
+    if (!enc) return EVDB_E_CUDA;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {pitch_elems * 2};
+    cuuint32_t box[2] = {(cuuint32_t)GK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? EVDB_OK : EVDB_E_CUDA;
+}
+
+static size_t gemm_smem_bytes(int KP) {
+    return 1024 + (size_t)kGemmStages * kStageBytes + (size_t)GM * KP * 8 + (2 * kGemmStages + 4) * 8 + 16;
+}
+
+bool gemm_plan_supported(evdb_store *s, int metric, int B, int KP) {
+    if (s->dtype != EVDB_F32 || !s->shadow || metric != EVDB_COSINE) return false;
+    if (KP > kGemmMaxKP || B < 1) return false;
+    if (s->count < (uint64_t)GN) return false;
+    if (s->shadow_valid < s->count) return false;
+    return get_encode() != nullptr;
+}
+
+int gemm_kp(int KP) { return KP < kGemmMaxKP ? kGemmMaxKP : KP; }
+
+int launch_gemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int *lists_per_query,
+                     cudaStream_t st) {
+    const int kpitch = s->spitch;
+    const int nblocks_q = (B + GM - 1) / GM;
+    // concurrent query blocks: the largest power of two <= 8 that does not exceed what exists
+    int MB = 1;
+    while (MB * 2 <= nblocks_q && MB * 2 <= 4) MB *= 2;
+    const int nchunks = (nblocks_q + MB - 1) / MB;
+    const int Bpad = nchunks * MB * GM;
+    int NG = s->sm_count / MB;
+    const int nt = (int)((s->count + GN - 1) / GN);
+    if (NG > nt) NG = nt;
+    EVDB_TRY(ensure_bytes((void **)&s->w_qh, &s->w_qh_cap, (size_t)Bpad * kpitch * sizeof(__half)));
+    EVDB_TRY(ensure_bytes((void **)&s->w_partial, &s->w_partial_cap, sizeof(uint64_t) * (size_t)Bpad * NG * KP));
+    prep_queries_gemm_kernel<<<Bpad, 256, 0, st>>>(d_q64, B, s->dim, (__half *)s->w_qh, kpitch);
+    EVDB_CUDA(cudaGetLastError());
+    CUtensorMap tmQ, tmV;
+    EVDB_TRY(make_map(&tmQ, s->w_qh, (uint64_t)Bpad, (uint64_t)kpitch, (uint64_t)kpitch, GM));
+    EVDB_TRY(make_map(&tmV, s->shadow, s->count, (uint64_t)kpitch, (uint64_t)kpitch, GN));
+    GemmArgs a;
+    a.n = s->count;
+    a.kblocks = (s->dim + GK - 1) / GK;
+    a.nt = nt;
+    a.MB = MB;
+    a.NG = NG;
+    a.nchunks = nchunks;
+    a.KP = KP;
+    a.partial = s->w_partial;
+    size_t smem = gemm_smem_bytes(KP);
+    EVDB_CUDA(cudaFuncSetAttribute((const void *)gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prof_begin(s, st);
+    gemm_topk_kernel<<<MB * NG, kGemmThreads, smem, st>>>(tmQ, tmV, a);
+    prof_end(s, st);
+    EVDB_CUDA(cudaGetLastError());
+    s->n_launches += 2;
+    *lists_per_query = NG;
+    return EVDB_OK;
 }
 
 }  // namespace evdb

@@ -14,14 +14,14 @@ namespace evdb {
 // ----------------------------------------------------------------------------
 template <int DTYPE>
 __global__ void __launch_bounds__(256) finalize_rows_kernel(uint8_t *__restrict__ rows,
-                                                            size_t row_bytes, int d, int dpad,
+                                                            size_t row_bytes, int d, int spitch,
                                                             uint64_t slot0, uint64_t n,
                                                             double *__restrict__ norm64,
                                                             float *__restrict__ inv_norm,
                                                             float *__restrict__ norm_sq,
                                                             float2 *__restrict__ qcoef,
                                                             const double2 *__restrict__ qms64,
-                                                            __nv_bfloat16 *__restrict__ shadow) {
+                                                            __half *__restrict__ shadow) {
     __shared__ double sp_all[8 * kExactChunk];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *sp = sp_all + warp * kExactChunk;
@@ -45,9 +45,11 @@ __global__ void __launch_bounds__(256) finalize_rows_kernel(uint8_t *__restrict_
                                      : make_float2(0.f, 0.f);
         }
         if (DTYPE == EVDB_F32 && shadow) {
+            // tcgen05 operand: the unit-norm row in fp16 (|x| <= 1: no overflow for any input scale)
             const float *fr = reinterpret_cast<const float *>(row);
-            __nv_bfloat16 *sh = shadow + r * (size_t)dpad;
-            for (int c = lane; c < dpad; c += 32) sh[c] = __float2bfloat16_rn(fr[c]);
+            const float inv = nrm > 0.0 ? (float)(1.0 / nrm) : 0.0f;
+            __half *sh = shadow + r * (size_t)spitch;
+            for (int c = lane; c < spitch; c += 32) sh[c] = __float2half_rn(c < d ? fr[c] * inv : 0.0f);
         }
     }
 }
@@ -58,7 +60,7 @@ int launch_finalize_rows(evdb_store *s, uint64_t slot0, uint64_t n, cudaStream_t
     uint64_t cap = (uint64_t)s->sm_count * 8;
     int grid = (int)(blocks < cap ? blocks : cap);
 #define EVDB_FIN(DT)                                                                              \
-    finalize_rows_kernel<DT><<<grid, 256, 0, st>>>(s->rows, s->row_bytes, s->dim, s->dpad, slot0, \
+    finalize_rows_kernel<DT><<<grid, 256, 0, st>>>(s->rows, s->row_bytes, s->dim, s->spitch, slot0, \
                                                    n, s->norm64, s->inv_norm, s->norm_sq,         \
                                                    s->qcoef, s->qms64, s->shadow)
     switch (s->dtype) {

@@ -41,13 +41,15 @@ struct evdb_store {
     float *norm_sq = nullptr;      // (float)(norm64^2)   (GEMM euclidean)
     float2 *qcoef = nullptr;       // U8/U4: {scale/||y||, min/||y||}
     double2 *qms64 = nullptr;      // U8/U4: {min, scale} fp64 (exact re-rank, read-back)
-    __nv_bfloat16 *shadow = nullptr; // F32 + gemm_shadow: bf16 copy for the tcgen05 path
+    __half *shadow = nullptr;      // F32 + gemm_shadow: fp16 of v/||v||, [capacity][spitch] (tcgen05 path)
+    int spitch = 0;                // shadow row pitch in elements (dim rounded up to 8)
     uint64_t shadow_valid = 0;     // rows [0, shadow_valid) of the shadow are current
 
     // ---- workspace (grown on demand) ----
     double *w_q64 = nullptr;   size_t w_q64_cap = 0;    // [B][dim]
     float *w_q32 = nullptr;    size_t w_q32_cap = 0;    // [B][dpad32]
     uint8_t *w_qdig = nullptr; size_t w_qdig_cap = 0;   // [B][3][dpad] digit planes
+    void *w_qh = nullptr;      size_t w_qh_cap = 0;     // [Bpad][spitch] fp16 unit-norm queries (GEMM)
     evdb::QStat *w_qstat = nullptr; size_t w_qstat_cap = 0;
     uint64_t *w_partial = nullptr; size_t w_partial_cap = 0; // [B][G][KP]
     uint64_t *w_ids = nullptr;  size_t w_ids_cap = 0;   // [B][k]
@@ -110,8 +112,9 @@ int launch_merge_topk(const uint64_t *ids, const double *dists, const int32_t *c
                       cudaStream_t st);
 // tcgen05 path (gemm_tcgen05.cu)
 bool gemm_plan_supported(evdb_store *s, int metric, int B, int KP);
-int launch_gemm_topk(evdb_store *s, int metric, int B, int KP, uint64_t *partial,
-                     int *lists_per_query, cudaStream_t st);
+int gemm_kp(int KP);
+int launch_gemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int *lists_per_query,
+                     cudaStream_t st);
 
 int ensure_bytes(void **p, size_t *cap, size_t need, bool pinned = false);
 void prof_begin(evdb_store *s, cudaStream_t st);

@@ -57,24 +57,58 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectArgs a)
     const int KP = a.KP;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    // ---- 1. merge L lists of KP keys into the KP smallest ----
+    // ---- 1. merge L ascending lists of KP keys into the KP smallest ----
+    // Fast path: the KP-th smallest list HEAD is an upper bound T on the global KP-th smallest
+    // key (KP distinct keys are <= it), so only keys <= T can matter -- typically a few dozen.
     const uint64_t *src = a.partial + (size_t)b * a.L * KP;
     const size_t total = (size_t)a.L * KP;
-    size_t pos = 0;
-    int carried = 0;
-    while (true) {
-        size_t room = (size_t)kSelSort - carried;
-        size_t take = total - pos < room ? total - pos : room;
-        int filled = carried + (int)take;
-        int nsort = KP;
-        while (nsort < filled) nsort <<= 1;
-        for (int i = threadIdx.x; i < nsort - carried; i += blockDim.x)
-            buf[carried + i] = (size_t)i < take ? src[pos + i] : kKeyMax;
+    __shared__ int s_cnt;
+    bool merged = false;
+    if (a.L <= kSelSort) {
+        int Lp = 2;
+        while (Lp < a.L) Lp <<= 1;
+        for (int i = threadIdx.x; i < Lp; i += blockDim.x) buf[i] = i < a.L ? src[(size_t)i * KP] : kKeyMax;
+        if (threadIdx.x == 0) s_cnt = 0;
         __syncthreads();
-        block_bitonic_sort(buf, nsort);
-        pos += take;
-        carried = KP;
-        if (pos >= total) break;
+        block_bitonic_sort(buf, Lp);
+        const uint64_t T = a.L >= KP ? buf[KP - 1] : kKeyMax;
+        __syncthreads();
+        for (size_t i = threadIdx.x; i < total; i += blockDim.x) {
+            uint64_t key = src[i];
+            if (key <= T && key != kKeyMax) {
+                int p = atomicAdd(&s_cnt, 1);
+                if (p < kSelSort) buf[p] = key;
+            }
+        }
+        __syncthreads();
+        const int cnt = s_cnt;
+        if (cnt <= kSelSort) {
+            int nsort = KP;
+            while (nsort < cnt) nsort <<= 1;
+            for (int i = cnt + threadIdx.x; i < nsort; i += blockDim.x) buf[i] = kKeyMax;
+            __syncthreads();
+            block_bitonic_sort(buf, nsort);
+            merged = true;
+        }
+        __syncthreads();
+    }
+    if (!merged) {  // general path: chunked sort, carrying the KP best
+        size_t pos = 0;
+        int carried = 0;
+        while (true) {
+            size_t room = (size_t)kSelSort - carried;
+            size_t take = total - pos < room ? total - pos : room;
+            int filled = carried + (int)take;
+            int nsort = KP;
+            while (nsort < filled) nsort <<= 1;
+            for (int i = threadIdx.x; i < nsort - carried; i += blockDim.x)
+                buf[carried + i] = (size_t)i < take ? src[pos + i] : kKeyMax;
+            __syncthreads();
+            block_bitonic_sort(buf, nsort);
+            pos += take;
+            carried = KP;
+            if (pos >= total) break;
+        }
     }
     // ---- count valid candidates (keys are ascending; kKeyMax pads) ----
     if (threadIdx.x == 0) s_ncand = 0;

@@ -63,6 +63,7 @@ static void set_dim(evdb_store *s, int d) {
         case EVDB_U8: s->dpad = round_up(d, 16); s->nch = s->dpad / 16; s->row_bytes = (size_t)s->dpad; break;
         default: s->dpad = round_up(d, 32); s->nch = s->dpad / 32; s->row_bytes = (size_t)s->dpad / 2; break;
     }
+    s->spitch = round_up(d, 8);
 }
 
 template <typename T>
@@ -92,7 +93,7 @@ static int ensure_capacity(evdb_store *s, uint64_t need) {
         EVDB_TRY(regrow(&s->qms64, live, ncap, sizeof(double2), s->stream));
     }
     if (s->dtype == EVDB_F32 && s->gemm_shadow)
-        EVDB_TRY(regrow(&s->shadow, live, ncap, (size_t)s->dpad * sizeof(__nv_bfloat16), s->stream));
+        EVDB_TRY(regrow(&s->shadow, live, ncap, (size_t)s->spitch * sizeof(__half), s->stream));
     s->capacity = ncap;
     return EVDB_OK;
 }
@@ -100,9 +101,9 @@ static int ensure_capacity(evdb_store *s, uint64_t need) {
 static uint64_t device_bytes(const evdb_store *s) {
     uint64_t per = s->row_bytes + sizeof(double) + 2 * sizeof(float);
     if (is_quant(s)) per += sizeof(float2) + sizeof(double2);
-    if (s->shadow) per += (uint64_t)s->dpad * 2;
+    if (s->shadow) per += (uint64_t)s->spitch * 2;
     return per * s->capacity + s->w_q64_cap + s->w_q32_cap + s->w_qdig_cap + s->w_qstat_cap +
-           s->w_partial_cap + s->w_ids_cap + s->w_dists_cap + s->w_counts_cap + s->w_tmp_cap;
+           s->w_partial_cap + s->w_qh_cap + s->w_ids_cap + s->w_dists_cap + s->w_counts_cap + s->w_tmp_cap;
 }
 
 // ----------------------------------------------------------------------------
@@ -140,16 +141,16 @@ static int search_core(evdb_store *s, const double *d_q64, int B, int k, int kst
         use_gemm = gemm_plan_supported(s, metric, B, KP);
     if (plan == EVDB_PLAN_GEMM && !use_gemm) return EVDB_E_UNSUPPORTED;
 
-    EVDB_TRY(launch_prep_queries(s, d_q64, B, st));
     if (use_gemm) {
         s->last_plan = EVDB_PLAN_GEMM;
-        prof_begin(s, st);
-        EVDB_TRY(launch_gemm_topk(s, metric, B, KP, nullptr, &lists, st));
-        prof_end(s, st);
-        // bf16 operands (2^-9 each, round-to-nearest) + fp32 accumulation in the tensor core
-        eps_abs = (float)(0.00390625 * 1.02 + (double)s->dim * 4.0 * u);
-        if (metric != EVDB_COSINE) return EVDB_E_UNSUPPORTED;
+        KP = gemm_kp(KP);
+        EVDB_TRY(launch_gemm_topk(s, d_q64, B, KP, &lists, st));
+        // |score - cos| bound: both operands are unit vectors rounded to fp16 (2^-11 relative each,
+        // 2^-25 absolute in the subnormal range), fp32 accumulation over dim terms in the tensor
+        // core (bounded as dim * 2^-22, truncation included), one fp32 subtract.
+        eps_abs = (float)(0.0009765625 * 1.01 + sqrt((double)s->dim) * u + (double)s->dim * 4.0 * u);
     } else {
+        EVDB_TRY(launch_prep_queries(s, d_q64, B, st));
         s->last_plan = EVDB_PLAN_SCAN;
         int G = 0;
         int rc = scan_grid_size(s, metric, KP, &G);
@@ -486,7 +487,7 @@ void evdb_store_destroy(evdb_store *s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     cudaFree(s->rows); cudaFree(s->norm64); cudaFree(s->inv_norm); cudaFree(s->norm_sq);
     cudaFree(s->qcoef); cudaFree(s->qms64); cudaFree(s->shadow);
-    cudaFree(s->w_q64); cudaFree(s->w_q32); cudaFree(s->w_qdig); cudaFree(s->w_qstat);
+    cudaFree(s->w_q64); cudaFree(s->w_q32); cudaFree(s->w_qdig); cudaFree(s->w_qh); cudaFree(s->w_qstat);
     cudaFree(s->w_partial); cudaFree(s->w_ids); cudaFree(s->w_dists); cudaFree(s->w_counts);
     cudaFree(s->w_tmp);
     if (s->h_pin) cudaFreeHost(s->h_pin);
@@ -612,7 +613,7 @@ int evdb_store_delete(evdb_store *s, uint32_t slot, int64_t *moved_from) {
             EVDB_CUDA(cudaMemcpyAsync(s->qms64 + slot, s->qms64 + last, sizeof(double2), cudaMemcpyDeviceToDevice, st));
         }
         if (s->shadow)
-            EVDB_CUDA(cudaMemcpyAsync(s->shadow + (size_t)slot * s->dpad, s->shadow + last * (size_t)s->dpad, (size_t)s->dpad * 2, cudaMemcpyDeviceToDevice, st));
+            EVDB_CUDA(cudaMemcpyAsync(s->shadow + (size_t)slot * s->spitch, s->shadow + last * (size_t)s->spitch, (size_t)s->spitch * 2, cudaMemcpyDeviceToDevice, st));
         EVDB_CUDA(cudaStreamSynchronize(st));
         if (moved_from) *moved_from = (int64_t)last;
     }

@@ -48,6 +48,13 @@ def gather_layout(t: torch.Tensor, world: int, group=None) -> torch.Tensor:
     return out
 
 
+def _stream_handle(dev) -> int:
+    """cudaStream_t of torch's current stream for the C ABI.  The ABI reads NULL as "the store's
+    own stream", so torch's default stream (handle 0) is passed as cudaStreamLegacy (0x1)."""
+    h = torch.cuda.current_stream(dev).cuda_stream
+    return h if h else 1
+
+
 class ShardedStore:
     """One shard of a row-sharded store (call from every rank of the process group)."""
 
@@ -61,6 +68,7 @@ class ShardedStore:
         self._local_search = local_search or self._cuda_local_search
         self._merge = merge or self._cuda_merge
         self._dev = None if local_search else DeviceStore(dtype=dtype, device=device)
+        self._bufs = {}
         self.lo = self.hi = 0
         self.n_total = 0
         self.dim = 0
@@ -84,12 +92,15 @@ class ShardedStore:
     def _cuda_local_search(self, q: torch.Tensor, k: int, metric: str):
         B, d = q.shape
         dev = q.device
-        ids = torch.empty((B, k), dtype=torch.int64, device=dev)
-        dists = torch.empty((B, k), dtype=torch.float64, device=dev)
-        counts = torch.zeros((B,), dtype=torch.int32, device=dev)
-        flags = torch.zeros((B,), dtype=torch.int32, device=dev)
+        key = (B, k, dev)
+        if key not in self._bufs:  # reuse output buffers: no allocator / fill kernels per search
+            self._bufs[key] = (torch.empty((B, k), dtype=torch.int64, device=dev),
+                               torch.empty((B, k), dtype=torch.float64, device=dev),
+                               torch.zeros((B,), dtype=torch.int32, device=dev),
+                               torch.zeros((B,), dtype=torch.int32, device=dev))
+        ids, dists, counts, flags = self._bufs[key]
         if self.hi > self.lo:
-            stream = torch.cuda.current_stream(dev).cuda_stream
+            stream = _stream_handle(dev)
             self._dev.search_dev(q.data_ptr(), B, d, k, metric, self.lo, ids.data_ptr(), dists.data_ptr(),
                                  counts.data_ptr(), flags.data_ptr(), stream)
         return ids, dists, counts, flags
@@ -100,7 +111,7 @@ class ShardedStore:
         out_ids = torch.empty((B, k), dtype=torch.int64, device=dev)
         out_d = torch.empty((B, k), dtype=torch.float64, device=dev)
         out_c = torch.empty((B,), dtype=torch.int32, device=dev)
-        stream = torch.cuda.current_stream(dev).cuda_stream
+        stream = _stream_handle(dev)
         merge_topk_dev(dev.index or 0, ids.data_ptr(), dists.data_ptr(), counts.data_ptr(), G, B, k,
                        out_ids.data_ptr(), out_d.data_ptr(), out_c.data_ptr(), stream)
         return out_ids, out_d, out_c

@@ -156,7 +156,7 @@ int evdb_store_search_f32(evdb_store *s, const float *queries, int B, int d, int
 /* Device-resident variant: d_queries (B x d fp64), d_out_slots (B x k u32),
  * d_out_dists (B x k fp64), d_out_counts (B i32) are DEVICE pointers on the
  * store's device; work is enqueued on `stream` (a cudaStream_t; NULL = the
- * store's own stream) and NOT synchronised.  slot_base is added to every
+ * store's own stream; pass cudaStreamLegacy for the default stream) and NOT synchronised.  slot_base is added to every
  * returned slot (global row ids for a row-sharded corpus).  Escalation of the
  * candidate window needs a host decision, so this variant reports a query
  * whose window could not be proven complete in d_out_flags[b] != 0 (may be
