@@ -11,7 +11,7 @@
 //
 // Kernel anatomy (one persistent CTA per SM, 256 threads, no cluster):
 //   warp 0   TMA producer: cp.async.bulk.tensor 2D tiles (128B swizzle) of Q [128 x 64] and
-//            V [256 x 64] into a 3-stage shared-memory ring, mbarrier complete_tx
+//            V [256 x 64] into a 4-stage shared-memory ring, mbarrier complete_tx
 //   warp 1   MMA issuer: one elected thread, tcgen05.mma cta_group::1 kind::f16, M=128 N=256
 //            K=16, 4 per stage; tcgen05.commit frees the stage / publishes the accumulator
 //   warp 2   TMEM allocator (512 columns = 2 accumulator stages x 256 fp32 columns)
@@ -23,6 +23,7 @@
 // candidate lists never leave shared memory until the final flush.  The 256-row corpus tile
 // is shared by the MB CTAs working on different query blocks at the same time (L2 hits).
 #include <cuda.h>
+#include <stdlib.h>
 #include <cuda_fp16.h>
 
 #include "internal.h"
@@ -34,8 +35,9 @@ constexpr int GM = 128;        // queries per CTA tile (UMMA M)
 constexpr int GN = 256;        // corpus rows per tile (UMMA N)
 constexpr int GK = 64;         // K elements per stage (64 fp16 = one 128-byte swizzle row)
 constexpr int GUK = 16;        // UMMA K
-constexpr int kGemmStages = 3;
-constexpr int kGemmThreads = 256;
+constexpr int kGemmStages = 4;
+constexpr int kGemmThreads = 384;   // 4 control warps + 8 epilogue warps
+constexpr int kEpiWarps = 8;
 constexpr uint32_t kStageABytes = GM * GK * 2;   // 16 KB
 constexpr uint32_t kStageBBytes = GN * GK * 2;   // 32 KB
 constexpr uint32_t kStageBytes = kStageABytes + kStageBBytes;
@@ -49,7 +51,9 @@ struct GemmArgs {
     int NG;              // CTAs per query block (lists per query)
     int nchunks;         // sweeps: query blocks [c*MB, (c+1)*MB)
     int KP;
-    uint64_t *partial;   // [Bpad][NG][KP]
+    uint64_t *partial;   // [Bpad][2*NG][KP]
+    uint64_t *cand;      // [CTAs][2][kCandCap][128] append buffers
+    int debug;           // EVDB_GEMM_DEBUG (measurement only): 1 = no list inserts, 2 = no TMEM loads either
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------
@@ -131,6 +135,74 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
          | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+constexpr int kCandCap = 256;   // candidate buffer entries per (query, CTA)
+
+// Selection without sorting: tau = the `need`-th smallest 32-bit score (orderable encoding, high
+// word of the key) among up to 256 keys held 8 per lane (kKeyMax pads), by 4-way search on the
+// value with warp-wide population counts.  Returns tau; *n_less = number of keys with score < tau.
+__device__ __forceinline__ uint32_t warp_select_score(const uint64_t (&x)[8], int need, int *n_less) {
+    uint32_t sc[8];
+    uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        sc[r] = (uint32_t)(x[r] >> 32);
+        mn = min(mn, sc[r]);
+        if (x[r] != kKeyMax) mx = max(mx, sc[r]);
+    }
+    uint32_t lo = __reduce_min_sync(0xffffffffu, mn);
+    uint32_t hi = __reduce_max_sync(0xffffffffu, mx);  // invariant: count(score <= hi) >= need
+#pragma unroll 1
+    while (lo < hi) {
+        const uint32_t span = hi - lo;
+        const uint32_t q = span >> 2;
+        const uint32_t p2 = lo + (span >> 1);
+        const uint32_t p1 = q ? lo + q : p2;
+        const uint32_t p3 = q ? p2 + q : p2;
+        int c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            c1 += sc[r] <= p1 ? 1 : 0;
+            c2 += sc[r] <= p2 ? 1 : 0;
+            c3 += sc[r] <= p3 ? 1 : 0;
+        }
+        c1 = __reduce_add_sync(0xffffffffu, c1);
+        c2 = __reduce_add_sync(0xffffffffu, c2);
+        c3 = __reduce_add_sync(0xffffffffu, c3);
+        if (c1 >= need) hi = p1;
+        else if (c2 >= need) { lo = p1 + 1; hi = p2; }
+        else if (c3 >= need) { lo = p2 + 1; hi = p3; }
+        else lo = p3 + 1;
+    }
+    int c = 0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) c += sc[r] < lo ? 1 : 0;
+    *n_less = __reduce_add_sync(0xffffffffu, c);
+    return lo;
+}
+
+// Ascending bitonic sort of 64 u64 keys held 2 per lane (element lane in e0, lane + 32 in e1).
+__device__ __forceinline__ void warp_sort64(uint64_t &e0, uint64_t &e1, const int lane) {
+#pragma unroll 1
+    for (int k2 = 2; k2 <= 64; k2 <<= 1) {
+#pragma unroll 1
+        for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+            if (j2 == 32) {  // k2 == 64: partner is the other register, direction ascending
+                const uint64_t lo = e0 < e1 ? e0 : e1, hi = e0 < e1 ? e1 : e0;
+                e0 = lo;
+                e1 = hi;
+            } else {
+                const uint64_t p0 = __shfl_xor_sync(0xffffffffu, e0, j2);
+                const uint64_t p1 = __shfl_xor_sync(0xffffffffu, e1, j2);
+                const bool lower = (lane & j2) == 0;
+                const bool asc0 = (lane & k2) == 0;
+                const bool asc1 = ((lane + 32) & k2) == 0;
+                e0 = (lower == asc0) ? (e0 < p0 ? e0 : p0) : (e0 > p0 ? e0 : p0);
+                e1 = (lower == asc1) ? (e1 < p1 ? e1 : p1) : (e1 > p1 ? e1 : p1);
+            }
+        }
+    }
+}
+
 // ---- the kernel ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmV,
@@ -139,8 +211,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     // dynamic smem is only guaranteed 16-byte aligned: realign to 1024 for the 128B swizzle
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *stage_base = smem;                                            // [stages][A|B]
-    uint64_t *lists = reinterpret_cast<uint64_t *>(smem + kGemmStages * kStageBytes);  // [128][KP]
-    uint64_t *bars = lists + GM * a.KP;                                    // full[S] empty[S] tfull[2] tempty[2]
+    float4 *scratch = reinterpret_cast<float4 *>(smem + kGemmStages * kStageBytes);  // [8 warps][8][32] float4
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kGemmStages * kStageBytes + kEpiWarps * 4096);  // full[S] empty[S] tfull[2] tempty[2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kGemmStages + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -155,7 +227,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(tfull0 + 8 * i, 1);
-            mbar_init(tempty0 + 8 * i, 4);  // one arrive per epilogue warp
+            mbar_init(tempty0 + 8 * i, kEpiWarps);  // one arrive per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -228,56 +300,111 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             }
         }
     } else if (active && warp >= 4) {
-        // ===== epilogue: thread <-> TMEM lane <-> query =====
-        const int ew = warp - 4;                 // == warp % 4: TMEM lanes [32*ew, 32*ew+32)
-        const int qloc = ew * 32 + lane;         // query within the CTA's block
-        uint64_t *wlists = lists + (size_t)(ew * 32) * KP;  // this warp's 32 lists
+        // ===== epilogue: 8 warps; thread <-> TMEM lane <-> query, warp pair splits the columns =====
+        // Selection is decoupled from the score stream: a thread only APPENDS keys that beat its
+        // query's admission threshold to a private candidate buffer (global memory, L2-resident,
+        // [entry][thread] so warm-up appends coalesce).  When a buffer nears capacity the warp
+        // selects the KP-th best score by value bisection (population counts, no sort), compacts
+        // the buffer to the KP best and tightens the threshold.  ~KP*ln(n/KP) appends and a
+        // handful of selections per query per sweep instead of a list update per admitted score.
+        const int ew = warp - 4;                 // 0..7
+        const int lg = ew & 3;                   // == warp % 4: TMEM lanes [32*lg, 32*lg+32)
+        const int half = ew >> 2;                // columns [128*half, 128*half+128) of every tile
+        const int et = lg * 32 + lane;           // query within the CTA's block
+        uint64_t *cbase = a.cand + (size_t)(cta * 2 + half) * kCandCap * GM;  // entry i of thread e at [i*GM + e]
+        uint64_t *mybuf = cbase + et;
+        float4 *sd = scratch + ew * 256 + lane;  // this lane's column: row r at sd[r * 32]
+        uint64_t *wscratch = reinterpret_cast<uint64_t *>(scratch + ew * 256);  // 512 u64 per warp
+        const float kInf = __int_as_float(0x7f800000);
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int c = 0; c < a.nchunks; ++c) {
-            for (int i = lane; i < 32 * KP; i += 32) wlists[i] = kKeyMax;
-            __syncwarp();
-            float thr = __int_as_float(0x7f800000);  // +inf
+            int cnt = 0;
+            float thr = kInf;
+            // load lane `src`'s buffer into registers (8 per lane), return its fill count
+            auto load_buf = [&](int src, uint64_t (&x)[8]) -> int {
+                const int n = __shfl_sync(0xffffffffu, cnt, src);
+                const uint64_t *b = cbase + (lg * 32 + src);
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const int e = r * 32 + lane;
+                    x[r] = e < n ? __ldcg(b + (size_t)e * GM) : kKeyMax;
+                }
+                return n;
+            };
+            // keep the `need` best keys of x: below tau first, then ties at tau; dst[i * stride]
+            auto compact = [&](const uint64_t (&x)[8], int need, uint64_t *dst, size_t stride) -> uint32_t {
+                int n_less;
+                const uint32_t tau = warp_select_score(x, need, &n_less);
+                int base_less = 0, base_tie = n_less, ties_left = need - n_less;
+                const unsigned below = (1u << lane) - 1u;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const uint32_t scr = (uint32_t)(x[r] >> 32);
+                    const bool is_less = scr < tau;
+                    const bool is_tie = scr == tau && x[r] != kKeyMax;
+                    const unsigned ml = __ballot_sync(0xffffffffu, is_less);
+                    const unsigned mt = __ballot_sync(0xffffffffu, is_tie);
+                    if (is_less) dst[(size_t)(base_less + __popc(ml & below)) * stride] = x[r];
+                    const int trank = __popc(mt & below);
+                    if (is_tie && trank < ties_left) dst[(size_t)(base_tie + trank) * stride] = x[r];
+                    base_less += __popc(ml);
+                    const int used = min(__popc(mt), ties_left);
+                    base_tie += used;
+                    ties_left -= used;
+                }
+                return tau;
+            };
             for (int t = 0; t < my_tiles; ++t) {
                 const uint32_t row0 = (uint32_t)(ng + t * a.NG) * GN;
                 const uint32_t valid = a.n - row0 < (uint64_t)GN ? (uint32_t)(a.n - row0) : (uint32_t)GN;
                 mbar_wait(tfull0 + 8 * acc, acc_phase);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)acc * GN;
+                const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)acc * GN + half * (GN / 2);
 #pragma unroll 1
-                for (int cb = 0; cb < GN / 32; ++cb) {
+                for (int cb = 0; cb < ((a.debug & 2) ? 0 : GN / 64); ++cb) {
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(taddr + cb * 32, v);
                     tmem_ld_wait();
+                    const uint32_t col0 = half * (GN / 2) + cb * 32;
                     float dist[32];
-                    float mn = __int_as_float(0x7f800000);
+                    uint32_t mask = 0;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         dist[j] = 1.0f - __uint_as_float(v[j]);
-                        mn = fminf(mn, dist[j]);
+                        if (col0 + 32 > valid && col0 + j >= valid) dist[j] = kInf;  // rows past the end
+                        mask |= (dist[j] < thr) ? (1u << j) : 0u;
                     }
-                    const uint32_t col0 = cb * 32;
-                    if (col0 + 32 > valid) {  // rows past the end of the store (zero-filled by TMA)
+                    if (a.debug & 1) mask = 0;
+                    if (mask) {
+                        // stage this thread's 32 scores for dynamic indexing, then visit the set bits
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (col0 + j >= valid) dist[j] = __int_as_float(0x7f800000);
-                        mn = __int_as_float(0x7f800000);
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) mn = fminf(mn, dist[j]);
+                        for (int r = 0; r < 8; ++r)
+                            sd[r * 32] = make_float4(dist[4 * r], dist[4 * r + 1], dist[4 * r + 2], dist[4 * r + 3]);
+                        while (mask) {
+                            const int j = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            const float d = reinterpret_cast<const float *>(&sd[(j >> 2) * 32])[j & 3];
+                            mybuf[(size_t)cnt * GM] = make_key(d, row0 + col0 + j);
+                            ++cnt;
+                        }
                     }
-                    if (__ballot_sync(0xffffffffu, mn < thr)) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            unsigned m = __ballot_sync(0xffffffffu, dist[j] < thr);
-                            while (m) {
-                                const int src = __ffs(m) - 1;
-                                m &= m - 1;
-                                const float dd = __shfl_sync(0xffffffffu, dist[j], src);
-                                const uint64_t key = make_key(dd, row0 + col0 + j);
-                                const uint64_t tail = warp_list_insert(wlists + (size_t)src * KP, KP, key, lane);
-                                if (lane == src) thr = tail == kKeyMax ? __int_as_float(0x7f800000) : key_score(tail);
+                    // a chunk appends at most 32 keys: prune any buffer that could overflow next
+                    unsigned need = __ballot_sync(0xffffffffu, cnt > kCandCap - 32);
+                    if (need) {
+                        __syncwarp();
+                        while (need) {
+                            const int src = __ffs(need) - 1;
+                            need &= need - 1;
+                            uint64_t x[8];
+                            load_buf(src, x);  // > KP keys here
+                            const uint32_t tau = compact(x, KP, cbase + (lg * 32 + src), GM);
+                            if (lane == src) {
+                                cnt = KP;
+                                thr = fminf(thr, f32_from_orderable(tau));
                             }
                         }
+                        __syncwarp();
                     }
                 }
                 tc_fence_before();
@@ -285,15 +412,24 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            // flush this sweep's lists: partial[query][ng][KP]
+            // flush: every query's KP best, sorted ascending -> partial[q][2*ng + half][KP]
             __syncwarp();
-            const size_t q0 = (size_t)(c * a.MB + mb_local) * GM + ew * 32;
             for (int ql = 0; ql < 32; ++ql) {
-                uint64_t *dst = a.partial + ((q0 + ql) * a.NG + ng) * KP;
-                for (int i = lane; i < KP; i += 32) dst[i] = wlists[(size_t)ql * KP + i];
+                uint64_t x[8];
+                const int n = load_buf(ql, x);
+                const int keep = n < KP ? n : KP;
+                __syncwarp();
+                if (keep > 0) compact(x, keep, wscratch, 1);
+                __syncwarp();
+                uint64_t e0 = lane < keep ? wscratch[lane] : kKeyMax;
+                uint64_t e1 = lane + 32 < keep ? wscratch[lane + 32] : kKeyMax;
+                warp_sort64(e0, e1, lane);
+                const size_t qg = (size_t)(c * a.MB + mb_local) * GM + lg * 32 + ql;
+                uint64_t *dst = a.partial + (qg * (2 * a.NG) + 2 * ng + half) * KP;
+                if (lane < KP) dst[lane] = e0;
+                if (lane + 32 < KP) dst[lane + 32] = e1;
             }
             __syncwarp();
-            (void)qloc;
         }
     }
 
@@ -361,7 +497,8 @@ static int make_map(CUtensorMap *tm, const void *base, uint64_t rows, uint64_t c
 }
 
 static size_t gemm_smem_bytes(int KP) {
-    return 1024 + (size_t)kGemmStages * kStageBytes + (size_t)GM * KP * 8 + (2 * kGemmStages + 4) * 8 + 16;
+    (void)KP;
+    return 1024 + (size_t)kGemmStages * kStageBytes + kEpiWarps * 4096 + (2 * kGemmStages + 4) * 8 + 16;
 }
 
 bool gemm_plan_supported(evdb_store *s, int metric, int B, int KP) {
@@ -386,8 +523,11 @@ int launch_gemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int *lis
     int NG = s->sm_count / MB;
     const int nt = (int)((s->count + GN - 1) / GN);
     if (NG > nt) NG = nt;
-    EVDB_TRY(ensure_bytes((void **)&s->w_qh, &s->w_qh_cap, (size_t)Bpad * kpitch * sizeof(__half)));
-    EVDB_TRY(ensure_bytes((void **)&s->w_partial, &s->w_partial_cap, sizeof(uint64_t) * (size_t)Bpad * NG * KP));
+    const size_t qh_bytes = round_up64((size_t)Bpad * kpitch * sizeof(__half), 256);
+    const size_t cand_bytes = (size_t)MB * NG * 2 * kCandCap * GM * sizeof(uint64_t);
+    EVDB_TRY(ensure_bytes((void **)&s->w_qh, &s->w_qh_cap, qh_bytes + cand_bytes));
+    uint64_t *cand = (uint64_t *)((uint8_t *)s->w_qh + qh_bytes);
+    EVDB_TRY(ensure_bytes((void **)&s->w_partial, &s->w_partial_cap, sizeof(uint64_t) * (size_t)Bpad * 2 * NG * KP));
     prep_queries_gemm_kernel<<<Bpad, 256, 0, st>>>(d_q64, B, s->dim, (__half *)s->w_qh, kpitch);
     EVDB_CUDA(cudaGetLastError());
     CUtensorMap tmQ, tmV;
@@ -402,6 +542,8 @@ int launch_gemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int *lis
     a.nchunks = nchunks;
     a.KP = KP;
     a.partial = s->w_partial;
+    a.cand = cand;
+    { const char *e = getenv("EVDB_GEMM_DEBUG"); a.debug = e ? atoi(e) : 0; }
     size_t smem = gemm_smem_bytes(KP);
     EVDB_CUDA(cudaFuncSetAttribute((const void *)gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     prof_begin(s, st);
@@ -409,7 +551,7 @@ int launch_gemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int *lis
     prof_end(s, st);
     EVDB_CUDA(cudaGetLastError());
     s->n_launches += 2;
-    *lists_per_query = NG;
+    *lists_per_query = 2 * NG;
     return EVDB_OK;
 }
 
