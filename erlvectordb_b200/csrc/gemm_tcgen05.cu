@@ -53,7 +53,8 @@ struct GemmArgs {
     int KP;
     uint64_t *partial;   // [Bpad][2*NG][KP]
     uint64_t *cand;      // [CTAs][2][kCandCap][128] append buffers
-    int debug;           // EVDB_GEMM_DEBUG (measurement only): 1 = no list inserts, 2 = no TMEM loads either
+    int debug;           // EVDB_GEMM_DEBUG (measurement only): 1 = no appends, 2 = no TMEM loads, 8 = cycle breakdown
+    unsigned long long *dbg;  // [CTAs][8 warps][4]: wait, chunk, prune, flush cycles
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------
@@ -318,6 +319,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const float kInf = __int_as_float(0x7f800000);
         int acc = 0;
         uint32_t acc_phase = 0;
+        long long t_wait = 0, t_chunk = 0, t_prune = 0, t_flush = 0, n_prune = 0, n_app = 0;
         for (int c = 0; c < a.nchunks; ++c) {
             int cnt = 0;
             float thr = kInf;
@@ -358,14 +360,22 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             for (int t = 0; t < my_tiles; ++t) {
                 const uint32_t row0 = (uint32_t)(ng + t * a.NG) * GN;
                 const uint32_t valid = a.n - row0 < (uint64_t)GN ? (uint32_t)(a.n - row0) : (uint32_t)GN;
+                long long tw0 = clock64();
                 mbar_wait(tfull0 + 8 * acc, acc_phase);
                 tc_fence_after();
+                long long tw1 = clock64();
+                t_wait += tw1 - tw0;
                 const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)acc * GN + half * (GN / 2);
-#pragma unroll 1
-                for (int cb = 0; cb < ((a.debug & 2) ? 0 : GN / 64); ++cb) {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(taddr + cb * 32, v);
+                constexpr int kChunks = GN / 64;  // 32-column chunks per warp per tile
+                uint32_t vbuf[2][32];
+                if (!(a.debug & 2)) tmem_ld_32x32b_x32(taddr, vbuf[0]);
+#pragma unroll
+                for (int cb = 0; cb < kChunks; ++cb) {
+                    if (a.debug & 2) break;
                     tmem_ld_wait();
+                    // prefetch the next chunk while this one is processed
+                    if (cb + 1 < kChunks) tmem_ld_32x32b_x32(taddr + (cb + 1) * 32, vbuf[(cb + 1) & 1]);
+                    uint32_t (&v)[32] = vbuf[cb & 1];
                     const uint32_t col0 = half * (GN / 2) + cb * 32;
                     float dist[32];
                     uint32_t mask = 0;
@@ -392,21 +402,38 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     // a chunk appends at most 32 keys: prune any buffer that could overflow next
                     unsigned need = __ballot_sync(0xffffffffu, cnt > kCandCap - 32);
                     if (need) {
+                        long long tp0 = clock64();
                         __syncwarp();
-                        while (need) {
-                            const int src = __ffs(need) - 1;
-                            need &= need - 1;
-                            uint64_t x[8];
-                            load_buf(src, x);  // > KP keys here
+                        // software-pipelined: the next buffer's loads are in flight while the
+                        // current one is selected and compacted (prunes come in bursts)
+                        int src = __ffs(need) - 1;
+                        need &= need - 1;
+                        uint64_t x[8];
+                        load_buf(src, x);  // > KP keys here
+                        while (true) {
+                            ++n_prune;
+                            int nsrc = -1;
+                            uint64_t y[8];
+                            if (need) {
+                                nsrc = __ffs(need) - 1;
+                                need &= need - 1;
+                                load_buf(nsrc, y);
+                            }
                             const uint32_t tau = compact(x, KP, cbase + (lg * 32 + src), GM);
                             if (lane == src) {
                                 cnt = KP;
                                 thr = fminf(thr, f32_from_orderable(tau));
                             }
+                            if (nsrc < 0) break;
+#pragma unroll
+                            for (int r = 0; r < 8; ++r) x[r] = y[r];
+                            src = nsrc;
                         }
                         __syncwarp();
+                        t_prune += clock64() - tp0;
                     }
                 }
+                t_chunk += clock64() - tw1;
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
@@ -414,6 +441,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             }
             // flush: every query's KP best, sorted ascending -> partial[q][2*ng + half][KP]
             __syncwarp();
+            long long tf0 = clock64();
             for (int ql = 0; ql < 32; ++ql) {
                 uint64_t x[8];
                 const int n = load_buf(ql, x);
@@ -430,6 +458,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 if (lane + 32 < KP) dst[lane + 32] = e1;
             }
             __syncwarp();
+            t_flush += clock64() - tf0;
+        }
+        if ((a.debug & 8) && lane == 0) {
+            unsigned long long *d = a.dbg + ((size_t)cta * kEpiWarps + ew) * 8;
+            d[0] = t_wait; d[1] = t_chunk; d[2] = t_prune; d[3] = t_flush; d[4] = n_prune;
         }
     }
 
@@ -517,7 +550,7 @@ int launch_gemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int *lis
     const int nblocks_q = (B + GM - 1) / GM;
     // concurrent query blocks: the largest power of two <= 8 that does not exceed what exists
     int MB = 1;
-    while (MB * 2 <= nblocks_q && MB * 2 <= 4) MB *= 2;
+    while (MB * 2 <= nblocks_q && MB * 2 <= 8) MB *= 2;
     const int nchunks = (nblocks_q + MB - 1) / MB;
     const int Bpad = nchunks * MB * GM;
     int NG = s->sm_count / MB;
@@ -544,12 +577,28 @@ int launch_gemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int *lis
     a.partial = s->w_partial;
     a.cand = cand;
     { const char *e = getenv("EVDB_GEMM_DEBUG"); a.debug = e ? atoi(e) : 0; }
+    a.dbg = nullptr;
+    static unsigned long long *g_dbg = nullptr;
+    if (a.debug & 8) {
+        if (!g_dbg) cudaMalloc((void **)&g_dbg, sizeof(unsigned long long) * 148 * kEpiWarps * 8);
+        a.dbg = g_dbg;
+    }
     size_t smem = gemm_smem_bytes(KP);
     EVDB_CUDA(cudaFuncSetAttribute((const void *)gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     prof_begin(s, st);
     gemm_topk_kernel<<<MB * NG, kGemmThreads, smem, st>>>(tmQ, tmV, a);
     prof_end(s, st);
     EVDB_CUDA(cudaGetLastError());
+    if (a.debug & 8) {
+        cudaStreamSynchronize(st);
+        static unsigned long long h[148 * kEpiWarps * 8];
+        cudaMemcpy(h, g_dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        double sum[5] = {0, 0, 0, 0, 0};
+        int nw = MB * NG * kEpiWarps;
+        for (int i = 0; i < nw; ++i) for (int j = 0; j < 5; ++j) sum[j] += (double)h[i * 8 + j];
+        fprintf(stderr, "[gemm dbg] per epilogue warp (cycles): wait=%.0f chunk=%.0f (of which prune=%.0f) flush=%.0f prunes=%.1f\n",
+                sum[0] / nw, sum[1] / nw, sum[2] / nw, sum[3] / nw, sum[4] / nw);
+    }
     s->n_launches += 2;
     *lists_per_query = 2 * NG;
     return EVDB_OK;

@@ -21,8 +21,6 @@
 
 namespace evdb {
 
-constexpr int kSelThreads = 1024;
-constexpr int kSelWarps = kSelThreads / 32;
 constexpr int kSelSort = 4096;  // keys sorted per merge round
 
 struct SelectArgs {
@@ -43,8 +41,10 @@ struct SelectArgs {
     int32_t *out_flags;
 };
 
-template <int DTYPE>
-__global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectArgs a) {
+// THREADS = 1024 for a lone query (latency), 256 for batches (more CTAs per SM, cheaper barriers).
+template <int DTYPE, int THREADS>
+__global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
+    constexpr int kSelWarps = THREADS / 32;
     extern __shared__ __align__(16) uint8_t smem[];
     uint64_t *buf = reinterpret_cast<uint64_t *>(smem);                       // [kSelSort]
     double *sp_all = reinterpret_cast<double *>(smem + sizeof(uint64_t) * kSelSort);  // [warps][2*chunk]
@@ -123,10 +123,27 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectArgs a)
     const float bound = s_bound;
 
     // ---- 2. exact fp64 distance per candidate, one warp each ----
+    // Only candidates that can still reach the top k are re-ranked: a true top-k row r has
+    // exact D_r <= D_(k) <= s_k + eps (the k best approximate scores bound the k-th exact one),
+    // hence approximate score <= s_k + 2*eps.  Scores are ascending, so that set is a prefix.
+    const int kout = a.kk < ncand ? a.kk : ncand;
+    __shared__ int s_nrer;
+    if (threadIdx.x == 0) s_nrer = kout;
+    __syncthreads();
+    if (kout > 0) {
+        const float sk = key_score(buf[kout - 1]);
+        const float lim = sk + 2.0f * (a.eps_abs + a.eps_rel * fabsf(sk)) * 1.0001f;
+        for (int i = kout + threadIdx.x; i < ncand; i += blockDim.x)
+            if (key_score(buf[i]) <= lim && (i + 1 == ncand || !(key_score(buf[i + 1]) <= lim))) s_nrer = i + 1;
+    }
+    __syncthreads();
+    const int nrer = s_nrer;
+    int nsort = 2;
+    while (nsort < nrer) nsort <<= 1;
     const double *q = a.q64 + (size_t)b * a.d;
     double *sp = sp_all + warp * 2 * kExactChunk;
-    for (int j = warp; j < KP; j += kSelWarps) {
-        if (j < ncand) {
+    for (int j = warp; j < nsort; j += kSelWarps) {
+        if (j < nrer) {
             uint32_t slot = key_slot(buf[j]);
             const uint8_t *row = a.rows + (size_t)slot * a.row_bytes;
             double mn = 0.0, sc = 0.0;
@@ -149,8 +166,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectArgs a)
     __syncthreads();
 
     // ---- 3. final order by (exact distance, slot); emit k; completeness proof ----
-    block_bitonic_sort_pairs(dkey, dslot, KP);
-    const int kout = a.kk < ncand ? a.kk : ncand;
+    block_bitonic_sort_pairs(dkey, dslot, nsort);
     for (int i = threadIdx.x; i < a.kstride; i += blockDim.x) {
         size_t o = (size_t)b * a.kstride + i;
         if (i < kout) {
@@ -177,8 +193,8 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectArgs a)
     }
 }
 
-static size_t select_smem() {
-    return sizeof(uint64_t) * kSelSort + sizeof(double) * kSelWarps * 2 * kExactChunk +
+static size_t select_smem(int threads) {
+    return sizeof(uint64_t) * kSelSort + sizeof(double) * (threads / 32) * 2 * kExactChunk +
            sizeof(uint64_t) * 2 * kMaxKP;
 }
 
@@ -192,16 +208,19 @@ int launch_select(evdb_store *s, const double *d_q64, const uint64_t *partial, i
     a.kk = kk; a.kstride = kstride; a.metric = metric; a.eps_abs = eps_abs; a.eps_rel = eps_rel;
     a.slot_base = slot_base; a.out_ids = d_out_ids; a.out_dists = d_out_dists;
     a.out_counts = d_out_counts; a.out_flags = d_out_flags;
-    size_t smem = select_smem();
+    const int threads = B >= 8 ? 256 : 1024;
+    size_t smem = select_smem(threads);
     void (*fn)(const SelectArgs) = nullptr;
+#define EVDB_SEL(DT) fn = threads == 256 ? select_kernel<DT, 256> : select_kernel<DT, 1024>
     switch (s->dtype) {
-        case EVDB_F32: fn = select_kernel<EVDB_F32>; break;
-        case EVDB_BF16: fn = select_kernel<EVDB_BF16>; break;
-        case EVDB_U8: fn = select_kernel<EVDB_U8>; break;
-        default: fn = select_kernel<EVDB_U4>; break;
+        case EVDB_F32: EVDB_SEL(EVDB_F32); break;
+        case EVDB_BF16: EVDB_SEL(EVDB_BF16); break;
+        case EVDB_U8: EVDB_SEL(EVDB_U8); break;
+        default: EVDB_SEL(EVDB_U4); break;
     }
+#undef EVDB_SEL
     EVDB_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fn<<<B, kSelThreads, smem, st>>>(a);
+    fn<<<B, threads, smem, st>>>(a);
     s->n_launches++;
     EVDB_CUDA(cudaGetLastError());
     return EVDB_OK;
