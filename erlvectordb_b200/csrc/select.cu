@@ -58,20 +58,26 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     // ---- 1. merge L ascending lists of KP keys into the KP smallest ----
-    // Fast path: the KP-th smallest list HEAD is an upper bound T on the global KP-th smallest
-    // key (KP distinct keys are <= it), so only keys <= T can matter -- typically a few dozen.
+    // Fast path: pool the first P = ceil(KP/L) keys of every list; the KP-th smallest of the pool
+    // is an upper bound T on the global KP-th smallest key (KP distinct keys are <= it), so only
+    // keys <= T can matter -- typically not many more than KP.
     const uint64_t *src = a.partial + (size_t)b * a.L * KP;
     const size_t total = (size_t)a.L * KP;
     __shared__ int s_cnt;
     bool merged = false;
-    if (a.L <= kSelSort) {
+    // heads per list so that the pool holds at least KP keys (lists are ascending)
+    const int P = (KP + a.L - 1) / a.L;
+    const bool pool_ok = (size_t)a.L * P <= (size_t)kSelSort && P <= KP;
+    if (pool_ok) {
+        const int pool = a.L * P;
         int Lp = 2;
-        while (Lp < a.L) Lp <<= 1;
-        for (int i = threadIdx.x; i < Lp; i += blockDim.x) buf[i] = i < a.L ? src[(size_t)i * KP] : kKeyMax;
+        while (Lp < pool) Lp <<= 1;
+        for (int i = threadIdx.x; i < Lp; i += blockDim.x)
+            buf[i] = i < pool ? src[(size_t)(i / P) * KP + (i % P)] : kKeyMax;
         if (threadIdx.x == 0) s_cnt = 0;
         __syncthreads();
         block_bitonic_sort(buf, Lp);
-        const uint64_t T = a.L >= KP ? buf[KP - 1] : kKeyMax;
+        const uint64_t T = buf[KP - 1];  // >= KP keys are <= T (kKeyMax if the lists hold fewer)
         __syncthreads();
         for (size_t i = threadIdx.x; i < total; i += blockDim.x) {
             uint64_t key = src[i];
