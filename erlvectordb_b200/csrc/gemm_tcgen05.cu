@@ -24,6 +24,7 @@
 // is shared by the MB CTAs working on different query blocks at the same time (L2 hits).
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 #include <cuda_fp16.h>
 
 #include "internal.h"
@@ -53,6 +54,10 @@ struct GemmArgs {
     int KP;
     uint64_t *partial;   // [Bpad][2*NG][KP]
     uint64_t *cand;      // [CTAs][2][kCandCap][128] append buffers
+    int mode;            // 0 = fused top-k, 1 = dump raw scores of a row sample (threshold seeding)
+    float *dump;         // mode 1: [Bpad][dump_ld] scores
+    int dump_ld;
+    const float *thr0;   // mode 0: per-query admission threshold to start from (NULL = +inf)
     int debug;           // EVDB_GEMM_DEBUG (measurement only): 1 = no appends, 2 = no TMEM loads, 8 = cycle breakdown
     unsigned long long *dbg;  // [CTAs][8 warps][4]: wait, chunk, prune, flush cycles
 };
@@ -322,7 +327,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         long long t_wait = 0, t_chunk = 0, t_prune = 0, t_flush = 0, n_prune = 0, n_app = 0;
         for (int c = 0; c < a.nchunks; ++c) {
             int cnt = 0;
-            float thr = kInf;
+            const size_t qglob = (size_t)(c * a.MB + mb_local) * GM + et;
+            // admission threshold: seeded by the sampled pre-pass (a valid upper bound on the
+            // query's KP-th best score), tightened by every prune
+            float thr = a.thr0 ? a.thr0[qglob] : kInf;
             // load lane `src`'s buffer into registers (8 per lane), return its fill count
             auto load_buf = [&](int src, uint64_t (&x)[8]) -> int {
                 const int n = __shfl_sync(0xffffffffu, cnt, src);
@@ -385,6 +393,13 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                         if (col0 + 32 > valid && col0 + j >= valid) dist[j] = kInf;  // rows past the end
                         mask |= (dist[j] < thr) ? (1u << j) : 0u;
                     }
+                    if (a.mode == 1) {  // sampled pre-pass: dump the scores, no selection
+                        float4 *o = reinterpret_cast<float4 *>(a.dump + qglob * a.dump_ld + row0 + col0);
+#pragma unroll
+                        for (int r = 0; r < 8; ++r)
+                            o[r] = make_float4(dist[4 * r], dist[4 * r + 1], dist[4 * r + 2], dist[4 * r + 3]);
+                        continue;
+                    }
                     if (a.debug & 1) mask = 0;
                     if (mask) {
                         // stage this thread's 32 scores for dynamic indexing, then visit the set bits
@@ -442,7 +457,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             // flush: every query's KP best, sorted ascending -> partial[q][2*ng + half][KP]
             __syncwarp();
             long long tf0 = clock64();
-            for (int ql = 0; ql < 32; ++ql) {
+            for (int ql = 0; ql < (a.mode == 1 ? 0 : 32); ++ql) {
                 uint64_t x[8];
                 const int n = load_buf(ql, x);
                 const int keep = n < KP ? n : KP;
@@ -497,6 +512,51 @@ __global__ void __launch_bounds__(256) prep_queries_gemm_kernel(const double *__
         o[i] = __float2half_rn(i < d ? (float)q[i] * inv : 0.f);
 }
 
+// ---- threshold seeding: KP-th smallest score of each query over the sampled rows -------------
+// One CTA per query, values in registers, bisection on the order-preserving bits with block-wide
+// counts.  thr0[q] is an upper bound on the query's global KP-th best approximate score: the
+// sample rows are rows of the corpus, scored by the same MMA path as the main sweep.
+constexpr int kSeedThreads = 256;
+constexpr int kSeedVpt = 64;  // sample size <= 256 * 64
+__global__ void __launch_bounds__(kSeedThreads) seed_threshold_kernel(const float *__restrict__ dump, int ld,
+                                                                      int S, int need, float *__restrict__ thr0) {
+    __shared__ int s_cnt[2];
+    __shared__ uint32_t s_lo, s_hi;
+    const int q = blockIdx.x;
+    const float *row = dump + (size_t)q * ld;
+    uint32_t v[kSeedVpt];
+    uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+#pragma unroll
+    for (int i = 0; i < kSeedVpt; ++i) {
+        const int idx = i * kSeedThreads + threadIdx.x;
+        v[i] = idx < S ? f32_orderable(row[idx]) : 0xFFFFFFFFu;
+        mn = min(mn, v[i]);
+        if (idx < S) mx = max(mx, v[i]);
+    }
+    if (threadIdx.x == 0) { s_cnt[0] = 0; s_cnt[1] = 0; s_lo = 0xFFFFFFFFu; s_hi = 0u; }
+    __syncthreads();
+    atomicMin(&s_lo, __reduce_min_sync(0xffffffffu, mn));
+    atomicMax(&s_hi, __reduce_max_sync(0xffffffffu, mx));
+    __syncthreads();
+    uint32_t lo = s_lo, hi = s_hi;  // invariant: count(v <= hi) >= need
+    int it = 0;
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < kSeedVpt; ++i) c += v[i] <= mid ? 1 : 0;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&s_cnt[it & 1], c);
+        __syncthreads();
+        const int tot = s_cnt[it & 1];
+        if (threadIdx.x == 0) s_cnt[(it + 1) & 1] = 0;
+        if (tot >= need) hi = mid; else lo = mid + 1;
+        ++it;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) thr0[q] = f32_from_orderable(lo);
+}
+
 // ---- host side ------------------------------------------------------------------------------
 typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
@@ -515,6 +575,8 @@ static encode_tiled_fn get_encode() {
     return fn;
 }
 
+// rows x cols fp16, `pitch_elems` elements between consecutive rows of the MAP (a multiple of the
+// storage pitch selects every step-th stored row: the strided sample needs no gather)
 static int make_map(CUtensorMap *tm, const void *base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
                     uint32_t box_rows) {
     encode_tiled_fn enc = get_encode();
@@ -567,15 +629,47 @@ int launch_gemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int *lis
     EVDB_TRY(make_map(&tmQ, s->w_qh, (uint64_t)Bpad, (uint64_t)kpitch, (uint64_t)kpitch, GM));
     EVDB_TRY(make_map(&tmV, s->shadow, s->count, (uint64_t)kpitch, (uint64_t)kpitch, GN));
     GemmArgs a;
-    a.n = s->count;
+    memset(&a, 0, sizeof(a));
     a.kblocks = (s->dim + GK - 1) / GK;
-    a.nt = nt;
     a.MB = MB;
-    a.NG = NG;
     a.nchunks = nchunks;
     a.KP = KP;
     a.partial = s->w_partial;
     a.cand = cand;
+    size_t smem = gemm_smem_bytes(KP);
+    EVDB_CUDA(cudaFuncSetAttribute((const void *)gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+    // ---- sampled pre-pass: seed every query's admission threshold ----
+    // S strided sample rows (a TMA map with a multiplied row stride), scores dumped, KP-th smallest
+    // per query selected.  Kills the per-(CTA, query) warm-up of the main sweep.
+    const float *thr0 = nullptr;
+    const char *noseed = getenv("EVDB_GEMM_NOSEED");
+    if (s->count >= 32768 && !(noseed && atoi(noseed))) {
+        uint64_t S = 16384;
+        while (S * 16 > s->count && S > 1024) S >>= 1;  // at most ~6% extra rows scored
+        const uint64_t step = s->count / S;
+        const int snt = (int)(S / GN);
+        int sNG = s->sm_count / MB;
+        if (sNG > snt) sNG = snt;
+        const size_t dump_bytes = round_up64((size_t)Bpad * S * sizeof(float), 256);
+        EVDB_TRY(ensure_bytes((void **)&s->w_seed, &s->w_seed_cap, dump_bytes + (size_t)Bpad * sizeof(float)));
+        float *dump = (float *)s->w_seed;
+        float *thr = (float *)((uint8_t *)s->w_seed + dump_bytes);
+        CUtensorMap tmVs;
+        EVDB_TRY(make_map(&tmVs, s->shadow, S, (uint64_t)kpitch, (uint64_t)kpitch * step, GN));
+        GemmArgs p = a;
+        p.n = S; p.nt = snt; p.NG = sNG; p.mode = 1; p.dump = dump; p.dump_ld = (int)S;
+        gemm_topk_kernel<<<MB * sNG, kGemmThreads, smem, st>>>(tmQ, tmVs, p);
+        EVDB_CUDA(cudaGetLastError());
+        seed_threshold_kernel<<<Bpad, kSeedThreads, 0, st>>>(dump, (int)S, (int)S, KP, thr);
+        EVDB_CUDA(cudaGetLastError());
+        s->n_launches += 2;
+        thr0 = thr;
+    }
+    a.thr0 = thr0;
+    a.n = s->count;
+    a.nt = nt;
+    a.NG = NG;
     { const char *e = getenv("EVDB_GEMM_DEBUG"); a.debug = e ? atoi(e) : 0; }
     a.dbg = nullptr;
     static unsigned long long *g_dbg = nullptr;
@@ -583,8 +677,6 @@ int launch_gemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int *lis
         if (!g_dbg) cudaMalloc((void **)&g_dbg, sizeof(unsigned long long) * 148 * kEpiWarps * 8);
         a.dbg = g_dbg;
     }
-    size_t smem = gemm_smem_bytes(KP);
-    EVDB_CUDA(cudaFuncSetAttribute((const void *)gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     prof_begin(s, st);
     gemm_topk_kernel<<<MB * NG, kGemmThreads, smem, st>>>(tmQ, tmV, a);
     prof_end(s, st);

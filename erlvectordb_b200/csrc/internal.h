@@ -49,6 +49,7 @@ struct evdb_store {
     double *w_q64 = nullptr;   size_t w_q64_cap = 0;    // [B][dim]
     float *w_q32 = nullptr;    size_t w_q32_cap = 0;    // [B][dpad32]
     uint8_t *w_qdig = nullptr; size_t w_qdig_cap = 0;   // [B][3][dpad] digit planes
+    void *w_seed = nullptr;    size_t w_seed_cap = 0;   // [Bpad][S] sampled scores + [Bpad] seeded thresholds (GEMM)
     void *w_qh = nullptr;      size_t w_qh_cap = 0;     // [Bpad][spitch] fp16 unit-norm queries (GEMM)
     evdb::QStat *w_qstat = nullptr; size_t w_qstat_cap = 0;
     uint64_t *w_partial = nullptr; size_t w_partial_cap = 0; // [B][G][KP]

@@ -194,7 +194,10 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
             double dk = __longlong_as_double((long long)bits);
             double lim = (double)bound - (double)a.eps_abs - (double)a.eps_rel * fabs((double)bound);
             flag = !(dk < lim);
+            // threshold-admitted candidates can be fewer than k (e.g. massive exact ties): escalate
+            if ((uint64_t)a.kk <= a.n ? ncand < a.kk : false) flag = 1;
         }
+        if (kout == 0 && a.kk > 0 && a.n > 0) flag = 1;
         if (a.out_flags) a.out_flags[b] = flag;
     }
 }

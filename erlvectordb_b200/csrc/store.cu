@@ -103,7 +103,7 @@ static uint64_t device_bytes(const evdb_store *s) {
     if (is_quant(s)) per += sizeof(float2) + sizeof(double2);
     if (s->shadow) per += (uint64_t)s->spitch * 2;
     return per * s->capacity + s->w_q64_cap + s->w_q32_cap + s->w_qdig_cap + s->w_qstat_cap +
-           s->w_partial_cap + s->w_qh_cap + s->w_ids_cap + s->w_dists_cap + s->w_counts_cap + s->w_tmp_cap;
+           s->w_partial_cap + s->w_qh_cap + s->w_seed_cap + s->w_ids_cap + s->w_dists_cap + s->w_counts_cap + s->w_tmp_cap;
 }
 
 // ----------------------------------------------------------------------------
@@ -438,13 +438,19 @@ const char *evdb_strerror(int code) {
 const char *evdb_last_cuda_error(void) { return g_cuda_err; }
 
 static int check_device(int dev) {
+    // cudaGetDeviceProperties costs milliseconds: probe each ordinal once per process
+    static int verdict[64];
+    static bool probed[64];
+    if (dev >= 0 && dev < 64 && probed[dev]) return verdict[dev];
+    int rc = EVDB_OK;
     int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); return EVDB_E_NO_DEVICE; }
-    if (dev < 0 || dev >= n) return EVDB_E_NO_DEVICE;
     cudaDeviceProp p;
-    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) { cudaGetLastError(); return EVDB_E_NO_DEVICE; }
-    if (p.major != 10) return EVDB_E_NO_DEVICE;  // sm_100a SASS only: no fallback
-    return EVDB_OK;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); rc = EVDB_E_NO_DEVICE; }
+    else if (dev < 0 || dev >= n) rc = EVDB_E_NO_DEVICE;
+    else if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) { cudaGetLastError(); rc = EVDB_E_NO_DEVICE; }
+    else if (p.major != 10) rc = EVDB_E_NO_DEVICE;  // sm_100a SASS only: no fallback
+    if (dev >= 0 && dev < 64 && rc == EVDB_OK) { verdict[dev] = rc; probed[dev] = true; }
+    return rc;
 }
 
 int evdb_init(const int *devices, int n_dev) {
@@ -487,7 +493,7 @@ void evdb_store_destroy(evdb_store *s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     cudaFree(s->rows); cudaFree(s->norm64); cudaFree(s->inv_norm); cudaFree(s->norm_sq);
     cudaFree(s->qcoef); cudaFree(s->qms64); cudaFree(s->shadow);
-    cudaFree(s->w_q64); cudaFree(s->w_q32); cudaFree(s->w_qdig); cudaFree(s->w_qh); cudaFree(s->w_qstat);
+    cudaFree(s->w_q64); cudaFree(s->w_q32); cudaFree(s->w_qdig); cudaFree(s->w_qh); cudaFree(s->w_seed); cudaFree(s->w_qstat);
     cudaFree(s->w_partial); cudaFree(s->w_ids); cudaFree(s->w_dists); cudaFree(s->w_counts);
     cudaFree(s->w_tmp);
     if (s->h_pin) cudaFreeHost(s->h_pin);
