@@ -60,20 +60,39 @@ __device__ double exact_distance_warp(const uint8_t *row, double mn, double sc, 
                                       int d, int metric, double vnorm, double *sp, int lane) {
     double s = 0.0, sq = 0.0;
     double *sp2 = sp + kExactChunk;
+    constexpr int kPer = kExactChunk / kWarp;  // terms per lane per round
+    // operands of the NEXT chunk are loaded while one lane folds the current one
+    double nv[kPer], nq[kPer];
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+        const int t = i * kWarp + lane;
+        nv[i] = t < d ? row_elem<DTYPE>(row, t, mn, sc) : 0.0;
+        nq[i] = t < d ? q[t] : 0.0;
+    }
     for (int base = 0; base < d; base += kExactChunk) {
         int cnt = min(kExactChunk, d - base);
-        for (int t = lane; t < cnt; t += kWarp) {
-            double v = row_elem<DTYPE>(row, base + t, mn, sc);
-            double qq = q[base + t];
-            if (metric == EVDB_COSINE) {
-                sp[t] = __dmul_rn(qq, v);    // dot_product: X*Y
-                sp2[t] = __dmul_rn(qq, qq);  // vector_norm(Query): X*X
-            } else if (metric == EVDB_EUCLIDEAN) {
-                double t0 = __dsub_rn(qq, v);  // vector_subtract
-                sp[t] = __dmul_rn(t0, t0);
-            } else {
-                sp[t] = fabs(__dsub_rn(qq, v));  // abs(X - Y)
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) {
+            const int t = i * kWarp + lane;
+            const double v = nv[i], qq = nq[i];
+            if (t < cnt) {
+                if (metric == EVDB_COSINE) {
+                    sp[t] = __dmul_rn(qq, v);    // dot_product: X*Y
+                    sp2[t] = __dmul_rn(qq, qq);  // vector_norm(Query): X*X
+                } else if (metric == EVDB_EUCLIDEAN) {
+                    double t0 = __dsub_rn(qq, v);  // vector_subtract
+                    sp[t] = __dmul_rn(t0, t0);
+                } else {
+                    sp[t] = fabs(__dsub_rn(qq, v));  // abs(X - Y)
+                }
             }
+        }
+        const int nb = base + kExactChunk;
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) {
+            const int t = nb + i * kWarp + lane;
+            nv[i] = t < d ? row_elem<DTYPE>(row, t, mn, sc) : 0.0;
+            nq[i] = t < d ? q[t] : 0.0;
         }
         __syncwarp();
         if (lane == 0) {

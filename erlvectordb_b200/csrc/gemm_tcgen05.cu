@@ -520,7 +520,7 @@ constexpr int kSeedThreads = 256;
 constexpr int kSeedVpt = 64;  // sample size <= 256 * 64
 __global__ void __launch_bounds__(kSeedThreads) seed_threshold_kernel(const float *__restrict__ dump, int ld,
                                                                       int S, int need, float *__restrict__ thr0) {
-    __shared__ int s_cnt[2];
+    __shared__ int s_cnt[6];
     __shared__ uint32_t s_lo, s_hi;
     const int q = blockIdx.x;
     const float *row = dump + (size_t)q * ld;
@@ -533,24 +533,39 @@ __global__ void __launch_bounds__(kSeedThreads) seed_threshold_kernel(const floa
         mn = min(mn, v[i]);
         if (idx < S) mx = max(mx, v[i]);
     }
-    if (threadIdx.x == 0) { s_cnt[0] = 0; s_cnt[1] = 0; s_lo = 0xFFFFFFFFu; s_hi = 0u; }
+    if (threadIdx.x < 6) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x == 0) { s_lo = 0xFFFFFFFFu; s_hi = 0u; }
     __syncthreads();
     atomicMin(&s_lo, __reduce_min_sync(0xffffffffu, mn));
     atomicMax(&s_hi, __reduce_max_sync(0xffffffffu, mx));
     __syncthreads();
     uint32_t lo = s_lo, hi = s_hi;  // invariant: count(v <= hi) >= need
     int it = 0;
-    while (lo < hi) {
-        const uint32_t mid = lo + ((hi - lo) >> 1);
-        int c = 0;
+    while (lo < hi) {  // 4-way search: three pivots per round, one barrier pair per round
+        const uint32_t span = hi - lo;
+        const uint32_t qd = span >> 2;
+        const uint32_t p2 = lo + (span >> 1);
+        const uint32_t p1 = qd ? lo + qd : p2;
+        const uint32_t p3 = qd ? p2 + qd : p2;
+        int c1 = 0, c2 = 0, c3 = 0;
 #pragma unroll
-        for (int i = 0; i < kSeedVpt; ++i) c += v[i] <= mid ? 1 : 0;
-        c = __reduce_add_sync(0xffffffffu, c);
-        if ((threadIdx.x & 31) == 0) atomicAdd(&s_cnt[it & 1], c);
+        for (int i = 0; i < kSeedVpt; ++i) {
+            c1 += v[i] <= p1 ? 1 : 0;
+            c2 += v[i] <= p2 ? 1 : 0;
+            c3 += v[i] <= p3 ? 1 : 0;
+        }
+        c1 = __reduce_add_sync(0xffffffffu, c1);
+        c2 = __reduce_add_sync(0xffffffffu, c2);
+        c3 = __reduce_add_sync(0xffffffffu, c3);
+        int *cc = s_cnt + (it & 1) * 3;
+        if ((threadIdx.x & 31) == 0) { atomicAdd(cc, c1); atomicAdd(cc + 1, c2); atomicAdd(cc + 2, c3); }
         __syncthreads();
-        const int tot = s_cnt[it & 1];
-        if (threadIdx.x == 0) s_cnt[(it + 1) & 1] = 0;
-        if (tot >= need) hi = mid; else lo = mid + 1;
+        const int t1 = cc[0], t2 = cc[1], t3 = cc[2];
+        if (threadIdx.x < 3) s_cnt[((it + 1) & 1) * 3 + threadIdx.x] = 0;
+        if (t1 >= need) hi = p1;
+        else if (t2 >= need) { lo = p1 + 1; hi = p2; }
+        else if (t3 >= need) { lo = p2 + 1; hi = p3; }
+        else lo = p3 + 1;
         ++it;
         __syncthreads();
     }
