@@ -1,28 +1,41 @@
-// gemm_tcgen05.cu -- batched cosine search as a TMA-fed tcgen05/TMEM GEMM with a fused
-// per-query top-k epilogue (family B).
+// gemm_tcgen05.cu -- batched cosine / euclidean search as a TMA-fed tcgen05/TMEM GEMM with a
+// fused per-query top-k epilogue (family B).
 //
 // Replaces, for query batches, the same reference text as the scans: the maps:fold of
-// cosine_distance/2 over all rows (reference src/vector_store.erl:227-252) -- here for B
-// queries at once as  D[q][r] = <q_hat_q, v_hat_r>  with q_hat = q/||q||, v_hat = v/||v||
-// held in fp16 (the "shadow" column of an F32 store), fp32 accumulation in tensor memory.
-// The GEMM only GENERATES CANDIDATES: scores carry a rigorous error bound eps (two fp16
-// roundings + fp32 accumulation), the KP best per query go to select.cu, which re-ranks them
-// in exact fp64 and proves the window complete -- returned distances never see fp16.
+// cosine_distance/2 over all rows (reference src/vector_store.erl:227-252) and the
+// euclidean form of src/vector_utils.erl:38-40 -- here for B queries at once as one GEMM
+//     acc[q][r] = sum_k Qh[q][k] * Vh[r][k]          (fp16 operands, fp32 accumulate in TMEM)
+//   cosine   : Qh = q/||q||, Vh = v/||v||                      key score = 1 - acc
+//   euclidean: Qh = [s*q, 1, 1, 1], Vh = [s*v, h1, h2, h3]     key score = ||q||^2 - (2/s^2)*acc
+//              with h1+h2+h3 = -s^2*||v||^2/2 split over three fp16 columns, s a power of two
+//              chosen from the store's largest row norm, so acc = s^2*(q.v - ||v||^2/2): the row
+//              norms ride in the K dimension and the epilogue is the same for both metrics.
+// The GEMM only GENERATES CANDIDATES: key scores carry a rigorous per-query error bound eps
+// (fp16 operand rounding + fp32 accumulation), the KP best per query go to select.cu, which
+// re-ranks them in exact fp64 and proves the window complete -- returned distances never see
+// fp16.
 //
-// Kernel anatomy (one persistent CTA per SM, 256 threads, no cluster):
+// Kernel anatomy (one persistent CTA per SM, 384 threads, no cluster):
 //   warp 0   TMA producer: cp.async.bulk.tensor 2D tiles (128B swizzle) of Q [128 x 64] and
 //            V [256 x 64] into a 4-stage shared-memory ring, mbarrier complete_tx
 //   warp 1   MMA issuer: one elected thread, tcgen05.mma cta_group::1 kind::f16, M=128 N=256
-//            K=16, 4 per stage; tcgen05.commit frees the stage / publishes the accumulator
+//            K=16, up to 4 per stage; tcgen05.commit frees the stage / publishes the accumulator
 //   warp 2   TMEM allocator (512 columns = 2 accumulator stages x 256 fp32 columns)
-//   warps 4-7 epilogue: thread t owns TMEM lane t == query t of the CTA's 128-query block;
-//            tcgen05.ld 32 columns at a time, dist = 1 - acc, compare against the query's
-//            running threshold (register); rare hits are inserted warp-cooperatively into
-//            the query's sorted candidate list in shared memory.
-// A CTA keeps one query block for a whole sweep over its share of the corpus tiles, so the
-// candidate lists never leave shared memory until the final flush.  The 256-row corpus tile
-// is shared by the MB CTAs working on different query blocks at the same time (L2 hits).
+//   warps 4-11 epilogue: thread t owns TMEM lane t == query t of the CTA's 128-query block, two
+//            warps per lane quarter split the 256 columns; tcgen05.ld 32 columns at a time.
+//            The score stream is filtered in the ACCUMULATOR domain: a 3-input-max tree over
+//            the 32 values (20 FMNMX3/FMNMX) against the query's admission threshold; only a
+//            chunk that beats it is expanded, and its hits are appended to the query's private
+//            candidate buffer (global memory, L2 resident).  A buffer that nears capacity is
+//            reduced to its KP best by value bisection with warp population counts (no sort),
+//            which also tightens the threshold.
+// A CTA keeps one query block for a whole sweep over its share of the corpus tiles; the 256-row
+// corpus tile is shared by the MB CTAs working on different query blocks at the same time (L2
+// hits).  Thresholds start from a sampled pre-pass (the same kernel in pooling mode over a strided
+// row sample).  A separate flush kernel (one warp per list) turns the buffers into the sorted
+// KP-key lists select.cu merges.
 #include <cuda.h>
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 #include <cuda_fp16.h>
@@ -37,29 +50,41 @@ constexpr int GN = 256;        // corpus rows per tile (UMMA N)
 constexpr int GK = 64;         // K elements per stage (64 fp16 = one 128-byte swizzle row)
 constexpr int GUK = 16;        // UMMA K
 constexpr int kGemmStages = 4;
-constexpr int kGemmThreads = 384;   // 4 control warps + 8 epilogue warps
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;       // tcgen05.ld is latency-bound per warp (tools/micro/ldtm_bench.cu): 4 warps per lane quarter
+constexpr int kEpiParts = kEpiWarps / 4;   // column parts of a tile, one candidate list each
+constexpr int kGemmThreads = 128 + 32 * kEpiWarps;   // 4 control warps + the epilogue warps
 constexpr uint32_t kStageABytes = GM * GK * 2;   // 16 KB
 constexpr uint32_t kStageBBytes = GN * GK * 2;   // 32 KB
 constexpr uint32_t kStageBytes = kStageABytes + kStageBBytes;
-constexpr int kGemmMaxKP = 64;
+constexpr int kGemmMaxKP = 128;
+constexpr int kCandCapMax = 256;    // candidate buffer entries per (query, CTA, column part): 128 for KP <= 32, else 256
+constexpr int kMaxSweeps = 8;       // query-block sweeps per launch (bounds the candidate buffers)
+constexpr uint32_t kTailABytes = GM * GUK * 2;   // 4 KB: the norm K-step of the euclidean plan (Q side)
+constexpr uint32_t kTailBBytes = GN * GUK * 2;   // 8 KB (V side)
+constexpr uint32_t kTailBytes = kTailABytes + kTailBBytes;
 
 struct GemmArgs {
     uint64_t n;          // corpus rows
-    int kblocks;         // ceil(dim / 64)
+    int B;               // live queries (rows >= B of the padded batch are never admitted)
+    int kblocks;         // ceil(K / 64), K = operand columns (dim, or dim + 3 for euclidean)
+    int last_ksteps;     // UMMA K-steps in the last k-block (1..4)
+    int tail;            // euclidean: one more K-step from the [rows][16] norm operands (32B swizzle)
+    int cap;             // candidate buffer capacity in use (<= kCandCapMax)
     int nt;              // corpus tiles = ceil(n / 256)
     int MB;              // query blocks processed concurrently
-    int NG;              // CTAs per query block (lists per query)
+    int NG;              // CTAs per query block (2*NG lists per query)
     int nchunks;         // sweeps: query blocks [c*MB, (c+1)*MB)
     int KP;
-    uint64_t *partial;   // [Bpad][2*NG][KP]
-    uint64_t *cand;      // [CTAs][2][kCandCap][128] append buffers
-    int mode;            // 0 = fused top-k, 1 = dump raw scores of a row sample (threshold seeding)
-    float *dump;         // mode 1: [Bpad][dump_ld] scores
+    uint64_t *cand;      // [sweep][CTA][part][cap][128] append buffers
+    int *cand_cnt;       // [sweep][CTA][part][128] fill counts at the end of the sweep
+    int mode;            // 0 = fused top-k, 1 = pooled key scores of a row sample (threshold seeding)
+    float *dump;         // mode 1: [Bpad][dump_ld] best key score of every 32-row chunk
     int dump_ld;
-    const float *thr0;   // mode 0: per-query admission threshold to start from (NULL = +inf)
+    const uint32_t *thr0;  // mode 0: per-query starting threshold, orderable key score (NULL = none)
+    const float *qc0;    // [Bpad] key score = fma(acc, c1, qc0[q])
+    float c1;            // < 0
     int debug;           // EVDB_GEMM_DEBUG (measurement only): 1 = no appends, 2 = no TMEM loads, 8 = cycle breakdown
-    unsigned long long *dbg;  // [CTAs][8 warps][4]: wait, chunk, prune, flush cycles
+    unsigned long long *dbg;  // [CTAs][epilogue warps][8]
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------
@@ -133,6 +158,16 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t saddr) {
     d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
     return d;
 }
+// K = 16 fp16 operand tile (32-byte rows), 32-byte swizzle: 8-row groups 256 bytes apart
+__device__ __forceinline__ uint64_t make_sw32_kmajor_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(256 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;                       // SWIZZLE_32B
+    return d;
+}
 // kind::f16 instruction descriptor: fp16 x fp16 -> fp32, both K-major, M=128, N=256
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
     return (1u << 4)                 // c_format = F32
@@ -140,8 +175,6 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
          | (0u << 15) | (0u << 16)   // a_major = b_major = K
          | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-
-constexpr int kCandCap = 256;   // candidate buffer entries per (query, CTA)
 
 // Selection without sorting: tau = the `need`-th smallest 32-bit score (orderable encoding, high
 // word of the key) among up to 256 keys held 8 per lane (kKeyMax pads), by 4-way search on the
@@ -186,45 +219,192 @@ __device__ __forceinline__ uint32_t warp_select_score(const uint64_t (&x)[8], in
     return lo;
 }
 
-// Ascending bitonic sort of 64 u64 keys held 2 per lane (element lane in e0, lane + 32 in e1).
-__device__ __forceinline__ void warp_sort64(uint64_t &e0, uint64_t &e1, const int lane) {
-#pragma unroll 1
-    for (int k2 = 2; k2 <= 64; k2 <<= 1) {
-#pragma unroll 1
+// Keep the `need` best keys of x (8 per lane): those below tau first, then ties at tau, written
+// densely to dst[i * stride].  Returns tau (orderable score of the need-th best).
+__device__ __forceinline__ uint32_t warp_compact(const uint64_t (&x)[8], int need, uint64_t *dst,
+                                                 size_t stride, int lane) {
+    int n_less;
+    const uint32_t tau = warp_select_score(x, need, &n_less);
+    int base_less = 0, base_tie = n_less, ties_left = need - n_less;
+    const unsigned below = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const uint32_t scr = (uint32_t)(x[r] >> 32);
+        const bool is_less = scr < tau;
+        const bool is_tie = scr == tau && x[r] != kKeyMax;
+        const unsigned ml = __ballot_sync(0xffffffffu, is_less);
+        const unsigned mt = __ballot_sync(0xffffffffu, is_tie);
+        if (is_less) dst[(size_t)(base_less + __popc(ml & below)) * stride] = x[r];
+        const int trank = __popc(mt & below);
+        if (is_tie && trank < ties_left) dst[(size_t)(base_tie + trank) * stride] = x[r];
+        base_less += __popc(ml);
+        const int used = min(__popc(mt), ties_left);
+        base_tie += used;
+        ties_left -= used;
+    }
+    return tau;
+}
+
+// Ascending bitonic sort of 32*NPL u64 keys held NPL per lane (element r*32 + lane in e[r]).
+template <int NPL>
+__device__ __forceinline__ void warp_sort(uint64_t (&e)[NPL], const int lane) {
+#pragma unroll
+    for (int k2 = 2; k2 <= 32 * NPL; k2 <<= 1) {
+#pragma unroll
         for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
-            if (j2 == 32) {  // k2 == 64: partner is the other register, direction ascending
-                const uint64_t lo = e0 < e1 ? e0 : e1, hi = e0 < e1 ? e1 : e0;
-                e0 = lo;
-                e1 = hi;
+            if (j2 >= 32) {  // partner is another register of the same lane
+                const int rj = j2 >> 5;
+#pragma unroll
+                for (int r = 0; r < NPL; ++r) {
+                    if ((r & rj) == 0) {
+                        const bool asc = ((r << 5) & k2) == 0;
+                        const uint64_t a = e[r], b = e[r | rj];
+                        const bool sw = asc ? (a > b) : (a < b);
+                        e[r] = sw ? b : a;
+                        e[r | rj] = sw ? a : b;
+                    }
+                }
             } else {
-                const uint64_t p0 = __shfl_xor_sync(0xffffffffu, e0, j2);
-                const uint64_t p1 = __shfl_xor_sync(0xffffffffu, e1, j2);
-                const bool lower = (lane & j2) == 0;
-                const bool asc0 = (lane & k2) == 0;
-                const bool asc1 = ((lane + 32) & k2) == 0;
-                e0 = (lower == asc0) ? (e0 < p0 ? e0 : p0) : (e0 > p0 ? e0 : p0);
-                e1 = (lower == asc1) ? (e1 < p1 ? e1 : p1) : (e1 > p1 ? e1 : p1);
+#pragma unroll
+                for (int r = 0; r < NPL; ++r) {
+                    const uint64_t p = __shfl_xor_sync(0xffffffffu, e[r], j2);
+                    const bool lower = (lane & j2) == 0;
+                    const bool asc = (((r << 5) + lane) & k2) == 0;
+                    e[r] = (lower == asc) ? (e[r] < p ? e[r] : p) : (e[r] > p ? e[r] : p);
+                }
             }
         }
     }
 }
 
+// Largest accumulator value a (to a few ulps) with fma(a, c1, c0) >= tau, c1 < 0: a row whose
+// accumulator is <= a has key score >= tau and can be skipped.  Never errs towards skipping more.
+__device__ __forceinline__ float acc_threshold(float tau, float c0, float c1) {
+    const float kInf = __int_as_float(0x7f800000);
+    if (!(tau < kInf)) return -kInf;  // no threshold: admit everything
+    uint32_t o = f32_orderable((tau - c0) / c1);
+    uint32_t step = 1;
+#pragma unroll 1
+    for (int i = 0; i < 40 && fmaf(f32_from_orderable(o), c1, c0) < tau; ++i) {
+        o = o > step ? o - step : 1u;
+        step <<= 1;
+        if (o <= 0x00800000u) return -kInf;  // ran off the float range: give up, admit everything
+    }
+    if (fmaf(f32_from_orderable(o), c1, c0) < tau) return -kInf;
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i)
+        if (fmaf(f32_from_orderable(o + 1), c1, c0) >= tau) ++o;
+    return f32_from_orderable(o);
+}
+
+// Out-of-line (rare): reduce every buffer of this warp flagged in `need` to its KP best keys and
+// tighten the owning lane's threshold.  wbase = the warp's first buffer column (entry i of lane e
+// at wbase[i*GM + e]).  Software-pipelined: the next buffer's loads are in flight while the current
+// one is selected and compacted (prunes come in bursts).  Returns the number of buffers pruned.
+__device__ __noinline__ int prune_buffers(uint64_t *wbase, unsigned need, const int KP, const int lane,
+                                          const float c0, const float c1, int &cnt, float &tau, float &thrS) {
+    auto load_buf = [&](int src, uint64_t (&x)[8]) {
+        const int n = __shfl_sync(0xffffffffu, cnt, src);
+        const uint64_t *b = wbase + src;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int e = r * 32 + lane;
+            x[r] = e < n ? __ldcg(b + (size_t)e * GM) : kKeyMax;
+        }
+    };
+    __syncwarp();
+    int done = 0;
+    int src = __ffs(need) - 1;
+    need &= need - 1;
+    uint64_t x[8];
+    load_buf(src, x);  // > KP keys here
+    while (true) {
+        ++done;
+        int nsrc = -1;
+        uint64_t y[8];
+        if (need) {
+            nsrc = __ffs(need) - 1;
+            need &= need - 1;
+            load_buf(nsrc, y);
+        }
+        const uint32_t tau_o = warp_compact(x, KP, wbase + src, GM, lane);
+        if (lane == src) {
+            cnt = KP;
+            tau = fminf(tau, f32_from_orderable(tau_o));
+            thrS = fmaxf(thrS, acc_threshold(tau, c0, c1));
+        }
+        if (nsrc < 0) break;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) x[r] = y[r];
+        src = nsrc;
+    }
+    __syncwarp();
+    return done;
+}
+
+// One 32-column chunk of one query's accumulator row: pooled maximum, and -- only when it beats
+// the admission threshold -- the expansion that appends the hits.  Returns the chunk maximum.
+// Columns past the end of the store hold acc = 0 (TMA zero fill); they can only cause a spurious
+// expansion, the row bound is checked where a key is appended.  Kept small on purpose: the
+// expansion is divergent code that every epilogue warp enters at a different time, and it has
+// to stay resident in the instruction cache.
+__device__ __forceinline__ float epi_chunk(const uint32_t (&v)[32], const float thrS, const uint32_t rowbase,
+                                           const uint32_t nrows, const float c0, const float c1,
+                                           uint64_t *__restrict__ mybuf, int &cnt, const bool admit) {
+    float x[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+    float g[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = fmaxf(fmaxf(x[4 * i], x[4 * i + 1]), fmaxf(x[4 * i + 2], x[4 * i + 3]));
+    const float m = fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])), fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])));
+    if (admit && m > thrS) {
+        // which 4-column groups hold a hit; each is fetched with selects (no dynamic register
+        // index, no per-group branch) and expanded by one shared copy of the append code
+        unsigned gm = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) gm |= (g[i] > thrS) ? (1u << i) : 0u;
+#pragma unroll 1
+        while (gm) {
+            const int gi = __ffs(gm) - 1;
+            gm &= gm - 1;
+            float y0 = x[0], y1 = x[1], y2 = x[2], y3 = x[3];
+#pragma unroll
+            for (int i = 1; i < 8; ++i) {
+                const bool sel = gi == i;
+                y0 = sel ? x[4 * i] : y0;
+                y1 = sel ? x[4 * i + 1] : y1;
+                y2 = sel ? x[4 * i + 2] : y2;
+                y3 = sel ? x[4 * i + 3] : y3;
+            }
+            const uint32_t r0 = rowbase + 4 * gi;
+            if (y0 > thrS && r0 < nrows) { mybuf[(size_t)cnt * GM] = make_key(fmaf(y0, c1, c0), r0); ++cnt; }
+            if (y1 > thrS && r0 + 1 < nrows) { mybuf[(size_t)cnt * GM] = make_key(fmaf(y1, c1, c0), r0 + 1); ++cnt; }
+            if (y2 > thrS && r0 + 2 < nrows) { mybuf[(size_t)cnt * GM] = make_key(fmaf(y2, c1, c0), r0 + 2); ++cnt; }
+            if (y3 > thrS && r0 + 3 < nrows) { mybuf[(size_t)cnt * GM] = make_key(fmaf(y3, c1, c0), r0 + 3); ++cnt; }
+        }
+    }
+    return m;
+}
+
 // ---- the kernel ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmV,
+                 const __grid_constant__ CUtensorMap tmQt, const __grid_constant__ CUtensorMap tmVt,
                  const GemmArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // dynamic smem is only guaranteed 16-byte aligned: realign to 1024 for the 128B swizzle
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *stage_base = smem;                                            // [stages][A|B]
-    float4 *scratch = reinterpret_cast<float4 *>(smem + kGemmStages * kStageBytes);  // [8 warps][8][32] float4
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kGemmStages * kStageBytes + kEpiWarps * 4096);  // full[S] empty[S] tfull[2] tempty[2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kGemmStages + 4);
+    uint8_t *tail_base = smem + kGemmStages * kStageBytes;                 // [2][A tail | B tail]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tail_base + 2 * kTailBytes);  // full[S] empty[S] tfull[2] tempty[2] nfull[2] nempty[2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kGemmStages + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int KP = a.KP;
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kGemmStages);
     const uint32_t tfull0 = smem_u32(bars + 2 * kGemmStages), tempty0 = smem_u32(bars + 2 * kGemmStages + 2);
+    const uint32_t nfull0 = smem_u32(bars + 2 * kGemmStages + 4), nempty0 = smem_u32(bars + 2 * kGemmStages + 6);
 
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kGemmStages; ++i) {
@@ -234,6 +414,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int i = 0; i < 2; ++i) {
             mbar_init(tfull0 + 8 * i, 1);
             mbar_init(tempty0 + 8 * i, kEpiWarps);  // one arrive per epilogue warp
+            mbar_init(nfull0 + 8 * i, 1);
+            mbar_init(nempty0 + 8 * i, 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -247,7 +429,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t tmem_base = *tmem_slot;
 
     const int cta = blockIdx.x;
-    const bool active = cta < a.MB * a.NG;
+    const int nCTA = a.MB * a.NG;
+    const bool active = cta < nCTA;
     const int mb_local = cta % a.MB, ng = cta / a.MB;
     int my_tiles = 0;
     if (active) my_tiles = (a.nt - ng + a.NG - 1) / a.NG;  // tiles ng, ng+NG, ...
@@ -255,8 +438,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     if (active && warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
+            int stage = 0, ts = 0;
+            uint32_t phase = 0, tphase = 0;
             for (int c = 0; c < a.nchunks; ++c) {
                 const int qrow = (c * a.MB + mb_local) * GM;
                 for (int t = 0; t < my_tiles; ++t) {
@@ -269,6 +452,14 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                         tma_load_2d(sa + kStageABytes, &tmV, full0 + 8 * stage, kb * GK, vrow);
                         if (++stage == kGemmStages) { stage = 0; phase ^= 1; }
                     }
+                    if (a.tail) {  // the norm K-step: [128 x 16] ones-pattern and [256 x 16] split row norms
+                        mbar_wait(nempty0 + 8 * ts, tphase ^ 1);
+                        const uint32_t sa = smem_u32(tail_base + ts * kTailBytes);
+                        mbar_arrive_expect_tx(nfull0 + 8 * ts, kTailBytes);
+                        tma_load_2d(sa, &tmQt, nfull0 + 8 * ts, 0, qrow);
+                        tma_load_2d(sa + kTailABytes, &tmVt, nfull0 + 8 * ts, 0, vrow);
+                        if (++ts == 2) { ts = 0; tphase ^= 1; }
+                    }
                 }
             }
         }
@@ -276,8 +467,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         // ===== MMA issuer =====
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_f16(GM, GN);
-            int stage = 0;
-            uint32_t phase = 0;
+            int stage = 0, ts = 0;
+            uint32_t phase = 0, tphase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int c = 0; c < a.nchunks; ++c) {
@@ -291,14 +482,24 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                         const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
                         const uint64_t adesc = make_sw128_kmajor_desc(sa);
                         const uint64_t bdesc = make_sw128_kmajor_desc(sa + kStageABytes);
+                        const int ksteps = kb + 1 == a.kblocks ? a.last_ksteps : GK / GUK;
 #pragma unroll
                         for (int k = 0; k < GK / GUK; ++k) {
                             // advance 16 fp16 = 32 bytes along K inside the swizzled row: +2 in >>4 units
-                            umma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                     (uint32_t)((kb | k) != 0));
+                            if (k < ksteps)
+                                umma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                         (uint32_t)((kb | k) != 0));
                         }
                         umma_commit(empty0 + 8 * stage);  // stage reusable once these MMAs retire
                         if (++stage == kGemmStages) { stage = 0; phase ^= 1; }
+                    }
+                    if (a.tail) {
+                        mbar_wait(nfull0 + 8 * ts, tphase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(tail_base + ts * kTailBytes);
+                        umma_f16(tmem_d, make_sw32_kmajor_desc(sa), make_sw32_kmajor_desc(sa + kTailABytes), idesc, 1u);
+                        umma_commit(nempty0 + 8 * ts);
+                        if (++ts == 2) { ts = 0; tphase ^= 1; }
                     }
                     umma_commit(tfull0 + 8 * acc);        // accumulator complete
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -306,178 +507,72 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             }
         }
     } else if (active && warp >= 4) {
-        // ===== epilogue: 8 warps; thread <-> TMEM lane <-> query, warp pair splits the columns =====
-        // Selection is decoupled from the score stream: a thread only APPENDS keys that beat its
-        // query's admission threshold to a private candidate buffer (global memory, L2-resident,
-        // [entry][thread] so warm-up appends coalesce).  When a buffer nears capacity the warp
-        // selects the KP-th best score by value bisection (population counts, no sort), compacts
-        // the buffer to the KP best and tightens the threshold.  ~KP*ln(n/KP) appends and a
-        // handful of selections per query per sweep instead of a list update per admitted score.
-        const int ew = warp - 4;                 // 0..7
+        // ===== epilogue: 16 warps; thread <-> TMEM lane <-> query, 4 warps per lane quarter split the columns =====
+        const int ew = warp - 4;                 // 0..15
         const int lg = ew & 3;                   // == warp % 4: TMEM lanes [32*lg, 32*lg+32)
-        const int half = ew >> 2;                // columns [128*half, 128*half+128) of every tile
+        const int part = ew >> 2;                // columns [64*part, 64*part+64) of every tile
         const int et = lg * 32 + lane;           // query within the CTA's block
-        uint64_t *cbase = a.cand + (size_t)(cta * 2 + half) * kCandCap * GM;  // entry i of thread e at [i*GM + e]
-        uint64_t *mybuf = cbase + et;
-        float4 *sd = scratch + ew * 256 + lane;  // this lane's column: row r at sd[r * 32]
-        uint64_t *wscratch = reinterpret_cast<uint64_t *>(scratch + ew * 256);  // 512 u64 per warp
         const float kInf = __int_as_float(0x7f800000);
+        const float c1 = a.c1;
         int acc = 0;
         uint32_t acc_phase = 0;
-        long long t_wait = 0, t_chunk = 0, t_prune = 0, t_flush = 0, n_prune = 0, n_app = 0;
+        long long t_wait = 0, t_chunk = 0, t_prune = 0, n_prune = 0;
         for (int c = 0; c < a.nchunks; ++c) {
+            const size_t lbase = ((size_t)c * nCTA + cta) * kEpiParts + part;
+            uint64_t *cbase = a.cand + lbase * a.cap * GM;  // entry i of thread e at [i*GM + e]
+            uint64_t *mybuf = cbase + et;
             int cnt = 0;
             const size_t qglob = (size_t)(c * a.MB + mb_local) * GM + et;
+            const float c0 = a.qc0[qglob];
+            const bool admit = a.mode == 0 && qglob < (size_t)a.B && !(a.debug & 1);
             // admission threshold: seeded by the sampled pre-pass (a valid upper bound on the
-            // query's KP-th best score), tightened by every prune
-            float thr = a.thr0 ? a.thr0[qglob] : kInf;
-            // load lane `src`'s buffer into registers (8 per lane), return its fill count
-            auto load_buf = [&](int src, uint64_t (&x)[8]) -> int {
-                const int n = __shfl_sync(0xffffffffu, cnt, src);
-                const uint64_t *b = cbase + (lg * 32 + src);
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    const int e = r * 32 + lane;
-                    x[r] = e < n ? __ldcg(b + (size_t)e * GM) : kKeyMax;
-                }
-                return n;
-            };
-            // keep the `need` best keys of x: below tau first, then ties at tau; dst[i * stride]
-            auto compact = [&](const uint64_t (&x)[8], int need, uint64_t *dst, size_t stride) -> uint32_t {
-                int n_less;
-                const uint32_t tau = warp_select_score(x, need, &n_less);
-                int base_less = 0, base_tie = n_less, ties_left = need - n_less;
-                const unsigned below = (1u << lane) - 1u;
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    const uint32_t scr = (uint32_t)(x[r] >> 32);
-                    const bool is_less = scr < tau;
-                    const bool is_tie = scr == tau && x[r] != kKeyMax;
-                    const unsigned ml = __ballot_sync(0xffffffffu, is_less);
-                    const unsigned mt = __ballot_sync(0xffffffffu, is_tie);
-                    if (is_less) dst[(size_t)(base_less + __popc(ml & below)) * stride] = x[r];
-                    const int trank = __popc(mt & below);
-                    if (is_tie && trank < ties_left) dst[(size_t)(base_tie + trank) * stride] = x[r];
-                    base_less += __popc(ml);
-                    const int used = min(__popc(mt), ties_left);
-                    base_tie += used;
-                    ties_left -= used;
-                }
-                return tau;
-            };
+            // query's KP-th best key score), tightened by every prune; held in the accumulator domain
+            float tau = a.thr0 ? f32_from_orderable(a.thr0[qglob]) : kInf;
+            float thrS = acc_threshold(tau, c0, c1);
             for (int t = 0; t < my_tiles; ++t) {
-                const uint32_t row0 = (uint32_t)(ng + t * a.NG) * GN;
-                const uint32_t valid = a.n - row0 < (uint64_t)GN ? (uint32_t)(a.n - row0) : (uint32_t)GN;
-                long long tw0 = clock64();
+                const int tile = ng + t * a.NG;
+                const uint32_t row0 = (uint32_t)tile * GN;
+                long long tw0 = 0, tw1 = 0;
+                if (a.debug & 8) tw0 = clock64();
                 mbar_wait(tfull0 + 8 * acc, acc_phase);
                 tc_fence_after();
-                long long tw1 = clock64();
-                t_wait += tw1 - tw0;
-                const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)acc * GN + half * (GN / 2);
-                constexpr int kChunks = GN / 64;  // 32-column chunks per warp per tile
-                uint32_t vbuf[2][32];
-                if (!(a.debug & 2)) tmem_ld_32x32b_x32(taddr, vbuf[0]);
-#pragma unroll
-                for (int cb = 0; cb < kChunks; ++cb) {
-                    if (a.debug & 2) break;
+                if (a.debug & 8) { tw1 = clock64(); t_wait += tw1 - tw0; }
+                const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)acc * GN + part * (GN / kEpiParts);
+                constexpr int kChunks = GN / kEpiParts / 32;  // 32-column chunks per warp per tile
+                const uint32_t nrows = (uint32_t)a.n;
+                // No register double-buffering: the other three warps of this scheduler cover the
+                // load latency (one tcgen05.ld in flight per warp, four per scheduler).
+#pragma unroll 1
+                for (int cb = 0; cb < kChunks && !(a.debug & 2); ++cb) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(taddr + cb * 32, v);
                     tmem_ld_wait();
-                    // prefetch the next chunk while this one is processed
-                    if (cb + 1 < kChunks) tmem_ld_32x32b_x32(taddr + (cb + 1) * 32, vbuf[(cb + 1) & 1]);
-                    uint32_t (&v)[32] = vbuf[cb & 1];
-                    const uint32_t col0 = half * (GN / 2) + cb * 32;
-                    float dist[32];
-                    uint32_t mask = 0;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        dist[j] = 1.0f - __uint_as_float(v[j]);
-                        if (col0 + 32 > valid && col0 + j >= valid) dist[j] = kInf;  // rows past the end
-                        mask |= (dist[j] < thr) ? (1u << j) : 0u;
-                    }
-                    if (a.mode == 1) {  // sampled pre-pass: dump the scores, no selection
-                        float4 *o = reinterpret_cast<float4 *>(a.dump + qglob * a.dump_ld + row0 + col0);
-#pragma unroll
-                        for (int r = 0; r < 8; ++r)
-                            o[r] = make_float4(dist[4 * r], dist[4 * r + 1], dist[4 * r + 2], dist[4 * r + 3]);
+                    const uint32_t col0 = part * (GN / kEpiParts) + cb * 32;
+                    const float m = epi_chunk(v, thrS, row0 + col0, nrows, c0, c1, mybuf, cnt, admit);
+                    if (a.mode == 1) {  // sampled pre-pass: best key score of the chunk
+                        a.dump[qglob * a.dump_ld + (size_t)tile * 8 + part * kChunks + cb] = fmaf(m, c1, c0);
                         continue;
                     }
-                    if (a.debug & 1) mask = 0;
-                    if (mask) {
-                        // stage this thread's 32 scores for dynamic indexing, then visit the set bits
-#pragma unroll
-                        for (int r = 0; r < 8; ++r)
-                            sd[r * 32] = make_float4(dist[4 * r], dist[4 * r + 1], dist[4 * r + 2], dist[4 * r + 3]);
-                        while (mask) {
-                            const int j = __ffs(mask) - 1;
-                            mask &= mask - 1;
-                            const float d = reinterpret_cast<const float *>(&sd[(j >> 2) * 32])[j & 3];
-                            mybuf[(size_t)cnt * GM] = make_key(d, row0 + col0 + j);
-                            ++cnt;
-                        }
-                    }
                     // a chunk appends at most 32 keys: prune any buffer that could overflow next
-                    unsigned need = __ballot_sync(0xffffffffu, cnt > kCandCap - 32);
+                    const unsigned need = __ballot_sync(0xffffffffu, cnt > a.cap - 32);
                     if (need) {
-                        long long tp0 = clock64();
-                        __syncwarp();
-                        // software-pipelined: the next buffer's loads are in flight while the
-                        // current one is selected and compacted (prunes come in bursts)
-                        int src = __ffs(need) - 1;
-                        need &= need - 1;
-                        uint64_t x[8];
-                        load_buf(src, x);  // > KP keys here
-                        while (true) {
-                            ++n_prune;
-                            int nsrc = -1;
-                            uint64_t y[8];
-                            if (need) {
-                                nsrc = __ffs(need) - 1;
-                                need &= need - 1;
-                                load_buf(nsrc, y);
-                            }
-                            const uint32_t tau = compact(x, KP, cbase + (lg * 32 + src), GM);
-                            if (lane == src) {
-                                cnt = KP;
-                                thr = fminf(thr, f32_from_orderable(tau));
-                            }
-                            if (nsrc < 0) break;
-#pragma unroll
-                            for (int r = 0; r < 8; ++r) x[r] = y[r];
-                            src = nsrc;
-                        }
-                        __syncwarp();
-                        t_prune += clock64() - tp0;
+                        long long tp0 = 0;
+                        if (a.debug & 8) tp0 = clock64();
+                        n_prune += prune_buffers(cbase + lg * 32, need, KP, lane, c0, c1, cnt, tau, thrS);
+                        if (a.debug & 8) t_prune += clock64() - tp0;
                     }
                 }
-                t_chunk += clock64() - tw1;
+                if (a.debug & 8) t_chunk += clock64() - tw1;
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            // flush: every query's KP best, sorted ascending -> partial[q][2*ng + half][KP]
-            __syncwarp();
-            long long tf0 = clock64();
-            for (int ql = 0; ql < (a.mode == 1 ? 0 : 32); ++ql) {
-                uint64_t x[8];
-                const int n = load_buf(ql, x);
-                const int keep = n < KP ? n : KP;
-                __syncwarp();
-                if (keep > 0) compact(x, keep, wscratch, 1);
-                __syncwarp();
-                uint64_t e0 = lane < keep ? wscratch[lane] : kKeyMax;
-                uint64_t e1 = lane + 32 < keep ? wscratch[lane + 32] : kKeyMax;
-                warp_sort64(e0, e1, lane);
-                const size_t qg = (size_t)(c * a.MB + mb_local) * GM + lg * 32 + ql;
-                uint64_t *dst = a.partial + (qg * (2 * a.NG) + 2 * ng + half) * KP;
-                if (lane < KP) dst[lane] = e0;
-                if (lane + 32 < KP) dst[lane + 32] = e1;
-            }
-            __syncwarp();
-            t_flush += clock64() - tf0;
+            if (a.mode == 0) a.cand_cnt[lbase * GM + et] = cnt;
         }
         if ((a.debug & 8) && lane == 0) {
             unsigned long long *d = a.dbg + ((size_t)cta * kEpiWarps + ew) * 8;
-            d[0] = t_wait; d[1] = t_chunk; d[2] = t_prune; d[3] = t_flush; d[4] = n_prune;
+            d[0] = t_wait; d[1] = t_chunk; d[2] = t_prune; d[3] = 0; d[4] = n_prune;
         }
     }
 
@@ -489,37 +584,158 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
 }
 
-// ---- query preparation: q_hat = q / ||q|| in fp16, zero padded to [Bpad][kpitch] ------------
-__global__ void __launch_bounds__(256) prep_queries_gemm_kernel(const double *__restrict__ q64, int B,
-                                                                int d, __half *__restrict__ qh, int kpitch) {
+// ---- flush: candidate buffers -> sorted KP-key lists, one warp per (sweep, CTA, part, query) ----
+template <int NPL>
+__global__ void __launch_bounds__(256) gemm_flush_kernel(const uint64_t *__restrict__ cand,
+                                                         const int *__restrict__ cand_cnt, int nCTA,
+                                                         int MB, int NG, int nchunks, int KP, int cap,
+                                                         uint64_t *__restrict__ partial) {
+    __shared__ uint64_t scratch[8][kCandCapMax];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t w = (size_t)blockIdx.x * 8 + warp;
+    const size_t total = (size_t)nchunks * nCTA * kEpiParts * GM;
+    if (w >= total) return;
+    const int et = (int)(w % GM);
+    const size_t lbase = w / GM;             // (sweep * nCTA + cta) * kEpiParts + part
+    const int part = (int)(lbase % kEpiParts);
+    const int cta = (int)((lbase / kEpiParts) % nCTA);
+    const int c = (int)((lbase / kEpiParts) / nCTA);
+    const int mb_local = cta % MB, ng = cta / MB;
+    const int n = cand_cnt[lbase * GM + et];
+    const uint64_t *b = cand + lbase * cap * GM + et;
+    uint64_t x[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int e = r * 32 + lane;
+        x[r] = e < n ? __ldcg(b + (size_t)e * GM) : kKeyMax;
+    }
+    const int keep = n < KP ? n : KP;
+    uint64_t *ws = scratch[warp];
+    if (keep > 0) warp_compact(x, keep, ws, 1, lane);
+    __syncwarp();
+    uint64_t e[NPL];
+#pragma unroll
+    for (int r = 0; r < NPL; ++r) e[r] = r * 32 + lane < keep ? ws[r * 32 + lane] : kKeyMax;
+    warp_sort<NPL>(e, lane);
+    const size_t qg = (size_t)(c * MB + mb_local) * GM + et;
+    uint64_t *dst = partial + (qg * (kEpiParts * NG) + kEpiParts * ng + part) * KP;
+#pragma unroll
+    for (int r = 0; r < NPL; ++r)
+        if (r * 32 + lane < KP) dst[r * 32 + lane] = e[r];
+}
+
+// ---- query preparation -------------------------------------------------------------------------
+// cosine   : Qh = q / ||q|| (fp16, zero padded to [Bpad][kpitch]); key = 1 - acc
+// euclidean: Qh = [sigma*q, 1, 1, 1]; key = ||q||^2 - (2/sigma^2) * acc  (approximate dist^2)
+// eps_q[b] = rigorous bound on |key - ideal| for every row of the store (see the derivation in
+// DESIGN.md section 4); +inf marks a query the fp16 operands cannot carry (select.cu then flags it
+// and the host path re-issues it through the scan plan).
+__global__ void __launch_bounds__(256) prep_queries_gemm_kernel(const double *__restrict__ q64, int B, int d,
+                                                                int metric, float sigma, double vmax,
+                                                                __half *__restrict__ qh, int kpitch,
+                                                                __half *__restrict__ qtail,
+                                                                float *__restrict__ qc0,
+                                                                float *__restrict__ eps_q) {
     __shared__ double red[8];
+    __shared__ double redm[8];
     const int b = blockIdx.x;
     __half *o = qh + (size_t)b * kpitch;
+    // the norm K-step multiplies the three fp16 pieces of -sigma^2*||v||^2/2 by exactly 1
+    if (qtail && threadIdx.x < GUK) qtail[(size_t)b * GUK + threadIdx.x] = __float2half_rn(threadIdx.x < 3 ? 1.0f : 0.0f);
     if (b >= B) {
         for (int i = threadIdx.x; i < kpitch; i += blockDim.x) o[i] = __float2half_rn(0.f);
+        if (threadIdx.x == 0) { qc0[b] = metric == EVDB_COSINE ? 1.0f : 0.0f; eps_q[b] = 0.f; }
         return;
     }
     const double *q = q64 + (size_t)b * d;
-    double ss = 0.0;
-    for (int i = threadIdx.x; i < d; i += blockDim.x) ss += q[i] * q[i];
-    for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    double ss = 0.0, mx = 0.0;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) {
+        ss += q[i] * q[i];
+        mx = fmax(mx, fabs(q[i]));
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        ss += __shfl_xor_sync(0xffffffffu, ss, off);
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    }
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = ss; redm[threadIdx.x >> 5] = mx; }
     __syncthreads();
-    ss = 0.0;
-    for (int i = 0; i < 8; ++i) ss += red[i];
-    const float inv = ss > 0.0 ? (float)(1.0 / sqrt(ss)) : 0.0f;
-    for (int i = threadIdx.x; i < kpitch; i += blockDim.x)
-        o[i] = __float2half_rn(i < d ? (float)q[i] * inv : 0.f);
+    ss = 0.0; mx = 0.0;
+    for (int i = 0; i < 8; ++i) { ss += red[i]; mx = fmax(mx, redm[i]); }
+    const double u = 5.9604644775390625e-08;  // 2^-24
+    if (metric == EVDB_COSINE) {
+        const float inv = ss > 0.0 ? (float)(1.0 / sqrt(ss)) : 0.0f;
+        for (int i = threadIdx.x; i < kpitch; i += blockDim.x)
+            o[i] = __float2half_rn(i < d ? (float)q[i] * inv : 0.f);
+        if (threadIdx.x == 0) {
+            qc0[b] = 1.0f;
+            // both operands are unit vectors rounded to fp16 (2^-11 relative each, 2^-25 absolute
+            // in the subnormal range), fp32 accumulation over dim terms in the tensor core
+            // (bounded as dim * 2^-22, truncation included), one fp32 subtract
+            eps_q[b] = (float)(0.0009765625 * 1.01 + sqrt((double)d) * u + (double)d * 4.0 * u);
+        }
+    } else {
+        const double sg = (double)sigma;
+        const bool fits = mx * sg <= 60000.0;
+        for (int i = threadIdx.x; i < kpitch; i += blockDim.x) {
+            float v = 0.f;
+            if (i < d) v = fits ? (float)(q[i] * sg) : 0.f;
+            o[i] = __float2half_rn(v);
+        }
+        if (threadIdx.x == 0) {
+            const double K = (double)(d + 3);
+            const double Q = sg * sqrt(ss), V = sg * vmax;
+            const double e_dot = (0.0009765625 + 4.8e-7) * Q * V + 0.5 * u * sqrt(K) * (Q + V) * 1.001 + K * u * u * 4.0;
+            const double e_norm = 0.5 * V * V * 4.66e-10 + 3.0 * 0.5 * u;
+            const double e_acc = K * 4.0 * u * (Q * V + 0.5 * V * V);
+            const double scale = 2.0 / (sg * sg);
+            const double e_key = (ss + scale * (Q * V + 0.5 * V * V)) * 3.0 * u;
+            const double eps = 1.01 * ((e_dot + e_norm + e_acc) * scale + e_key);
+            qc0[b] = (float)ss;
+            eps_q[b] = fits && eps < 3.0e38 ? (float)eps : __int_as_float(0x7f800000);
+        }
+    }
 }
 
-// ---- threshold seeding: KP-th smallest score of each query over the sampled rows -------------
+// ---- euclidean operands: fp16(sigma*v) [pitch] and the norm tail {h1, h2, h3, 0 x 13}, one warp per row ----
+__global__ void __launch_bounds__(256) build_l2_shadow_kernel(const uint8_t *__restrict__ rows, size_t row_bytes,
+                                                              const double *__restrict__ norm64, int d,
+                                                              int pitch, float sigma, uint64_t slot0, uint64_t n,
+                                                              __half *__restrict__ out, __half *__restrict__ tail) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint64_t i = (uint64_t)blockIdx.x * 8 + warp; i < n; i += (uint64_t)gridDim.x * 8) {
+        const uint64_t r = slot0 + i;
+        const float *fr = reinterpret_cast<const float *>(rows + r * row_bytes);
+        __half *sh = out + r * (size_t)pitch;
+        for (int c = lane; c < pitch; c += 32) sh[c] = __float2half_rn(c < d ? fr[c] * sigma : 0.f);
+        if (lane < GUK) {
+            const double nr = norm64[r] * (double)sigma;
+            double x = -0.5 * nr * nr;
+            const __half h1 = __double2half(x);
+            x -= (double)__half2float(h1);
+            const __half h2 = __double2half(x);
+            x -= (double)__half2float(h2);
+            const __half h3 = __double2half(x);
+            tail[r * GUK + lane] = lane == 0 ? h1 : lane == 1 ? h2 : lane == 2 ? h3 : __float2half_rn(0.f);
+        }
+    }
+}
+
+__global__ void max_norm_kernel(const double *__restrict__ norm64, uint64_t n, unsigned long long *out) {
+    double m = 0.0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        m = fmax(m, norm64[i]);
+    for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(m));  // m >= 0
+}
+
+// ---- threshold seeding: KP-th smallest pooled key score of each query over the sampled rows ------
 // One CTA per query, values in registers, bisection on the order-preserving bits with block-wide
-// counts.  thr0[q] is an upper bound on the query's global KP-th best approximate score: the
-// sample rows are rows of the corpus, scored by the same MMA path as the main sweep.
+// counts.  Every pooled value is the key score of an actual (distinct) row, so the KP-th smallest is
+// an upper bound on the query's global KP-th best key score.
 constexpr int kSeedThreads = 256;
-constexpr int kSeedVpt = 64;  // sample size <= 256 * 64
+constexpr int kSeedVpt = 32;  // pooled values per query <= 256 * 32 (sample <= 262144 rows)
 __global__ void __launch_bounds__(kSeedThreads) seed_threshold_kernel(const float *__restrict__ dump, int ld,
-                                                                      int S, int need, float *__restrict__ thr0) {
+                                                                      int S, int need, uint32_t *__restrict__ thr0) {
     __shared__ int s_cnt[6];
     __shared__ uint32_t s_lo, s_hi;
     const int q = blockIdx.x;
@@ -569,7 +785,7 @@ __global__ void __launch_bounds__(kSeedThreads) seed_threshold_kernel(const floa
         ++it;
         __syncthreads();
     }
-    if (threadIdx.x == 0) thr0[q] = f32_from_orderable(lo);
+    if (threadIdx.x == 0) thr0[q] = lo;
 }
 
 // ---- host side ------------------------------------------------------------------------------
@@ -593,90 +809,200 @@ static encode_tiled_fn get_encode() {
 // rows x cols fp16, `pitch_elems` elements between consecutive rows of the MAP (a multiple of the
 // storage pitch selects every step-th stored row: the strided sample needs no gather)
 static int make_map(CUtensorMap *tm, const void *base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
-                    uint32_t box_rows) {
+                    uint32_t box_rows, bool tail = false) {
     encode_tiled_fn enc = get_encode();
     if (!enc) return EVDB_E_CUDA;
     cuuint64_t dims[2] = {cols, rows};
     cuuint64_t strides[1] = {pitch_elems * 2};
-    cuuint32_t box[2] = {(cuuint32_t)GK, box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)(tail ? GUK : GK), box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, tail ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? EVDB_OK : EVDB_E_CUDA;
 }
 
-static size_t gemm_smem_bytes(int KP) {
-    (void)KP;
-    return 1024 + (size_t)kGemmStages * kStageBytes + kEpiWarps * 4096 + (2 * kGemmStages + 4) * 8 + 16;
+static size_t gemm_smem_bytes() {
+    return 1024 + (size_t)kGemmStages * kStageBytes + 2 * kTailBytes + (2 * kGemmStages + 8) * 8 + 16;
 }
 
 bool gemm_plan_supported(evdb_store *s, int metric, int B, int KP) {
-    if (s->dtype != EVDB_F32 || !s->shadow || metric != EVDB_COSINE) return false;
+    if (s->dtype != EVDB_F32 || !s->shadow) return false;
+    if (metric != EVDB_COSINE && metric != EVDB_EUCLIDEAN) return false;
     if (KP > kGemmMaxKP || B < 1) return false;
     if (s->count < (uint64_t)GN) return false;
-    if (s->shadow_valid < s->count) return false;
+    if (metric == EVDB_COSINE && s->shadow_valid < s->count) return false;
     return get_encode() != nullptr;
 }
 
-int gemm_kp(int KP) { return KP < kGemmMaxKP ? kGemmMaxKP : KP; }
+int gemm_kp(int KP) { return KP <= 32 ? 32 : (KP <= 64 ? 64 : (KP <= 128 ? 128 : KP)); }
+int gemm_max_batch() { return kMaxSweeps * 8 * GM; }
 
-int launch_gemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int *lists_per_query,
-                     cudaStream_t st) {
+// Bring the euclidean operand column up to date: rows [l2_valid, count) are converted with the
+// current scale; the scale itself (a power of two with sigma * max||v|| in [64, 128)) is redone,
+// and the whole column rebuilt, when a larger row norm has arrived.
+static int ensure_l2_shadow(evdb_store *s, cudaStream_t st) {
+    const int pitch = s->spitch;
+    bool rebuild = false;
+    if (!s->shadow_l2 || s->l2_pitch != pitch || s->l2_cap < s->capacity) {
+        if (s->shadow_l2) {
+            EVDB_CUDA(cudaStreamSynchronize(st));
+            cudaFree(s->shadow_l2); s->shadow_l2 = nullptr;
+            cudaFree(s->l2_tail); s->l2_tail = nullptr;
+        }
+        EVDB_CUDA(cudaMalloc((void **)&s->shadow_l2, (size_t)s->capacity * pitch * sizeof(__half)));
+        EVDB_CUDA(cudaMalloc((void **)&s->l2_tail, (size_t)s->capacity * GUK * sizeof(__half)));
+        s->l2_pitch = pitch;
+        s->l2_cap = s->capacity;
+        rebuild = true;
+    }
+    if (!s->d_scalar) EVDB_CUDA(cudaMalloc((void **)&s->d_scalar, 64));
+    if (s->max_norm_dirty) {
+        // the bound only ever needs to cover the live rows; recomputed after ingest, never after delete
+        EVDB_CUDA(cudaMemsetAsync(s->d_scalar, 0, 8, st));
+        max_norm_kernel<<<s->sm_count * 4, 256, 0, st>>>(s->norm64, s->count, (unsigned long long *)s->d_scalar);
+        EVDB_CUDA(cudaGetLastError());
+        unsigned long long bits = 0;
+        EVDB_CUDA(cudaMemcpyAsync(&bits, s->d_scalar, 8, cudaMemcpyDeviceToHost, st));
+        EVDB_CUDA(cudaStreamSynchronize(st));
+        double m;
+        memcpy(&m, &bits, 8);
+        s->max_norm = m;
+        s->max_norm_dirty = 0;
+        s->n_launches++;
+    }
+    float sigma = 1.0f;
+    if (s->max_norm > 0.0) {
+        int x;
+        frexp(s->max_norm, &x);  // max_norm = m * 2^x, m in [0.5, 1)  =>  max_norm * 2^(7-x) in [64, 128)
+        int e = 7 - x;
+        if (e > 100) e = 100;
+        if (e < -100) e = -100;
+        sigma = (float)ldexp(1.0, e);
+    }
+    if (sigma != s->l2_sigma) rebuild = true;
+    if (rebuild) { s->l2_valid = 0; s->l2_sigma = sigma; }
+    if (s->l2_valid < s->count) {
+        const uint64_t n = s->count - s->l2_valid;
+        uint64_t blocks = (n + 7) / 8;
+        const uint64_t cap = (uint64_t)s->sm_count * 16;
+        build_l2_shadow_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(
+            s->rows, s->row_bytes, s->norm64, s->dim, pitch, sigma, s->l2_valid, n, s->shadow_l2, s->l2_tail);
+        EVDB_CUDA(cudaGetLastError());
+        s->n_launches++;
+        s->l2_valid = s->count;
+    }
+    return EVDB_OK;
+}
+
+// ingest hook: keep rows [slot0, slot0+n) of an existing euclidean operand column current.  A row
+// whose norm outgrows the scale is caught at the next search (max_norm_dirty -> new sigma -> rebuild).
+int launch_l2_shadow_rows(evdb_store *s, uint64_t slot0, uint64_t n, cudaStream_t st) {
+    if (!s->shadow_l2 || n == 0 || s->l2_sigma == 0.f) return EVDB_OK;
+    if (slot0 > s->l2_valid || slot0 + n > s->l2_cap) return EVDB_OK;  // picked up by ensure_l2_shadow
+    uint64_t blocks = (n + 7) / 8;
+    const uint64_t cap = (uint64_t)s->sm_count * 16;
+    build_l2_shadow_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(
+        s->rows, s->row_bytes, s->norm64, s->dim, s->l2_pitch, s->l2_sigma, slot0, n, s->shadow_l2, s->l2_tail);
+    EVDB_CUDA(cudaGetLastError());
+    s->n_launches++;
+    if (slot0 + n > s->l2_valid) s->l2_valid = slot0 + n;
+    return EVDB_OK;
+}
+
+int launch_gemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int metric, int *lists_per_query,
+                     const float **d_eps_q, cudaStream_t st) {
+    const bool l2 = metric == EVDB_EUCLIDEAN;
+    if (l2) EVDB_TRY(ensure_l2_shadow(s, st));
+    const int kcols = s->dim;
     const int kpitch = s->spitch;
+    const __half *vcol = l2 ? s->shadow_l2 : s->shadow;
+    const float sigma = l2 ? s->l2_sigma : 1.0f;
     const int nblocks_q = (B + GM - 1) / GM;
     // concurrent query blocks: the largest power of two <= 8 that does not exceed what exists
     int MB = 1;
     while (MB * 2 <= nblocks_q && MB * 2 <= 8) MB *= 2;
     const int nchunks = (nblocks_q + MB - 1) / MB;
+    if (nchunks > kMaxSweeps) return EVDB_E_BAD_ARG;  // search_core splits larger batches
     const int Bpad = nchunks * MB * GM;
     int NG = s->sm_count / MB;
     const int nt = (int)((s->count + GN - 1) / GN);
     if (NG > nt) NG = nt;
+    const int nCTA = MB * NG;
+    const int cap = KP <= 32 ? 128 : kCandCapMax;
+
+    // workspace: [Qh][Q tail][qc0][eps_q][thr0][cand_cnt][cand]
     const size_t qh_bytes = round_up64((size_t)Bpad * kpitch * sizeof(__half), 256);
-    const size_t cand_bytes = (size_t)MB * NG * 2 * kCandCap * GM * sizeof(uint64_t);
-    EVDB_TRY(ensure_bytes((void **)&s->w_qh, &s->w_qh_cap, qh_bytes + cand_bytes));
-    uint64_t *cand = (uint64_t *)((uint8_t *)s->w_qh + qh_bytes);
-    EVDB_TRY(ensure_bytes((void **)&s->w_partial, &s->w_partial_cap, sizeof(uint64_t) * (size_t)Bpad * 2 * NG * KP));
-    prep_queries_gemm_kernel<<<Bpad, 256, 0, st>>>(d_q64, B, s->dim, (__half *)s->w_qh, kpitch);
+    const size_t qt_bytes = round_up64((size_t)Bpad * GUK * sizeof(__half), 256);
+    const size_t vec_bytes = round_up64((size_t)Bpad * 4, 256);
+    const size_t cnt_bytes = round_up64((size_t)nchunks * nCTA * kEpiParts * GM * sizeof(int), 256);
+    const size_t cand_bytes = (size_t)nchunks * nCTA * kEpiParts * cap * GM * sizeof(uint64_t);
+    EVDB_TRY(ensure_bytes((void **)&s->w_qh, &s->w_qh_cap, qh_bytes + qt_bytes + 3 * vec_bytes + cnt_bytes + cand_bytes));
+    uint8_t *wp = (uint8_t *)s->w_qh;
+    __half *qh = (__half *)wp; wp += qh_bytes;
+    __half *qtail = (__half *)wp; wp += qt_bytes;
+    float *qc0 = (float *)wp; wp += vec_bytes;
+    float *eps_q = (float *)wp; wp += vec_bytes;
+    uint32_t *thr = (uint32_t *)wp; wp += vec_bytes;
+    int *cand_cnt = (int *)wp; wp += cnt_bytes;
+    uint64_t *cand = (uint64_t *)wp;
+    EVDB_TRY(ensure_bytes((void **)&s->w_partial, &s->w_partial_cap,
+                          sizeof(uint64_t) * (size_t)Bpad * kEpiParts * NG * KP));
+
+    prep_queries_gemm_kernel<<<Bpad, 256, 0, st>>>(d_q64, B, s->dim, metric, sigma, s->max_norm, qh, kpitch,
+                                                   l2 ? qtail : nullptr, qc0, eps_q);
     EVDB_CUDA(cudaGetLastError());
-    CUtensorMap tmQ, tmV;
-    EVDB_TRY(make_map(&tmQ, s->w_qh, (uint64_t)Bpad, (uint64_t)kpitch, (uint64_t)kpitch, GM));
-    EVDB_TRY(make_map(&tmV, s->shadow, s->count, (uint64_t)kpitch, (uint64_t)kpitch, GN));
+    CUtensorMap tmQ, tmV, tmQt, tmVt;
+    EVDB_TRY(make_map(&tmQ, qh, (uint64_t)Bpad, (uint64_t)kpitch, (uint64_t)kpitch, GM));
+    EVDB_TRY(make_map(&tmV, vcol, s->count, (uint64_t)kpitch, (uint64_t)kpitch, GN));
+    if (l2) {
+        EVDB_TRY(make_map(&tmQt, qtail, (uint64_t)Bpad, GUK, GUK, GM, true));
+        EVDB_TRY(make_map(&tmVt, s->l2_tail, s->count, GUK, GUK, GN, true));
+    } else {
+        tmQt = tmQ;  // never dereferenced
+        tmVt = tmV;
+    }
     GemmArgs a;
     memset(&a, 0, sizeof(a));
-    a.kblocks = (s->dim + GK - 1) / GK;
+    a.B = B;
+    a.kblocks = (kcols + GK - 1) / GK;
+    a.last_ksteps = (kcols - (a.kblocks - 1) * GK + GUK - 1) / GUK;
+    a.tail = l2 ? 1 : 0;
+    a.cap = cap;
     a.MB = MB;
     a.nchunks = nchunks;
     a.KP = KP;
-    a.partial = s->w_partial;
     a.cand = cand;
-    size_t smem = gemm_smem_bytes(KP);
+    a.cand_cnt = cand_cnt;
+    a.qc0 = qc0;
+    a.c1 = l2 ? -2.0f / (sigma * sigma) : -1.0f;
+    const size_t smem = gemm_smem_bytes();
     EVDB_CUDA(cudaFuncSetAttribute((const void *)gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     // ---- sampled pre-pass: seed every query's admission threshold ----
-    // S strided sample rows (a TMA map with a multiplied row stride), scores dumped, KP-th smallest
-    // per query selected.  Kills the per-(CTA, query) warm-up of the main sweep.
-    const float *thr0 = nullptr;
+    // S strided sample rows (a TMA map with a multiplied row stride), the best key score of every
+    // 32-row chunk pooled, KP-th smallest per query selected.  Kills the warm-up of the main sweep.
+    const uint32_t *thr0 = nullptr;
     const char *noseed = getenv("EVDB_GEMM_NOSEED");
-    if (s->count >= 32768 && !(noseed && atoi(noseed))) {
-        uint64_t S = 16384;
-        while (S * 16 > s->count && S > 1024) S >>= 1;  // at most ~6% extra rows scored
+    uint64_t S = 262144;
+    { const char *e = getenv("EVDB_GEMM_SAMPLE"); if (e && atoi(e) >= 1024) S = (uint64_t)atoi(e); }
+    while (S * 16 > s->count && S > 1024) S >>= 1;
+    if (S >= (uint64_t)64 * KP && S * 16 <= s->count && !(noseed && atoi(noseed))) {
         const uint64_t step = s->count / S;
         const int snt = (int)(S / GN);
         int sNG = s->sm_count / MB;
         if (sNG > snt) sNG = snt;
-        const size_t dump_bytes = round_up64((size_t)Bpad * S * sizeof(float), 256);
-        EVDB_TRY(ensure_bytes((void **)&s->w_seed, &s->w_seed_cap, dump_bytes + (size_t)Bpad * sizeof(float)));
+        const int pooled = (int)(S / 32);
+        EVDB_TRY(ensure_bytes((void **)&s->w_seed, &s->w_seed_cap, (size_t)Bpad * pooled * sizeof(float)));
         float *dump = (float *)s->w_seed;
-        float *thr = (float *)((uint8_t *)s->w_seed + dump_bytes);
-        CUtensorMap tmVs;
-        EVDB_TRY(make_map(&tmVs, s->shadow, S, (uint64_t)kpitch, (uint64_t)kpitch * step, GN));
+        CUtensorMap tmVs, tmVts = tmVt;
+        EVDB_TRY(make_map(&tmVs, vcol, S, (uint64_t)kpitch, (uint64_t)kpitch * step, GN));
+        if (l2) EVDB_TRY(make_map(&tmVts, s->l2_tail, S, GUK, (uint64_t)GUK * step, GN, true));
         GemmArgs p = a;
-        p.n = S; p.nt = snt; p.NG = sNG; p.mode = 1; p.dump = dump; p.dump_ld = (int)S;
-        gemm_topk_kernel<<<MB * sNG, kGemmThreads, smem, st>>>(tmQ, tmVs, p);
+        p.n = S; p.nt = snt; p.NG = sNG; p.mode = 1; p.dump = dump; p.dump_ld = pooled;
+        gemm_topk_kernel<<<MB * sNG, kGemmThreads, smem, st>>>(tmQ, tmVs, tmQt, tmVts, p);
         EVDB_CUDA(cudaGetLastError());
-        seed_threshold_kernel<<<Bpad, kSeedThreads, 0, st>>>(dump, (int)S, (int)S, KP, thr);
+        seed_threshold_kernel<<<Bpad, kSeedThreads, 0, st>>>(dump, pooled, pooled, KP, thr);
         EVDB_CUDA(cudaGetLastError());
         s->n_launches += 2;
         thr0 = thr;
@@ -693,21 +1019,30 @@ int launch_gemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int *lis
         a.dbg = g_dbg;
     }
     prof_begin(s, st);
-    gemm_topk_kernel<<<MB * NG, kGemmThreads, smem, st>>>(tmQ, tmV, a);
+    gemm_topk_kernel<<<nCTA, kGemmThreads, smem, st>>>(tmQ, tmV, tmQt, tmVt, a);
     prof_end(s, st);
     EVDB_CUDA(cudaGetLastError());
+    {
+        const size_t warps = (size_t)nchunks * nCTA * kEpiParts * GM;
+        const int grid = (int)((warps + 7) / 8);
+        if (KP <= 32) gemm_flush_kernel<1><<<grid, 256, 0, st>>>(cand, cand_cnt, nCTA, MB, NG, nchunks, KP, cap, s->w_partial);
+        else if (KP <= 64) gemm_flush_kernel<2><<<grid, 256, 0, st>>>(cand, cand_cnt, nCTA, MB, NG, nchunks, KP, cap, s->w_partial);
+        else gemm_flush_kernel<4><<<grid, 256, 0, st>>>(cand, cand_cnt, nCTA, MB, NG, nchunks, KP, cap, s->w_partial);
+        EVDB_CUDA(cudaGetLastError());
+    }
     if (a.debug & 8) {
         cudaStreamSynchronize(st);
         static unsigned long long h[148 * kEpiWarps * 8];
         cudaMemcpy(h, g_dbg, sizeof(h), cudaMemcpyDeviceToHost);
         double sum[5] = {0, 0, 0, 0, 0};
-        int nw = MB * NG * kEpiWarps;
+        int nw = nCTA * kEpiWarps;
         for (int i = 0; i < nw; ++i) for (int j = 0; j < 5; ++j) sum[j] += (double)h[i * 8 + j];
-        fprintf(stderr, "[gemm dbg] per epilogue warp (cycles): wait=%.0f chunk=%.0f (of which prune=%.0f) flush=%.0f prunes=%.1f\n",
-                sum[0] / nw, sum[1] / nw, sum[2] / nw, sum[3] / nw, sum[4] / nw);
+        fprintf(stderr, "[gemm dbg] per epilogue warp (cycles): wait=%.0f chunk=%.0f (of which prune=%.0f) prunes=%.1f\n",
+                sum[0] / nw, sum[1] / nw, sum[2] / nw, sum[4] / nw);
     }
-    s->n_launches += 2;
-    *lists_per_query = 2 * NG;
+    s->n_launches += 3;
+    *lists_per_query = kEpiParts * NG;
+    *d_eps_q = eps_q;
     return EVDB_OK;
 }
 

@@ -42,8 +42,16 @@ struct evdb_store {
     float2 *qcoef = nullptr;       // U8/U4: {scale/||y||, min/||y||}
     double2 *qms64 = nullptr;      // U8/U4: {min, scale} fp64 (exact re-rank, read-back)
     __half *shadow = nullptr;      // F32 + gemm_shadow: fp16 of v/||v||, [capacity][spitch] (tcgen05 path)
-    int spitch = 0;                // shadow row pitch in elements (dim rounded up to 8)
+    int spitch = 0;                // shadow row pitch in elements (dim rounded up to 64: 128-byte aligned rows)
     uint64_t shadow_valid = 0;     // rows [0, shadow_valid) of the shadow are current
+    __half *shadow_l2 = nullptr;   // euclidean tcgen05 operand: fp16(sigma*v) [capacity][spitch], built on first use
+    __half *l2_tail = nullptr;     // its norm K-step: [capacity][16] = {h1, h2, h3, 0...}, h1+h2+h3 = -sigma^2*||v||^2/2
+    int l2_pitch = 0;              // row pitch of shadow_l2 in elements (== spitch)
+    uint64_t l2_cap = 0, l2_valid = 0;  // rows allocated / rows [0, l2_valid) current
+    float l2_sigma = 0.f;          // power-of-two scale: sigma * max||v|| in [64, 128)
+    double max_norm = 0.0;         // upper bound on the largest row norm (valid when !max_norm_dirty)
+    int max_norm_dirty = 1;
+    void *d_scalar = nullptr;      // 64-byte device scratch (reductions)
 
     // ---- workspace (grown on demand) ----
     double *w_q64 = nullptr;   size_t w_q64_cap = 0;    // [B][dim]
@@ -94,9 +102,11 @@ struct ScanArgs {
 int launch_prep_queries(evdb_store *s, const double *d_q64, int B, cudaStream_t st);
 int scan_grid_size(evdb_store *s, int metric, int KP, int *G_out);
 int launch_scan(evdb_store *s, int metric, const ScanArgs &a, cudaStream_t st);
+// eps_q: optional per-query absolute bound added to eps_abs; squared: key scores are squared
+// distances (euclidean GEMM plan)
 int launch_select(evdb_store *s, const double *d_q64, const uint64_t *partial, int lists_per_query,
                   int KP, int B, int kk, int kstride, int metric, float eps_abs, float eps_rel,
-                  uint64_t slot_base, uint64_t *d_out_ids, double *d_out_dists,
+                  const float *eps_q, int squared, uint64_t slot_base, uint64_t *d_out_ids, double *d_out_dists,
                   int32_t *d_out_counts, int32_t *d_out_flags, cudaStream_t st);
 int launch_finalize_rows(evdb_store *s, uint64_t slot0, uint64_t n, cudaStream_t st);
 int launch_fill_synthetic(evdb_store *s, uint64_t seed, uint64_t row0, uint64_t n, cudaStream_t st);
@@ -114,8 +124,10 @@ int launch_merge_topk(const uint64_t *ids, const double *dists, const int32_t *c
 // tcgen05 path (gemm_tcgen05.cu)
 bool gemm_plan_supported(evdb_store *s, int metric, int B, int KP);
 int gemm_kp(int KP);
-int launch_gemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int *lists_per_query,
-                     cudaStream_t st);
+int gemm_max_batch();
+int launch_gemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int metric, int *lists_per_query,
+                     const float **d_eps_q, cudaStream_t st);
+int launch_l2_shadow_rows(evdb_store *s, uint64_t slot0, uint64_t n, cudaStream_t st);
 
 int ensure_bytes(void **p, size_t *cap, size_t need, bool pinned = false);
 void prof_begin(evdb_store *s, cudaStream_t st);

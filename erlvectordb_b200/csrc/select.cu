@@ -34,6 +34,8 @@ struct SelectArgs {
     const uint64_t *partial;  // [B][L][KP]
     int L, KP, kk, kstride, metric;
     float eps_abs, eps_rel;
+    const float *eps_q;  // optional [B]: per-query absolute bound (GEMM plans)
+    int squared;         // key scores are squared distances (euclidean GEMM plan)
     uint64_t slot_base;
     uint64_t *out_ids;
     double *out_dists;
@@ -56,6 +58,7 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
     const int b = blockIdx.x;
     const int KP = a.KP;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float eps_abs = a.eps_abs + (a.eps_q ? a.eps_q[b] : 0.f);
 
     // ---- 1. merge L ascending lists of KP keys into the KP smallest ----
     // Fast path: pool the first P = ceil(KP/L) keys of every list; the KP-th smallest of the pool
@@ -138,7 +141,7 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
     __syncthreads();
     if (kout > 0) {
         const float sk = key_score(buf[kout - 1]);
-        const float lim = sk + 2.0f * (a.eps_abs + a.eps_rel * fabsf(sk)) * 1.0001f;
+        const float lim = sk + 2.0f * (eps_abs + a.eps_rel * fabsf(sk)) * 1.0001f;
         for (int i = kout + threadIdx.x; i < ncand; i += blockDim.x)
             if (key_score(buf[i]) <= lim && (i + 1 == ncand || !(key_score(buf[i + 1]) <= lim))) s_nrer = i + 1;
     }
@@ -192,7 +195,9 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
             uint64_t ob = dkey[kout - 1];
             uint64_t bits = ob ^ ((ob >> 63) ? 0x8000000000000000ull : 0xFFFFFFFFFFFFFFFFull);
             double dk = __longlong_as_double((long long)bits);
-            double lim = (double)bound - (double)a.eps_abs - (double)a.eps_rel * fabs((double)bound);
+            double lim = (double)bound - (double)eps_abs - (double)a.eps_rel * fabs((double)bound);
+            // squared keys: compare the exact distance in the same domain (rounded up a hair)
+            if (a.squared) dk = __dmul_rn(__dmul_rn(dk, dk), 1.0 + 1e-15);
             flag = !(dk < lim);
             // threshold-admitted candidates can be fewer than k (e.g. massive exact ties): escalate
             if ((uint64_t)a.kk <= a.n ? ncand < a.kk : false) flag = 1;
@@ -208,13 +213,14 @@ static size_t select_smem(int threads) {
 }
 
 int launch_select(evdb_store *s, const double *d_q64, const uint64_t *partial, int L, int KP, int B,
-                  int kk, int kstride, int metric, float eps_abs, float eps_rel, uint64_t slot_base,
-                  uint64_t *d_out_ids, double *d_out_dists, int32_t *d_out_counts,
+                  int kk, int kstride, int metric, float eps_abs, float eps_rel, const float *eps_q,
+                  int squared, uint64_t slot_base, uint64_t *d_out_ids, double *d_out_dists, int32_t *d_out_counts,
                   int32_t *d_out_flags, cudaStream_t st) {
     SelectArgs a;
     a.rows = s->rows; a.row_bytes = s->row_bytes; a.norm64 = s->norm64; a.qms64 = s->qms64;
     a.n = s->count; a.d = s->dim; a.q64 = d_q64; a.partial = partial; a.L = L; a.KP = KP;
     a.kk = kk; a.kstride = kstride; a.metric = metric; a.eps_abs = eps_abs; a.eps_rel = eps_rel;
+    a.eps_q = eps_q; a.squared = squared;
     a.slot_base = slot_base; a.out_ids = d_out_ids; a.out_dists = d_out_dists;
     a.out_counts = d_out_counts; a.out_flags = d_out_flags;
     const int threads = B >= 8 ? 256 : 1024;

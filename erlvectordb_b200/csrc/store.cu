@@ -63,7 +63,7 @@ static void set_dim(evdb_store *s, int d) {
         case EVDB_U8: s->dpad = round_up(d, 16); s->nch = s->dpad / 16; s->row_bytes = (size_t)s->dpad; break;
         default: s->dpad = round_up(d, 32); s->nch = s->dpad / 32; s->row_bytes = (size_t)s->dpad / 2; break;
     }
-    s->spitch = round_up(d, 8);
+    s->spitch = round_up(d, 64);  // 128-byte row pitch: every TMA box row is one aligned line
 }
 
 template <typename T>
@@ -102,7 +102,7 @@ static uint64_t device_bytes(const evdb_store *s) {
     uint64_t per = s->row_bytes + sizeof(double) + 2 * sizeof(float);
     if (is_quant(s)) per += sizeof(float2) + sizeof(double2);
     if (s->shadow) per += (uint64_t)s->spitch * 2;
-    return per * s->capacity + s->w_q64_cap + s->w_q32_cap + s->w_qdig_cap + s->w_qstat_cap +
+    return per * s->capacity + (s->shadow_l2 ? s->l2_cap * (uint64_t)(s->l2_pitch + 16) * 2 : 0) + s->w_q64_cap + s->w_q32_cap + s->w_qdig_cap + s->w_qstat_cap +
            s->w_partial_cap + s->w_qh_cap + s->w_seed_cap + s->w_ids_cap + s->w_dists_cap + s->w_counts_cap + s->w_tmp_cap;
 }
 
@@ -135,20 +135,31 @@ static int search_core(evdb_store *s, const double *d_q64, int B, int k, int kst
     }
     const double u = 5.9604644775390625e-08;  // 2^-24
     float eps_abs = 0.f, eps_rel = 0.f;
+    const float *eps_q = nullptr;
+    int squared = 0;
     int lists = 0;
     bool use_gemm = false;
     if (plan == EVDB_PLAN_GEMM || (plan == EVDB_PLAN_AUTO && B >= 16))
-        use_gemm = gemm_plan_supported(s, metric, B, KP);
+        use_gemm = gemm_plan_supported(s, metric, B, gemm_kp(KP));
     if (plan == EVDB_PLAN_GEMM && !use_gemm) return EVDB_E_UNSUPPORTED;
 
+    if (use_gemm && B > gemm_max_batch()) {
+        // the candidate buffers are sized per sweep: larger batches go through in slices
+        const int slice = gemm_max_batch();
+        for (int b0 = 0; b0 < B; b0 += slice) {
+            const int nb = B - b0 < slice ? B - b0 : slice;
+            EVDB_TRY(search_core(s, d_q64 + (size_t)b0 * s->dim, nb, k, kstride, metric, kp_min, plan, slot_base,
+                                 d_ids + (size_t)b0 * kstride, d_dists + (size_t)b0 * kstride, d_counts + b0,
+                                 d_flags ? d_flags + b0 : nullptr, st));
+        }
+        return EVDB_OK;
+    }
     if (use_gemm) {
         s->last_plan = EVDB_PLAN_GEMM;
         KP = gemm_kp(KP);
-        EVDB_TRY(launch_gemm_topk(s, d_q64, B, KP, &lists, st));
-        // |score - cos| bound: both operands are unit vectors rounded to fp16 (2^-11 relative each,
-        // 2^-25 absolute in the subnormal range), fp32 accumulation over dim terms in the tensor
-        // core (bounded as dim * 2^-22, truncation included), one fp32 subtract.
-        eps_abs = (float)(0.0009765625 * 1.01 + sqrt((double)s->dim) * u + (double)s->dim * 4.0 * u);
+        // the per-query error bound of the fp16 operands comes back in eps_q (device)
+        EVDB_TRY(launch_gemm_topk(s, d_q64, B, KP, metric, &lists, &eps_q, st));
+        squared = metric == EVDB_EUCLIDEAN;
     } else {
         EVDB_TRY(launch_prep_queries(s, d_q64, B, st));
         s->last_plan = EVDB_PLAN_SCAN;
@@ -178,7 +189,7 @@ static int search_core(evdb_store *s, const double *d_q64, int B, int k, int kst
         else { eps_rel = (float)(depth * u); eps_abs = 1e-37f; }
     }
     EVDB_TRY(launch_select(s, d_q64, s->w_partial, lists, KP, B, kk, kstride, metric, eps_abs,
-                           eps_rel, slot_base, d_ids, d_dists, d_counts, d_flags, st));
+                           eps_rel, eps_q, squared, slot_base, d_ids, d_dists, d_counts, d_flags, st));
     s->n_rows_scanned += (uint64_t)B * s->count;
     return EVDB_OK;
 }
@@ -345,8 +356,10 @@ static int ingest_rows(evdb_store *s, uint64_t slot0, const void *rows, bool is_
             s->n_launches++;
         }
         EVDB_TRY(launch_finalize_rows(s, dst0, cnt, st));
+        EVDB_TRY(launch_l2_shadow_rows(s, dst0, cnt, st));
         EVDB_CUDA(cudaStreamSynchronize(st));
     }
+    s->max_norm_dirty = 1;
     return EVDB_OK;
 }
 
@@ -396,13 +409,14 @@ static int upsert_any(evdb_store *s, uint32_t slot, const T *vec, int d, bool is
 template <typename T>
 static int bulk_any(evdb_store *s, const T *rows, uint64_t n, int d, bool is_f64) {
     if (!s || (n > 0 && !rows)) return EVDB_E_BAD_ARG;
-    if (n == 0) { s->count = 0; s->shadow_valid = 0; return EVDB_OK; }
+    if (n == 0) { s->count = 0; s->shadow_valid = 0; s->l2_valid = 0; return EVDB_OK; }
     EVDB_TRY(check_dim(s, d));
     if (n > 0xFFFFFFF0ull) return EVDB_E_BAD_ARG;
     EVDB_TRY(set_device(s));
     EVDB_TRY(ensure_capacity(s, n));
     s->count = 0;
     s->shadow_valid = 0;
+    s->l2_valid = 0;
     EVDB_TRY(ingest_rows(s, 0, rows, is_f64, n));
     s->count = n;
     return EVDB_OK;
@@ -492,7 +506,7 @@ void evdb_store_destroy(evdb_store *s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     cudaFree(s->rows); cudaFree(s->norm64); cudaFree(s->inv_norm); cudaFree(s->norm_sq);
-    cudaFree(s->qcoef); cudaFree(s->qms64); cudaFree(s->shadow);
+    cudaFree(s->qcoef); cudaFree(s->qms64); cudaFree(s->shadow); cudaFree(s->shadow_l2); cudaFree(s->l2_tail); cudaFree(s->d_scalar);
     cudaFree(s->w_q64); cudaFree(s->w_q32); cudaFree(s->w_qdig); cudaFree(s->w_qh); cudaFree(s->w_seed); cudaFree(s->w_qstat);
     cudaFree(s->w_partial); cudaFree(s->w_ids); cudaFree(s->w_dists); cudaFree(s->w_counts);
     cudaFree(s->w_tmp);
@@ -620,11 +634,21 @@ int evdb_store_delete(evdb_store *s, uint32_t slot, int64_t *moved_from) {
         }
         if (s->shadow)
             EVDB_CUDA(cudaMemcpyAsync(s->shadow + (size_t)slot * s->spitch, s->shadow + last * (size_t)s->spitch, (size_t)s->spitch * 2, cudaMemcpyDeviceToDevice, st));
+        if (s->shadow_l2 && (uint64_t)slot < s->l2_valid) {
+            if (last < s->l2_valid)
+            {
+                EVDB_CUDA(cudaMemcpyAsync(s->shadow_l2 + (size_t)slot * s->l2_pitch, s->shadow_l2 + last * (size_t)s->l2_pitch, (size_t)s->l2_pitch * 2, cudaMemcpyDeviceToDevice, st));
+                EVDB_CUDA(cudaMemcpyAsync(s->l2_tail + (size_t)slot * 16, s->l2_tail + last * 16, 32, cudaMemcpyDeviceToDevice, st));
+            }
+            else
+                s->l2_valid = slot;
+        }
         EVDB_CUDA(cudaStreamSynchronize(st));
         if (moved_from) *moved_from = (int64_t)last;
     }
     s->count = last;
     if (s->shadow_valid > s->count) s->shadow_valid = s->count;
+    if (s->l2_valid > s->count) s->l2_valid = s->count;
     return EVDB_OK;
 }
 
@@ -682,6 +706,8 @@ int evdb_store_fill_synthetic(evdb_store *s, uint64_t seed, uint64_t row0, uint6
     EVDB_TRY(ensure_capacity(s, n));
     s->count = 0;
     s->shadow_valid = 0;
+    s->l2_valid = 0;
+    s->max_norm_dirty = 1;
     EVDB_TRY(launch_fill_synthetic(s, seed, row0, n, s->stream));
     EVDB_TRY(launch_finalize_rows(s, 0, n, s->stream));
     EVDB_CUDA(cudaStreamSynchronize(s->stream));
