@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libevdb_b200.so")
+# EVDB_LIB_PATH: A/B timing of two builds of the same ABI (tools/); never a fallback
+LIB_PATH = os.environ.get("EVDB_LIB_PATH") or os.path.join(PKG, "libevdb_b200.so")
 
 F32, BF16, U8, U4 = 0, 1, 2, 3
 COSINE, EUCLIDEAN, MANHATTAN = 0, 1, 2

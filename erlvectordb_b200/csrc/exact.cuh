@@ -117,4 +117,80 @@ __device__ double exact_distance_warp(const uint8_t *row, double mn, double sc, 
     return s;
 }
 
+// ----------------------------------------------------------------------------
+// Lane-parallel variant (select.cu): every lane folds ONE row by itself, strictly left to right,
+// so a warp re-ranks up to 32 candidates for the price of one sequential chain -- the fp64 pipe
+// issues per warp instruction, whatever the number of active lanes.  A lane with `qlane` set
+// folds the query's own squares instead (vector_norm(Query) of cosine_distance/2).
+// ----------------------------------------------------------------------------
+template <int DTYPE>
+__device__ __forceinline__ void load8(const uint8_t *row, int t8, double mn, double sc, double (&v)[8]) {
+    if (DTYPE == EVDB_F32) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(row) + 2 * t8);
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(row) + 2 * t8 + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else if (DTYPE == EVDB_BF16) {
+        const uint4 w = __ldg(reinterpret_cast<const uint4 *>(row) + t8);
+        const uint32_t u[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            v[2 * i] = (double)__uint_as_float(u[i] << 16);
+            v[2 * i + 1] = (double)__uint_as_float(u[i] & 0xFFFF0000u);
+        }
+    } else if (DTYPE == EVDB_U8) {
+        const uint2 w = __ldg(reinterpret_cast<const uint2 *>(row) + t8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t c = ((i < 4 ? w.x : w.y) >> (8 * (i & 3))) & 0xFFu;
+            v[i] = __dadd_rn(mn, __dmul_rn((double)c, sc));   // Min + (Q * Scale)
+        }
+    } else {
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(row) + t8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t byte = (w >> (8 * (i >> 1))) & 0xFFu;
+            const uint32_t c = (i & 1) ? (byte & 0x0Fu) : (byte >> 4);   // first element in the high nibble
+            v[i] = __dadd_rn(mn, __dmul_rn((double)c, sc));
+        }
+    }
+}
+
+// Returns the reference's left-to-right sum for this lane's row: sum(q*v) (cosine; sum(q*q) on the
+// qlane), sum((q-v)^2) (euclidean), sum(|q-v|) (manhattan).  q: the fp64 query in global memory.
+template <int DTYPE>
+__device__ __forceinline__ double exact_fold_lane(const uint8_t *row, double mn, double sc,
+                                                  const double *__restrict__ q, int d, int metric, bool qlane) {
+    double s = 0.0;
+    const int full = d >> 3;
+    for (int t8 = 0; t8 < full; ++t8) {
+        double v[8], qq[8];
+        load8<DTYPE>(row, t8, mn, sc, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) qq[i] = __ldg(q + 8 * t8 + i);  // same address in every lane: one broadcast each
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const double x = qlane ? qq[i] : v[i];
+            double term;
+            if (metric == EVDB_COSINE) term = __dmul_rn(qq[i], x);
+            else {
+                const double t0 = __dsub_rn(qq[i], x);
+                term = metric == EVDB_EUCLIDEAN ? __dmul_rn(t0, t0) : fabs(t0);
+            }
+            s = __dadd_rn(s, term);
+        }
+    }
+    for (int t = full << 3; t < d; ++t) {
+        const double qv = q[t];
+        const double x = qlane ? qv : row_elem<DTYPE>(row, t, mn, sc);
+        double term;
+        if (metric == EVDB_COSINE) term = __dmul_rn(qv, x);
+        else {
+            const double t0 = __dsub_rn(qv, x);
+            term = metric == EVDB_EUCLIDEAN ? __dmul_rn(t0, t0) : fabs(t0);
+        }
+        s = __dadd_rn(s, term);
+    }
+    return s;
+}
+
 }  // namespace evdb

@@ -75,7 +75,7 @@ struct GemmArgs {
     int NG;              // CTAs per query block (2*NG lists per query)
     int nchunks;         // sweeps: query blocks [c*MB, (c+1)*MB)
     int KP;
-    uint64_t *cand;      // [sweep][CTA][part][cap][128] append buffers
+    uint64_t *cand;      // [sweep][CTA][part][cap][128] append buffers (entry-major: thread t's i-th key at [i][t])
     int *cand_cnt;       // [sweep][CTA][part][128] fill counts at the end of the sweep
     int mode;            // 0 = fused top-k, 1 = pooled key scores of a row sample (threshold seeding)
     float *dump;         // mode 1: [Bpad][dump_ld] best key score of every 32-row chunk
@@ -243,38 +243,6 @@ __device__ __forceinline__ uint32_t warp_compact(const uint64_t (&x)[8], int nee
         ties_left -= used;
     }
     return tau;
-}
-
-// Ascending bitonic sort of 32*NPL u64 keys held NPL per lane (element r*32 + lane in e[r]).
-template <int NPL>
-__device__ __forceinline__ void warp_sort(uint64_t (&e)[NPL], const int lane) {
-#pragma unroll
-    for (int k2 = 2; k2 <= 32 * NPL; k2 <<= 1) {
-#pragma unroll
-        for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
-            if (j2 >= 32) {  // partner is another register of the same lane
-                const int rj = j2 >> 5;
-#pragma unroll
-                for (int r = 0; r < NPL; ++r) {
-                    if ((r & rj) == 0) {
-                        const bool asc = ((r << 5) & k2) == 0;
-                        const uint64_t a = e[r], b = e[r | rj];
-                        const bool sw = asc ? (a > b) : (a < b);
-                        e[r] = sw ? b : a;
-                        e[r | rj] = sw ? a : b;
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < NPL; ++r) {
-                    const uint64_t p = __shfl_xor_sync(0xffffffffu, e[r], j2);
-                    const bool lower = (lane & j2) == 0;
-                    const bool asc = (((r << 5) + lane) & k2) == 0;
-                    e[r] = (lower == asc) ? (e[r] < p ? e[r] : p) : (e[r] > p ? e[r] : p);
-                }
-            }
-        }
-    }
 }
 
 // Largest accumulator value a (to a few ulps) with fma(a, c1, c0) >= tau, c1 < 0: a row whose
@@ -519,7 +487,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         long long t_wait = 0, t_chunk = 0, t_prune = 0, n_prune = 0;
         for (int c = 0; c < a.nchunks; ++c) {
             const size_t lbase = ((size_t)c * nCTA + cta) * kEpiParts + part;
-            uint64_t *cbase = a.cand + lbase * a.cap * GM;  // entry i of thread e at [i*GM + e]
+            // entry i of thread e at [i*GM + e]: lanes appending at similar fill levels share sectors
+            uint64_t *cbase = a.cand + lbase * a.cap * GM;
             uint64_t *mybuf = cbase + et;
             int cnt = 0;
             const size_t qglob = (size_t)(c * a.MB + mb_local) * GM + et;
@@ -582,46 +551,6 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
-}
-
-// ---- flush: candidate buffers -> sorted KP-key lists, one warp per (sweep, CTA, part, query) ----
-template <int NPL>
-__global__ void __launch_bounds__(256) gemm_flush_kernel(const uint64_t *__restrict__ cand,
-                                                         const int *__restrict__ cand_cnt, int nCTA,
-                                                         int MB, int NG, int nchunks, int KP, int cap,
-                                                         uint64_t *__restrict__ partial) {
-    __shared__ uint64_t scratch[8][kCandCapMax];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const size_t w = (size_t)blockIdx.x * 8 + warp;
-    const size_t total = (size_t)nchunks * nCTA * kEpiParts * GM;
-    if (w >= total) return;
-    const int et = (int)(w % GM);
-    const size_t lbase = w / GM;             // (sweep * nCTA + cta) * kEpiParts + part
-    const int part = (int)(lbase % kEpiParts);
-    const int cta = (int)((lbase / kEpiParts) % nCTA);
-    const int c = (int)((lbase / kEpiParts) / nCTA);
-    const int mb_local = cta % MB, ng = cta / MB;
-    const int n = cand_cnt[lbase * GM + et];
-    const uint64_t *b = cand + lbase * cap * GM + et;
-    uint64_t x[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        const int e = r * 32 + lane;
-        x[r] = e < n ? __ldcg(b + (size_t)e * GM) : kKeyMax;
-    }
-    const int keep = n < KP ? n : KP;
-    uint64_t *ws = scratch[warp];
-    if (keep > 0) warp_compact(x, keep, ws, 1, lane);
-    __syncwarp();
-    uint64_t e[NPL];
-#pragma unroll
-    for (int r = 0; r < NPL; ++r) e[r] = r * 32 + lane < keep ? ws[r * 32 + lane] : kKeyMax;
-    warp_sort<NPL>(e, lane);
-    const size_t qg = (size_t)(c * MB + mb_local) * GM + et;
-    uint64_t *dst = partial + (qg * (kEpiParts * NG) + kEpiParts * ng + part) * KP;
-#pragma unroll
-    for (int r = 0; r < NPL; ++r)
-        if (r * 32 + lane < KP) dst[r * 32 + lane] = e[r];
 }
 
 // ---- query preparation -------------------------------------------------------------------------
@@ -733,7 +662,10 @@ __global__ void max_norm_kernel(const double *__restrict__ norm64, uint64_t n, u
 // counts.  Every pooled value is the key score of an actual (distinct) row, so the KP-th smallest is
 // an upper bound on the query's global KP-th best key score.
 constexpr int kSeedThreads = 256;
-constexpr int kSeedVpt = 32;  // pooled values per query <= 256 * 32 (sample <= 262144 rows)
+constexpr int kSeedMaxVpt = 32;  // pooled values per query <= 256 * 32 (sample <= 262144 rows)
+// The search stops after 10 four-way rounds (the bracket is then 2^-20 of the value range) and
+// returns the bracket's upper end, which still has >= need values at or below it.
+template <int kSeedVpt>
 __global__ void __launch_bounds__(kSeedThreads) seed_threshold_kernel(const float *__restrict__ dump, int ld,
                                                                       int S, int need, uint32_t *__restrict__ thr0) {
     __shared__ int s_cnt[6];
@@ -757,7 +689,7 @@ __global__ void __launch_bounds__(kSeedThreads) seed_threshold_kernel(const floa
     __syncthreads();
     uint32_t lo = s_lo, hi = s_hi;  // invariant: count(v <= hi) >= need
     int it = 0;
-    while (lo < hi) {  // 4-way search: three pivots per round, one barrier pair per round
+    while (lo < hi && it < 10) {  // 4-way search: three pivots per round, one barrier pair per round
         const uint32_t span = hi - lo;
         const uint32_t qd = span >> 2;
         const uint32_t p2 = lo + (span >> 1);
@@ -785,7 +717,7 @@ __global__ void __launch_bounds__(kSeedThreads) seed_threshold_kernel(const floa
         ++it;
         __syncthreads();
     }
-    if (threadIdx.x == 0) thr0[q] = lo;
+    if (threadIdx.x == 0) thr0[q] = hi;
 }
 
 // ---- host side ------------------------------------------------------------------------------
@@ -911,7 +843,7 @@ int launch_l2_shadow_rows(evdb_store *s, uint64_t slot0, uint64_t n, cudaStream_
 }
 
 int launch_gemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int metric, int *lists_per_query,
-                     const float **d_eps_q, cudaStream_t st) {
+                     const float **d_eps_q, RawCands *raw, cudaStream_t st) {
     const bool l2 = metric == EVDB_EUCLIDEAN;
     if (l2) EVDB_TRY(ensure_l2_shadow(s, st));
     const int kcols = s->dim;
@@ -946,8 +878,6 @@ int launch_gemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int metr
     uint32_t *thr = (uint32_t *)wp; wp += vec_bytes;
     int *cand_cnt = (int *)wp; wp += cnt_bytes;
     uint64_t *cand = (uint64_t *)wp;
-    EVDB_TRY(ensure_bytes((void **)&s->w_partial, &s->w_partial_cap,
-                          sizeof(uint64_t) * (size_t)Bpad * kEpiParts * NG * KP));
 
     prep_queries_gemm_kernel<<<Bpad, 256, 0, st>>>(d_q64, B, s->dim, metric, sigma, s->max_norm, qh, kpitch,
                                                    l2 ? qtail : nullptr, qc0, eps_q);
@@ -1002,7 +932,11 @@ int launch_gemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int metr
         p.n = S; p.nt = snt; p.NG = sNG; p.mode = 1; p.dump = dump; p.dump_ld = pooled;
         gemm_topk_kernel<<<MB * sNG, kGemmThreads, smem, st>>>(tmQ, tmVs, tmQt, tmVts, p);
         EVDB_CUDA(cudaGetLastError());
-        seed_threshold_kernel<<<Bpad, kSeedThreads, 0, st>>>(dump, pooled, pooled, KP, thr);
+        const int vpt = (pooled + kSeedThreads - 1) / kSeedThreads;
+        if (vpt <= 4) seed_threshold_kernel<4><<<Bpad, kSeedThreads, 0, st>>>(dump, pooled, pooled, KP, thr);
+        else if (vpt <= 8) seed_threshold_kernel<8><<<Bpad, kSeedThreads, 0, st>>>(dump, pooled, pooled, KP, thr);
+        else if (vpt <= 16) seed_threshold_kernel<16><<<Bpad, kSeedThreads, 0, st>>>(dump, pooled, pooled, KP, thr);
+        else seed_threshold_kernel<kSeedMaxVpt><<<Bpad, kSeedThreads, 0, st>>>(dump, pooled, pooled, KP, thr);
         EVDB_CUDA(cudaGetLastError());
         s->n_launches += 2;
         thr0 = thr;
@@ -1022,14 +956,6 @@ int launch_gemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int metr
     gemm_topk_kernel<<<nCTA, kGemmThreads, smem, st>>>(tmQ, tmV, tmQt, tmVt, a);
     prof_end(s, st);
     EVDB_CUDA(cudaGetLastError());
-    {
-        const size_t warps = (size_t)nchunks * nCTA * kEpiParts * GM;
-        const int grid = (int)((warps + 7) / 8);
-        if (KP <= 32) gemm_flush_kernel<1><<<grid, 256, 0, st>>>(cand, cand_cnt, nCTA, MB, NG, nchunks, KP, cap, s->w_partial);
-        else if (KP <= 64) gemm_flush_kernel<2><<<grid, 256, 0, st>>>(cand, cand_cnt, nCTA, MB, NG, nchunks, KP, cap, s->w_partial);
-        else gemm_flush_kernel<4><<<grid, 256, 0, st>>>(cand, cand_cnt, nCTA, MB, NG, nchunks, KP, cap, s->w_partial);
-        EVDB_CUDA(cudaGetLastError());
-    }
     if (a.debug & 8) {
         cudaStreamSynchronize(st);
         static unsigned long long h[148 * kEpiWarps * 8];
@@ -1040,7 +966,9 @@ int launch_gemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int metr
         fprintf(stderr, "[gemm dbg] per epilogue warp (cycles): wait=%.0f chunk=%.0f (of which prune=%.0f) prunes=%.1f\n",
                 sum[0] / nw, sum[1] / nw, sum[2] / nw, sum[4] / nw);
     }
-    s->n_launches += 3;
+    s->n_launches += 2;
+    raw->cand = cand; raw->cnt = cand_cnt; raw->cap = cap; raw->nCTA = nCTA; raw->MB = MB; raw->NG = NG;
+    raw->parts = kEpiParts; raw->gm = GM;
     *lists_per_query = kEpiParts * NG;
     *d_eps_q = eps_q;
     return EVDB_OK;

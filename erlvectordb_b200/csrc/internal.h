@@ -98,13 +98,23 @@ struct ScanArgs {
     int B;
 };
 
+// Unsorted candidate buffers left by the tcgen05 GEMM plan: query q = (sweep c, block mb, thread et)
+// has one buffer per (row group ng, column part): set l = (c*nCTA + ng*MB + mb)*parts + part, its i-th
+// key at cand[(l*cap + i)*gm + et], fill count at cnt[l*gm + et].
+struct RawCands {
+    const uint64_t *cand;
+    const int *cnt;
+    int cap, nCTA, MB, NG, parts, gm;
+};
+constexpr int kRawMaxLists = 640;  // NG * parts <= 148 * 4
+
 // ---- launchers (each returns EVDB_OK or an error; all async on `st`) ----
 int launch_prep_queries(evdb_store *s, const double *d_q64, int B, cudaStream_t st);
 int scan_grid_size(evdb_store *s, int metric, int KP, int *G_out);
 int launch_scan(evdb_store *s, int metric, const ScanArgs &a, cudaStream_t st);
 // eps_q: optional per-query absolute bound added to eps_abs; squared: key scores are squared
 // distances (euclidean GEMM plan)
-int launch_select(evdb_store *s, const double *d_q64, const uint64_t *partial, int lists_per_query,
+int launch_select(evdb_store *s, const double *d_q64, const uint64_t *partial, const RawCands *raw, int lists_per_query,
                   int KP, int B, int kk, int kstride, int metric, float eps_abs, float eps_rel,
                   const float *eps_q, int squared, uint64_t slot_base, uint64_t *d_out_ids, double *d_out_dists,
                   int32_t *d_out_counts, int32_t *d_out_flags, cudaStream_t st);
@@ -126,7 +136,7 @@ bool gemm_plan_supported(evdb_store *s, int metric, int B, int KP);
 int gemm_kp(int KP);
 int gemm_max_batch();
 int launch_gemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int metric, int *lists_per_query,
-                     const float **d_eps_q, cudaStream_t st);
+                     const float **d_eps_q, RawCands *raw, cudaStream_t st);
 int launch_l2_shadow_rows(evdb_store *s, uint64_t slot0, uint64_t n, cudaStream_t st);
 
 int ensure_bytes(void **p, size_t *cap, size_t need, bool pinned = false);

@@ -13,6 +13,8 @@
 // Also: the exhaustive fp64 plan (every row, then a stable radix sort) that
 // backs k > kMaxKP, metrics without a fast scan, and failed escalations; and
 // the G-way merge that follows the cross-GPU allgather.
+#include <string.h>
+
 #include <cub/device/device_radix_sort.cuh>
 
 #include "exact.cuh"
@@ -21,7 +23,7 @@
 
 namespace evdb {
 
-constexpr int kSelSort = 4096;  // keys sorted per merge round
+constexpr int kSelSort = 4096;  // keys sorted / selected per merge round
 
 struct SelectArgs {
     const uint8_t *rows;
@@ -31,7 +33,8 @@ struct SelectArgs {
     uint64_t n;
     int d;
     const double *q64;        // [B][d]
-    const uint64_t *partial;  // [B][L][KP]
+    const uint64_t *partial;  // [B][L][KP] ascending lists (scan plans), or NULL with `raw` set
+    RawCands raw;             // unsorted per-(CTA, part) candidate buffers of the GEMM plan
     int L, KP, kk, kstride, metric;
     float eps_abs, eps_rel;
     const float *eps_q;  // optional [B]: per-query absolute bound (GEMM plans)
@@ -43,14 +46,85 @@ struct SelectArgs {
     int32_t *out_flags;
 };
 
+// Block-wide selection: keep the `need` smallest of buf[0, n) (need < n <= kSelSort), compacted
+// to buf[0, need) in arbitrary order.  Bisection on the 32-bit score with block-wide counts
+// (4-way, one barrier pair per round), then one compaction pass; ties at the cut are taken
+// first come first served (any `need` keys not above the cut are a valid window).
+// tmp: >= need u64 of scratch.  Every thread of the block must call.
+__device__ void block_select_smallest(uint64_t *buf, int n, int need, uint64_t *tmp) {
+    __shared__ uint32_t s_lo, s_hi;
+    __shared__ int s_c[8];
+    uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t sc = (uint32_t)(buf[i] >> 32);
+        mn = min(mn, sc);
+        mx = max(mx, sc);
+    }
+    if (threadIdx.x == 0) { s_lo = 0xFFFFFFFFu; s_hi = 0u; }
+    if (threadIdx.x < 8) s_c[threadIdx.x] = 0;
+    __syncthreads();
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0) { atomicMin(&s_lo, mn); atomicMax(&s_hi, mx); }
+    __syncthreads();
+    uint32_t lo = s_lo, hi = s_hi;  // invariant: count(score <= hi) >= need, count(score < lo) < need
+    int it = 0;
+    while (lo < hi) {
+        const uint32_t span = hi - lo;
+        const uint32_t qd = span >> 2;
+        const uint32_t p2 = lo + (span >> 1);
+        const uint32_t p1 = qd ? lo + qd : p2;
+        const uint32_t p3 = qd ? p2 + qd : p2;
+        int c1 = 0, c2 = 0, c3 = 0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint32_t sc = (uint32_t)(buf[i] >> 32);
+            c1 += sc <= p1 ? 1 : 0;
+            c2 += sc <= p2 ? 1 : 0;
+            c3 += sc <= p3 ? 1 : 0;
+        }
+        c1 = __reduce_add_sync(0xffffffffu, c1);
+        c2 = __reduce_add_sync(0xffffffffu, c2);
+        c3 = __reduce_add_sync(0xffffffffu, c3);
+        int *cc = s_c + (it & 1) * 3;
+        if ((threadIdx.x & 31) == 0) { atomicAdd(cc, c1); atomicAdd(cc + 1, c2); atomicAdd(cc + 2, c3); }
+        __syncthreads();
+        const int t1 = cc[0], t2 = cc[1], t3 = cc[2];
+        if (threadIdx.x < 3) s_c[((it + 1) & 1) * 3 + threadIdx.x] = 0;
+        if (t1 >= need) hi = p1;
+        else if (t2 >= need) { lo = p1 + 1; hi = p2; }
+        else if (t3 >= need) { lo = p2 + 1; hi = p3; }
+        else lo = p3 + 1;
+        ++it;
+        __syncthreads();
+    }
+    // lo == the need-th smallest score.  Compact: everything below it, then ties up to `need`.
+    if (threadIdx.x < 2) s_c[6 + threadIdx.x] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint64_t key = buf[i];
+        if ((uint32_t)(key >> 32) < lo) tmp[atomicAdd(&s_c[6], 1)] = key;
+    }
+    __syncthreads();
+    const int n_less = s_c[6];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint64_t key = buf[i];
+        if ((uint32_t)(key >> 32) == lo) {
+            const int t = atomicAdd(&s_c[7], 1);
+            if (n_less + t < need) tmp[n_less + t] = key;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < need; i += blockDim.x) buf[i] = tmp[i];
+    __syncthreads();
+}
+
 // THREADS = 1024 for a lone query (latency), 256 for batches (more CTAs per SM, cheaper barriers).
 template <int DTYPE, int THREADS>
 __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
     constexpr int kSelWarps = THREADS / 32;
     extern __shared__ __align__(16) uint8_t smem[];
     uint64_t *buf = reinterpret_cast<uint64_t *>(smem);                       // [kSelSort]
-    double *sp_all = reinterpret_cast<double *>(smem + sizeof(uint64_t) * kSelSort);  // [warps][2*chunk]
-    uint64_t *dkey = reinterpret_cast<uint64_t *>(sp_all + kSelWarps * 2 * kExactChunk);  // [kMaxKP]
+    uint64_t *dkey = buf + kSelSort;                                          // [kMaxKP]
     uint64_t *dslot = dkey + kMaxKP;                                          // [kMaxKP]
     __shared__ int s_ncand;
     __shared__ float s_bound;
@@ -60,7 +134,66 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float eps_abs = a.eps_abs + (a.eps_q ? a.eps_q[b] : 0.f);
 
-    // ---- 1. merge L ascending lists of KP keys into the KP smallest ----
+    if (a.raw.cand) {
+        // ---- 1a. GEMM plan: gather this query's unsorted candidate buffers, keep the KP best ----
+        __shared__ int s_off[kRawMaxLists + 1];  // exclusive prefix of the buffer fill counts
+        const RawCands &rw = a.raw;
+        const int L = a.L;                       // NG * parts buffers hold candidates of this query
+        const int blk = b / rw.gm, et = b % rw.gm;
+        const int c = blk / rw.MB, mb_local = blk % rw.MB;
+        auto list_index = [&](int l) -> size_t {  // buffer set of (row group ng, column part)
+            const int ng = l / rw.parts, part = l % rw.parts;
+            const int cta = ng * rw.MB + mb_local;
+            return ((size_t)c * rw.nCTA + cta) * rw.parts + part;
+        };
+        for (int l = threadIdx.x; l < L; l += blockDim.x) s_off[l + 1] = rw.cnt[list_index(l) * rw.gm + et];
+        if (threadIdx.x == 0) s_off[0] = 0;
+        __syncthreads();
+        if (warp == 0) {  // inclusive scan of s_off[1..L], 32 at a time
+            int carry = 0;
+            for (int base = 1; base <= L; base += 32) {
+                const int i = base + lane;
+                int v = i <= L ? s_off[i] : 0;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u = __shfl_up_sync(0xffffffffu, v, o);
+                    if (lane >= o) v += u;
+                }
+                if (i <= L) s_off[i] = v + carry;
+                carry += __shfl_sync(0xffffffffu, v, 31);
+            }
+        }
+        __syncthreads();
+        int carried = 0, l0 = 0;
+        while (l0 < L) {
+            // as many whole buffers as fit next to the carried keys (a buffer holds <= 256 keys)
+            int lo = l0 + 1, hi = L;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (carried + s_off[mid] - s_off[l0] <= kSelSort) lo = mid; else hi = mid - 1;
+            }
+            const int l1 = lo;
+            for (int l = l0 + warp; l < l1; l += kSelWarps) {
+                const int n = s_off[l + 1] - s_off[l];
+                const uint64_t *src = rw.cand + list_index(l) * rw.cap * rw.gm + et;  // entry i at [i*gm]
+                uint64_t *dst = buf + carried + (s_off[l] - s_off[l0]);
+                for (int i = lane; i < n; i += 32) dst[i] = __ldcg(src + (size_t)i * rw.gm);
+            }
+            const int filled = carried + s_off[l1] - s_off[l0];
+            __syncthreads();
+            if (filled > KP) {
+                block_select_smallest(buf, filled, KP, dkey);
+                carried = KP;
+            } else {
+                carried = filled;
+            }
+            l0 = l1;
+        }
+        for (int i = carried + threadIdx.x; i < KP; i += blockDim.x) buf[i] = kKeyMax;
+        __syncthreads();
+        block_bitonic_sort(buf, KP);
+    } else {
+    // ---- 1b. scan plans: merge L ascending lists of KP keys into the KP smallest ----
     // Fast path: pool the first P = ceil(KP/L) keys of every list; the KP-th smallest of the pool
     // is an upper bound T on the global KP-th smallest key (KP distinct keys are <= it), so only
     // keys <= T can matter -- typically not many more than KP.
@@ -119,6 +252,7 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
             if (pos >= total) break;
         }
     }
+    }
     // ---- count valid candidates (keys are ascending; kKeyMax pads) ----
     if (threadIdx.x == 0) s_ncand = 0;
     __syncthreads();
@@ -131,7 +265,7 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
     const int ncand = s_ncand;
     const float bound = s_bound;
 
-    // ---- 2. exact fp64 distance per candidate, one warp each ----
+    // ---- 2. exact fp64 distance per candidate, one LANE each ----
     // Only candidates that can still reach the top k are re-ranked: a true top-k row r has
     // exact D_r <= D_(k) <= s_k + eps (the k best approximate scores bound the k-th exact one),
     // hence approximate score <= s_k + 2*eps.  Scores are ascending, so that set is a prefix.
@@ -150,24 +284,44 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
     int nsort = 2;
     while (nsort < nrer) nsort <<= 1;
     const double *q = a.q64 + (size_t)b * a.d;
-    double *sp = sp_all + warp * 2 * kExactChunk;
-    for (int j = warp; j < nsort; j += kSelWarps) {
-        if (j < nrer) {
-            uint32_t slot = key_slot(buf[j]);
+    {
+        // The fold of one row is a strictly sequential fp64 chain (reference order), so candidates
+        // are spread one per lane: cpw per warp, plus -- for cosine -- lane 31 of every working
+        // warp folding the query's own squares.
+        const bool cosine = a.metric == EVDB_COSINE;
+        const int max_cpw = cosine ? 31 : 32;
+        int cpw = (nrer + kSelWarps - 1) / kSelWarps;
+        if (cpw < 4) cpw = 4;
+        if (cpw > max_cpw) cpw = max_cpw;
+        for (int base = warp * cpw; base < nrer; base += kSelWarps * cpw) {
+            const int j = base + lane;
+            const bool mine = lane < cpw && j < nrer;
+            const bool qlane = cosine && lane == 31;
+            const uint32_t slot = mine ? key_slot(buf[j]) : key_slot(buf[base]);
             const uint8_t *row = a.rows + (size_t)slot * a.row_bytes;
             double mn = 0.0, sc = 0.0;
             if (DTYPE == EVDB_U8 || DTYPE == EVDB_U4) {
-                double2 ms = a.qms64[slot];
+                const double2 ms = a.qms64[slot];
                 mn = ms.x;
                 sc = ms.y;
             }
-            double dist = exact_distance_warp<DTYPE>(row, mn, sc, q, a.d, a.metric,
-                                                     a.norm64[slot], sp, lane);
-            if (lane == 0) {
+            const double s = exact_fold_lane<DTYPE>(row, mn, sc, q, a.d, a.metric, qlane);
+            double dist;
+            if (cosine) {
+                const double sq = __shfl_sync(0xffffffffu, s, 31);
+                const double n1 = __dsqrt_rn(sq), n2 = a.norm64[slot];
+                dist = (n1 == 0.0 || n2 == 0.0) ? 1.0 : __dsub_rn(1.0, __ddiv_rn(s, __dmul_rn(n1, n2)));
+            } else if (a.metric == EVDB_EUCLIDEAN) {
+                dist = __dsqrt_rn(s);
+            } else {
+                dist = s;
+            }
+            if (mine) {
                 dkey[j] = f64_orderable(dist);
                 dslot[j] = slot;
             }
-        } else if (lane == 0) {
+        }
+        for (int j = nrer + threadIdx.x; j < nsort; j += blockDim.x) {
             dkey[j] = kKeyMax;
             dslot[j] = kKeyMax;
         }
@@ -208,17 +362,22 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
 }
 
 static size_t select_smem(int threads) {
-    return sizeof(uint64_t) * kSelSort + sizeof(double) * (threads / 32) * 2 * kExactChunk +
-           sizeof(uint64_t) * 2 * kMaxKP;
+    (void)threads;
+    return sizeof(uint64_t) * kSelSort + sizeof(uint64_t) * 2 * kMaxKP;
 }
 
-int launch_select(evdb_store *s, const double *d_q64, const uint64_t *partial, int L, int KP, int B,
+int launch_select(evdb_store *s, const double *d_q64, const uint64_t *partial, const RawCands *raw, int L, int KP, int B,
                   int kk, int kstride, int metric, float eps_abs, float eps_rel, const float *eps_q,
                   int squared, uint64_t slot_base, uint64_t *d_out_ids, double *d_out_dists, int32_t *d_out_counts,
                   int32_t *d_out_flags, cudaStream_t st) {
     SelectArgs a;
     a.rows = s->rows; a.row_bytes = s->row_bytes; a.norm64 = s->norm64; a.qms64 = s->qms64;
     a.n = s->count; a.d = s->dim; a.q64 = d_q64; a.partial = partial; a.L = L; a.KP = KP;
+    memset(&a.raw, 0, sizeof(a.raw));
+    if (raw) {
+        a.raw = *raw;
+        if (L > kRawMaxLists) return EVDB_E_UNSUPPORTED;
+    }
     a.kk = kk; a.kstride = kstride; a.metric = metric; a.eps_abs = eps_abs; a.eps_rel = eps_rel;
     a.eps_q = eps_q; a.squared = squared;
     a.slot_base = slot_base; a.out_ids = d_out_ids; a.out_dists = d_out_dists;

@@ -136,6 +136,8 @@ static int search_core(evdb_store *s, const double *d_q64, int B, int k, int kst
     const double u = 5.9604644775390625e-08;  // 2^-24
     float eps_abs = 0.f, eps_rel = 0.f;
     const float *eps_q = nullptr;
+    RawCands raw;
+    bool have_raw = false;
     int squared = 0;
     int lists = 0;
     bool use_gemm = false;
@@ -158,7 +160,8 @@ static int search_core(evdb_store *s, const double *d_q64, int B, int k, int kst
         s->last_plan = EVDB_PLAN_GEMM;
         KP = gemm_kp(KP);
         // the per-query error bound of the fp16 operands comes back in eps_q (device)
-        EVDB_TRY(launch_gemm_topk(s, d_q64, B, KP, metric, &lists, &eps_q, st));
+        EVDB_TRY(launch_gemm_topk(s, d_q64, B, KP, metric, &lists, &eps_q, &raw, st));
+        have_raw = true;
         squared = metric == EVDB_EUCLIDEAN;
     } else {
         EVDB_TRY(launch_prep_queries(s, d_q64, B, st));
@@ -188,7 +191,7 @@ static int search_core(evdb_store *s, const double *d_q64, int B, int k, int kst
         else if (metric == EVDB_COSINE) eps_abs = (float)(depth * u);
         else { eps_rel = (float)(depth * u); eps_abs = 1e-37f; }
     }
-    EVDB_TRY(launch_select(s, d_q64, s->w_partial, lists, KP, B, kk, kstride, metric, eps_abs,
+    EVDB_TRY(launch_select(s, d_q64, have_raw ? nullptr : s->w_partial, have_raw ? &raw : nullptr, lists, KP, B, kk, kstride, metric, eps_abs,
                            eps_rel, eps_q, squared, slot_base, d_ids, d_dists, d_counts, d_flags, st));
     s->n_rows_scanned += (uint64_t)B * s->count;
     return EVDB_OK;
