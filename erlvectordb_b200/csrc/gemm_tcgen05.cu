@@ -176,75 +176,6 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
          | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// Selection without sorting: tau = the `need`-th smallest 32-bit score (orderable encoding, high
-// word of the key) among up to 256 keys held 8 per lane (kKeyMax pads), by 4-way search on the
-// value with warp-wide population counts.  Returns tau; *n_less = number of keys with score < tau.
-__device__ __forceinline__ uint32_t warp_select_score(const uint64_t (&x)[8], int need, int *n_less) {
-    uint32_t sc[8];
-    uint32_t mn = 0xFFFFFFFFu, mx = 0u;
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        sc[r] = (uint32_t)(x[r] >> 32);
-        mn = min(mn, sc[r]);
-        if (x[r] != kKeyMax) mx = max(mx, sc[r]);
-    }
-    uint32_t lo = __reduce_min_sync(0xffffffffu, mn);
-    uint32_t hi = __reduce_max_sync(0xffffffffu, mx);  // invariant: count(score <= hi) >= need
-#pragma unroll 1
-    while (lo < hi) {
-        const uint32_t span = hi - lo;
-        const uint32_t q = span >> 2;
-        const uint32_t p2 = lo + (span >> 1);
-        const uint32_t p1 = q ? lo + q : p2;
-        const uint32_t p3 = q ? p2 + q : p2;
-        int c1 = 0, c2 = 0, c3 = 0;
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            c1 += sc[r] <= p1 ? 1 : 0;
-            c2 += sc[r] <= p2 ? 1 : 0;
-            c3 += sc[r] <= p3 ? 1 : 0;
-        }
-        c1 = __reduce_add_sync(0xffffffffu, c1);
-        c2 = __reduce_add_sync(0xffffffffu, c2);
-        c3 = __reduce_add_sync(0xffffffffu, c3);
-        if (c1 >= need) hi = p1;
-        else if (c2 >= need) { lo = p1 + 1; hi = p2; }
-        else if (c3 >= need) { lo = p2 + 1; hi = p3; }
-        else lo = p3 + 1;
-    }
-    int c = 0;
-#pragma unroll
-    for (int r = 0; r < 8; ++r) c += sc[r] < lo ? 1 : 0;
-    *n_less = __reduce_add_sync(0xffffffffu, c);
-    return lo;
-}
-
-// Keep the `need` best keys of x (8 per lane): those below tau first, then ties at tau, written
-// densely to dst[i * stride].  Returns tau (orderable score of the need-th best).
-__device__ __forceinline__ uint32_t warp_compact(const uint64_t (&x)[8], int need, uint64_t *dst,
-                                                 size_t stride, int lane) {
-    int n_less;
-    const uint32_t tau = warp_select_score(x, need, &n_less);
-    int base_less = 0, base_tie = n_less, ties_left = need - n_less;
-    const unsigned below = (1u << lane) - 1u;
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        const uint32_t scr = (uint32_t)(x[r] >> 32);
-        const bool is_less = scr < tau;
-        const bool is_tie = scr == tau && x[r] != kKeyMax;
-        const unsigned ml = __ballot_sync(0xffffffffu, is_less);
-        const unsigned mt = __ballot_sync(0xffffffffu, is_tie);
-        if (is_less) dst[(size_t)(base_less + __popc(ml & below)) * stride] = x[r];
-        const int trank = __popc(mt & below);
-        if (is_tie && trank < ties_left) dst[(size_t)(base_tie + trank) * stride] = x[r];
-        base_less += __popc(ml);
-        const int used = min(__popc(mt), ties_left);
-        base_tie += used;
-        ties_left -= used;
-    }
-    return tau;
-}
-
 // Largest accumulator value a (to a few ulps) with fma(a, c1, c0) >= tau, c1 < 0: a row whose
 // accumulator is <= a has key score >= tau and can be skipped.  Never errs towards skipping more.
 __device__ __forceinline__ float acc_threshold(float tau, float c0, float c1) {

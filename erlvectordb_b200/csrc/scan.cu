@@ -13,6 +13,8 @@
 // (score, slot) keys in a sorted shared-memory list guarded by a register
 // threshold.  The CTA bitonic-merges its warps' lists and writes KP keys; the
 // select kernel (select.cu) merges CTAs and re-ranks exactly in fp64.
+#include <stdlib.h>
+
 #include "internal.h"
 #include "topk.cuh"
 
@@ -165,11 +167,54 @@ __device__ __forceinline__ void cta_merge_and_store(uint64_t *lists, int KP, uin
     for (int i = threadIdx.x; i < KP; i += blockDim.x) out[i] = lists[i];
 }
 
+// Per-warp candidate state: append-and-prune buffers (KP <= 128) or the sorted-list insert
+// (wider escalation windows).  Region of warp w: lists + w * stride.
+struct WarpCands {
+    uint64_t *mine;
+    uint64_t thr;
+    int cnt, cap, KP;
+    bool append;
+    __device__ __forceinline__ void init(uint64_t *lists, int KP_, int warp) {
+        KP = KP_;
+        append = KP_ <= kAppendMaxKP;
+        cap = append ? append_cap(KP_) : KP_;
+        mine = lists + (size_t)warp * cap;
+        thr = kKeyMax;
+        cnt = 0;
+    }
+    __device__ __forceinline__ void offer(uint64_t key, int lane) {
+        if (append) offer_append(key, thr, mine, cnt, cap, KP, lane);
+        else evdb::offer(key, thr, mine, KP, lane);
+    }
+    // compact every warp's best <= KP keys to lists[w*KP ..], padded with kKeyMax (whole CTA calls)
+    __device__ __forceinline__ void finish(uint64_t *lists, int warp, int lane) {
+        if (!append) return;
+        if (cnt > KP) warp_buf_prune(mine, cnt, thr, KP, lane);
+        uint64_t e[kAppendMaxKP / 32];
+#pragma unroll
+        for (int r = 0; r < kAppendMaxKP / 32; ++r) {
+            const int i = r * 32 + lane;
+            e[r] = (i < cnt && i < KP) ? mine[i] : kKeyMax;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < kAppendMaxKP / 32; ++r) {
+            const int i = r * 32 + lane;
+            if (i < KP) lists[(size_t)warp * KP + i] = e[r];
+        }
+    }
+};
+
+static inline size_t scan_list_bytes(int KP) {
+    const int per = KP <= kAppendMaxKP ? append_cap(KP) : KP;
+    return (size_t)kScanWarps * per * sizeof(uint64_t);
+}
+
 // ----------------------------------------------------------------------------
 // fp32 / bf16 rows: cosine, euclidean, manhattan
 // ----------------------------------------------------------------------------
 template <int METRIC, int DTYPE, int TPR, int R>
-__global__ void __launch_bounds__(kScanWarps * 32)
+__global__ void __launch_bounds__(kScanWarps * 32, DTYPE == EVDB_F32 ? 4 : 3)   // F32: 4 CTAs (32 warps) per SM -- the loads in flight are what hides HBM latency
 scan_float_kernel(const ScanArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr int QPC = (DTYPE == EVDB_F32) ? 1 : 2;  // query float4s per 16-byte row chunk
@@ -182,11 +227,12 @@ scan_float_kernel(const ScanArgs a) {
 
     const float4 *qsrc = reinterpret_cast<const float4 *>(a.q32 + (size_t)b * a.q32_stride);
     for (int i = threadIdx.x; i < nch * QPC; i += blockDim.x) sq[i] = qsrc[i];
-    for (int i = threadIdx.x; i < kScanWarps * KP; i += blockDim.x) lists[i] = kKeyMax;
+    if (KP > kAppendMaxKP)
+        for (int i = threadIdx.x; i < kScanWarps * KP; i += blockDim.x) lists[i] = kKeyMax;
     __syncthreads();
     const float q_inv = a.qstat[b].inv_norm;
-    uint64_t *mylist = lists + warp * KP;
-    uint64_t thr = kKeyMax;
+    WarpCands wc;
+    wc.init(lists, KP, warp);
 
     const int g = lane / TPR, gl = lane % TPR;
     const uint64_t rows_per_wi = (uint64_t)GPW * R;
@@ -204,6 +250,12 @@ scan_float_kernel(const ScanArgs a) {
             rix[j] = r;
             rp[j] = reinterpret_cast<const uint4 *>(a.rows + (valid[j] ? r : a.n - 1) * a.row_bytes);
         }
+        // the per-row side value is requested up front, with the rows: issued after the
+        // reduction it would put a second DRAM latency on every warp-iteration
+        float inv[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+            inv[j] = (METRIC == EVDB_COSINE && valid[j] && gl == 0) ? __ldg(a.inv_norm + rix[j]) : 0.f;
         float4 acc[R];
 #pragma unroll
         for (int j = 0; j < R; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -236,17 +288,17 @@ scan_float_kernel(const ScanArgs a) {
             for (int o = TPR / 2; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
             float score;
             if (METRIC == EVDB_COSINE) {
-                float inv = (valid[j] && gl == 0) ? __ldg(a.inv_norm + rix[j]) : 0.f;
-                score = (inv == 0.f || q_inv == 0.f) ? 1.0f : 1.0f - sacc * inv * q_inv;
+                score = (inv[j] == 0.f || q_inv == 0.f) ? 1.0f : 1.0f - sacc * inv[j] * q_inv;
             } else if (METRIC == EVDB_EUCLIDEAN) {
                 score = sqrtf(sacc);
             } else {
                 score = sacc;
             }
             uint64_t key = (valid[j] && gl == 0) ? make_key(score, (uint32_t)rix[j]) : kKeyMax;
-            offer(key, thr, mylist, KP, lane);
+            wc.offer(key, lane);
         }
     }
+    wc.finish(lists, warp, lane);
     cta_merge_and_store(lists, KP, a.partial + ((size_t)b * a.G + blockIdx.x) * KP);
 }
 
@@ -256,7 +308,7 @@ scan_float_kernel(const ScanArgs a) {
 //   Q = a*2^16 + b*2^8 + c (a signed, b,c unsigned digits), three dp4a per word.
 // ----------------------------------------------------------------------------
 template <int DTYPE, int TPR, int R>
-__global__ void __launch_bounds__(kScanWarps * 32)
+__global__ void __launch_bounds__(kScanWarps * 32, 2)
 scan_quant_kernel(const ScanArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr int GPW = 32 / TPR;
@@ -270,11 +322,12 @@ scan_quant_kernel(const ScanArgs a) {
 
     const uint4 *dsrc = reinterpret_cast<const uint4 *>(a.qdig + (size_t)b * 3 * a.qdig_stride);
     for (int i = threadIdx.x; i < 3 * plane_u4; i += blockDim.x) sd[i] = dsrc[i];
-    for (int i = threadIdx.x; i < kScanWarps * KP; i += blockDim.x) lists[i] = kKeyMax;
+    if (KP > kAppendMaxKP)
+        for (int i = threadIdx.x; i < kScanWarps * KP; i += blockDim.x) lists[i] = kKeyMax;
     __syncthreads();
     const QStat qs = a.qstat[b];
-    uint64_t *mylist = lists + warp * KP;
-    uint64_t thr = kKeyMax;
+    WarpCands wc;
+    wc.init(lists, KP, warp);
 
     const int g = lane / TPR, gl = lane % TPR;
     const uint64_t rows_per_wi = (uint64_t)GPW * R;
@@ -292,6 +345,11 @@ scan_quant_kernel(const ScanArgs a) {
             rix[j] = r;
             rp[j] = reinterpret_cast<const uint4 *>(a.rows + (valid[j] ? r : a.n - 1) * a.row_bytes);
         }
+        // per-row coefficients requested up front, together with the codes
+        float2 co[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+            co[j] = (valid[j] && gl == 0) ? __ldg(a.qcoef + rix[j]) : make_float2(0.f, 0.f);  // {scale/||y||, min/||y||}
         int A[R], Bm[R], Cl[R];
 #pragma unroll
         for (int j = 0; j < R; ++j) A[j] = Bm[j] = Cl[j] = 0;
@@ -343,15 +401,15 @@ scan_quant_kernel(const ScanArgs a) {
             uint64_t key = kKeyMax;
             if (valid[j] && gl == 0) {
                 long long S = ((long long)sa << 16) + ((long long)sb << 8) + (long long)sc;
-                float2 co = __ldg(a.qcoef + rix[j]);  // {scale/||y||, min/||y||}
-                float dotn = fmaf(co.x, __ll2float_rn(S) * qs.fx, co.y * qs.sum);
-                bool zero = (co.x == 0.f && co.y == 0.f) || qs.inv_norm == 0.f;
+                float dotn = fmaf(co[j].x, __ll2float_rn(S) * qs.fx, co[j].y * qs.sum);
+                bool zero = (co[j].x == 0.f && co[j].y == 0.f) || qs.inv_norm == 0.f;
                 float score = zero ? 1.0f : 1.0f - dotn * qs.inv_norm;
                 key = make_key(score, (uint32_t)rix[j]);
             }
-            offer(key, thr, mylist, KP, lane);
+            wc.offer(key, lane);
         }
     }
+    wc.finish(lists, warp, lane);
     cta_merge_and_store(lists, KP, a.partial + ((size_t)b * a.G + blockIdx.x) * KP);
 }
 
@@ -360,9 +418,13 @@ scan_quant_kernel(const ScanArgs a) {
 // ----------------------------------------------------------------------------
 typedef void (*scan_fn_t)(const ScanArgs);
 
-static int pick_tpr(int nch) {
+static int pick_tpr(int nch, int dtype) {
     int t = 1;
-    while (t < 32 && t * 2 <= nch / 2) t <<= 1;
+    static int env_div = -1;
+    if (env_div < 0) { const char *e = getenv("EVDB_SCAN_CPL"); env_div = e && atoi(e) > 0 ? atoi(e) : 0; }
+    (void)dtype;
+    const int div = env_div ? env_div : 4;  // measured on B200 (tools/sweep.py): 4 beats 2 for every dtype
+    while (t < 32 && (t < 2 ? nch >= 2 : t * 2 <= nch / div)) t <<= 1;  // >= 2 lanes per row (whole sectors), then >= `div` chunks per lane
     return t;
 }
 
@@ -396,7 +458,7 @@ struct ScanPlan {
 };
 
 static int make_scan_plan(evdb_store *s, int metric, int KP, ScanPlan *p) {
-    int tpr = pick_tpr(s->nch);
+    int tpr = pick_tpr(s->nch, s->dtype);
     p->tpr = tpr;
     int R = 4;
     size_t qbytes;
@@ -429,7 +491,7 @@ static int make_scan_plan(evdb_store *s, int metric, int KP, ScanPlan *p) {
             return EVDB_E_BAD_ARG;
     }
     p->rows_per_wi = (32 / tpr) * R;
-    p->smem = qbytes + (size_t)kScanWarps * KP * sizeof(uint64_t);
+    p->smem = qbytes + scan_list_bytes(KP);
     if (p->smem > 200 * 1024) return EVDB_E_UNSUPPORTED;
     return EVDB_OK;
 }
@@ -444,8 +506,8 @@ int scan_grid_size(evdb_store *s, int metric, int KP, int *G_out) {
     if (occ < 1) occ = 1;
     if (occ > 4) occ = 4;
     uint64_t total_wi = (s->count + p.rows_per_wi - 1) / p.rows_per_wi;
-    // at least 4 warp-iterations per warp, so the warp-list warm-up amortises
-    uint64_t want = (total_wi + (uint64_t)kScanWarps * 4 - 1) / ((uint64_t)kScanWarps * 4);
+    // small stores are latency-bound: one warp-iteration per warp spreads them over the most SMs
+    uint64_t want = (total_wi + (uint64_t)kScanWarps - 1) / (uint64_t)kScanWarps;
     uint64_t cap = (uint64_t)s->sm_count * occ;
     uint64_t G = want < cap ? want : cap;
     if (G < 1) G = 1;

@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
     uint64_t *buf = reinterpret_cast<uint64_t *>(smem);                       // [kSelSort]
     uint64_t *dkey = buf + kSelSort;                                          // [kMaxKP]
     uint64_t *dslot = dkey + kMaxKP;                                          // [kMaxKP]
+    double *sp_all = reinterpret_cast<double *>(dslot + kMaxKP);              // lone-query variant: [warps][2*chunk]
     __shared__ int s_ncand;
     __shared__ float s_bound;
 
@@ -284,8 +285,32 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
     int nsort = 2;
     while (nsort < nrer) nsort <<= 1;
     const double *q = a.q64 + (size_t)b * a.d;
-    {
-        // The fold of one row is a strictly sequential fp64 chain (reference order), so candidates
+    if (THREADS == 1024) {
+        // Lone query: latency matters, not fp64-pipe occupancy.  One warp per candidate: 32 lanes
+        // form the independent products, one lane folds them in the reference order.
+        double *sp = sp_all + warp * 2 * kExactChunk;
+        for (int j = warp; j < nsort; j += kSelWarps) {
+            if (j < nrer) {
+                const uint32_t slot = key_slot(buf[j]);
+                const uint8_t *row = a.rows + (size_t)slot * a.row_bytes;
+                double mn = 0.0, sc = 0.0;
+                if (DTYPE == EVDB_U8 || DTYPE == EVDB_U4) {
+                    const double2 ms = a.qms64[slot];
+                    mn = ms.x;
+                    sc = ms.y;
+                }
+                const double dist = exact_distance_warp<DTYPE>(row, mn, sc, q, a.d, a.metric, a.norm64[slot], sp, lane);
+                if (lane == 0) {
+                    dkey[j] = f64_orderable(dist);
+                    dslot[j] = slot;
+                }
+            } else if (lane == 0) {
+                dkey[j] = kKeyMax;
+                dslot[j] = kKeyMax;
+            }
+        }
+    } else {
+        // Batches: the fold of one row is a strictly sequential fp64 chain (reference order), so candidates
         // are spread one per lane: cpw per warp, plus -- for cosine -- lane 31 of every working
         // warp folding the query's own squares.
         const bool cosine = a.metric == EVDB_COSINE;
@@ -362,8 +387,8 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
 }
 
 static size_t select_smem(int threads) {
-    (void)threads;
-    return sizeof(uint64_t) * kSelSort + sizeof(uint64_t) * 2 * kMaxKP;
+    return sizeof(uint64_t) * kSelSort + sizeof(uint64_t) * 2 * kMaxKP +
+           (threads == 1024 ? sizeof(double) * (threads / 32) * 2 * kExactChunk : 0);
 }
 
 int launch_select(evdb_store *s, const double *d_q64, const uint64_t *partial, const RawCands *raw, int L, int KP, int B,
