@@ -232,11 +232,15 @@ def run_ours(args):
         for _ in range(min(warmup, 3)):
             e2e_step()
         barrier()
+        lat = []
         t0 = time.perf_counter()
         for _ in range(steps):
+            t1 = time.perf_counter()
             e2e_step()
+            lat.append(time.perf_counter() - t1)
         barrier()
         e2e_s = time.perf_counter() - t0
+        lat.sort()
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -245,7 +249,13 @@ def run_ours(args):
                 "kernel_ms": (kms / nsamp) if nsamp else None, "kernel_samples": nsamp, "plan": plan,
                 "launches": launches, "clocks": clocks, "flagged": flagged,
                 "e2e_qps": batch * steps / e2e_s, "e2e_ms_per_step": e2e_s / steps * 1e3,
-                "h2d": batch * DIM * 8, "d2h": batch * K * (8 + (4 if world == 1 else 8)) + (batch * 8 if world == 1 else 0)}
+                "lat_p50_ms": lat[len(lat) // 2] * 1e3, "lat_p99_ms": lat[min(len(lat) - 1, int(len(lat) * 0.99))] * 1e3,
+                "h2d": batch * DIM * 8, "d2h": batch * K * 16 + batch * 8}
+
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the committed ncu --set full captures
+    if os.path.exists(tp):
+        traffic = json.load(open(tp))
 
     def roofline(r, batch):
         rows_local = st.hi - st.lo
@@ -255,13 +265,15 @@ def run_ours(args):
             flops = 2.0 * rows_local * DIM * batch
             ach = flops / (r["kernel_ms"] * 1e-3) / 1e12
             return {"bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / pk["tf_sustained"], "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
+                    "frac": ach / pk["tf_sustained"], "traffic": traffic.get("gemm_topk_kernel") if world == 1 else None,
+                    "algorithmic_flops": flops, "peak_source": pk["src"] + " bf16 sustained",
                     "frac_of_burst": ach / pk["tf_burst"], "kernel": "gemm_topk_kernel (tcgen05 kind::f16, fp32 accumulate in TMEM)",
                     "kernel_ms": r["kernel_ms"]}
         byts = float(rows_local) * DIM * 4 * batch  # one corpus pass per query in the scan plan
         ach = byts / (r["kernel_ms"] * 1e-3) / 1e9
         return {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["src"] + " copy bandwidth",
+                "frac": ach / pk["hbm_gbs"], "traffic": traffic.get("scan_float_kernel") if world == 1 else None,
+                "algorithmic_bytes": byts, "peak_source": pk["src"] + " copy bandwidth",
                 "frac_of_8TBs_nominal": ach / 8000.0, "kernel": "scan_float_kernel", "kernel_ms": r["kernel_ms"]}
 
     main = timed(args.batch, args.steps, args.warmup, sample_clocks=True)
@@ -282,7 +294,8 @@ def run_ours(args):
             "metric": METRIC_NAME if args.batch == BATCH_MAIN else f"QPS (k=10, 1Mx768 cosine, batch {args.batch})",
             "value": main["qps"], "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32" if main["plan"] != N.PLAN_GEMM else "f16",
+            "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32" if main["plan"] != N.PLAN_GEMM else "f16 (tcgen05 candidates, fp32 accumulate) + f64 exact re-rank",
             "data": "synthetic",
             "config": {"workload": "1Mx768 fp32 cosine k=10 (BASELINE.json configs[1])", "rows": N_ROWS,
                        "dim": DIM, "k": K, "batch": args.batch, "plan": {1: "scan", 2: "gemm", 3: "exact"}.get(main["plan"]),
@@ -299,6 +312,8 @@ def run_ours(args):
         }
         if one is not None:
             out["batch1"] = {"value": one["qps"], "unit": "queries/s", "ms_per_step": one["ms_per_step"],
+                             "latency_ms": {"p50": one["lat_p50_ms"], "p99": one["lat_p99_ms"],
+                                            "how": "wall clock around the host-buffer call"},
                              "e2e": {"value": one["e2e_qps"], "unit": "queries/s",
                                      "h2d_bytes_per_step": one["h2d"], "d2h_bytes_per_step": one["d2h"]},
                              "roofline": roofline(one, BATCH_ONE), "gpu_launches": one["launches"],

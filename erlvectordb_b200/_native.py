@@ -76,6 +76,7 @@ SYMBOLS = [
     ("evdb_store_search_f32", _i, [_vp, _pf, _i, _i, _i, _i, _pu32, _pd, _pi32]),
     ("evdb_store_search_dev", _i, [_vp, _vp, _i, _i, _i, _i, _u64, _vp, _vp, _vp, _vp, _vp]),
     ("evdb_merge_topk_dev", _i, [_i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    ("evdb_merge_topk_packed_dev", _i, [_i, _vp, _i, _i, _i, _vp, _vp]),
     ("evdb_quantize_8bit", _i, [_i, _pd, _u64, _i, _pu8, _pd, _pd, _pd, _pu8]),
     ("evdb_quantize_4bit", _i, [_i, _pd, _u64, _i, _pu8, _pd, _pd, _pd, _pu8]),
     ("evdb_dequantize_8bit", _i, [_i, _pu8, _pd, _pd, _u64, _i, _pd]),

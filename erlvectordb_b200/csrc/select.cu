@@ -514,25 +514,34 @@ int exact_plan_search(evdb_store *s, const double *d_q64, int B, int kk, int kst
 // ----------------------------------------------------------------------------
 // G-way merge of per-shard (distance, id) lists after the allgather
 // ----------------------------------------------------------------------------
+// Rank g's list of query b: ids/dists at [g*stride8 + b*k ..], count at counts[g*stride4 + b]
+// (flags likewise, optional).  The same kernel serves separate [G][B][k] arrays and the packed
+// per-rank blobs of the one-collective exchange.
 __global__ void __launch_bounds__(1024) merge_topk_kernel(const uint64_t *__restrict__ ids,
                                                           const double *__restrict__ dists,
-                                                          const int32_t *__restrict__ counts, int G,
+                                                          const int32_t *__restrict__ counts,
+                                                          const int32_t *__restrict__ flags,
+                                                          size_t stride8, size_t stride4, int G,
                                                           int B, int k, int nsort,
                                                           uint64_t *__restrict__ out_ids,
                                                           double *__restrict__ out_dists,
-                                                          int32_t *__restrict__ out_counts) {
+                                                          int32_t *__restrict__ out_counts,
+                                                          int32_t *__restrict__ out_flags) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint64_t *dk = reinterpret_cast<uint64_t *>(smem);
     uint64_t *di = dk + nsort;
     const int b = blockIdx.x;
-    int total = 0;
-    for (int g = 0; g < G; ++g) total += counts[(size_t)g * B + b];
+    int total = 0, flag = 0;
+    for (int g = 0; g < G; ++g) {
+        total += counts[(size_t)g * stride4 + b];
+        if (flags) flag |= flags[(size_t)g * stride4 + b];
+    }
     for (int i = threadIdx.x; i < nsort; i += blockDim.x) {
         uint64_t key = kKeyMax, id = kKeyMax;
         if (i < G * k) {
             int g = i / k, j = i % k;
-            if (j < counts[(size_t)g * B + b]) {
-                size_t o = ((size_t)g * B + b) * k + j;
+            if (j < counts[(size_t)g * stride4 + b]) {
+                size_t o = (size_t)g * stride8 + (size_t)b * k + j;
                 key = f64_orderable(dists[o]);
                 id = ids[o];
             }
@@ -555,20 +564,42 @@ __global__ void __launch_bounds__(1024) merge_topk_kernel(const uint64_t *__rest
             out_ids[o] = kKeyMax;
         }
     }
-    if (threadIdx.x == 0) out_counts[b] = kout;
+    if (threadIdx.x == 0) {
+        out_counts[b] = kout;
+        if (out_flags) out_flags[b] = flag;
+    }
+}
+
+static int merge_launch(const uint64_t *ids, const double *dists, const int32_t *counts, const int32_t *flags,
+                        size_t stride8, size_t stride4, int G, int B, int k, uint64_t *out_ids,
+                        double *out_dists, int32_t *out_counts, int32_t *out_flags, cudaStream_t st) {
+    if (G <= 0 || B <= 0 || k <= 0) return EVDB_E_BAD_ARG;
+    int nsort = next_pow2(G * k);
+    if (nsort < 2) nsort = 2;
+    size_t smem = (size_t)nsort * 16;
+    if (smem > 200 * 1024) return EVDB_E_UNSUPPORTED;
+    EVDB_CUDA(cudaFuncSetAttribute((const void *)merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int threads = nsort >= 2048 ? 1024 : (nsort >= 512 ? 256 : 128);
+    merge_topk_kernel<<<B, threads, smem, st>>>(ids, dists, counts, flags, stride8, stride4, G, B, k, nsort,
+                                                out_ids, out_dists, out_counts, out_flags);
+    EVDB_CUDA(cudaGetLastError());
+    return EVDB_OK;
 }
 
 int launch_merge_topk(const uint64_t *ids, const double *dists, const int32_t *counts, int G, int B,
                       int k, uint64_t *out_ids, double *out_dists, int32_t *out_counts,
                       cudaStream_t st) {
-    if (G <= 0 || B <= 0 || k <= 0) return EVDB_E_BAD_ARG;
-    int nsort = next_pow2(G * k);
-    size_t smem = (size_t)nsort * 16;
-    if (smem > 200 * 1024) return EVDB_E_UNSUPPORTED;
-    EVDB_CUDA(cudaFuncSetAttribute((const void *)merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    merge_topk_kernel<<<B, 1024, smem, st>>>(ids, dists, counts, G, B, k, nsort, out_ids, out_dists, out_counts);
-    EVDB_CUDA(cudaGetLastError());
-    return EVDB_OK;
+    return merge_launch(ids, dists, counts, nullptr, (size_t)B * k, (size_t)B, G, B, k, out_ids, out_dists,
+                        out_counts, nullptr, st);
+}
+
+// Packed blobs (one per rank, `blob_words` u64 words apart): [B*k ids][B*k dists][B counts i32][B flags i32]
+int launch_merge_topk_packed(const uint64_t *blobs, int G, int B, int k, uint64_t *out_blob, cudaStream_t st) {
+    const size_t nk = (size_t)B * k, words = 2 * nk + (size_t)B;
+    const int32_t *cf = reinterpret_cast<const int32_t *>(blobs + 2 * nk);
+    int32_t *ocf = reinterpret_cast<int32_t *>(out_blob + 2 * nk);
+    return merge_launch(blobs, reinterpret_cast<const double *>(blobs + nk), cf, cf + B, words, 2 * words, G, B, k,
+                        out_blob, reinterpret_cast<double *>(out_blob + nk), ocf, ocf + B, st);
 }
 
 }  // namespace evdb

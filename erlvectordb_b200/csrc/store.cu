@@ -210,6 +210,17 @@ static int ensure_out(evdb_store *s, int B, int kstride) {
     return EVDB_OK;
 }
 
+static bool all_finite(const void *v, bool is_f64, size_t n) {
+    if (is_f64) {
+        const double *q = (const double *)v;
+        for (size_t i = 0; i < n; ++i) if (!isfinite(q[i])) return false;
+    } else {
+        const float *q = (const float *)v;
+        for (size_t i = 0; i < n; ++i) if (!isfinite(q[i])) return false;
+    }
+    return true;
+}
+
 // Host-facing search: H2D queries, search, D2H results, escalate flagged queries.
 static int search_host(evdb_store *s, const void *queries, bool is_f64, int B, int d, int k,
                        int metric, uint32_t *out_slots, double *out_dists, int32_t *out_counts) {
@@ -224,13 +235,11 @@ static int search_host(evdb_store *s, const void *queries, bool is_f64, int B, i
     }
     if (d != s->dim) return EVDB_E_DIM_MISMATCH;
     size_t nq = (size_t)B * d;
-    if (is_f64) {
-        const double *q = (const double *)queries;
-        for (size_t i = 0; i < nq; ++i) if (!isfinite(q[i])) return EVDB_E_BAD_VECTOR;
-    } else {
-        const float *q = (const float *)queries;
-        for (size_t i = 0; i < nq; ++i) if (!isfinite(q[i])) return EVDB_E_BAD_VECTOR;
-    }
+    // validate_vector/2 (lists:all(is_number)): a small query is checked before anything is
+    // enqueued; a large batch is checked on the host WHILE the device works on it (the result is
+    // discarded if the check fails), so the check costs no latency.
+    const bool check_late = nq >= 65536;
+    if (!check_late && !all_finite(queries, is_f64, nq)) return EVDB_E_BAD_VECTOR;
     EVDB_TRY(set_device(s));
     if (k == 0) {
         for (int b = 0; b < B; ++b) out_counts[b] = 0;
@@ -265,7 +274,9 @@ static int search_host(evdb_store *s, const void *queries, bool is_f64, int B, i
     EVDB_CUDA(cudaMemcpyAsync(h_d, s->w_dists, nk * sizeof(double), cudaMemcpyDeviceToHost, st));
     EVDB_CUDA(cudaMemcpyAsync(h_c, s->w_counts, sizeof(int32_t) * 2 * (size_t)B, cudaMemcpyDeviceToHost, st));
     EVDB_CUDA(cudaEventRecord(s->ev1, st));
+    const bool bad_query = check_late && !all_finite(queries, is_f64, nq);
     EVDB_CUDA(cudaStreamSynchronize(st));
+    if (bad_query) return EVDB_E_BAD_VECTOR;
     float ms = 0.f;
     cudaEventElapsedTime(&ms, s->ev0, s->ev1);
     s->last_search_ms = ms;
@@ -753,6 +764,14 @@ int evdb_merge_topk_dev(int device, const void *d_ids_u64, const void *d_dists_f
     return launch_merge_topk((const uint64_t *)d_ids_u64, (const double *)d_dists_f64,
                              (const int32_t *)d_counts_i32, G, B, k, (uint64_t *)d_out_ids_u64,
                              (double *)d_out_dists_f64, (int32_t *)d_out_counts_i32, (cudaStream_t)stream);
+}
+
+int evdb_merge_topk_packed_dev(int device, const void *d_blobs, int G, int B, int k, void *d_out_blob,
+                               void *stream) {
+    if (!d_blobs || !d_out_blob) return EVDB_E_BAD_ARG;
+    EVDB_TRY(check_device(device));
+    EVDB_CUDA(cudaSetDevice(device));
+    return launch_merge_topk_packed((const uint64_t *)d_blobs, G, B, k, (uint64_t *)d_out_blob, (cudaStream_t)stream);
 }
 
 // ---- standalone codecs ------------------------------------------------------

@@ -158,3 +158,8 @@ class DeviceStore:
 def merge_topk_dev(device, d_ids, d_dists, d_counts, G, B, k, d_out_ids, d_out_dists, d_out_counts, stream=0):
     N.check(N.lib().evdb_merge_topk_dev(device, d_ids, d_dists, d_counts, G, B, k, d_out_ids, d_out_dists,
                                         d_out_counts, stream), "evdb_merge_topk_dev")
+
+
+def merge_topk_packed_dev(device, d_blobs, G, B, k, d_out_blob, stream=0):
+    N.check(N.lib().evdb_merge_topk_packed_dev(device, d_blobs, G, B, k, d_out_blob, stream),
+            "evdb_merge_topk_packed_dev")

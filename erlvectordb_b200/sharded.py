@@ -6,8 +6,9 @@ associative merge, so the corpus splits by contiguous row blocks:
 
     rank r owns global rows [lo_r, hi_r);  every rank sees every query
     local:   evdb_store_search_dev  -> (global id u64, exact fp64 distance) x k
-    exchange: torch.distributed all_gather over NCCL/NVLink  (B*k*16 B + B*4 B per rank)
-    merge:   evdb_merge_topk_dev on every rank -> identical global top-k everywhere
+    exchange: ONE torch.distributed all_gather_into_tensor over NCCL/NVLink of the packed
+             per-rank result blob (B*k*16 B + B*8 B per rank)
+    merge:   evdb_merge_topk_packed_dev on every rank -> identical global top-k everywhere
 
 Because each shard's distances are the exact fp64 values and ids are global rows,
 the merged result is bit-identical to the single-GPU result.
@@ -21,7 +22,7 @@ import torch
 import torch.distributed as dist
 
 from . import _native as N
-from .device_store import DeviceStore, merge_topk_dev
+from .device_store import DeviceStore, merge_topk_packed_dev
 
 
 def shard_bounds(n_total: int, world: int, rank: int) -> tuple[int, int]:
@@ -32,19 +33,33 @@ def shard_bounds(n_total: int, world: int, rank: int) -> tuple[int, int]:
     return lo, hi
 
 
-def gather_layout(t: torch.Tensor, world: int, group=None) -> torch.Tensor:
-    """all_gather `t` from every rank into a new leading axis: out[g] = rank g's tensor."""
-    out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+def blob_words(B: int, k: int) -> int:
+    """64-bit words of one rank's packed result: [B*k ids][B*k dists][B counts i32][B flags i32]."""
+    return 2 * B * k + B
+
+
+def blob_views(blob: torch.Tensor, B: int, k: int):
+    """(ids (B,k) int64, dists (B,k) float64, counts (B,) int32, flags (B,) int32) views of a blob."""
+    nk = B * k
+    ids = blob[:nk].view(B, k)
+    dists = blob[nk:2 * nk].view(torch.float64).view(B, k)
+    cf = blob[2 * nk:].view(torch.int32)
+    return ids, dists, cf[:B], cf[B:]
+
+
+def gather_blobs(blob: torch.Tensor, world: int, group=None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """ONE collective per search: all_gather every rank's packed blob -> (world, words)."""
+    if out is None:
+        out = torch.empty((world, blob.numel()), dtype=blob.dtype, device=blob.device)
     if world == 1:
-        out[0].copy_(t)
-        return out
-    if t.is_cuda:  # NCCL: one fused allgather into the [world, ...] buffer
-        dist.all_gather_into_tensor(out.view(-1), t.contiguous().view(-1), group=group)
-    else:          # gloo (CPU tests of the host logic)
-        parts = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(parts, t.contiguous(), group=group)
-        for g, p in enumerate(parts):
-            out[g].copy_(p)
+        out[0].copy_(blob)
+    elif blob.is_cuda:  # NCCL over NVLink
+        dist.all_gather_into_tensor(out.view(-1), blob, group=group)
+    else:               # gloo (CPU tests of the host logic)
+        parts = [torch.empty_like(blob) for _ in range(world)]
+        dist.all_gather(parts, blob, group=group)
+        for g, p_ in enumerate(parts):
+            out[g].copy_(p_)
     return out
 
 
@@ -65,8 +80,8 @@ class ShardedStore:
         self.world = dist.get_world_size(group) if world is None else world
         self.device = device
         self.dtype = dtype
-        self._local_search = local_search or self._cuda_local_search
-        self._merge = merge or self._cuda_merge
+        self._local_search = local_search   # None -> the CUDA library
+        self._merge = merge                 # None -> the CUDA merge kernel
         self._dev = None if local_search else DeviceStore(dtype=dtype, device=device)
         self._bufs = {}
         self.lo = self.hi = 0
@@ -89,45 +104,51 @@ class ShardedStore:
             self._dev.bulk_load(rows)
 
     # -- search ----------------------------------------------------------------------
-    def _cuda_local_search(self, q: torch.Tensor, k: int, metric: str):
-        B, d = q.shape
-        dev = q.device
+    def _buffers(self, B: int, k: int, dev):
         key = (B, k, dev)
-        if key not in self._bufs:  # reuse output buffers: no allocator / fill kernels per search
-            self._bufs[key] = (torch.empty((B, k), dtype=torch.int64, device=dev),
-                               torch.empty((B, k), dtype=torch.float64, device=dev),
-                               torch.zeros((B,), dtype=torch.int32, device=dev),
-                               torch.zeros((B,), dtype=torch.int32, device=dev))
-        ids, dists, counts, flags = self._bufs[key]
-        if self.hi > self.lo:
-            stream = _stream_handle(dev)
-            self._dev.search_dev(q.data_ptr(), B, d, k, metric, self.lo, ids.data_ptr(), dists.data_ptr(),
-                                 counts.data_ptr(), flags.data_ptr(), stream)
-        return ids, dists, counts, flags
+        if key not in self._bufs:  # reused across searches: no allocator / fill kernels per call
+            w = blob_words(B, k)
+            local = torch.zeros((w,), dtype=torch.int64, device=dev)
+            gathered = torch.zeros((self.world, w), dtype=torch.int64, device=dev)
+            merged = torch.zeros((w,), dtype=torch.int64, device=dev)
+            self._bufs[key] = (local, gathered, merged)
+        return self._bufs[key]
 
-    def _cuda_merge(self, ids, dists, counts, k):
-        G, B = counts.shape
-        dev = ids.device
-        out_ids = torch.empty((B, k), dtype=torch.int64, device=dev)
-        out_d = torch.empty((B, k), dtype=torch.float64, device=dev)
-        out_c = torch.empty((B,), dtype=torch.int32, device=dev)
-        stream = _stream_handle(dev)
-        merge_topk_dev(dev.index or 0, ids.data_ptr(), dists.data_ptr(), counts.data_ptr(), G, B, k,
-                       out_ids.data_ptr(), out_d.data_ptr(), out_c.data_ptr(), stream)
-        return out_ids, out_d, out_c
+    def _cuda_local_search(self, q: torch.Tensor, k: int, metric: str, blob: torch.Tensor):
+        """The library writes this shard's result straight into the packed blob."""
+        B, d = q.shape
+        ids, dists, counts, flags = blob_views(blob, B, k)
+        if self.hi > self.lo:
+            self._dev.search_dev(q.data_ptr(), B, d, k, metric, self.lo, ids.data_ptr(), dists.data_ptr(),
+                                 counts.data_ptr(), flags.data_ptr(), _stream_handle(q.device))
+        # an empty shard keeps the zero counts the blob was created with
+
+    def _cuda_merge(self, gathered: torch.Tensor, B: int, k: int, merged: torch.Tensor):
+        dev = gathered.device
+        merge_topk_packed_dev(dev.index or 0, gathered.data_ptr(), self.world, B, k, merged.data_ptr(),
+                              _stream_handle(dev))
 
     def search(self, q: torch.Tensor, k: int, metric: str = "cosine"):
         """q: (B, d) float64 on this rank's device (identical on every rank).
         Returns (ids (B,k) int64 global rows, dists (B,k) float64, counts (B,) int32, flags (B,))."""
-        ids, dists, counts, flags = self._local_search(q, k, metric)
+        B = q.shape[0]
+        local, gathered, merged = self._buffers(B, k, q.device)
+        if self._local_search is not None:      # injected (CPU tests): tensors in, packed here
+            ids, dists, counts, flags = self._local_search(q, k, metric)
+            v = blob_views(local, B, k)
+            v[0].copy_(ids); v[1].copy_(dists); v[2].copy_(counts); v[3].copy_(flags)
+        else:
+            self._cuda_local_search(q, k, metric, local)
         if self.world == 1:
-            return ids, dists, counts, flags
-        g_ids = gather_layout(ids, self.world, self.group)
-        g_d = gather_layout(dists, self.world, self.group)
-        g_c = gather_layout(counts, self.world, self.group)
-        g_f = gather_layout(flags, self.world, self.group)
-        out_ids, out_d, out_c = self._merge(g_ids, g_d, g_c, k)
-        return out_ids, out_d, out_c, g_f.amax(dim=0)
+            return blob_views(local, B, k)
+        gather_blobs(local, self.world, self.group, out=gathered)
+        if self._merge is not None:             # injected (CPU tests)
+            g = [blob_views(gathered[r], B, k) for r in range(self.world)]
+            out_ids, out_d, out_c = self._merge(torch.stack([x[0] for x in g]), torch.stack([x[1] for x in g]),
+                                                torch.stack([x[2] for x in g]), k)
+            return out_ids, out_d, out_c, torch.stack([x[3] for x in g]).amax(dim=0)
+        self._cuda_merge(gathered, B, k, merged)
+        return blob_views(merged, B, k)
 
     def close(self):
         if self._dev is not None:

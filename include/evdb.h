@@ -173,6 +173,13 @@ int evdb_merge_topk_dev(int device, const void *d_ids_u64, const void *d_dists_f
                         const void *d_counts_i32, int G, int B, int k, void *d_out_ids_u64,
                         void *d_out_dists_f64, void *d_out_counts_i32, void *stream);
 
+/* Same merge over PACKED per-rank results, the layout of the one-collective exchange: each
+ * rank's blob is 2*B*k + B 64-bit words = [B*k ids u64][B*k dists fp64][B counts i32][B flags i32];
+ * d_blobs holds G of them back to back (the allgather output), d_out_blob receives one blob
+ * (flags OR-ed over the ranks).  evdb_store_search_dev can write straight into a blob.        */
+int evdb_merge_topk_packed_dev(int device, const void *d_blobs, int G, int B, int k,
+                               void *d_out_blob, void *stream);
+
 /* ---- codecs (vector_compression.erl:166-204), computed on the device ------
  * n rows of d fp64 -> codes (+ per-row fp64 min/max/scale).  ok[i] = 0 for a
  * row whose Max == Min (reference: badarith, caller stores it raw).          */

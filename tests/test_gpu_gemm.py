@@ -182,3 +182,21 @@ def test_gemm_large_k_window(native, oracle):
         r, dd = oracle.search(rows, qs[b], k, "cosine")
         assert gs[b].tolist() == r.tolist() and gd[b].tolist() == dd.tolist()
     st.close()
+
+
+def test_large_batch_with_a_non_finite_query_is_rejected(native, oracle):
+    """Batches are validated on the host while the device already works on them; a NaN/Inf anywhere
+    must still come back as invalid_vector_format, and the store must stay usable."""
+    n, d, B = 30_000, 256, 300
+    st = _mk(native, n, d, seed=oracle.SEED_CORPUS)
+    qs = oracle.synth_f64(oracle.SEED_QUERY, 0, B, d)
+    bad = qs.copy()
+    bad[211, 17] = np.nan
+    assert st.search(bad, 10, "cosine") == native.E_BAD_VECTOR
+    bad[211, 17] = np.inf
+    assert st.search(bad, 10, "euclidean") == native.E_BAD_VECTOR
+    gs, gd, gc = st.search(qs, 10, "cosine")
+    rows = oracle.synth_f64(oracle.SEED_CORPUS, 0, n, d)
+    r, dd = oracle.search(rows, qs[211], 10, "cosine")
+    assert gs[211].tolist() == r.tolist() and gd[211].tolist() == dd.tolist()
+    st.close()

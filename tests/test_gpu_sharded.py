@@ -1,0 +1,54 @@
+"""Row-sharded search on ONE GPU: G shards as G store handles, each writing its result into a packed
+blob (evdb_store_search_dev), blobs laid out as the NCCL allgather would leave them, merged by
+evdb_merge_topk_packed_dev.  Must equal the single-store result bit for bit (ids and fp64 distances);
+the cross-process exchange itself is covered on CPU by tests/test_sharded_gloo.py."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dtype,metric,n,d,B,k,G", [
+    ("f32", "cosine", 40_000, 96, 3, 10, 4),       # scan plan per shard
+    ("f32", "cosine", 90_000, 128, 160, 10, 3),    # tcgen05 GEMM plan per shard, ragged shard sizes
+    ("f32", "euclidean", 60_000, 64, 64, 100, 2),  # euclidean GEMM plan, k = 100
+    ("u8", "cosine", 50_000, 96, 2, 10, 8),        # BASELINE configs[3] shape scaled down: int8 scan, 8 shards
+    ("f32", "cosine", 5, 16, 2, 10, 4),            # more shards than rows per shard: empty shards, k > N
+])
+def test_sharded_equals_single_store(native, oracle, dtype, metric, n, d, B, k, G):
+    import torch
+    from erlvectordb_b200.device_store import DeviceStore, merge_topk_packed_dev
+    from erlvectordb_b200.sharded import blob_views, blob_words, shard_bounds
+
+    dev = torch.device("cuda", 0)
+    q = torch.from_numpy(oracle.synth_f64(oracle.SEED_QUERY, 0, B, d)).to(dev)
+    w = blob_words(B, k)
+    gathered = torch.zeros((G, w), dtype=torch.int64, device=dev)
+    stores = []
+    for g in range(G):
+        lo, hi = shard_bounds(n, G, g)
+        if hi == lo:
+            continue
+        st = DeviceStore(dtype=dtype, device=0)
+        st.fill_synthetic(oracle.SEED_CORPUS, hi - lo, d, row0=lo)
+        ids, dists, counts, flags = blob_views(gathered[g], B, k)
+        st.search_dev(q.data_ptr(), B, d, k, metric, lo, ids.data_ptr(), dists.data_ptr(), counts.data_ptr(),
+                      flags.data_ptr(), 1)
+        stores.append(st)
+    merged = torch.zeros((w,), dtype=torch.int64, device=dev)
+    merge_topk_packed_dev(0, gathered.data_ptr(), G, B, k, merged.data_ptr(), 1)
+    torch.cuda.synchronize()
+    m_ids, m_d, m_c, m_f = [t.cpu().numpy() for t in blob_views(merged, B, k)]
+    assert int(m_f.sum()) == 0
+
+    one = DeviceStore(dtype=dtype, device=0)
+    one.fill_synthetic(oracle.SEED_CORPUS, n, d)
+    s_ids, s_d, s_c = one.search(q.cpu().numpy(), k, metric)
+    for b in range(B):
+        c = int(s_c[b])
+        assert int(m_c[b]) == c == min(k, n)
+        assert m_ids[b, :c].tolist() == s_ids[b, :c].tolist()
+        assert m_d[b, :c].tolist() == s_d[b, :c].tolist()
+    for st in stores:
+        st.close()
+    one.close()
