@@ -49,19 +49,29 @@ constexpr int GM = 128;        // queries per CTA tile (UMMA M)
 constexpr int GN = 256;        // corpus rows per tile (UMMA N)
 constexpr int GK = 64;         // K elements per stage (64 fp16 = one 128-byte swizzle row)
 constexpr int GUK = 16;        // UMMA K
-constexpr int kGemmStages = 4;
 constexpr int kEpiWarps = 16;       // tcgen05.ld is latency-bound per warp (tools/micro/ldtm_bench.cu): 4 warps per lane quarter
 constexpr int kEpiParts = kEpiWarps / 4;   // column parts of a tile, one candidate list each
 constexpr int kGemmThreads = 128 + 32 * kEpiWarps;   // 4 control warps + the epilogue warps
-constexpr uint32_t kStageABytes = GM * GK * 2;   // 16 KB
-constexpr uint32_t kStageBBytes = GN * GK * 2;   // 32 KB
-constexpr uint32_t kStageBytes = kStageABytes + kStageBBytes;
+constexpr uint32_t kStageABytes = GM * GK * 2;   // 16 KB: the CTA's 128 queries x 64 K
+constexpr uint32_t kTailABytes = GM * GUK * 2;   // 4 KB: the norm K-step of the euclidean plan (Q side)
+// PAIR = two CTAs of a cluster (an SM pair) run ONE tcgen05.mma.cta_group::2 of M = 256: each CTA
+// brings its own 128-query block and HALF of the 256-row corpus tile, so a stage is 32 KB instead
+// of 48 KB (a third less L2 -> shared-memory traffic per flop) and six stages fit instead of four.
+template <bool PAIR>
+struct GemmCfg {
+    static constexpr int kStages = PAIR ? 6 : 4;
+    static constexpr uint32_t kBRows = PAIR ? GN / 2 : GN;           // corpus rows this CTA loads per tile
+    static constexpr uint32_t kStageBBytes = kBRows * GK * 2;
+    static constexpr uint32_t kStageBytes = kStageABytes + kStageBBytes;
+    static constexpr uint32_t kTailBBytes = kBRows * GUK * 2;
+    static constexpr uint32_t kTailBytes = kTailABytes + kTailBBytes;
+    static constexpr int kBars = 2 * kStages + 8;                    // full[S] empty[S] tfull[2] tempty[2] nfull[2] nempty[2]
+    static constexpr size_t kSmem = 1024 + (size_t)kStages * kStageBytes + 2 * kTailBytes + kBars * 8 + 16;
+};
 constexpr int kGemmMaxKP = 128;
 constexpr int kCandCapMax = 256;    // candidate buffer entries per (query, CTA, column part): 128 for KP <= 32, else 256
 constexpr int kMaxSweeps = 8;       // query-block sweeps per launch (bounds the candidate buffers)
-constexpr uint32_t kTailABytes = GM * GUK * 2;   // 4 KB: the norm K-step of the euclidean plan (Q side)
-constexpr uint32_t kTailBBytes = GN * GUK * 2;   // 8 KB (V side)
-constexpr uint32_t kTailBytes = kTailABytes + kTailBBytes;
+
 
 struct GemmArgs {
     uint64_t n;          // corpus rows
@@ -146,6 +156,43 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
         : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- CTA-pair (cta_group::2) variants -----------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// shared::cluster address of the same shared-memory object in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load into THIS CTA's shared memory, completion signalled on a barrier that may live in the peer
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *tm, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(tm), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
 
 // K-major operand tile in shared memory, 128-byte swizzle: rows of 128 bytes, 8-row groups
 // 1024 bytes apart (SBO), descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.
@@ -287,6 +334,7 @@ __device__ __forceinline__ float epi_chunk(const uint32_t (&v)[32], const float 
 }
 
 // ---- the kernel ---------------------------------------------------------------------------
+template <bool PAIR>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmV,
                  const __grid_constant__ CUtensorMap tmQt, const __grid_constant__ CUtensorMap tmVt,
@@ -294,10 +342,16 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // dynamic smem is only guaranteed 16-byte aligned: realign to 1024 for the 128B swizzle
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    using Cfg = GemmCfg<PAIR>;
+    constexpr int kGemmStages = Cfg::kStages;
+    constexpr uint32_t kStageBytes = Cfg::kStageBytes, kTailBytes = Cfg::kTailBytes;
     uint8_t *stage_base = smem;                                            // [stages][A|B]
     uint8_t *tail_base = smem + kGemmStages * kStageBytes;                 // [2][A tail | B tail]
     uint64_t *bars = reinterpret_cast<uint64_t *>(tail_base + 2 * kTailBytes);  // full[S] empty[S] tfull[2] tempty[2] nfull[2] nempty[2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kGemmStages + 8);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + Cfg::kBars);
+    // PAIR: rank 0 of the cluster issues the MMAs; its full/tempty/nfull barriers collect both CTAs
+    const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = crank == 0;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int KP = a.KP;
@@ -312,18 +366,24 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(tfull0 + 8 * i, 1);
-            mbar_init(tempty0 + 8 * i, kEpiWarps);  // one arrive per epilogue warp
+            mbar_init(tempty0 + 8 * i, PAIR ? 2 * kEpiWarps : kEpiWarps);  // one arrive per epilogue warp (of both CTAs)
             mbar_init(nfull0 + 8 * i, 1);
             mbar_init(nempty0 + 8 * i, 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -346,26 +406,41 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     for (int kb = 0; kb < a.kblocks; ++kb) {
                         mbar_wait(empty0 + 8 * stage, phase ^ 1);
                         const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
-                        mbar_arrive_expect_tx(full0 + 8 * stage, kStageBytes);
-                        tma_load_2d(sa, &tmQ, full0 + 8 * stage, kb * GK, qrow);
-                        tma_load_2d(sa + kStageABytes, &tmV, full0 + 8 * stage, kb * GK, vrow);
+                        if (PAIR) {
+                            // both CTAs' tiles complete on the LEADER's barrier; it alone posts the byte count
+                            const uint32_t fb = mapa_u32(full0 + 8 * stage, 0);
+                            if (leader) mbar_arrive_expect_tx(full0 + 8 * stage, 2 * kStageBytes);
+                            tma_load_2d_pair(sa, &tmQ, fb, kb * GK, qrow);
+                            tma_load_2d_pair(sa + kStageABytes, &tmV, fb, kb * GK, vrow + (int)(crank * Cfg::kBRows));
+                        } else {
+                            mbar_arrive_expect_tx(full0 + 8 * stage, kStageBytes);
+                            tma_load_2d(sa, &tmQ, full0 + 8 * stage, kb * GK, qrow);
+                            tma_load_2d(sa + kStageABytes, &tmV, full0 + 8 * stage, kb * GK, vrow);
+                        }
                         if (++stage == kGemmStages) { stage = 0; phase ^= 1; }
                     }
                     if (a.tail) {  // the norm K-step: [128 x 16] ones-pattern and [256 x 16] split row norms
                         mbar_wait(nempty0 + 8 * ts, tphase ^ 1);
                         const uint32_t sa = smem_u32(tail_base + ts * kTailBytes);
-                        mbar_arrive_expect_tx(nfull0 + 8 * ts, kTailBytes);
-                        tma_load_2d(sa, &tmQt, nfull0 + 8 * ts, 0, qrow);
-                        tma_load_2d(sa + kTailABytes, &tmVt, nfull0 + 8 * ts, 0, vrow);
+                        if (PAIR) {
+                            const uint32_t fb = mapa_u32(nfull0 + 8 * ts, 0);
+                            if (leader) mbar_arrive_expect_tx(nfull0 + 8 * ts, 2 * kTailBytes);
+                            tma_load_2d_pair(sa, &tmQt, fb, 0, qrow);
+                            tma_load_2d_pair(sa + kTailABytes, &tmVt, fb, 0, vrow + (int)(crank * Cfg::kBRows));
+                        } else {
+                            mbar_arrive_expect_tx(nfull0 + 8 * ts, kTailBytes);
+                            tma_load_2d(sa, &tmQt, nfull0 + 8 * ts, 0, qrow);
+                            tma_load_2d(sa + kTailABytes, &tmVt, nfull0 + 8 * ts, 0, vrow);
+                        }
                         if (++ts == 2) { ts = 0; tphase ^= 1; }
                     }
                 }
             }
         }
     } else if (active && warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16(GM, GN);
+        // ===== MMA issuer (PAIR: the leader CTA only, for both) =====
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc = make_idesc_f16(PAIR ? 2 * GM : GM, GN);
             int stage = 0, ts = 0;
             uint32_t phase = 0, tphase = 0;
             int acc = 0;
@@ -385,22 +460,32 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
                         for (int k = 0; k < GK / GUK; ++k) {
                             // advance 16 fp16 = 32 bytes along K inside the swizzled row: +2 in >>4 units
-                            if (k < ksteps)
-                                umma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                         (uint32_t)((kb | k) != 0));
+                            if (k < ksteps) {
+                                if (PAIR) umma_f16_pair(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                                        (uint32_t)((kb | k) != 0));
+                                else umma_f16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                              (uint32_t)((kb | k) != 0));
+                            }
                         }
-                        umma_commit(empty0 + 8 * stage);  // stage reusable once these MMAs retire
+                        // stage reusable (in both CTAs) once these MMAs retire
+                        if (PAIR) umma_commit_pair(empty0 + 8 * stage); else umma_commit(empty0 + 8 * stage);
                         if (++stage == kGemmStages) { stage = 0; phase ^= 1; }
                     }
                     if (a.tail) {
                         mbar_wait(nfull0 + 8 * ts, tphase);
                         tc_fence_after();
                         const uint32_t sa = smem_u32(tail_base + ts * kTailBytes);
-                        umma_f16(tmem_d, make_sw32_kmajor_desc(sa), make_sw32_kmajor_desc(sa + kTailABytes), idesc, 1u);
-                        umma_commit(nempty0 + 8 * ts);
+                        if (PAIR) {
+                            umma_f16_pair(tmem_d, make_sw32_kmajor_desc(sa), make_sw32_kmajor_desc(sa + kTailABytes), idesc, 1u);
+                            umma_commit_pair(nempty0 + 8 * ts);
+                        } else {
+                            umma_f16(tmem_d, make_sw32_kmajor_desc(sa), make_sw32_kmajor_desc(sa + kTailABytes), idesc, 1u);
+                            umma_commit(nempty0 + 8 * ts);
+                        }
                         if (++ts == 2) { ts = 0; tphase ^= 1; }
                     }
-                    umma_commit(tfull0 + 8 * acc);        // accumulator complete
+                    // accumulator complete (each CTA's epilogue drains its own 128 TMEM lanes)
+                    if (PAIR) umma_commit_pair(tfull0 + 8 * acc); else umma_commit(tfull0 + 8 * acc);
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
             }
@@ -465,7 +550,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 if (a.debug & 8) t_chunk += clock64() - tw1;
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+                if (lane == 0) {
+                    if (PAIR) mbar_arrive_cluster(mapa_u32(tempty0 + 8 * acc, 0));  // the leader's issuer waits for both CTAs
+                    else mbar_arrive(tempty0 + 8 * acc);
+                }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
             if (a.mode == 0) a.cand_cnt[lbase * GM + et] = cnt;
@@ -478,9 +566,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();  // neither CTA leaves (or frees TMEM) while the pair's MMAs can touch it
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
 
@@ -685,8 +775,33 @@ static int make_map(CUtensorMap *tm, const void *base, uint64_t rows, uint64_t c
     return r == CUDA_SUCCESS ? EVDB_OK : EVDB_E_CUDA;
 }
 
-static size_t gemm_smem_bytes() {
-    return 1024 + (size_t)kGemmStages * kStageBytes + 2 * kTailBytes + (2 * kGemmStages + 8) * 8 + 16;
+// One launch of the GEMM kernel: plain for a lone query block, as 2-CTA clusters otherwise.
+static int launch_gemm_kernel(bool pair, int grid, cudaStream_t st, const CUtensorMap &tmQ, const CUtensorMap &tmV,
+                              const CUtensorMap &tmQt, const CUtensorMap &tmVt, const GemmArgs &a) {
+    if (!pair) {
+        const size_t smem = GemmCfg<false>::kSmem;
+        EVDB_CUDA(cudaFuncSetAttribute((const void *)gemm_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gemm_topk_kernel<false><<<grid, kGemmThreads, smem, st>>>(tmQ, tmV, tmQt, tmVt, a);
+        EVDB_CUDA(cudaGetLastError());
+        return EVDB_OK;
+    }
+    const size_t smem = GemmCfg<true>::kSmem;
+    EVDB_CUDA(cudaFuncSetAttribute((const void *)gemm_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    EVDB_CUDA(cudaLaunchKernelEx(&cfg, gemm_topk_kernel<true>, tmQ, tmV, tmQt, tmVt, a));
+    return EVDB_OK;
 }
 
 bool gemm_plan_supported(evdb_store *s, int metric, int B, int KP) {
@@ -793,6 +908,12 @@ int launch_gemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int metr
     if (NG > nt) NG = nt;
     const int nCTA = MB * NG;
     const int cap = KP <= 32 ? 128 : kCandCapMax;
+    // >= 2 concurrent query blocks: CTAs (2p, 2p+1) share a row group and run as one cta_group::2 pair
+    // Measured on B200 (tools/sweep.py, r01): +1 % at d = 768, where the MMA pipe is the limit, but -17 % at
+    // d = 128, where the TMEM drain is and the issuer has to wait for the slower of two epilogues.
+    bool pair = MB >= 2 && kcols >= 512;
+    { const char *e = getenv("EVDB_GEMM_PAIR"); if (e) pair = MB >= 2 && atoi(e) != 0; }
+    const uint32_t vbox = pair ? GN / 2 : GN;
 
     // workspace: [Qh][Q tail][qc0][eps_q][thr0][cand_cnt][cand]
     const size_t qh_bytes = round_up64((size_t)Bpad * kpitch * sizeof(__half), 256);
@@ -815,10 +936,10 @@ int launch_gemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int metr
     EVDB_CUDA(cudaGetLastError());
     CUtensorMap tmQ, tmV, tmQt, tmVt;
     EVDB_TRY(make_map(&tmQ, qh, (uint64_t)Bpad, (uint64_t)kpitch, (uint64_t)kpitch, GM));
-    EVDB_TRY(make_map(&tmV, vcol, s->count, (uint64_t)kpitch, (uint64_t)kpitch, GN));
+    EVDB_TRY(make_map(&tmV, vcol, s->count, (uint64_t)kpitch, (uint64_t)kpitch, vbox));
     if (l2) {
         EVDB_TRY(make_map(&tmQt, qtail, (uint64_t)Bpad, GUK, GUK, GM, true));
-        EVDB_TRY(make_map(&tmVt, s->l2_tail, s->count, GUK, GUK, GN, true));
+        EVDB_TRY(make_map(&tmVt, s->l2_tail, s->count, GUK, GUK, vbox, true));
     } else {
         tmQt = tmQ;  // never dereferenced
         tmVt = tmV;
@@ -837,8 +958,6 @@ int launch_gemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int metr
     a.cand_cnt = cand_cnt;
     a.qc0 = qc0;
     a.c1 = l2 ? -2.0f / (sigma * sigma) : -1.0f;
-    const size_t smem = gemm_smem_bytes();
-    EVDB_CUDA(cudaFuncSetAttribute((const void *)gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     // ---- sampled pre-pass: seed every query's admission threshold ----
     // S strided sample rows (a TMA map with a multiplied row stride), the best key score of every
@@ -857,12 +976,11 @@ int launch_gemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int metr
         EVDB_TRY(ensure_bytes((void **)&s->w_seed, &s->w_seed_cap, (size_t)Bpad * pooled * sizeof(float)));
         float *dump = (float *)s->w_seed;
         CUtensorMap tmVs, tmVts = tmVt;
-        EVDB_TRY(make_map(&tmVs, vcol, S, (uint64_t)kpitch, (uint64_t)kpitch * step, GN));
-        if (l2) EVDB_TRY(make_map(&tmVts, s->l2_tail, S, GUK, (uint64_t)GUK * step, GN, true));
+        EVDB_TRY(make_map(&tmVs, vcol, S, (uint64_t)kpitch, (uint64_t)kpitch * step, vbox));
+        if (l2) EVDB_TRY(make_map(&tmVts, s->l2_tail, S, GUK, (uint64_t)GUK * step, vbox, true));
         GemmArgs p = a;
         p.n = S; p.nt = snt; p.NG = sNG; p.mode = 1; p.dump = dump; p.dump_ld = pooled;
-        gemm_topk_kernel<<<MB * sNG, kGemmThreads, smem, st>>>(tmQ, tmVs, tmQt, tmVts, p);
-        EVDB_CUDA(cudaGetLastError());
+        EVDB_TRY(launch_gemm_kernel(pair, MB * sNG, st, tmQ, tmVs, tmQt, tmVts, p));
         const int vpt = (pooled + kSeedThreads - 1) / kSeedThreads;
         if (vpt <= 4) seed_threshold_kernel<4><<<Bpad, kSeedThreads, 0, st>>>(dump, pooled, pooled, KP, thr);
         else if (vpt <= 8) seed_threshold_kernel<8><<<Bpad, kSeedThreads, 0, st>>>(dump, pooled, pooled, KP, thr);
@@ -884,9 +1002,8 @@ int launch_gemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int metr
         a.dbg = g_dbg;
     }
     prof_begin(s, st);
-    gemm_topk_kernel<<<nCTA, kGemmThreads, smem, st>>>(tmQ, tmV, tmQt, tmVt, a);
+    EVDB_TRY(launch_gemm_kernel(pair, nCTA, st, tmQ, tmV, tmQt, tmVt, a));
     prof_end(s, st);
-    EVDB_CUDA(cudaGetLastError());
     if (a.debug & 8) {
         cudaStreamSynchronize(st);
         static unsigned long long h[148 * kEpiWarps * 8];

@@ -39,6 +39,7 @@ struct SelectArgs {
     float eps_abs, eps_rel;
     const float *eps_q;  // optional [B]: per-query absolute bound (GEMM plans)
     int squared;         // key scores are squared distances (euclidean GEMM plan)
+    int variant;         // tuning: bit 0 = L1 prefetch pre-pass, bit 1 = pipelined fold, bit 2 = L2 prefetch instead
     uint64_t slot_base;
     uint64_t *out_ids;
     double *out_dists;
@@ -118,6 +119,10 @@ __device__ void block_select_smallest(uint64_t *buf, int n, int need, uint64_t *
     __syncthreads();
 }
 
+// EVDB_SEL_VARIANT bit 4 (tuning aid): cycles per phase, summed over CTAs
+__device__ unsigned long long g_sel_dbg[8];
+#define SEL_MARK(i) do { if ((a.variant & 16) && threadIdx.x == 0) { long long _t = clock64(); atomicAdd(&g_sel_dbg[i], (unsigned long long)(_t - t_mark)); t_mark = _t; } } while (0)
+
 // THREADS = 1024 for a lone query (latency), 256 for batches (more CTAs per SM, cheaper barriers).
 template <int DTYPE, int THREADS>
 __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
@@ -134,6 +139,7 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
     const int KP = a.KP;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float eps_abs = a.eps_abs + (a.eps_q ? a.eps_q[b] : 0.f);
+    long long t_mark = clock64();
 
     if (a.raw.cand) {
         // ---- 1a. GEMM plan: gather this query's unsorted candidate buffers, keep the KP best ----
@@ -165,6 +171,7 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
             }
         }
         __syncthreads();
+        SEL_MARK(0);
         int carried = 0, l0 = 0;
         while (l0 < L) {
             // as many whole buffers as fit next to the carried keys (a buffer holds <= 256 keys)
@@ -182,6 +189,7 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
             }
             const int filled = carried + s_off[l1] - s_off[l0];
             __syncthreads();
+            SEL_MARK(1);
             if (filled > KP) {
                 block_select_smallest(buf, filled, KP, dkey);
                 carried = KP;
@@ -189,6 +197,7 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
                 carried = filled;
             }
             l0 = l1;
+            SEL_MARK(2);
         }
         for (int i = carried + threadIdx.x; i < KP; i += blockDim.x) buf[i] = kKeyMax;
         __syncthreads();
@@ -255,6 +264,7 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
     }
     }
     // ---- count valid candidates (keys are ascending; kKeyMax pads) ----
+    SEL_MARK(3);
     if (threadIdx.x == 0) s_ncand = 0;
     __syncthreads();
     for (int i = threadIdx.x; i < KP; i += blockDim.x)
@@ -282,6 +292,8 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
     }
     __syncthreads();
     const int nrer = s_nrer;
+    SEL_MARK(4);
+    if ((a.variant & 16) && threadIdx.x == 0) atomicAdd(&g_sel_dbg[7], (unsigned long long)nrer);
     int nsort = 2;
     while (nsort < nrer) nsort <<= 1;
     const double *q = a.q64 + (size_t)b * a.d;
@@ -313,11 +325,30 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
         // Batches: the fold of one row is a strictly sequential fp64 chain (reference order), so candidates
         // are spread one per lane: cpw per warp, plus -- for cosine -- lane 31 of every working
         // warp folding the query's own squares.
+        // Pull the candidate rows (and the query) towards L1 first, with every thread of the CTA:
+        // each fold lane walks its row alone, and a DRAM miss per step would dominate the chain.
+        if (a.variant & 5) {
+            const int used = DTYPE == EVDB_F32 ? a.d * 4 : DTYPE == EVDB_BF16 ? a.d * 2 : DTYPE == EVDB_U8 ? a.d : (a.d + 1) / 2;
+            const int lines = (used + 127) >> 7;
+            for (int i = threadIdx.x; i < nrer * lines; i += blockDim.x) {
+                const int j = i / lines, l = i - j * lines;
+                const uint8_t *pp = a.rows + (size_t)key_slot(buf[j]) * a.row_bytes + (size_t)l * 128;
+                if (a.variant & 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
+                else prefetch_l1(pp);
+            }
+            const int qlines = (a.d * 8 + 127) >> 7;
+            for (int i = threadIdx.x; i < qlines; i += blockDim.x) prefetch_l1(reinterpret_cast<const uint8_t *>(q) + (size_t)i * 128);
+        }
         const bool cosine = a.metric == EVDB_COSINE;
         const int max_cpw = cosine ? 31 : 32;
-        int cpw = (nrer + kSelWarps - 1) / kSelWarps;
-        if (cpw < 4) cpw = 4;
-        if (cpw > max_cpw) cpw = max_cpw;
+        // as few warps as possible: the fp64 pipe issues per warp instruction whatever the number of
+        // active lanes, and the chain is no shorter with fewer rows per warp (EVDB_SEL_VARIANT bit 3: old split)
+        int cpw = max_cpw;
+        if (a.variant & 8) {
+            cpw = (nrer + kSelWarps - 1) / kSelWarps;
+            if (cpw < 4) cpw = 4;
+            if (cpw > max_cpw) cpw = max_cpw;
+        }
         for (int base = warp * cpw; base < nrer; base += kSelWarps * cpw) {
             const int j = base + lane;
             const bool mine = lane < cpw && j < nrer;
@@ -330,7 +361,8 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
                 mn = ms.x;
                 sc = ms.y;
             }
-            const double s = exact_fold_lane<DTYPE>(row, mn, sc, q, a.d, a.metric, qlane);
+            const double s = (a.variant & 2) ? exact_fold_lane<DTYPE>(row, mn, sc, q, a.d, a.metric, qlane)
+                                             : exact_fold_lane_simple<DTYPE>(row, mn, sc, q, a.d, a.metric, qlane);
             double dist;
             if (cosine) {
                 const double sq = __shfl_sync(0xffffffffu, s, 31);
@@ -354,6 +386,7 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
     __syncthreads();
 
     // ---- 3. final order by (exact distance, slot); emit k; completeness proof ----
+    SEL_MARK(5);
     block_bitonic_sort_pairs(dkey, dslot, nsort);
     for (int i = threadIdx.x; i < a.kstride; i += blockDim.x) {
         size_t o = (size_t)b * a.kstride + i;
@@ -384,6 +417,406 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
         if (kout == 0 && a.kk > 0 && a.n > 0) flag = 1;
         if (a.out_flags) a.out_flags[b] = flag;
     }
+    SEL_MARK(6);
+}
+
+// ============================================================================
+// Warp-per-query select for the GEMM plan's query batches: no block barriers anywhere.
+//   gather the query's candidate buffers into shared memory (passes of up to 2048 keys),
+//   keep the KP best by bisection with warp population counts, order them, then re-rank:
+//   the warp stages 128-element chunks of up to 32 candidate rows in shared memory with
+//   coalesced loads, and every lane folds ONE row from there in the reference's strict
+//   left-to-right fp64 order (lane 31 folds the query's own squares for cosine).
+// The key buffer and the row staging area share storage: they are never live together.
+// ============================================================================
+constexpr int kSwWarps = 8;        // queries per CTA: 8 consecutive queries' keys share 64 contiguous bytes of every buffer row
+constexpr int kSwKeys = 2048;      // keys per selection pass
+constexpr int kSwKC = 64;          // elements per staged row chunk
+constexpr int kSwMaxKP = 128;
+
+constexpr int kSwRows = 32;                               // staged product rows per round (candidates + the query's own squares): one per lane
+constexpr int kSwProdStride = kSwKC * 8 + 16;             // bytes between staged product rows (bank spread)
+struct SwLayout {
+    static constexpr int kUnion = (kSwRows * kSwProdStride > kSwKeys * 8) ? kSwRows * kSwProdStride : kSwKeys * 8;
+    static constexpr int kPerWarp = kUnion + kSwMaxKP * 8 * 3;  // + ckeys/dkey/dslot
+};
+
+// Exact f32 -> f64 widening with integer instructions (the fp64 pipe of this part issues one warp
+// instruction per ~16 cycles whatever the number of active lanes: conversions do not belong there).
+__device__ __forceinline__ double widen_f32(uint32_t u) {
+    const uint32_t e = (u >> 23) & 0xFFu;
+    if (e == 0u) {
+        if ((u << 1) == 0u) return __hiloint2double((int)(u & 0x80000000u), 0);  // +-0
+        return (double)__uint_as_float(u);                                        // subnormal: rare
+    }
+    const uint32_t hi = (u & 0x80000000u) | ((e + 896u) << 20) | ((u >> 3) & 0xFFFFFu);
+    return __hiloint2double((int)hi, (int)(u << 29));
+}
+
+// ascending bitonic sort of n (power of two) u64 keys in shared memory by one warp
+__device__ __forceinline__ void warp_bitonic_smem(uint64_t *k, int n, int lane) {
+    for (int k2 = 2; k2 <= n; k2 <<= 1)
+        for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+            for (int i = lane; i < n; i += 32) {
+                const int ixj = i ^ j2;
+                if (ixj > i) {
+                    const uint64_t x = k[i], y = k[ixj];
+                    if ((x > y) == ((i & k2) == 0)) { k[i] = y; k[ixj] = x; }
+                }
+            }
+            __syncwarp();
+        }
+}
+__device__ __forceinline__ void warp_bitonic_smem_pairs(uint64_t *k, uint64_t *v, int n, int lane) {
+    for (int k2 = 2; k2 <= n; k2 <<= 1)
+        for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+            for (int i = lane; i < n; i += 32) {
+                const int ixj = i ^ j2;
+                if (ixj > i) {
+                    const uint64_t x = k[i], y = k[ixj], vx = v[i], vy = v[ixj];
+                    const bool gt = x > y || (x == y && vx > vy);
+                    if (gt == ((i & k2) == 0)) { k[i] = y; k[ixj] = x; v[i] = vy; v[ixj] = vx; }
+                }
+            }
+            __syncwarp();
+        }
+}
+
+// keep the `need` smallest of keys[0, T) (need < T), compacted in place to keys[0, need)
+__device__ __forceinline__ void warp_select_inplace(uint64_t *keys, int T, int need, int lane) {
+    const uint32_t *hi32 = reinterpret_cast<const uint32_t *>(keys) + 1;  // score word of key i at hi32[2*i]
+    uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+    for (int i = lane; i < T; i += 32) {
+        const uint32_t sc = hi32[2 * i];
+        mn = min(mn, sc);
+        mx = max(mx, sc);
+    }
+    uint32_t lo = __reduce_min_sync(0xffffffffu, mn), hi = __reduce_max_sync(0xffffffffu, mx);
+    while (lo < hi) {  // invariant: count(score <= hi) >= need > count(score < lo)
+        const uint32_t span = hi - lo, qd = span >> 2;
+        const uint32_t p2 = lo + (span >> 1), p1 = qd ? lo + qd : p2, p3 = qd ? p2 + qd : p2;
+        int c1 = 0, c2 = 0, c3 = 0;
+        for (int i = lane; i < T; i += 32) {
+            const uint32_t sc = hi32[2 * i];
+            c1 += sc <= p1 ? 1 : 0;
+            c2 += sc <= p2 ? 1 : 0;
+            c3 += sc <= p3 ? 1 : 0;
+        }
+        c1 = __reduce_add_sync(0xffffffffu, c1);
+        c2 = __reduce_add_sync(0xffffffffu, c2);
+        c3 = __reduce_add_sync(0xffffffffu, c3);
+        if (c1 >= need) hi = p1;
+        else if (c2 >= need) { lo = p1 + 1; hi = p2; }
+        else if (c3 >= need) { lo = p2 + 1; hi = p3; }
+        else lo = p3 + 1;
+    }
+    int nl = 0;
+    for (int i = lane; i < T; i += 32) nl += hi32[2 * i] < lo ? 1 : 0;
+    int ties_left = need - __reduce_add_sync(0xffffffffu, nl);
+    // one in-order pass: everything below the cut, and ties at the cut while the budget lasts;
+    // the write cursor never passes the read cursor
+    int out = 0;
+    const unsigned below = (1u << lane) - 1u;
+    for (int base = 0; base < T; base += 32) {
+        const int i = base + lane;
+        const uint64_t key = i < T ? keys[i] : kKeyMax;
+        const uint32_t sc = (uint32_t)(key >> 32);
+        const bool tie = i < T && sc == lo;
+        const unsigned mt = __ballot_sync(0xffffffffu, tie);
+        const bool keep = i < T && (sc < lo || (tie && __popc(mt & below) < ties_left));
+        const unsigned mk = __ballot_sync(0xffffffffu, keep);
+        ties_left -= min(__popc(mt), max(ties_left, 0));
+        __syncwarp();
+        if (keep) keys[out + __popc(mk & below)] = key;
+        out += __popc(mk);
+        __syncwarp();
+    }
+}
+
+// F32 stores only (the GEMM plan's precondition).
+__global__ void __launch_bounds__(kSwWarps * 32) select_warp_kernel(const SelectArgs a, int B) {
+    using LY = SwLayout;
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b0 = blockIdx.x * kSwWarps;
+    const int b = b0 + warp;
+    uint8_t *wbase = smem + (size_t)warp * LY::kPerWarp;
+    // CTA-shared gather tables behind the per-warp regions
+    const int L = a.L;
+    uint16_t *s_cnt = reinterpret_cast<uint16_t *>(smem + (size_t)kSwWarps * LY::kPerWarp);  // [L][8] fill counts
+    int *s_off = reinterpret_cast<int *>(s_cnt + (size_t)(L + 1) * kSwWarps);                // [L+1][8] exclusive prefix of each query's counts
+    int *s_moff = s_off + (size_t)(L + 1) * kSwWarps;                                         // [L+1] prefix of max-over-queries counts
+    __shared__ int s_car[kSwWarps];
+    // ---- 1. gather: the CTA's 8 consecutive queries together ----
+    // The GEMM epilogue leaves thread t's i-th key of a buffer at [i][t]: 8 consecutive queries'
+    // keys are 64 contiguous bytes, so one pair of sectors serves all 8 warps (reading each query
+    // alone would use 8 of every 32 bytes fetched and open a DRAM page per key).
+    const RawCands &rw = a.raw;
+    const int blk = b0 / rw.gm, et0 = b0 % rw.gm;   // b0 is a multiple of 8, gm of 8: one block, one sweep
+    const int c = blk / rw.MB, mb_local = blk % rw.MB;
+    auto list_index = [&](int l) -> size_t {
+        const int ng = l / rw.parts, part = l % rw.parts;
+        return ((size_t)c * rw.nCTA + (size_t)ng * rw.MB + mb_local) * rw.parts + part;
+    };
+    for (int l = threadIdx.x; l < L; l += blockDim.x) {
+        const int4 *p = reinterpret_cast<const int4 *>(rw.cnt + list_index(l) * rw.gm + et0);
+        const int4 c0 = __ldcg(p), c1 = __ldcg(p + 1);
+        const int v[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        int mx = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const int n = b0 + w < B ? v[w] : 0;
+            s_cnt[l * 8 + w] = (uint16_t)n;
+            mx = n > mx ? n : mx;
+        }
+        s_moff[l + 1] = mx;
+    }
+    if (threadIdx.x == 0) s_moff[0] = 0;
+    __syncthreads();
+    {   // warp w: exclusive prefix of its query's counts; warp 0 also the prefix of the row maxima
+        int carry = 0;
+        for (int l0 = 0; l0 < L; l0 += 32) {
+            const int l = l0 + lane;
+            const int n = l < L ? (int)s_cnt[l * 8 + warp] : 0;
+            int incl = n;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += u;
+            }
+            if (l < L) s_off[l * 8 + warp] = carry + incl - n;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) { s_off[L * 8 + warp] = carry; s_car[warp] = 0; }
+        if (warp == 0) {
+            int mc = 0;
+            for (int l0 = 1; l0 <= L; l0 += 32) {
+                const int l = l0 + lane;
+                int incl = l <= L ? s_moff[l] : 0;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += u;
+                }
+                if (l <= L) s_moff[l] = mc + incl;
+                mc += __shfl_sync(0xffffffffu, incl, 31);
+            }
+        }
+    }
+    __syncthreads();
+    // Passes over ranges of buffers [l0, l1): as many whole buffers as fit next to every query's
+    // carried keys (a buffer holds <= 256 keys, the carry <= 128, a pass 2048: progress is certain).
+    uint64_t *keys = reinterpret_cast<uint64_t *>(wbase);              // selection passes
+    const int KP = a.KP;
+    int carried = 0, pos = 0;
+    for (int l0 = 0; l0 < L;) {
+        int lo = l0 + 1, hi = L;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            int worst = 0;
+#pragma unroll
+            for (int w = 0; w < kSwWarps; ++w) {
+                const int f = s_car[w] + s_off[mid * 8 + w] - s_off[l0 * 8 + w];
+                worst = f > worst ? f : worst;
+            }
+            if (worst <= kSwKeys) lo = mid; else hi = mid - 1;
+        }
+        const int l1 = lo;
+        // one work item = one buffer row (l, i): 64 bytes = the 8 queries' i-th keys of buffer l
+        for (int m = s_moff[l0] + threadIdx.x; m < s_moff[l1]; m += blockDim.x) {
+            int a0 = l0, a1 = l1 - 1;  // largest l with s_moff[l] <= m
+            while (a0 < a1) {
+                const int mid = (a0 + a1 + 1) >> 1;
+                if (s_moff[mid] <= m) a0 = mid; else a1 = mid - 1;
+            }
+            const int l = a0, i = m - s_moff[l];
+            const uint4 *src = reinterpret_cast<const uint4 *>(rw.cand + (list_index(l) * rw.cap + i) * rw.gm + et0);
+            const uint4 x0 = __ldcg(src), x1 = __ldcg(src + 1), x2 = __ldcg(src + 2), x3 = __ldcg(src + 3);
+            const uint64_t kk8[8] = {((uint64_t)x0.y << 32) | x0.x, ((uint64_t)x0.w << 32) | x0.z,
+                                     ((uint64_t)x1.y << 32) | x1.x, ((uint64_t)x1.w << 32) | x1.z,
+                                     ((uint64_t)x2.y << 32) | x2.x, ((uint64_t)x2.w << 32) | x2.z,
+                                     ((uint64_t)x3.y << 32) | x3.x, ((uint64_t)x3.w << 32) | x3.z};
+#pragma unroll
+            for (int w = 0; w < 8; ++w)
+                if (i < (int)s_cnt[l * 8 + w])
+                    reinterpret_cast<uint64_t *>(smem + (size_t)w * LY::kPerWarp)[s_car[w] + s_off[l * 8 + w] - s_off[l0 * 8 + w] + i] = kk8[w];
+        }
+        __syncthreads();
+        pos = carried + s_off[l1 * 8 + warp] - s_off[l0 * 8 + warp];
+        if (l1 < L) {  // more to come: reduce to the KP best so the next range fits
+            if (pos > KP) { warp_select_inplace(keys, pos, KP, lane); carried = KP; } else carried = pos;
+            __syncwarp();
+            if (lane == 0) s_car[warp] = carried;
+        }
+        __syncthreads();
+        l0 = l1;
+    }
+    if (b >= B) return;  // (after the last block barrier)
+    uint8_t *stage = wbase;                                            // ... later: staged fp64 product rows
+    uint64_t *ckeys = reinterpret_cast<uint64_t *>(wbase + LY::kUnion);  // [kSwMaxKP] the window, ascending
+    uint64_t *dkey = ckeys + kSwMaxKP, *dslot = dkey + kSwMaxKP;
+    const float eps_abs = a.eps_abs + (a.eps_q ? a.eps_q[b] : 0.f);
+    long long t_mark = clock64();
+#define SW_MARK(i) do { if ((a.variant & 16) && lane == 0) { long long _t = clock64(); atomicAdd(&g_sel_dbg[i], (unsigned long long)(_t - t_mark)); t_mark = _t; } } while (0)
+    __syncwarp();
+    SW_MARK(0);
+    if ((a.variant & 16) && lane == 0) atomicAdd(&g_sel_dbg[6], (unsigned long long)pos);
+    if (pos > KP) { warp_select_inplace(keys, pos, KP, lane); carried = KP; } else carried = pos;
+    SW_MARK(1);
+    int nk = 2;
+    while (nk < carried) nk <<= 1;
+    for (int i = carried + lane; i < nk; i += 32) keys[i] = kKeyMax;
+    __syncwarp();
+    warp_bitonic_smem(keys, nk, lane);
+    const int ncand = carried;
+    for (int i = lane; i < ncand; i += 32) ckeys[i] = keys[i];
+    __syncwarp();
+    const float bound = ncand > 0 ? key_score(ckeys[ncand - 1]) : 0.f;
+
+    // ---- 2. which candidates can still reach the top k (a prefix of the ascending window) ----
+    const int kout = a.kk < ncand ? a.kk : ncand;
+    int nrer = kout;
+    if (kout > 0) {
+        const float sk = key_score(ckeys[kout - 1]);
+        const float lim = sk + 2.0f * (eps_abs + a.eps_rel * fabsf(sk)) * 1.0001f;
+        int cntl = 0;
+        for (int i = kout + lane; i < ncand; i += 32) cntl += key_score(ckeys[i]) <= lim ? 1 : 0;
+        nrer = kout + __reduce_add_sync(0xffffffffu, cntl);
+    }
+
+    // ---- 3. exact distances: rows staged chunk by chunk, one lane folds one row ----
+    SW_MARK(2);
+    if ((a.variant & 16) && lane == 0) atomicAdd(&g_sel_dbg[7], (unsigned long long)nrer);
+    // The independent terms (q*v, (q-v)^2, |q-v|) are formed by all 32 lanes in parallel -- 32 useful
+    // fp64 multiplies per instruction -- and staged as fp64 in shared memory; then lane r folds row r
+    // strictly left to right.  For cosine one more staged row holds q*q (vector_norm(Query)).
+    const double *q = a.q64 + (size_t)b * a.d;
+    const bool cosine = a.metric == EVDB_COSINE;
+    const int RC = cosine ? kSwRows - 1 : kSwRows;   // candidates per round
+    for (int base = 0; base < nrer; base += RC) {
+        const int nr = nrer - base < RC ? nrer - base : RC;
+        const int nrows = nr + (cosine ? 1 : 0);
+        const bool mine = lane < nr;
+        const bool qlane = cosine && lane == nr;
+        const uint32_t slot = mine ? key_slot(ckeys[base + lane]) : 0u;
+        double s = 0.0;
+        for (int kb = 0; kb < a.d; kb += kSwKC) {
+            const int cnt = a.d - kb < kSwKC ? a.d - kb : kSwKC;
+            // a row chunk is 16 units of 4 elements: half a warp per row, two rows per step
+            const int unit = lane & 15, rsub = lane >> 4;
+            const int e0 = kb + 4 * unit;
+            double qd[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) qd[i] = e0 + i < a.d ? q[e0 + i] : 0.0;
+            __syncwarp();
+#pragma unroll 4
+            for (int r2 = 0; r2 < nrows; r2 += 2) {
+                const int r = r2 + rsub;
+                if (r >= nrows) continue;
+                double t[4];
+                if (r < nr) {
+                    uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+                    if ((size_t)e0 * 4 < a.row_bytes)
+                        raw = __ldg(reinterpret_cast<const uint4 *>(a.rows + (size_t)key_slot(ckeys[base + r]) * a.row_bytes) + (e0 >> 2));
+                    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const double x = widen_f32(w[i]);
+                        if (a.metric == EVDB_COSINE) t[i] = __dmul_rn(qd[i], x);
+                        else {
+                            const double df = __dsub_rn(qd[i], x);
+                            t[i] = a.metric == EVDB_EUCLIDEAN ? __dmul_rn(df, df) : fabs(df);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) t[i] = __dmul_rn(qd[i], qd[i]);
+                }
+                double2 *dst = reinterpret_cast<double2 *>(stage + (size_t)r * kSwProdStride) + 2 * unit;
+                dst[0] = make_double2(t[0], t[1]);
+                dst[1] = make_double2(t[2], t[3]);
+            }
+            __syncwarp();
+            if (mine || qlane) {
+                const double2 *p = reinterpret_cast<const double2 *>(stage + (size_t)lane * kSwProdStride);
+                const int pairs = cnt >> 1;
+#pragma unroll 4
+                for (int i = 0; i < pairs; ++i) {
+                    const double2 v = p[i];
+                    s = __dadd_rn(s, v.x);
+                    s = __dadd_rn(s, v.y);
+                }
+                if (cnt & 1) s = __dadd_rn(s, reinterpret_cast<const double *>(p)[cnt - 1]);
+            }
+        }
+        double dist;
+        if (cosine) {
+            const double sq = __shfl_sync(0xffffffffu, s, nr);
+            const double n1 = __dsqrt_rn(sq), n2 = mine ? a.norm64[slot] : 0.0;
+            dist = (n1 == 0.0 || n2 == 0.0) ? 1.0 : __dsub_rn(1.0, __ddiv_rn(s, __dmul_rn(n1, n2)));
+        } else if (a.metric == EVDB_EUCLIDEAN) {
+            dist = __dsqrt_rn(s);
+        } else {
+            dist = s;
+        }
+        if (mine) {
+            dkey[base + lane] = f64_orderable(dist);
+            dslot[base + lane] = slot;
+        }
+    }
+    int nsort = 2;
+    while (nsort < nrer) nsort <<= 1;
+    for (int j = nrer + lane; j < nsort; j += 32) { dkey[j] = kKeyMax; dslot[j] = kKeyMax; }
+    __syncwarp();
+    SW_MARK(3);
+
+    // ---- 4. final order by (exact distance, slot); emit k; completeness proof ----
+    warp_bitonic_smem_pairs(dkey, dslot, nsort, lane);
+    for (int i = lane; i < a.kstride; i += 32) {
+        const size_t o = (size_t)b * a.kstride + i;
+        if (i < kout) {
+            const uint64_t ob = dkey[i];
+            const uint64_t bits = ob ^ ((ob >> 63) ? 0x8000000000000000ull : 0xFFFFFFFFFFFFFFFFull);
+            a.out_dists[o] = __longlong_as_double((long long)bits);
+            a.out_ids[o] = a.slot_base + dslot[i];
+        } else {
+            a.out_dists[o] = 0.0;
+            a.out_ids[o] = kKeyMax;
+        }
+    }
+    if (lane == 0) {
+        a.out_counts[b] = kout;
+        int flag = 0;
+        if (kout > 0 && (uint64_t)ncand < a.n) {  // rows exist outside the window
+            const uint64_t ob = dkey[kout - 1];
+            const uint64_t bits = ob ^ ((ob >> 63) ? 0x8000000000000000ull : 0xFFFFFFFFFFFFFFFFull);
+            double dk = __longlong_as_double((long long)bits);
+            const double lim = (double)bound - (double)eps_abs - (double)a.eps_rel * fabs((double)bound);
+            if (a.squared) dk = __dmul_rn(__dmul_rn(dk, dk), 1.0 + 1e-15);
+            flag = !(dk < lim);
+            if ((uint64_t)a.kk <= a.n ? ncand < a.kk : false) flag = 1;
+        }
+        if (kout == 0 && a.kk > 0 && a.n > 0) flag = 1;
+        if (a.out_flags) a.out_flags[b] = flag;
+    }
+    SW_MARK(4);
+}
+
+static int launch_select_warp(const SelectArgs &a, int B, cudaStream_t st) {
+    const size_t smem = (size_t)kSwWarps * SwLayout::kPerWarp + (size_t)(a.L + 1) * kSwWarps * 6 + (size_t)(a.L + 1) * 4 + 16;
+    if (smem > 220 * 1024) return EVDB_E_UNSUPPORTED;
+    EVDB_CUDA(cudaFuncSetAttribute((const void *)select_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    select_warp_kernel<<<(B + kSwWarps - 1) / kSwWarps, kSwWarps * 32, smem, st>>>(a, B);
+    EVDB_CUDA(cudaGetLastError());
+    if (a.variant & 16) {
+        cudaStreamSynchronize(st);
+        unsigned long long h[8], z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        cudaMemcpyFromSymbol(h, g_sel_dbg, sizeof(h));
+        cudaMemcpyToSymbol(g_sel_dbg, z, sizeof(z));
+        fprintf(stderr, "[select-warp dbg] cycles/query: gather(slow path)=%.0f select=%.0f sort+window=%.0f fold=%.0f final=%.0f  keys=%.0f nrer=%.1f\n",
+                (double)h[0] / B, (double)h[1] / B, (double)h[2] / B, (double)h[3] / B, (double)h[4] / B, (double)h[6] / B, (double)h[7] / B);
+    }
+    return EVDB_OK;
 }
 
 static size_t select_smem(int threads) {
@@ -405,8 +838,13 @@ int launch_select(evdb_store *s, const double *d_q64, const uint64_t *partial, c
     }
     a.kk = kk; a.kstride = kstride; a.metric = metric; a.eps_abs = eps_abs; a.eps_rel = eps_rel;
     a.eps_q = eps_q; a.squared = squared;
+    { static int v = -1; if (v < 0) { const char *e = getenv("EVDB_SEL_VARIANT"); v = e ? atoi(e) : 0; } a.variant = v; }
     a.slot_base = slot_base; a.out_ids = d_out_ids; a.out_dists = d_out_dists;
     a.out_counts = d_out_counts; a.out_flags = d_out_flags;
+    if (raw && B >= 8 && KP <= kSwMaxKP && s->dtype == EVDB_F32 && !(a.variant & 32)) {  // GEMM plan, query batch
+        s->n_launches++;
+        return launch_select_warp(a, B, st);
+    }
     const int threads = B >= 8 ? 256 : 1024;
     size_t smem = select_smem(threads);
     void (*fn)(const SelectArgs) = nullptr;
@@ -422,6 +860,15 @@ int launch_select(evdb_store *s, const double *d_q64, const uint64_t *partial, c
     fn<<<B, threads, smem, st>>>(a);
     s->n_launches++;
     EVDB_CUDA(cudaGetLastError());
+    if (a.variant & 16) {
+        cudaStreamSynchronize(st);
+        unsigned long long h[8], z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        cudaMemcpyFromSymbol(h, g_sel_dbg, sizeof(h));
+        cudaMemcpyToSymbol(g_sel_dbg, z, sizeof(z));
+        fprintf(stderr, "[select dbg] cycles/CTA: counts+scan=%.0f gather=%.0f select=%.0f sort=%.0f ncand=%.0f fold=%.0f final=%.0f nrer=%.1f\n",
+                (double)h[0] / B, (double)h[1] / B, (double)h[2] / B, (double)h[3] / B, (double)h[4] / B, (double)h[5] / B,
+                (double)h[6] / B, (double)h[7] / B);
+    }
     return EVDB_OK;
 }
 

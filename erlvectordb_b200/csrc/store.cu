@@ -191,8 +191,13 @@ static int search_core(evdb_store *s, const double *d_q64, int B, int k, int kst
         else if (metric == EVDB_COSINE) eps_abs = (float)(depth * u);
         else { eps_rel = (float)(depth * u); eps_abs = 1e-37f; }
     }
+    // EVDB_PROF_SELECT=1 (tuning aid): the profiling bracket times the select kernel instead of the scan/GEMM
+    static int prof_sel = -1;
+    if (prof_sel < 0) { const char *e = getenv("EVDB_PROF_SELECT"); prof_sel = e && atoi(e) ? 1 : 0; }
+    if (prof_sel) { s->prof_n = s->prof_n > 0 ? s->prof_n - 1 : 0; prof_begin(s, st); }
     EVDB_TRY(launch_select(s, d_q64, have_raw ? nullptr : s->w_partial, have_raw ? &raw : nullptr, lists, KP, B, kk, kstride, metric, eps_abs,
                            eps_rel, eps_q, squared, slot_base, d_ids, d_dists, d_counts, d_flags, st));
+    if (prof_sel) prof_end(s, st);
     s->n_rows_scanned += (uint64_t)B * s->count;
     return EVDB_OK;
 }
