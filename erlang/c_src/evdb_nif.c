@@ -125,6 +125,22 @@ static ERL_NIF_TERM nif_bulk_load(ErlNifEnv *env, int argc, const ERL_NIF_TERM a
     return rc == EVDB_OK ? a_ok : mk_error(env, rc);
 }
 
+/* append(Ref, <<F:64/float-native,...>>, N, D) -> {ok, FirstSlot}
+ * N new ids in one call (a run of handle_call({insert,..}) with fresh keys)     */
+static ERL_NIF_TERM nif_append(ErlNifEnv *env, int argc, const ERL_NIF_TERM argv[]) {
+    store_res *r;
+    ErlNifBinary bin;
+    ErlNifUInt64 n;
+    int d;
+    if (argc != 4 || !enif_get_resource(env, argv[0], STORE_RT, (void **)&r) ||
+        !enif_inspect_binary(env, argv[1], &bin) || !enif_get_uint64(env, argv[2], &n) ||
+        !enif_get_int(env, argv[3], &d) || bin.size != n * (size_t)d * sizeof(double))
+        return enif_make_badarg(env);
+    uint64_t first = 0;
+    int rc = evdb_store_append_f64(r->s, (const double *)bin.data, n, d, &first);
+    return rc == EVDB_OK ? enif_make_tuple2(env, a_ok, enif_make_uint64(env, first)) : mk_error(env, rc);
+}
+
 /* bulk_load_codes(Ref, CodesBin, MinsBin(f64), ScalesBin(f64), N, D) -> ok
  * compressed records of vector_persistence straight to device code columns    */
 static ERL_NIF_TERM nif_bulk_load_codes(ErlNifEnv *env, int argc, const ERL_NIF_TERM argv[]) {
@@ -269,6 +285,7 @@ static ErlNifFunc nif_funcs[] = {
     {"new", 3, nif_new, 0},
     {"upsert", 3, nif_upsert, ERL_NIF_DIRTY_JOB_CPU_BOUND},
     {"bulk_load", 4, nif_bulk_load, ERL_NIF_DIRTY_JOB_CPU_BOUND},
+    {"append", 4, nif_append, ERL_NIF_DIRTY_JOB_CPU_BOUND},
     {"bulk_load_codes", 6, nif_bulk_load_codes, ERL_NIF_DIRTY_JOB_CPU_BOUND},
     {"delete", 2, nif_delete, ERL_NIF_DIRTY_JOB_CPU_BOUND},
     {"search", 4, nif_search, ERL_NIF_DIRTY_JOB_CPU_BOUND},

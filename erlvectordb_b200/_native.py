@@ -65,6 +65,8 @@ SYMBOLS = [
     ("evdb_store_profile_read", _i, [_vp, _pi32, _pd]),
     ("evdb_store_upsert_f64", _i, [_vp, _u32, _pd, _i]),
     ("evdb_store_upsert_f32", _i, [_vp, _u32, _pf, _i]),
+    ("evdb_store_append_f64", _i, [_vp, _pd, _u64, _i, C.POINTER(C.c_uint64)]),
+    ("evdb_store_append_f32", _i, [_vp, _pf, _u64, _i, C.POINTER(C.c_uint64)]),
     ("evdb_store_bulk_load_f32", _i, [_vp, _pf, _u64, _i]),
     ("evdb_store_bulk_load_f64", _i, [_vp, _pd, _u64, _i]),
     ("evdb_store_bulk_load_codes", _i, [_vp, _pu8, _pd, _pd, _u64, _i]),

@@ -441,6 +441,22 @@ static int bulk_any(evdb_store *s, const T *rows, uint64_t n, int d, bool is_f64
     return EVDB_OK;
 }
 
+// n rows appended at slots [count, count + n): one H2D and one finalize pass for the lot
+template <typename T>
+static int append_any(evdb_store *s, const T *rows, uint64_t n, int d, bool is_f64, uint64_t *first_slot) {
+    if (!s || (n > 0 && !rows)) return EVDB_E_BAD_ARG;
+    if (first_slot) *first_slot = s->count;
+    if (n == 0) return EVDB_OK;
+    EVDB_TRY(check_dim(s, d));
+    if (s->count + n > 0xFFFFFFF0ull) return EVDB_E_BAD_ARG;
+    for (uint64_t i = 0; i < n * (uint64_t)d; ++i) if (!isfinite((double)rows[i])) return EVDB_E_BAD_VECTOR;
+    EVDB_TRY(set_device(s));
+    EVDB_TRY(ensure_capacity(s, s->count + n));
+    EVDB_TRY(ingest_rows(s, s->count, rows, is_f64, n));
+    s->count += n;
+    return EVDB_OK;
+}
+
 }  // namespace evdb
 
 using namespace evdb;
@@ -608,6 +624,13 @@ int evdb_store_bulk_load_f32(evdb_store *s, const float *rows, uint64_t n, int d
 }
 int evdb_store_bulk_load_f64(evdb_store *s, const double *rows, uint64_t n, int d) {
     return bulk_any<double>(s, rows, n, d, true);
+}
+
+int evdb_store_append_f64(evdb_store *s, const double *rows, uint64_t n, int d, uint64_t *first_slot) {
+    return append_any<double>(s, rows, n, d, true, first_slot);
+}
+int evdb_store_append_f32(evdb_store *s, const float *rows, uint64_t n, int d, uint64_t *first_slot) {
+    return append_any<float>(s, rows, n, d, false, first_slot);
 }
 
 int evdb_store_bulk_load_codes(evdb_store *s, const uint8_t *codes, const double *mins,

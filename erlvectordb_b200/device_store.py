@@ -78,6 +78,22 @@ class DeviceStore:
             return rc
         raise N.EvdbError(rc, "evdb_store_upsert_f64")
 
+    def append(self, rows) -> int:
+        """Append n new rows in one call; returns the first slot (status code for the two reference errors)."""
+        rows = np.asarray(rows)
+        n, d = rows.shape
+        first = C.c_uint64(0)
+        if rows.dtype == np.float32:
+            r = np.ascontiguousarray(rows)
+            rc = N.lib().evdb_store_append_f32(self._h, _p(r, C.c_float), n, d, C.byref(first))
+        else:
+            r = np.ascontiguousarray(rows, dtype=np.float64)
+            rc = N.lib().evdb_store_append_f64(self._h, _p(r, C.c_double), n, d, C.byref(first))
+        if rc in (N.E_DIM_MISMATCH, N.E_BAD_VECTOR):
+            return rc
+        N.check(rc, "evdb_store_append")
+        return first.value
+
     def bulk_load(self, rows):
         rows = np.asarray(rows)
         if rows.ndim != 2:

@@ -42,6 +42,12 @@ def insert(store_name, vector_id, vector, metadata=None):
                                {"vector": vector, "metadata": {} if metadata is None else metadata})
 
 
+def insert_batch(store_name, items):
+    """Additive: ``[(Id, Vector, Metadata)]`` in one device call (new ids are appended together)."""
+    return vector_store.insert_batch(store_name, [(i, {"vector": v, "metadata": {} if m is None else m})
+                                                  for i, v, m in items])
+
+
 def search(store_name, query_vector, k, options=None):
     """search/3,4 (:88-92)."""
     metric = (options or {}).get("metric", "cosine")

@@ -109,6 +109,58 @@ class VectorStore:
             self.dimension = v[1]
             return "ok"
 
+    def insert_batch(self, items):
+        """Additive API: ``[(Id, #{vector, metadata})]`` inserted as ONE device call when every Id
+        is new (evdb_store_append_*); equals calling ``insert`` on each in order.  Stops at the first
+        invalid item with the reference's error tuple (items before it are kept, as N calls would)."""
+        pending = []          # new ids waiting for one append
+        seen = set()
+
+        def flush():
+            if not pending:
+                return "ok"
+            rows = np.stack([p[2] for p in pending])
+            with self._lock:
+                first = self._dev.append(rows)
+                if first == N.E_DIM_MISMATCH:
+                    return ("error", "dimension_mismatch")
+                if first == N.E_BAD_VECTOR:
+                    return ("error", "invalid_vector_format")
+                for j, (vid, meta, _) in enumerate(pending):
+                    if self._slot2id and self._ordered and not term_key(self._slot2id[-1]) < term_key(vid):
+                        self._ordered = False
+                    self._id2slot[vid] = first + j
+                    self._slot2id.append(vid)
+                    self._meta[vid] = meta
+                self.dimension = rows.shape[1]
+            pending.clear()
+            seen.clear()
+            return "ok"
+
+        for vid, data in items:
+            dim = self.dimension if self.dimension is not None else (pending[0][2].shape[0] if pending else None)
+            v = validate_vector(data["vector"], dim)
+            arr = None
+            if v[0] == "ok":
+                try:
+                    arr = np.asarray(data["vector"], dtype=np.float64)
+                except (OverflowError, ValueError):
+                    arr = None
+            if arr is None or arr.size == 0 or not np.all(np.isfinite(arr)):
+                r = flush()
+                return r if r != "ok" else (v if v[0] == "error" else ("error", "invalid_vector_format"))
+            if vid in self._id2slot or vid in seen:   # an overwrite: keep call order, one at a time
+                r = flush()
+                if r != "ok":
+                    return r
+                r = self.insert(vid, data)
+                if r != "ok":
+                    return r
+                continue
+            pending.append((vid, data["metadata"], arr))
+            seen.add(vid)
+        return flush()
+
     # -- handle_call({search, Q, K}) :143-150, perform_search/3 :227-236 --------
     def search(self, query_vector, k, metric="cosine"):
         r = self.search_batch([query_vector], k, metric)
@@ -273,6 +325,10 @@ def search(store_name, query_vector, k, metric="cosine"):
 
 def search_batch(store_name, queries, k, metric="cosine"):
     return _whereis(store_name).search_batch(queries, k, metric)
+
+
+def insert_batch(store_name, items):
+    return _whereis(store_name).insert_batch(items)
 
 
 def delete(store_name, vector_id):

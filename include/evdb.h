@@ -117,6 +117,11 @@ int evdb_store_profile_read(evdb_store *s, int32_t *n_samples, double *total_ms)
  * compress_{8,4}bit_quantization does (fp64); Max == Min -> EVDB_E_BADARITH. */
 int evdb_store_upsert_f64(evdb_store *s, uint32_t slot, const double *vec, int d);
 int evdb_store_upsert_f32(evdb_store *s, uint32_t slot, const float *vec, int d);
+/* Batched insert of NEW ids (a run of handle_call({insert,..}) with fresh keys, or a reload in
+ * pieces): n rows appended at slots [count, count + n), *first_slot = the first of them.  One
+ * transfer and one finalize pass instead of n; same validation and error codes as upsert.      */
+int evdb_store_append_f64(evdb_store *s, const double *rows, uint64_t n, int d, uint64_t *first_slot);
+int evdb_store_append_f32(evdb_store *s, const float *rows, uint64_t n, int d, uint64_t *first_slot);
 /* Replace the whole content with n rows (vector_store:init/1 bulk load). */
 int evdb_store_bulk_load_f32(evdb_store *s, const float *rows, uint64_t n, int d);
 int evdb_store_bulk_load_f64(evdb_store *s, const double *rows, uint64_t n, int d);

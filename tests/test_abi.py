@@ -72,3 +72,20 @@ def test_validate_vector_mirror():
     # Erlang term order: binaries bytewise then by length; numbers < atoms < binaries
     assert term_key(b"v1") < term_key(b"v2") < term_key(b"v2a")
     assert term_key(3) < term_key("atom") < term_key(b"bin")
+
+
+def test_erlang_nif_shim_compiles_against_the_abi(tmp_path):
+    """erlang/c_src/evdb_nif.c (the NIF a maintainer adds) must at least parse and
+    type-check against include/evdb.h.  No Erlang/OTP exists in this image, so erl_nif.h is the
+    declarations-only stub kept next to the shim."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    shutil.copy(os.path.join(root, "erlang", "c_src", "erl_nif_stub.h"), tmp_path / "erl_nif.h")
+    r = subprocess.run([gcc, "-fsyntax-only", "-Wall", "-Werror=implicit-function-declaration",
+                        f"-I{tmp_path}", f"-I{os.path.join(root, 'include')}",
+                        os.path.join(root, "erlang", "c_src", "evdb_nif.c")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

@@ -449,3 +449,32 @@ def test_compressed_records_load_straight_to_codes(native, oracle, fresh_name):
             assert [x[2] for x in res] == dd.tolist()
         finally:
             vs.stop(name)
+
+
+def test_insert_batch_equals_sequential_inserts(native, oracle, fresh_name):
+    """insert_batch (evdb_store_append_*) must leave the store exactly as N insert calls would:
+    same slots, same search results, overwrites inside the batch honoured in call order, and the
+    reference's error tuples for a bad item (items before it stay)."""
+    from erlvectordb_b200 import erlvectordb as db
+    rng = np.random.default_rng(21)
+    d = 48
+    vecs = rng.standard_normal((300, d))
+    a, b = fresh_name + "_a", fresh_name + "_b"
+    db.create_store(a)
+    db.create_store(b)
+    try:
+        items = [(f"id{i:04d}".encode(), vecs[i].tolist(), {"i": i}) for i in range(300)]
+        items[150] = (b"id0007", vecs[150].tolist(), {"i": "overwrite"})     # overwrite inside the batch
+        for vid, v, m in items:
+            assert db.insert(a, vid, v, m) == "ok"
+        assert db.insert_batch(b, items) == "ok"
+        assert db.get_stats(a)[1]["count"] == db.get_stats(b)[1]["count"] == 299
+        for qi in (0, 7, 150, 299):
+            q = (vecs[qi] + 0.01).tolist()
+            assert db.search(a, q, 5) == db.search(b, q, 5)
+        bad = [(b"new1", vecs[1].tolist(), {}), (b"new2", vecs[2][:5].tolist(), {}), (b"new3", vecs[3].tolist(), {})]
+        assert db.insert_batch(b, bad) == ("error", "dimension_mismatch")
+        assert db.get_stats(b)[1]["count"] == 300                                # new1 kept, new3 never reached
+    finally:
+        db.delete_store(a)
+        db.delete_store(b)
