@@ -173,7 +173,9 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    // default .release.cta semantics, as for the local arrive: the TMEM reads this orders are fenced
+    // by tcgen05.fence::before_thread_sync, and a cluster-scope release costs a MEMBAR + ERRBAR per tile per warp
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load into THIS CTA's shared memory, completion signalled on a barrier that may live in the peer
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *tm, uint32_t bar_cluster, int c0, int c1) {
@@ -909,9 +911,9 @@ int launch_gemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int metr
     const int nCTA = MB * NG;
     const int cap = KP <= 32 ? 128 : kCandCapMax;
     // >= 2 concurrent query blocks: CTAs (2p, 2p+1) share a row group and run as one cta_group::2 pair
-    // Measured on B200 (tools/sweep.py, r01): +1 % at d = 768, where the MMA pipe is the limit, but -17 % at
-    // d = 128, where the TMEM drain is and the issuer has to wait for the slower of two epilogues.
-    bool pair = MB >= 2 && kcols >= 512;
+    // Measured on B200 (tools/sweep.py, r01): +1 % at d = 768, -3 % at d = 128 (the issuer waits for the slower
+    // of two epilogues), -4 % at d = 1536: the kernel runs at the power cap, not at the L2 feed limit.
+    bool pair = MB >= 2 && kcols >= 512 && kcols <= 1024;
     { const char *e = getenv("EVDB_GEMM_PAIR"); if (e) pair = MB >= 2 && atoi(e) != 0; }
     const uint32_t vbox = pair ? GN / 2 : GN;
 
