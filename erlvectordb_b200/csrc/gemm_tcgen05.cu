@@ -782,13 +782,13 @@ static int launch_gemm_kernel(bool pair, int grid, cudaStream_t st, const CUtens
                               const CUtensorMap &tmQt, const CUtensorMap &tmVt, const GemmArgs &a) {
     if (!pair) {
         const size_t smem = GemmCfg<false>::kSmem;
-        EVDB_CUDA(cudaFuncSetAttribute((const void *)gemm_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        EVDB_TRY(ensure_func_smem((const void *)gemm_topk_kernel<false>, smem));
         gemm_topk_kernel<false><<<grid, kGemmThreads, smem, st>>>(tmQ, tmV, tmQt, tmVt, a);
         EVDB_CUDA(cudaGetLastError());
         return EVDB_OK;
     }
     const size_t smem = GemmCfg<true>::kSmem;
-    EVDB_CUDA(cudaFuncSetAttribute((const void *)gemm_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EVDB_TRY(ensure_func_smem((const void *)gemm_topk_kernel<true>, smem));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);

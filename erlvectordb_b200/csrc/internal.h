@@ -141,6 +141,8 @@ int launch_gemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int metr
 int launch_l2_shadow_rows(evdb_store *s, uint64_t slot0, uint64_t n, cudaStream_t st);
 
 int ensure_bytes(void **p, size_t *cap, size_t need, bool pinned = false);
+int ensure_func_smem(const void *fn, size_t smem);                        // cached cudaFuncSetAttribute(MaxDynamicSharedMemorySize)
+int cached_occupancy(const void *fn, int threads, size_t smem, int *occ);  // cached cudaOccupancyMaxActiveBlocksPerMultiprocessor
 void prof_begin(evdb_store *s, cudaStream_t st);
 void prof_end(evdb_store *s, cudaStream_t st);
 

@@ -500,9 +500,9 @@ int scan_grid_size(evdb_store *s, int metric, int KP, int *G_out) {
     ScanPlan p;
     EVDB_TRY(make_scan_plan(s, metric, KP, &p));
     if (p.smem > 48 * 1024)
-        EVDB_CUDA(cudaFuncSetAttribute((const void *)p.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+        EVDB_TRY(ensure_func_smem((const void *)p.fn, p.smem));
     int occ = 1;
-    EVDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)p.fn, kScanWarps * 32, p.smem));
+    EVDB_TRY(cached_occupancy((const void *)p.fn, kScanWarps * 32, p.smem, &occ));
     if (occ < 1) occ = 1;
     if (occ > 4) occ = 4;
     uint64_t total_wi = (s->count + p.rows_per_wi - 1) / p.rows_per_wi;

@@ -805,7 +805,7 @@ __global__ void __launch_bounds__(kSwWarps * 32) select_warp_kernel(const Select
 static int launch_select_warp(const SelectArgs &a, int B, cudaStream_t st) {
     const size_t smem = (size_t)kSwWarps * SwLayout::kPerWarp + (size_t)(a.L + 1) * kSwWarps * 6 + (size_t)(a.L + 1) * 4 + 16;
     if (smem > 220 * 1024) return EVDB_E_UNSUPPORTED;
-    EVDB_CUDA(cudaFuncSetAttribute((const void *)select_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EVDB_TRY(ensure_func_smem((const void *)select_warp_kernel, smem));
     select_warp_kernel<<<(B + kSwWarps - 1) / kSwWarps, kSwWarps * 32, smem, st>>>(a, B);
     EVDB_CUDA(cudaGetLastError());
     if (a.variant & 16) {
@@ -856,7 +856,7 @@ int launch_select(evdb_store *s, const double *d_q64, const uint64_t *partial, c
         default: EVDB_SEL(EVDB_U4); break;
     }
 #undef EVDB_SEL
-    EVDB_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EVDB_TRY(ensure_func_smem((const void *)fn, smem));
     fn<<<B, threads, smem, st>>>(a);
     s->n_launches++;
     EVDB_CUDA(cudaGetLastError());
@@ -1025,7 +1025,7 @@ static int merge_launch(const uint64_t *ids, const double *dists, const int32_t 
     if (nsort < 2) nsort = 2;
     size_t smem = (size_t)nsort * 16;
     if (smem > 200 * 1024) return EVDB_E_UNSUPPORTED;
-    EVDB_CUDA(cudaFuncSetAttribute((const void *)merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EVDB_TRY(ensure_func_smem((const void *)merge_topk_kernel, smem));
     const int threads = nsort >= 2048 ? 1024 : (nsort >= 512 ? 256 : 128);
     merge_topk_kernel<<<B, threads, smem, st>>>(ids, dists, counts, flags, stride8, stride4, G, B, k, nsort,
                                                 out_ids, out_dists, out_counts, out_flags);

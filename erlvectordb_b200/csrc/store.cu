@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <new>
 
 #include "internal.h"
@@ -46,6 +47,42 @@ void prof_end(evdb_store *s, cudaStream_t st) {
     if (!s->prof_on || s->prof_n >= kProfMax) return;
     cudaEventRecord(s->prof_ev[2 * s->prof_n + 1], st);
     s->prof_n++;
+}
+
+// cudaFuncSetAttribute / occupancy queries cost microseconds each and a lone query is launch-bound:
+// remember, per (device, kernel), the largest dynamic-smem opt-in made and the occupancy found.
+struct FuncCacheEntry { const void *fn; int dev; size_t smem_set; size_t occ_smem; int occ_threads; int occ; };
+static FuncCacheEntry g_fcache[128];
+static int g_fcache_n = 0;
+static std::mutex g_fcache_mu;
+
+static FuncCacheEntry *fcache_get(const void *fn) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    for (int i = 0; i < g_fcache_n; ++i)
+        if (g_fcache[i].fn == fn && g_fcache[i].dev == dev) return &g_fcache[i];
+    if (g_fcache_n >= 128) return nullptr;
+    FuncCacheEntry *e = &g_fcache[g_fcache_n++];
+    e->fn = fn; e->dev = dev; e->smem_set = 0; e->occ_smem = ~(size_t)0; e->occ_threads = 0; e->occ = 0;
+    return e;
+}
+
+int ensure_func_smem(const void *fn, size_t smem) {
+    std::lock_guard<std::mutex> lk(g_fcache_mu);
+    FuncCacheEntry *e = fcache_get(fn);
+    if (e && e->smem_set >= smem) return EVDB_OK;
+    EVDB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (e) e->smem_set = smem;
+    return EVDB_OK;
+}
+
+int cached_occupancy(const void *fn, int threads, size_t smem, int *occ) {
+    std::lock_guard<std::mutex> lk(g_fcache_mu);
+    FuncCacheEntry *e = fcache_get(fn);
+    if (e && e->occ_smem == smem && e->occ_threads == threads) { *occ = e->occ; return EVDB_OK; }
+    EVDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, fn, threads, smem));
+    if (e) { e->occ_smem = smem; e->occ_threads = threads; e->occ = *occ; }
+    return EVDB_OK;
 }
 
 static bool is_quant(const evdb_store *s) { return s->dtype == EVDB_U8 || s->dtype == EVDB_U4; }

@@ -111,16 +111,17 @@ class ShardedStore:
             local = torch.zeros((w,), dtype=torch.int64, device=dev)
             gathered = torch.zeros((self.world, w), dtype=torch.int64, device=dev)
             merged = torch.zeros((w,), dtype=torch.int64, device=dev)
-            self._bufs[key] = (local, gathered, merged)
+            # views and raw pointers are made once: a lone query on a small store is host-bound
+            lv, mv = blob_views(local, B, k), blob_views(merged, B, k)
+            self._bufs[key] = (local, gathered, merged, lv, mv, tuple(t.data_ptr() for t in lv))
         return self._bufs[key]
 
-    def _cuda_local_search(self, q: torch.Tensor, k: int, metric: str, blob: torch.Tensor):
-        """The library writes this shard's result straight into the packed blob."""
+    def _cuda_local_search(self, q: torch.Tensor, k: int, metric: str, ptrs):
+        """The library writes this shard's result straight into the packed blob (ptrs: its four views)."""
         B, d = q.shape
-        ids, dists, counts, flags = blob_views(blob, B, k)
         if self.hi > self.lo:
-            self._dev.search_dev(q.data_ptr(), B, d, k, metric, self.lo, ids.data_ptr(), dists.data_ptr(),
-                                 counts.data_ptr(), flags.data_ptr(), _stream_handle(q.device))
+            self._dev.search_dev(q.data_ptr(), B, d, k, metric, self.lo, ptrs[0], ptrs[1], ptrs[2], ptrs[3],
+                                 _stream_handle(q.device))
         # an empty shard keeps the zero counts the blob was created with
 
     def _cuda_merge(self, gathered: torch.Tensor, B: int, k: int, merged: torch.Tensor):
@@ -132,15 +133,14 @@ class ShardedStore:
         """q: (B, d) float64 on this rank's device (identical on every rank).
         Returns (ids (B,k) int64 global rows, dists (B,k) float64, counts (B,) int32, flags (B,))."""
         B = q.shape[0]
-        local, gathered, merged = self._buffers(B, k, q.device)
+        local, gathered, merged, lv, mv, lptrs = self._buffers(B, k, q.device)
         if self._local_search is not None:      # injected (CPU tests): tensors in, packed here
             ids, dists, counts, flags = self._local_search(q, k, metric)
-            v = blob_views(local, B, k)
-            v[0].copy_(ids); v[1].copy_(dists); v[2].copy_(counts); v[3].copy_(flags)
+            lv[0].copy_(ids); lv[1].copy_(dists); lv[2].copy_(counts); lv[3].copy_(flags)
         else:
-            self._cuda_local_search(q, k, metric, local)
+            self._cuda_local_search(q, k, metric, lptrs)
         if self.world == 1:
-            return blob_views(local, B, k)
+            return lv
         gather_blobs(local, self.world, self.group, out=gathered)
         if self._merge is not None:             # injected (CPU tests)
             g = [blob_views(gathered[r], B, k) for r in range(self.world)]
@@ -148,7 +148,7 @@ class ShardedStore:
                                                 torch.stack([x[2] for x in g]), k)
             return out_ids, out_d, out_c, torch.stack([x[3] for x in g]).amax(dim=0)
         self._cuda_merge(gathered, B, k, merged)
-        return blob_views(merged, B, k)
+        return mv
 
     def close(self):
         if self._dev is not None:

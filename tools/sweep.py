@@ -40,9 +40,12 @@ for spec in sys.argv[1:]:
     torch.cuda.synchronize()
     st._dev.profile(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import time
     e0.record()
+    t0 = time.perf_counter()
     for _ in range(iters):
         o = st.search(q, k, metric)
+    host_us = (time.perf_counter() - t0) / iters * 1e6   # host time to ENQUEUE one search (no sync)
     e1.record()
     torch.cuda.synchronize()
     ns, kms = st._dev.profile_read()
@@ -52,7 +55,7 @@ for spec in sys.argv[1:]:
     kern = kms / max(ns, 1)
     rec = {"case": spec, "plan": {1: "scan", 2: "gemm", 3: "exact"}.get(stt["last_plan"]),
            "step_ms": round(step, 4), "kernel_ms": round(kern, 4), "qps": round(B / step * 1e3, 1),
-           "flagged": int(o[3].sum())}
+           "flagged": int(o[3].sum()), "host_enqueue_us": round(host_us, 1)}
     if stt["last_plan"] == 2 and kern > 0:
         rec["tflops"] = round(2.0 * n * d * B / (kern * 1e-3) / 1e12, 1)
     elif stt["last_plan"] == 1 and kern > 0:
