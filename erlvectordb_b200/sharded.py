@@ -153,3 +153,64 @@ class ShardedStore:
     def close(self):
         if self._dev is not None:
             self._dev.close()
+
+
+class ReplicaGroup:
+    """Whole-store replicas, one per GPU, answering DISJOINT query blocks (the reference's own
+    scale-out model: cluster_manager replicates whole stores, reference src/cluster_manager.erl:148-171;
+    SURVEY 8f-4).  For a store that fits one GPU this scales QPS better than row sharding: every
+    per-query cost (threshold seeding, re-rank) divides by the number of ranks too, and no merge is
+    needed -- results of the blocks are simply all-gathered.  Row sharding (ShardedStore) is for
+    capacity; this is for throughput."""
+
+    def __init__(self, dtype="f32", device=0, rank=None, world=None, group=None, local_search=None):
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        self._local_search = local_search   # injected on CPU (tests); None -> the CUDA library
+        self._dev = None if local_search else DeviceStore(dtype=dtype, device=device)
+        self._bufs = {}
+        self.n_total = 0
+
+    def fill_synthetic(self, seed: int, n_total: int, d: int):
+        self.n_total = n_total
+        if self._dev is not None:
+            self._dev.fill_synthetic(seed, n_total, d)
+
+    def bulk_load(self, rows):
+        self.n_total = rows.shape[0]
+        if self._dev is not None:
+            self._dev.bulk_load(rows)
+
+    def search(self, q: torch.Tensor, k: int, metric: str = "cosine"):
+        """q: (B, d) float64, identical on every rank; rank r answers queries [r*per, (r+1)*per).
+        Returns the same tuple as ShardedStore.search, for all B queries, on every rank."""
+        B, d = q.shape
+        per = (B + self.world - 1) // self.world
+        key = (B, k, q.device)
+        if key not in self._bufs:
+            w = blob_words(per, k)
+            local = torch.zeros((w,), dtype=torch.int64, device=q.device)
+            gathered = torch.zeros((self.world, w), dtype=torch.int64, device=q.device)
+            self._bufs[key] = (local, gathered, blob_views(local, per, k))
+        local, gathered, lv = self._bufs[key]
+        b0 = min(B, self.rank * per)
+        nb = min(B, b0 + per) - b0
+        if nb > 0:
+            qb = q[b0:b0 + nb]
+            if self._local_search is not None:
+                ids, dists, counts, flags = self._local_search(qb, k, metric)
+                lv[0][:nb].copy_(ids); lv[1][:nb].copy_(dists); lv[2][:nb].copy_(counts); lv[3][:nb].copy_(flags)
+            else:
+                self._dev.search_dev(qb.data_ptr(), nb, d, k, metric, 0, lv[0].data_ptr(), lv[1].data_ptr(),
+                                     lv[2].data_ptr(), lv[3].data_ptr(), _stream_handle(q.device))
+        if self.world == 1:
+            return tuple(t[:B] for t in lv)
+        gather_blobs(local, self.world, self.group, out=gathered)
+        parts = [blob_views(gathered[r], per, k) for r in range(self.world)]
+        return tuple(torch.cat([p_[i] for p_ in parts])[:B] for i in range(4))
+
+    def close(self):
+        if self._dev is not None:
+            self._dev.close()
+

@@ -73,6 +73,26 @@ def _worker(rank, world, port, n, d, k, out_q):
     assert (st.lo, st.hi) == (lo, hi)
     q = torch.from_numpy(O.synth_f64(O.SEED_QUERY, 0, 3, d))
     ids, dd, cnt, flags = st.search(q, k, "cosine")
+
+    # replica group: every rank holds the whole store and answers a disjoint block of the queries
+    from erlvectordb_b200.sharded import ReplicaGroup
+    all_rows = O.synth_f64(O.SEED_CORPUS, 0, n, d)
+
+    def replica_search(qb, kk, metric):
+        B = qb.shape[0]
+        r_ids = torch.full((B, kk), -1, dtype=torch.int64)
+        r_dd = torch.zeros((B, kk), dtype=torch.float64)
+        r_cnt = torch.zeros((B,), dtype=torch.int32)
+        for b in range(B):
+            r, dist_ = O.search(all_rows, qb[b].numpy(), kk, metric)
+            r_ids[b, :len(r)] = torch.from_numpy(r)
+            r_dd[b, :len(r)] = torch.from_numpy(dist_)
+            r_cnt[b] = len(r)
+        return r_ids, r_dd, r_cnt, torch.zeros((B,), dtype=torch.int32)
+
+    rg = ReplicaGroup(rank=rank, world=world, local_search=replica_search)
+    g_ids, g_dd, g_cnt, _ = rg.search(q, k, "cosine")
+    assert torch.equal(g_ids, ids) and torch.equal(g_dd, dd) and torch.equal(g_cnt, cnt)
     out_q.put((rank, ids.numpy(), dd.numpy(), cnt.numpy()))
     dist.barrier()
     dist.destroy_process_group()
