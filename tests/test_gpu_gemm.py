@@ -200,3 +200,20 @@ def test_large_batch_with_a_non_finite_query_is_rejected(native, oracle):
     r, dd = oracle.search(rows, qs[211], 10, "cosine")
     assert gs[211].tolist() == r.tolist() and gd[211].tolist() == dd.tolist()
     st.close()
+
+
+def test_batch_larger_than_one_launch_is_sliced(native, oracle):
+    """More than 8192 queries do not fit one launch's candidate buffers: search_core slices the
+    batch; every slice must land in the right rows of the result."""
+    n, d, B, k = 3000, 64, 8192 + 300, 5
+    st = _mk(native, n, d, seed=oracle.SEED_CORPUS)
+    qs = oracle.synth_f64(oracle.SEED_QUERY, 0, B, d)
+    st.set_plan("gemm")
+    gs, gd, gc = st.search(qs, k, "cosine")
+    assert st.stats()["last_plan"] == native.PLAN_GEMM
+    rows = oracle.synth_f64(oracle.SEED_CORPUS, 0, n, d)
+    for b in (0, 8191, 8192, B - 1):
+        r, dd = oracle.search(rows, qs[b], k, "cosine")
+        assert gs[b].tolist() == r.tolist() and gd[b].tolist() == dd.tolist(), b
+    assert (gc == k).all()
+    st.close()
