@@ -79,6 +79,13 @@ SYMBOLS = [
     ("evdb_store_search_dev", _i, [_vp, _vp, _i, _i, _i, _i, _u64, _vp, _vp, _vp, _vp, _vp]),
     ("evdb_merge_topk_dev", _i, [_i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     ("evdb_merge_topk_packed_dev", _i, [_i, _vp, _i, _i, _i, _vp, _vp]),
+    ("evdb_exchange_create", _i, [_i, _i, _i, _u64, C.POINTER(_vp), _vp]),
+    ("evdb_exchange_connect", _i, [_vp, _vp]),
+    ("evdb_exchange_connect_ptrs", _i, [_vp, C.POINTER(_vp)]),
+    ("evdb_exchange_mailbox", _vp, [_vp]),
+    ("evdb_exchange_push", _i, [_vp, _vp, _i, _i, _vp]),
+    ("evdb_exchange_merge", _i, [_vp, _i, _i, _vp, _vp]),
+    ("evdb_exchange_destroy", None, [_vp]),
     ("evdb_quantize_8bit", _i, [_i, _pd, _u64, _i, _pu8, _pd, _pd, _pd, _pu8]),
     ("evdb_quantize_4bit", _i, [_i, _pd, _u64, _i, _pu8, _pd, _pd, _pd, _pu8]),
     ("evdb_dequantize_8bit", _i, [_i, _pu8, _pd, _pd, _u64, _i, _pd]),

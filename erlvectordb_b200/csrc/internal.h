@@ -131,7 +131,10 @@ int exact_plan_search(evdb_store *s, const double *d_q64, int B, int kk, int kst
 int launch_merge_topk(const uint64_t *ids, const double *dists, const int32_t *counts, int G, int B,
                       int k, uint64_t *out_ids, double *out_dists, int32_t *out_counts,
                       cudaStream_t st);
-int launch_merge_topk_packed(const uint64_t *blobs, int G, int B, int k, uint64_t *out_blob, cudaStream_t st);
+int launch_merge_topk_packed(const uint64_t *blobs, size_t blob_stride, int G, int B, int k, uint64_t *out_blob,
+                             cudaStream_t st, const unsigned long long *arrived = nullptr,
+                             unsigned long long epoch = 0);
+int check_device_public(int dev);
 // tcgen05 path (gemm_tcgen05.cu)
 bool gemm_plan_supported(evdb_store *s, int metric, int B, int KP);
 int gemm_kp(int KP);

@@ -973,24 +973,39 @@ __global__ void __launch_bounds__(1024) merge_topk_kernel(const uint64_t *__rest
                                                           uint64_t *__restrict__ out_ids,
                                                           double *__restrict__ out_dists,
                                                           int32_t *__restrict__ out_counts,
-                                                          int32_t *__restrict__ out_flags) {
+                                                          int32_t *__restrict__ out_flags,
+                                                          const unsigned long long *arrived,
+                                                          unsigned long long epoch) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint64_t *dk = reinterpret_cast<uint64_t *>(smem);
     uint64_t *di = dk + nsort;
     const int b = blockIdx.x;
+    if (arrived) {
+        // peer-memory exchange (exchange.cu): rank g's blob is complete once arrived[g] reaches
+        // this search's epoch.  Peers run on OTHER GPUs, so this wait depends on no kernel of this
+        // device; it is bounded -- a dead peer must trap, never hang the GPU.
+        if (threadIdx.x < G) {
+            const volatile unsigned long long *f = arrived + threadIdx.x;
+            const long long t0 = clock64();
+            while (*f < epoch)
+                if (clock64() - t0 > 8000000000ll) __trap();
+        }
+        __threadfence_system();
+        __syncthreads();
+    }
     int total = 0, flag = 0;
     for (int g = 0; g < G; ++g) {
-        total += counts[(size_t)g * stride4 + b];
-        if (flags) flag |= flags[(size_t)g * stride4 + b];
+        total += __ldcg(counts + (size_t)g * stride4 + b);
+        if (flags) flag |= __ldcg(flags + (size_t)g * stride4 + b);
     }
     for (int i = threadIdx.x; i < nsort; i += blockDim.x) {
         uint64_t key = kKeyMax, id = kKeyMax;
         if (i < G * k) {
             int g = i / k, j = i % k;
-            if (j < counts[(size_t)g * stride4 + b]) {
+            if (j < __ldcg(counts + (size_t)g * stride4 + b)) {  // L2 loads: peers write these buffers
                 size_t o = (size_t)g * stride8 + (size_t)b * k + j;
-                key = f64_orderable(dists[o]);
-                id = ids[o];
+                key = f64_orderable(__ldcg(dists + o));
+                id = __ldcg(ids + o);
             }
         }
         dk[i] = key;
@@ -1019,7 +1034,8 @@ __global__ void __launch_bounds__(1024) merge_topk_kernel(const uint64_t *__rest
 
 static int merge_launch(const uint64_t *ids, const double *dists, const int32_t *counts, const int32_t *flags,
                         size_t stride8, size_t stride4, int G, int B, int k, uint64_t *out_ids,
-                        double *out_dists, int32_t *out_counts, int32_t *out_flags, cudaStream_t st) {
+                        double *out_dists, int32_t *out_counts, int32_t *out_flags, cudaStream_t st,
+                        const unsigned long long *arrived = nullptr, unsigned long long epoch = 0) {
     if (G <= 0 || B <= 0 || k <= 0) return EVDB_E_BAD_ARG;
     int nsort = next_pow2(G * k);
     if (nsort < 2) nsort = 2;
@@ -1028,7 +1044,7 @@ static int merge_launch(const uint64_t *ids, const double *dists, const int32_t 
     EVDB_TRY(ensure_func_smem((const void *)merge_topk_kernel, smem));
     const int threads = nsort >= 2048 ? 1024 : (nsort >= 512 ? 256 : 128);
     merge_topk_kernel<<<B, threads, smem, st>>>(ids, dists, counts, flags, stride8, stride4, G, B, k, nsort,
-                                                out_ids, out_dists, out_counts, out_flags);
+                                                out_ids, out_dists, out_counts, out_flags, arrived, epoch);
     EVDB_CUDA(cudaGetLastError());
     return EVDB_OK;
 }
@@ -1041,12 +1057,14 @@ int launch_merge_topk(const uint64_t *ids, const double *dists, const int32_t *c
 }
 
 // Packed blobs (one per rank, `blob_words` u64 words apart): [B*k ids][B*k dists][B counts i32][B flags i32]
-int launch_merge_topk_packed(const uint64_t *blobs, int G, int B, int k, uint64_t *out_blob, cudaStream_t st) {
-    const size_t nk = (size_t)B * k, words = 2 * nk + (size_t)B;
+// blob_stride: u64 words between consecutive ranks' blobs (>= 2*B*k + B)
+int launch_merge_topk_packed(const uint64_t *blobs, size_t blob_stride, int G, int B, int k, uint64_t *out_blob,
+                             cudaStream_t st, const unsigned long long *arrived, unsigned long long epoch) {
+    const size_t nk = (size_t)B * k;
     const int32_t *cf = reinterpret_cast<const int32_t *>(blobs + 2 * nk);
     int32_t *ocf = reinterpret_cast<int32_t *>(out_blob + 2 * nk);
-    return merge_launch(blobs, reinterpret_cast<const double *>(blobs + nk), cf, cf + B, words, 2 * words, G, B, k,
-                        out_blob, reinterpret_cast<double *>(out_blob + nk), ocf, ocf + B, st);
+    return merge_launch(blobs, reinterpret_cast<const double *>(blobs + nk), cf, cf + B, blob_stride, 2 * blob_stride, G, B,
+                        k, out_blob, reinterpret_cast<double *>(out_blob + nk), ocf, ocf + B, st, arrived, epoch);
 }
 
 }  // namespace evdb

@@ -539,6 +539,10 @@ static int check_device(int dev) {
     return rc;
 }
 
+}  // extern "C"
+namespace evdb { int check_device_public(int dev) { return check_device(dev); } }
+extern "C" {
+
 int evdb_init(const int *devices, int n_dev) {
     if (!devices || n_dev <= 0) return check_device(0);
     for (int i = 0; i < n_dev; ++i) EVDB_TRY(check_device(devices[i]));
@@ -836,7 +840,8 @@ int evdb_merge_topk_packed_dev(int device, const void *d_blobs, int G, int B, in
     if (!d_blobs || !d_out_blob) return EVDB_E_BAD_ARG;
     EVDB_TRY(check_device(device));
     EVDB_CUDA(cudaSetDevice(device));
-    return launch_merge_topk_packed((const uint64_t *)d_blobs, G, B, k, (uint64_t *)d_out_blob, (cudaStream_t)stream);
+    return launch_merge_topk_packed((const uint64_t *)d_blobs, 2 * (size_t)B * k + (size_t)B, G, B, k,
+                                    (uint64_t *)d_out_blob, (cudaStream_t)stream);
 }
 
 // ---- standalone codecs ------------------------------------------------------

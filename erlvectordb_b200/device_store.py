@@ -179,3 +179,43 @@ def merge_topk_dev(device, d_ids, d_dists, d_counts, G, B, k, d_out_ids, d_out_d
 def merge_topk_packed_dev(device, d_blobs, G, B, k, d_out_blob, stream=0):
     N.check(N.lib().evdb_merge_topk_packed_dev(device, d_blobs, G, B, k, d_out_blob, stream),
             "evdb_merge_topk_packed_dev")
+
+
+class Exchange:
+    """Peer-memory exchange of packed result blobs (evdb_exchange_*): one object per rank."""
+
+    def __init__(self, device: int, rank: int, world: int, max_words: int):
+        self._h = C.c_void_p()
+        self.handle_bytes = (C.c_uint8 * 64)()
+        N.check(N.lib().evdb_exchange_create(device, rank, world, max_words, C.byref(self._h),
+                                             C.cast(self.handle_bytes, C.c_void_p)), "evdb_exchange_create")
+        self.world, self.max_words = world, max_words
+
+    @property
+    def mailbox(self) -> int:
+        return N.lib().evdb_exchange_mailbox(self._h)
+
+    def connect(self, all_handles: bytes):
+        buf = (C.c_uint8 * len(all_handles)).from_buffer_copy(all_handles)
+        N.check(N.lib().evdb_exchange_connect(self._h, C.cast(buf, C.c_void_p)), "evdb_exchange_connect")
+
+    def connect_ptrs(self, mailboxes):
+        arr = (C.c_void_p * len(mailboxes))(*mailboxes)
+        N.check(N.lib().evdb_exchange_connect_ptrs(self._h, arr), "evdb_exchange_connect_ptrs")
+
+    def push(self, d_blob: int, B: int, k: int, stream=0):
+        N.check(N.lib().evdb_exchange_push(self._h, d_blob, B, k, stream), "evdb_exchange_push")
+
+    def merge(self, B: int, k: int, d_out_blob: int, stream=0):
+        N.check(N.lib().evdb_exchange_merge(self._h, B, k, d_out_blob, stream), "evdb_exchange_merge")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            N.lib().evdb_exchange_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -22,7 +22,7 @@ import torch
 import torch.distributed as dist
 
 from . import _native as N
-from .device_store import DeviceStore, merge_topk_packed_dev
+from .device_store import DeviceStore, Exchange, merge_topk_packed_dev
 
 
 def shard_bounds(n_total: int, world: int, rank: int) -> tuple[int, int]:
@@ -74,7 +74,12 @@ class ShardedStore:
     """One shard of a row-sharded store (call from every rank of the process group)."""
 
     def __init__(self, dtype="f32", device=0, rank=None, world=None, group=None,
-                 local_search=None, merge=None):
+                 local_search=None, merge=None, exchange="p2p"):
+        """exchange: "p2p" = peer-memory pushes + on-device flag wait (evdb_exchange_*, the default on
+        GPUs; falls back to "nccl" if the peers cannot be mapped), "nccl" = one all_gather_into_tensor
+        followed by the merge kernel."""
+        self.exchange = exchange
+        self._xchg = {}
         self.group = group
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
@@ -124,6 +129,29 @@ class ShardedStore:
                                  _stream_handle(q.device))
         # an empty shard keeps the zero counts the blob was created with
 
+    def _p2p(self, B: int, k: int, dev):
+        """The (B, k) exchange object, created and connected on first use (a collective call)."""
+        key = (B, k)
+        if key not in self._xchg:
+            x = None
+            try:
+                x = Exchange(dev.index or 0, self.rank, self.world, blob_words(B, k))
+                mine = torch.tensor(list(bytes(x.handle_bytes)), dtype=torch.uint8, device=dev)
+                allh = torch.empty((self.world, 64), dtype=torch.uint8, device=dev)
+                dist.all_gather_into_tensor(allh.view(-1), mine, group=self.group)
+                x.connect(bytes(allh.cpu().numpy().tobytes()))
+                ok = torch.ones((1,), dtype=torch.int32, device=dev)
+            except Exception:  # peers not mappable (no P2P / IPC): everyone must agree to fall back
+                ok = torch.zeros((1,), dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if int(ok.item()) == 0:
+                if x is not None:
+                    x.close()
+                x = None
+                self.exchange = "nccl"
+            self._xchg[key] = x
+        return self._xchg[key]
+
     def _cuda_merge(self, gathered: torch.Tensor, B: int, k: int, merged: torch.Tensor):
         dev = gathered.device
         merge_topk_packed_dev(dev.index or 0, gathered.data_ptr(), self.world, B, k, merged.data_ptr(),
@@ -141,6 +169,13 @@ class ShardedStore:
             self._cuda_local_search(q, k, metric, lptrs)
         if self.world == 1:
             return lv
+        if self._merge is None and self.exchange == "p2p":
+            x = self._p2p(B, k, q.device)
+            if x is not None:
+                stream = _stream_handle(q.device)
+                x.push(local.data_ptr(), B, k, stream)      # my blob -> every rank's mailbox, then the epoch flag
+                x.merge(B, k, merged.data_ptr(), stream)    # waits on the device for all ranks' flags
+                return mv
         gather_blobs(local, self.world, self.group, out=gathered)
         if self._merge is not None:             # injected (CPU tests)
             g = [blob_views(gathered[r], B, k) for r in range(self.world)]
@@ -151,6 +186,10 @@ class ShardedStore:
         return mv
 
     def close(self):
+        for x in self._xchg.values():
+            if x is not None:
+                x.close()
+        self._xchg = {}
         if self._dev is not None:
             self._dev.close()
 

@@ -185,6 +185,21 @@ int evdb_merge_topk_dev(int device, const void *d_ids_u64, const void *d_dists_f
 int evdb_merge_topk_packed_dev(int device, const void *d_blobs, int G, int B, int k,
                                void *d_out_blob, void *stream);
 
+/* ---- peer-memory exchange for a row-sharded store (one rank per GPU/process) -------------
+ * Instead of an allgather + merge launch: every rank pushes its packed blob into a mailbox in
+ * every peer's memory (NVLink stores; peers mapped with CUDA IPC) and publishes an epoch flag;
+ * the merge kernel waits for the flags on the device.  create -> exchange the 64-byte handles
+ * among the ranks (any transport) -> connect -> per search: push, merge (both only enqueue).   */
+typedef struct evdb_exchange evdb_exchange;
+int evdb_exchange_create(int device, int rank, int world, uint64_t max_words, evdb_exchange **out,
+                         void *ipc_handle_out /* 64 bytes */);
+int evdb_exchange_connect(evdb_exchange *x, const void *all_handles /* world * 64 bytes */);
+int evdb_exchange_connect_ptrs(evdb_exchange *x, const void *const *mailboxes /* same process */);
+void *evdb_exchange_mailbox(evdb_exchange *x);
+int evdb_exchange_push(evdb_exchange *x, const void *d_local_blob, int B, int k, void *stream);
+int evdb_exchange_merge(evdb_exchange *x, int B, int k, void *d_out_blob, void *stream);
+void evdb_exchange_destroy(evdb_exchange *x);
+
 /* ---- codecs (vector_compression.erl:166-204), computed on the device ------
  * n rows of d fp64 -> codes (+ per-row fp64 min/max/scale).  ok[i] = 0 for a
  * row whose Max == Min (reference: badarith, caller stores it raw).          */

@@ -52,3 +52,48 @@ def test_sharded_equals_single_store(native, oracle, dtype, metric, n, d, B, k, 
     for st in stores:
         st.close()
     one.close()
+
+
+def test_peer_memory_exchange_equals_packed_merge(native, oracle):
+    """evdb_exchange_*: G "ranks" of one process on one GPU (mailboxes connected by pointer instead of
+    CUDA IPC).  All pushes are enqueued before any merge, so no kernel ever waits here; several
+    searches in a row exercise the epoch/parity double buffering.  Every rank's merged blob must
+    equal evdb_merge_topk_packed_dev over the same inputs."""
+    import torch
+    from erlvectordb_b200.device_store import DeviceStore, Exchange, merge_topk_packed_dev
+    from erlvectordb_b200.sharded import blob_views, blob_words, shard_bounds
+
+    G, n, d, B, k = 3, 30_000, 64, 5, 10
+    dev = torch.device("cuda", 0)
+    w = blob_words(B, k)
+    stores = []
+    for g in range(G):
+        lo, hi = shard_bounds(n, G, g)
+        st = DeviceStore(dtype="f32", device=0)
+        st.fill_synthetic(oracle.SEED_CORPUS, hi - lo, d, row0=lo)
+        stores.append((st, lo))
+    xs = [Exchange(0, g, G, w) for g in range(G)]
+    boxes = [x.mailbox for x in xs]
+    for x in xs:
+        x.connect_ptrs(boxes)
+    for step in range(5):   # > 2 searches: both parities reused
+        q = torch.from_numpy(oracle.synth_f64(oracle.SEED_QUERY, step * B, B, d)).to(dev)
+        gathered = torch.zeros((G, w), dtype=torch.int64, device=dev)
+        for g, (st, lo) in enumerate(stores):
+            ids, dists, counts, flags = blob_views(gathered[g], B, k)
+            st.search_dev(q.data_ptr(), B, d, k, "cosine", lo, ids.data_ptr(), dists.data_ptr(), counts.data_ptr(),
+                          flags.data_ptr(), 1)
+        ref = torch.zeros((w,), dtype=torch.int64, device=dev)
+        merge_topk_packed_dev(0, gathered.data_ptr(), G, B, k, ref.data_ptr(), 1)
+        for g in range(G):
+            xs[g].push(gathered[g].data_ptr(), B, k, 1)
+        outs = [torch.zeros((w,), dtype=torch.int64, device=dev) for _ in range(G)]
+        for g in range(G):
+            xs[g].merge(B, k, outs[g].data_ptr(), 1)
+        torch.cuda.synchronize()
+        for g in range(G):
+            assert torch.equal(outs[g], ref), (step, g)
+    for x in xs:
+        x.close()
+    for st, _ in stores:
+        st.close()

@@ -22,7 +22,15 @@ for dtype, metric, n, d, B, k in [("f32", "cosine", 200_000, 128, 4, 10), ("f32"
     st.fill_synthetic(synth.SEED_CORPUS, n, d)
     qh = synth.synth(synth.SEED_QUERY, 0, B, d)
     q = torch.from_numpy(qh).cuda()
-    ids, dd, cnt, flags = st.search(q, k, metric)
+    for _ in range(4):   # repeated searches: epoch/parity reuse of the peer mailboxes
+        ids, dd, cnt, flags = st.search(q, k, metric)
+    st2 = ShardedStore(dtype=dtype, device=local, rank=rank, world=world, exchange="nccl")
+    st2.fill_synthetic(synth.SEED_CORPUS, n, d)
+    i2, d2, c2, f2 = st2.search(q, k, metric)
+    assert torch.equal(i2, ids) and torch.equal(d2, dd), "p2p and nccl exchanges disagree"
+    st2.close()
+    if rank == 0:
+        print(f"  exchange used: {st.exchange}", flush=True)
     one = DeviceStore(dtype=dtype, device=local)
     one.fill_synthetic(synth.SEED_CORPUS, n, d)
     s_ids, s_d, s_c = one.search(qh, k, metric)
