@@ -86,6 +86,9 @@ SYMBOLS = [
     ("evdb_exchange_push", _i, [_vp, _vp, _i, _i, _vp]),
     ("evdb_exchange_merge", _i, [_vp, _i, _i, _vp, _vp]),
     ("evdb_exchange_destroy", None, [_vp]),
+    ("evdb_store_search_sharded_phase1", _i, [_vp, _vp, _vp, _i, _i, _i, _i, _u64, _u64, _vp]),
+    ("evdb_store_search_sharded_phase2", _i, [_vp, _vp, _vp, _vp, _i, _i, _i, _u64, _vp]),
+    ("evdb_store_search_sharded_phase3", _i, [_vp, _vp, _i, _i, _i, _u64, _vp, _vp]),
     ("evdb_quantize_8bit", _i, [_i, _pd, _u64, _i, _pu8, _pd, _pd, _pd, _pu8]),
     ("evdb_quantize_4bit", _i, [_i, _pd, _u64, _i, _pu8, _pd, _pd, _pd, _pu8]),
     ("evdb_dequantize_8bit", _i, [_i, _pu8, _pd, _pd, _u64, _i, _pd]),

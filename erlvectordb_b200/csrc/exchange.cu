@@ -12,21 +12,11 @@
 // stream order), the wait is bounded (trap), and the mailboxes are double-buffered by epoch
 // parity: a rank can be at most one search ahead of a peer, because its next push needs its own
 // merge done, which needed that peer's previous push.
+#include <string.h>
+
 #include <new>
 
 #include "internal.h"
-
-struct evdb_exchange {
-    int device = 0, rank = 0, world = 1;
-    uint64_t max_words = 0;              // blob capacity of a mailbox slot (u64 words)
-    uint64_t slot_words = 0;             // slot pitch (max_words rounded up to 32 words)
-    unsigned long long epoch = 0;
-    // local allocation: [2 parities][world slots][slot_words] u64, then [2][world] flags, then 1 counter
-    uint64_t *mailbox = nullptr;
-    uint64_t **d_peer_box = nullptr;     // device array [world]: base of each rank's mailbox (mine included)
-    void *peer_base[64] = {nullptr};     // host copy (IPC-opened pointers to close)
-    bool opened[64] = {false};
-};
 
 namespace evdb {
 
@@ -58,6 +48,30 @@ __global__ void __launch_bounds__(256) exchange_push_kernel(const uint64_t *__re
         }
         if (threadIdx.x == 0) *done_counter = 0;
     }
+}
+
+int exchange_push_words(evdb_exchange *x, const void *d_blob, size_t words, cudaStream_t st) {
+    if (!x || !d_blob || words == 0 || words > x->max_words) return EVDB_E_BAD_ARG;
+    EVDB_CUDA(cudaSetDevice(x->device));
+    x->epoch++;
+    const int parity = (int)(x->epoch & 1);
+    unsigned int *counter = reinterpret_cast<unsigned int *>(x->mailbox + box_words(x) + 2 * (size_t)x->world);
+    int grid = (int)((words + 255) / 256);
+    if (grid > 64) grid = 64;
+    exchange_push_kernel<<<grid, 256, 0, st>>>((const uint64_t *)d_blob, words, x->d_peer_box, x->rank, x->world,
+                                               x->slot_words, parity, x->epoch, counter);
+    EVDB_CUDA(cudaGetLastError());
+    return EVDB_OK;
+}
+
+ExchangeView exchange_view(const evdb_exchange *x) {
+    const int parity = (int)(x->epoch & 1);
+    ExchangeView v;
+    v.slots = x->mailbox + (size_t)parity * x->world * x->slot_words;
+    v.stride = x->slot_words;
+    v.flags = reinterpret_cast<const unsigned long long *>(x->mailbox + box_words(x)) + (size_t)parity * x->world;
+    v.epoch = x->epoch;
+    return v;
 }
 
 }  // namespace evdb
@@ -127,19 +141,8 @@ void *evdb_exchange_mailbox(evdb_exchange *x) { return x ? (void *)x->mailbox : 
 
 /* Enqueue the push of this rank's blob for the next search (no sync). */
 int evdb_exchange_push(evdb_exchange *x, const void *d_local_blob, int B, int k, void *stream) {
-    if (!x || !d_local_blob || B <= 0 || k <= 0) return EVDB_E_BAD_ARG;
-    const size_t words = 2 * (size_t)B * k + (size_t)B;
-    if (words > x->max_words) return EVDB_E_BAD_ARG;
-    EVDB_CUDA(cudaSetDevice(x->device));
-    x->epoch++;
-    const int parity = (int)(x->epoch & 1);
-    unsigned int *counter = reinterpret_cast<unsigned int *>(x->mailbox + box_words(x) + 2 * (size_t)x->world);
-    int grid = (int)((words + 255) / 256);
-    if (grid > 64) grid = 64;
-    exchange_push_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint64_t *)d_local_blob, words, x->d_peer_box,
-                                                              x->rank, x->world, x->slot_words, parity, x->epoch, counter);
-    EVDB_CUDA(cudaGetLastError());
-    return EVDB_OK;
+    if (B <= 0 || k <= 0) return EVDB_E_BAD_ARG;
+    return exchange_push_words(x, d_local_blob, 2 * (size_t)B * k + (size_t)B, (cudaStream_t)stream);
 }
 
 /* Enqueue the merge of the current search: waits (on the device) for every rank's push of this
@@ -147,12 +150,9 @@ int evdb_exchange_push(evdb_exchange *x, const void *d_local_blob, int B, int k,
 int evdb_exchange_merge(evdb_exchange *x, int B, int k, void *d_out_blob, void *stream) {
     if (!x || !d_out_blob || B <= 0 || k <= 0) return EVDB_E_BAD_ARG;
     EVDB_CUDA(cudaSetDevice(x->device));
-    const int parity = (int)(x->epoch & 1);
-    const uint64_t *slots = x->mailbox + (size_t)parity * x->world * x->slot_words;
-    const unsigned long long *flags = reinterpret_cast<const unsigned long long *>(x->mailbox + box_words(x)) +
-                                      (size_t)parity * x->world;
-    return launch_merge_topk_packed(slots, x->slot_words, x->world, B, k, (uint64_t *)d_out_blob, (cudaStream_t)stream,
-                                    flags, x->epoch);
+    const ExchangeView v = exchange_view(x);
+    return launch_merge_topk_packed(v.slots, v.stride, x->world, B, k, (uint64_t *)d_out_blob, (cudaStream_t)stream,
+                                    v.flags, v.epoch);
 }
 
 void evdb_exchange_destroy(evdb_exchange *x) {

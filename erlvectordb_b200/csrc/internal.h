@@ -65,6 +65,7 @@ struct evdb_store {
     double *w_dists = nullptr;  size_t w_dists_cap = 0; // [B][k]
     int32_t *w_counts = nullptr; size_t w_counts_cap = 0; // [B] counts + [B] flags
     void *w_tmp = nullptr;      size_t w_tmp_cap = 0;   // ingest staging / exact plan
+    void *w_shard = nullptr;    size_t w_shard_cap = 0; // sharded two-phase search: window blob, exact blob, global window, meta
     void *h_pin = nullptr;      size_t h_pin_cap = 0;   // pinned host staging
 
     // ---- dominant-kernel profiling (evdb_store_profile) ----
@@ -78,7 +79,30 @@ struct evdb_store {
     double last_search_ms = 0.0;
 };
 
+// Peer-memory mailbox of one rank (exchange.cu): [2 parities][world slots][slot_words] u64, then
+// [2][world] epoch flags, then a block counter.
+struct evdb_exchange {
+    int device = 0, rank = 0, world = 1;
+    uint64_t max_words = 0;              // blob capacity of a mailbox slot (u64 words)
+    uint64_t slot_words = 0;             // slot pitch (max_words rounded up to 32 words)
+    unsigned long long epoch = 0;
+    uint64_t *mailbox = nullptr;
+    uint64_t **d_peer_box = nullptr;     // device array [world]: base of each rank's mailbox (mine included)
+    void *peer_base[64] = {nullptr};     // IPC-opened pointers (to close)
+    bool opened[64] = {false};
+};
+
 namespace evdb {
+
+// what a consumer kernel of the CURRENT epoch needs: the world slots, their pitch, the flags to wait on
+struct ExchangeView {
+    const uint64_t *slots;
+    size_t stride;
+    const unsigned long long *flags;
+    unsigned long long epoch;
+};
+int exchange_push_words(evdb_exchange *x, const void *d_blob, size_t words, cudaStream_t st);
+ExchangeView exchange_view(const evdb_exchange *x);
 
 struct ScanArgs {
     const uint8_t *rows;
@@ -135,6 +159,16 @@ int launch_merge_topk_packed(const uint64_t *blobs, size_t blob_stride, int G, i
                              cudaStream_t st, const unsigned long long *arrived = nullptr,
                              unsigned long long epoch = 0);
 int check_device_public(int dev);
+// row-sharded two-phase GEMM search (select.cu)
+int launch_shard_window(evdb_store *s, const double *d_q64, const RawCands *raw, int L, int KP, int B, int kk,
+                        int metric, const float *eps_q, uint64_t slot_base, uint64_t *win_blob, cudaStream_t st);
+size_t shard_gmeta_bytes(int B);
+int launch_shard_rerank(evdb_store *s, const double *d_q64, int B, int KP, int k, int kk, int metric, int rank,
+                        int world, uint64_t n_total, const ExchangeView &win, double *e_out, uint64_t *g_out,
+                        void *g_meta, cudaStream_t st);
+int launch_shard_final(evdb_store *s, int B, int KP, int k, int kk, int metric, int rank, int world, uint64_t n_total,
+                       const ExchangeView &ex, const uint64_t *g_out, const void *g_meta, uint64_t *out_blob,
+                       cudaStream_t st);
 // tcgen05 path (gemm_tcgen05.cu)
 bool gemm_plan_supported(evdb_store *s, int metric, int B, int KP);
 int gemm_kp(int KP);

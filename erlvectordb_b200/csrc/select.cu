@@ -40,6 +40,8 @@ struct SelectArgs {
     const float *eps_q;  // optional [B]: per-query absolute bound (GEMM plans)
     int squared;         // key scores are squared distances (euclidean GEMM plan)
     int variant;         // tuning: bit 0 = L1 prefetch pre-pass, bit 1 = pipelined fold, bit 2 = L2 prefetch instead
+    uint64_t *win_out;   // sharded search, phase 1: write the ascending window (keys with GLOBAL rows) + meta and stop
+    uint64_t *win_meta;  //   [B]: (eps bits << 32) | ncand
     uint64_t slot_base;
     uint64_t *out_ids;
     double *out_dists;
@@ -533,6 +535,68 @@ __device__ __forceinline__ void warp_select_inplace(uint64_t *keys, int T, int n
     }
 }
 
+// One chain of the exact re-rank (F32 rows): lane r < nr passes the slot of the row it folds; with
+// `qrow`, lane nr folds q*q.  The independent terms (q*v, (q-v)^2, |q-v|) are formed by all 32 lanes
+// in parallel -- 32 useful fp64 multiplies per instruction -- and staged as fp64 in shared memory;
+// then every lane folds its row strictly left to right.  Returns the lane's sum.
+__device__ __forceinline__ double sw_fold_chain(const uint8_t *__restrict__ rows, size_t row_bytes,
+                                                const double *__restrict__ q, int d, int metric, uint8_t *stage,
+                                                uint32_t my_slot, int nr, bool qrow, int lane) {
+    const int nrows = nr + (qrow ? 1 : 0);
+    double s = 0.0;
+    for (int kb = 0; kb < d; kb += kSwKC) {
+        const int cnt = d - kb < kSwKC ? d - kb : kSwKC;
+        // a row chunk is 16 units of 4 elements: half a warp per row, two rows per step
+        const int unit = lane & 15, rsub = lane >> 4;
+        const int e0 = kb + 4 * unit;
+        double qd[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) qd[i] = e0 + i < d ? q[e0 + i] : 0.0;
+        __syncwarp();
+#pragma unroll 4
+        for (int r2 = 0; r2 < nrows; r2 += 2) {
+            const int r = r2 + rsub;
+            const uint32_t rslot = __shfl_sync(0xffffffffu, my_slot, r < nr ? r : 0);
+            if (r >= nrows) continue;
+            double t[4];
+            if (r < nr) {
+                uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+                if ((size_t)e0 * 4 < row_bytes)
+                    raw = __ldg(reinterpret_cast<const uint4 *>(rows + (size_t)rslot * row_bytes) + (e0 >> 2));
+                const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const double x = widen_f32(w[i]);
+                    if (metric == EVDB_COSINE) t[i] = __dmul_rn(qd[i], x);
+                    else {
+                        const double df = __dsub_rn(qd[i], x);
+                        t[i] = metric == EVDB_EUCLIDEAN ? __dmul_rn(df, df) : fabs(df);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) t[i] = __dmul_rn(qd[i], qd[i]);
+            }
+            double2 *dst = reinterpret_cast<double2 *>(stage + (size_t)r * kSwProdStride) + 2 * unit;
+            dst[0] = make_double2(t[0], t[1]);
+            dst[1] = make_double2(t[2], t[3]);
+        }
+        __syncwarp();
+        if (lane < nrows) {
+            const double2 *p = reinterpret_cast<const double2 *>(stage + (size_t)lane * kSwProdStride);
+            const int pairs = cnt >> 1;
+#pragma unroll 4
+            for (int i = 0; i < pairs; ++i) {
+                const double2 v = p[i];
+                s = __dadd_rn(s, v.x);
+                s = __dadd_rn(s, v.y);
+            }
+            if (cnt & 1) s = __dadd_rn(s, reinterpret_cast<const double *>(p)[cnt - 1]);
+        }
+    }
+    return s;
+}
+
 // F32 stores only (the GEMM plan's precondition).
 __global__ void __launch_bounds__(kSwWarps * 32) select_warp_kernel(const SelectArgs a, int B) {
     using LY = SwLayout;
@@ -672,6 +736,11 @@ __global__ void __launch_bounds__(kSwWarps * 32) select_warp_kernel(const Select
     for (int i = lane; i < ncand; i += 32) ckeys[i] = keys[i];
     __syncwarp();
     const float bound = ncand > 0 ? key_score(ckeys[ncand - 1]) : 0.f;
+    if (a.win_out) {  // sharded search, phase 1: the window travels, the re-rank happens after the global merge
+        for (int i = lane; i < KP; i += 32) a.win_out[(size_t)b * KP + i] = i < ncand ? ckeys[i] + a.slot_base : kKeyMax;
+        if (lane == 0) a.win_meta[b] = ((uint64_t)__float_as_uint(eps_abs) << 32) | (uint32_t)ncand;
+        return;
+    }
 
     // ---- 2. which candidates can still reach the top k (a prefix of the ascending window) ----
     const int kout = a.kk < ncand ? a.kk : ncand;
@@ -695,60 +764,9 @@ __global__ void __launch_bounds__(kSwWarps * 32) select_warp_kernel(const Select
     const int RC = cosine ? kSwRows - 1 : kSwRows;   // candidates per round
     for (int base = 0; base < nrer; base += RC) {
         const int nr = nrer - base < RC ? nrer - base : RC;
-        const int nrows = nr + (cosine ? 1 : 0);
         const bool mine = lane < nr;
-        const bool qlane = cosine && lane == nr;
         const uint32_t slot = mine ? key_slot(ckeys[base + lane]) : 0u;
-        double s = 0.0;
-        for (int kb = 0; kb < a.d; kb += kSwKC) {
-            const int cnt = a.d - kb < kSwKC ? a.d - kb : kSwKC;
-            // a row chunk is 16 units of 4 elements: half a warp per row, two rows per step
-            const int unit = lane & 15, rsub = lane >> 4;
-            const int e0 = kb + 4 * unit;
-            double qd[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) qd[i] = e0 + i < a.d ? q[e0 + i] : 0.0;
-            __syncwarp();
-#pragma unroll 4
-            for (int r2 = 0; r2 < nrows; r2 += 2) {
-                const int r = r2 + rsub;
-                if (r >= nrows) continue;
-                double t[4];
-                if (r < nr) {
-                    uint4 raw = make_uint4(0u, 0u, 0u, 0u);
-                    if ((size_t)e0 * 4 < a.row_bytes)
-                        raw = __ldg(reinterpret_cast<const uint4 *>(a.rows + (size_t)key_slot(ckeys[base + r]) * a.row_bytes) + (e0 >> 2));
-                    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const double x = widen_f32(w[i]);
-                        if (a.metric == EVDB_COSINE) t[i] = __dmul_rn(qd[i], x);
-                        else {
-                            const double df = __dsub_rn(qd[i], x);
-                            t[i] = a.metric == EVDB_EUCLIDEAN ? __dmul_rn(df, df) : fabs(df);
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) t[i] = __dmul_rn(qd[i], qd[i]);
-                }
-                double2 *dst = reinterpret_cast<double2 *>(stage + (size_t)r * kSwProdStride) + 2 * unit;
-                dst[0] = make_double2(t[0], t[1]);
-                dst[1] = make_double2(t[2], t[3]);
-            }
-            __syncwarp();
-            if (mine || qlane) {
-                const double2 *p = reinterpret_cast<const double2 *>(stage + (size_t)lane * kSwProdStride);
-                const int pairs = cnt >> 1;
-#pragma unroll 4
-                for (int i = 0; i < pairs; ++i) {
-                    const double2 v = p[i];
-                    s = __dadd_rn(s, v.x);
-                    s = __dadd_rn(s, v.y);
-                }
-                if (cnt & 1) s = __dadd_rn(s, reinterpret_cast<const double *>(p)[cnt - 1]);
-            }
-        }
+        const double s = sw_fold_chain(a.rows, a.row_bytes, q, a.d, a.metric, stage, slot, nr, cosine, lane);
         double dist;
         if (cosine) {
             const double sq = __shfl_sync(0xffffffffu, s, nr);
@@ -819,6 +837,264 @@ static int launch_select_warp(const SelectArgs &a, int B, cudaStream_t st) {
     return EVDB_OK;
 }
 
+// ============================================================================
+// Row-sharded GEMM batches, two phases.  Re-ranking every shard's local top-k would
+// repeat the exact fp64 work on every rank; instead the APPROXIMATE windows travel first:
+//   phase 1  (select_warp_kernel, win_out mode): each rank's ascending window of KP keys
+//            (score, global row) + its size and error bound -> pushed to every rank;
+//   phase 2  (shard_rerank_kernel): every rank merges the world windows into the same global
+//            window, derives the same completeness bound, and re-ranks in exact fp64 ONLY the
+//            candidates it owns (1/world of them) -> exact distances pushed to every rank;
+//   phase 3  (shard_final_kernel): every rank orders the global candidates by the owners' exact
+//            distances, emits the top k and proves the window complete.
+// Bound: a row outside the global window was either cut by the merge (score >= the window's last
+// score) or never entered its shard's window (score >= that shard's last key, which only matters
+// for a shard whose window does not cover all of its rows).
+// ============================================================================
+struct GMeta { int nrer, kout, flag, has_outside; float bound, eps; };
+
+struct ShardArgs {
+    const uint8_t *rows; size_t row_bytes; const double *norm64; int d; const double *q64;
+    int B, KP, kk, metric, squared, world, rank;
+    uint64_t n_total;
+    ExchangeView win;     // phase 2 input: per rank [B*KP keys][B meta]
+    double *e_out;        // phase 2 output: [B][KP] exact distances of the rows this rank owns (0 elsewhere)
+    uint64_t *g_out;      // [B][KP] the global window (each rank's own copy, identical everywhere)
+    GMeta *g_meta;        // [B]
+    ExchangeView ex;      // phase 3 input: per rank [B][KP] exact distances
+    uint64_t *out_blob;   // packed result: [B*k ids][B*k dists][B counts i32][B flags i32]
+    int k;
+};
+
+__device__ __forceinline__ void shard_range(uint64_t n, int world, int r, uint64_t *lo, uint64_t *hi) {
+    const uint64_t per = (n + world - 1) / world;
+    *lo = (uint64_t)r * per < n ? (uint64_t)r * per : n;
+    *hi = *lo + per < n ? *lo + per : n;
+}
+
+__device__ __forceinline__ void wait_flags(const unsigned long long *flags, unsigned long long epoch, int world, int lane) {
+    if (lane < world) {
+        const volatile unsigned long long *f = flags + lane;
+        const long long t0 = clock64();
+        while (*f < epoch)
+            if (clock64() - t0 > 8000000000ll) __trap();   // a dead peer must not hang the GPU
+    }
+    __syncwarp();
+    __threadfence_system();
+}
+
+constexpr int kShWarps = 4;
+constexpr int kShPerWarp = SwLayout::kUnion + kSwMaxKP * 8 * 2;   // keys / product staging + window copy + owned list
+
+__global__ void __launch_bounds__(kShWarps * 32) shard_rerank_kernel(const ShardArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x * kShWarps + warp;
+    if (b >= a.B) return;
+    uint8_t *wbase = smem + (size_t)warp * kShPerWarp;
+    uint64_t *keys = reinterpret_cast<uint64_t *>(wbase);
+    uint8_t *stage = wbase;
+    uint64_t *ckeys = reinterpret_cast<uint64_t *>(wbase + SwLayout::kUnion);   // [KP] global window
+    int *olist = reinterpret_cast<int *>(ckeys + kSwMaxKP);                      // [KP] window positions this rank owns
+    const int KP = a.KP;
+    wait_flags(a.win.flags, a.win.epoch, a.world, lane);
+
+    // ---- merge the world windows ----
+    int T = 0, flag = 0, has_outside = 0;
+    float eps = 0.f, bstar = __int_as_float(0x7f800000);
+    for (int r = 0; r < a.world; ++r) {
+        const uint64_t *wr = a.win.slots + (size_t)r * a.win.stride;
+        const uint64_t meta = __ldcg(wr + (size_t)a.B * KP + b);
+        const int nc = (int)(uint32_t)meta;
+        eps = fmaxf(eps, __uint_as_float((uint32_t)(meta >> 32)));
+        for (int j = lane; j < nc; j += 32) keys[T + j] = __ldcg(wr + (size_t)b * KP + j);
+        uint64_t lo, hi;
+        shard_range(a.n_total, a.world, r, &lo, &hi);
+        if ((uint64_t)nc < hi - lo) {          // rows of shard r exist outside its window
+            has_outside = 1;
+            if (nc > 0) bstar = fminf(bstar, key_score(__ldcg(wr + (size_t)b * KP + nc - 1)));
+            else flag = 1;                     // nothing admitted there: no bound to offer
+        }
+        T += nc;
+    }
+    __syncwarp();
+    int ng = T;
+    if (T > KP) { warp_select_inplace(keys, T, KP, lane); ng = KP; }
+    int nk = 2;
+    while (nk < ng) nk <<= 1;
+    for (int i = ng + lane; i < nk; i += 32) keys[i] = kKeyMax;
+    __syncwarp();
+    warp_bitonic_smem(keys, nk, lane);
+    if (T > KP) { has_outside = 1; bstar = fminf(bstar, key_score(keys[KP - 1])); }
+    for (int i = lane; i < KP; i += 32) {
+        const uint64_t key = i < ng ? keys[i] : kKeyMax;
+        ckeys[i] = key;
+        a.g_out[(size_t)b * KP + i] = key;
+        a.e_out[(size_t)b * KP + i] = 0.0;
+    }
+    __syncwarp();
+
+    // ---- which candidates can still reach the top k; which of those are mine ----
+    const int kout = a.kk < ng ? a.kk : ng;
+    int nrer = kout;
+    if (kout > 0) {
+        const float sk = key_score(ckeys[kout - 1]);
+        const float lim = sk + 2.0f * eps * 1.0001f;
+        int c = 0;
+        for (int i = kout + lane; i < ng; i += 32) c += key_score(ckeys[i]) <= lim ? 1 : 0;
+        nrer = kout + __reduce_add_sync(0xffffffffu, c);
+    }
+    if (ng < a.kk && has_outside) flag = 1;
+    uint64_t mylo, myhi;
+    shard_range(a.n_total, a.world, a.rank, &mylo, &myhi);
+    int no = 0;
+    for (int base = 0; base < nrer; base += 32) {
+        const int j = base + lane;
+        const uint64_t row = j < nrer ? (uint64_t)key_slot(ckeys[j]) : ~0ull;
+        const bool own = j < nrer && row >= mylo && row < myhi;
+        const unsigned m = __ballot_sync(0xffffffffu, own);
+        if (own) olist[no + __popc(m & ((1u << lane) - 1u))] = j;
+        no += __popc(m);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        GMeta gm;
+        gm.nrer = nrer; gm.kout = kout; gm.flag = flag; gm.has_outside = has_outside; gm.bound = bstar; gm.eps = eps;
+        a.g_meta[b] = gm;
+    }
+
+    // ---- exact fp64 distances of my rows ----
+    const double *q = a.q64 + (size_t)b * a.d;
+    const bool cosine = a.metric == EVDB_COSINE;
+    const int RC = cosine ? kSwRows - 1 : kSwRows;
+    for (int base = 0; base < no; base += RC) {
+        const int nr = no - base < RC ? no - base : RC;
+        const bool mine = lane < nr;
+        const int j = mine ? olist[base + lane] : 0;
+        const uint32_t slot = mine ? (uint32_t)((uint64_t)key_slot(ckeys[j]) - mylo) : 0u;
+        const double s = sw_fold_chain(a.rows, a.row_bytes, q, a.d, a.metric, stage, slot, nr, cosine, lane);
+        double dist;
+        if (cosine) {
+            const double sq = __shfl_sync(0xffffffffu, s, nr);
+            const double n1 = __dsqrt_rn(sq), n2 = mine ? a.norm64[slot] : 0.0;
+            dist = (n1 == 0.0 || n2 == 0.0) ? 1.0 : __dsub_rn(1.0, __ddiv_rn(s, __dmul_rn(n1, n2)));
+        } else if (a.metric == EVDB_EUCLIDEAN) {
+            dist = __dsqrt_rn(s);
+        } else {
+            dist = s;
+        }
+        if (mine) a.e_out[(size_t)b * KP + j] = dist;
+    }
+}
+
+__global__ void __launch_bounds__(kShWarps * 32) shard_final_kernel(const ShardArgs a) {
+    __shared__ uint64_t s_key[kShWarps][kSwMaxKP], s_id[kShWarps][kSwMaxKP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x * kShWarps + warp;
+    if (b >= a.B) return;
+    wait_flags(a.ex.flags, a.ex.epoch, a.world, lane);
+    const int KP = a.KP, k = a.k;
+    const GMeta gm = a.g_meta[b];
+    uint64_t *dk = s_key[warp], *di = s_id[warp];
+    const uint64_t per = (a.n_total + a.world - 1) / a.world;
+    int nsort = 2;
+    while (nsort < gm.nrer) nsort <<= 1;
+    for (int j = lane; j < nsort; j += 32) {
+        uint64_t key = kKeyMax, id = kKeyMax;
+        if (j < gm.nrer) {
+            id = (uint64_t)key_slot(a.g_out[(size_t)b * KP + j]);
+            const int owner = (int)(id / per);
+            key = f64_orderable(__ldcg(reinterpret_cast<const double *>(a.ex.slots + (size_t)owner * a.ex.stride) +
+                                       (size_t)b * KP + j));
+        }
+        dk[j] = key;
+        di[j] = id;
+    }
+    __syncwarp();
+    warp_bitonic_smem_pairs(dk, di, nsort, lane);
+    uint64_t *out_ids = a.out_blob;
+    double *out_d = reinterpret_cast<double *>(a.out_blob + (size_t)a.B * k);
+    int32_t *out_c = reinterpret_cast<int32_t *>(a.out_blob + 2 * (size_t)a.B * k);
+    for (int i = lane; i < k; i += 32) {
+        const size_t o = (size_t)b * k + i;
+        if (i < gm.kout) {
+            const uint64_t ob = dk[i];
+            const uint64_t bits = ob ^ ((ob >> 63) ? 0x8000000000000000ull : 0xFFFFFFFFFFFFFFFFull);
+            out_d[o] = __longlong_as_double((long long)bits);
+            out_ids[o] = di[i];
+        } else {
+            out_d[o] = 0.0;
+            out_ids[o] = kKeyMax;
+        }
+    }
+    if (lane == 0) {
+        out_c[b] = gm.kout;
+        int flag = gm.flag;
+        if (gm.kout > 0 && gm.has_outside) {
+            const uint64_t ob = dk[gm.kout - 1];
+            const uint64_t bits = ob ^ ((ob >> 63) ? 0x8000000000000000ull : 0xFFFFFFFFFFFFFFFFull);
+            double dkv = __longlong_as_double((long long)bits);
+            if (a.squared) dkv = __dmul_rn(__dmul_rn(dkv, dkv), 1.0 + 1e-15);
+            if (!(dkv < (double)gm.bound - (double)gm.eps)) flag = 1;
+        }
+        if (gm.kout == 0 && a.kk > 0) flag = 1;
+        out_c[a.B + b] = flag;
+    }
+}
+
+// phase 1: local window of every query -> win_blob ([B*KP keys][B meta])
+int launch_shard_window(evdb_store *s, const double *d_q64, const RawCands *raw, int L, int KP, int B, int kk,
+                        int metric, const float *eps_q, uint64_t slot_base, uint64_t *win_blob, cudaStream_t st) {
+    if (!raw || s->dtype != EVDB_F32 || KP > kSwMaxKP || L > kRawMaxLists) return EVDB_E_UNSUPPORTED;
+    SelectArgs a;
+    memset(&a, 0, sizeof(a));
+    a.rows = s->rows; a.row_bytes = s->row_bytes; a.norm64 = s->norm64; a.qms64 = s->qms64;
+    a.n = s->count; a.d = s->dim; a.q64 = d_q64; a.L = L; a.KP = KP; a.raw = *raw;
+    a.kk = kk; a.kstride = kk; a.metric = metric; a.eps_q = eps_q; a.slot_base = slot_base;
+    a.win_out = win_blob; a.win_meta = win_blob + (size_t)B * KP;
+    s->n_launches++;
+    return launch_select_warp(a, B, st);
+}
+
+static void fill_shard_args(ShardArgs *a, evdb_store *s, const double *d_q64, int B, int KP, int k, int kk, int metric,
+                            int rank, int world, uint64_t n_total, double *e_out, uint64_t *g_out, void *g_meta) {
+    memset(a, 0, sizeof(*a));
+    a->rows = s->rows; a->row_bytes = s->row_bytes; a->norm64 = s->norm64; a->d = s->dim; a->q64 = d_q64;
+    a->B = B; a->KP = KP; a->kk = kk; a->k = k; a->metric = metric; a->squared = metric == EVDB_EUCLIDEAN;
+    a->world = world; a->rank = rank; a->n_total = n_total;
+    a->e_out = e_out; a->g_out = g_out; a->g_meta = (GMeta *)g_meta;
+}
+
+size_t shard_gmeta_bytes(int B) { return sizeof(GMeta) * (size_t)B; }
+
+int launch_shard_rerank(evdb_store *s, const double *d_q64, int B, int KP, int k, int kk, int metric, int rank,
+                        int world, uint64_t n_total, const ExchangeView &win, double *e_out, uint64_t *g_out,
+                        void *g_meta, cudaStream_t st) {
+    ShardArgs a;
+    fill_shard_args(&a, s, d_q64, B, KP, k, kk, metric, rank, world, n_total, e_out, g_out, g_meta);
+    a.win = win;
+    const size_t smem = (size_t)kShWarps * kShPerWarp;
+    EVDB_TRY(ensure_func_smem((const void *)shard_rerank_kernel, smem));
+    shard_rerank_kernel<<<(B + kShWarps - 1) / kShWarps, kShWarps * 32, smem, st>>>(a);
+    EVDB_CUDA(cudaGetLastError());
+    s->n_launches++;
+    return EVDB_OK;
+}
+
+int launch_shard_final(evdb_store *s, int B, int KP, int k, int kk, int metric, int rank, int world, uint64_t n_total,
+                       const ExchangeView &ex, const uint64_t *g_out, const void *g_meta, uint64_t *out_blob,
+                       cudaStream_t st) {
+    ShardArgs a;
+    fill_shard_args(&a, s, nullptr, B, KP, k, kk, metric, rank, world, n_total, nullptr, const_cast<uint64_t *>(g_out),
+                    const_cast<void *>(g_meta));
+    a.ex = ex;
+    a.out_blob = out_blob;
+    shard_final_kernel<<<(B + kShWarps - 1) / kShWarps, kShWarps * 32, 0, st>>>(a);
+    EVDB_CUDA(cudaGetLastError());
+    s->n_launches++;
+    return EVDB_OK;
+}
+
 static size_t select_smem(int threads) {
     return sizeof(uint64_t) * kSelSort + sizeof(uint64_t) * 2 * kMaxKP +
            (threads == 1024 ? sizeof(double) * (threads / 32) * 2 * kExactChunk : 0);
@@ -838,6 +1114,7 @@ int launch_select(evdb_store *s, const double *d_q64, const uint64_t *partial, c
     }
     a.kk = kk; a.kstride = kstride; a.metric = metric; a.eps_abs = eps_abs; a.eps_rel = eps_rel;
     a.eps_q = eps_q; a.squared = squared;
+    a.win_out = nullptr; a.win_meta = nullptr;
     { static int v = -1; if (v < 0) { const char *e = getenv("EVDB_SEL_VARIANT"); v = e ? atoi(e) : 0; } a.variant = v; }
     a.slot_base = slot_base; a.out_ids = d_out_ids; a.out_dists = d_out_dists;
     a.out_counts = d_out_counts; a.out_flags = d_out_flags;

@@ -140,7 +140,7 @@ static uint64_t device_bytes(const evdb_store *s) {
     if (is_quant(s)) per += sizeof(float2) + sizeof(double2);
     if (s->shadow) per += (uint64_t)s->spitch * 2;
     return per * s->capacity + (s->shadow_l2 ? s->l2_cap * (uint64_t)(s->l2_pitch + 16) * 2 : 0) + s->w_q64_cap + s->w_q32_cap + s->w_qdig_cap + s->w_qstat_cap +
-           s->w_partial_cap + s->w_qh_cap + s->w_seed_cap + s->w_ids_cap + s->w_dists_cap + s->w_counts_cap + s->w_tmp_cap;
+           s->w_partial_cap + s->w_qh_cap + s->w_seed_cap + s->w_ids_cap + s->w_dists_cap + s->w_counts_cap + s->w_tmp_cap + s->w_shard_cap;
 }
 
 // ----------------------------------------------------------------------------
@@ -585,7 +585,7 @@ void evdb_store_destroy(evdb_store *s) {
     cudaFree(s->qcoef); cudaFree(s->qms64); cudaFree(s->shadow); cudaFree(s->shadow_l2); cudaFree(s->l2_tail); cudaFree(s->d_scalar);
     cudaFree(s->w_q64); cudaFree(s->w_q32); cudaFree(s->w_qdig); cudaFree(s->w_qh); cudaFree(s->w_seed); cudaFree(s->w_qstat);
     cudaFree(s->w_partial); cudaFree(s->w_ids); cudaFree(s->w_dists); cudaFree(s->w_counts);
-    cudaFree(s->w_tmp);
+    cudaFree(s->w_tmp); cudaFree(s->w_shard);
     if (s->h_pin) cudaFreeHost(s->h_pin);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
@@ -842,6 +842,72 @@ int evdb_merge_topk_packed_dev(int device, const void *d_blobs, int G, int B, in
     EVDB_CUDA(cudaSetDevice(device));
     return launch_merge_topk_packed((const uint64_t *)d_blobs, 2 * (size_t)B * k + (size_t)B, G, B, k,
                                     (uint64_t *)d_out_blob, (cudaStream_t)stream);
+}
+
+// ---- row-sharded GEMM batches in two phases (select.cu: windows travel, owners re-rank) ----
+struct ShardLayout { size_t win_words, e_off, g_off, m_off, total; int KP, kk; };
+static ShardLayout shard_layout(int B, int k, uint64_t n_total) {
+    ShardLayout l;
+    l.kk = (uint64_t)k < n_total ? k : (int)n_total;
+    l.KP = gemm_kp(choose_kp(l.kk, 0));
+    l.win_words = (size_t)B * l.KP + (size_t)B;
+    l.e_off = l.win_words * 8;
+    l.g_off = l.e_off + (size_t)B * l.KP * 8;
+    l.m_off = l.g_off + (size_t)B * l.KP * 8;
+    l.total = l.m_off + shard_gmeta_bytes(B);
+    return l;
+}
+
+int evdb_store_search_sharded_phase1(evdb_store *s, evdb_exchange *xw, const void *d_queries_f64, int B, int d, int k,
+                                     int metric, uint64_t slot_base, uint64_t n_total, void *stream) {
+    if (!s || !xw || !d_queries_f64 || B <= 0 || k <= 0) return EVDB_E_BAD_ARG;
+    if (s->dim == 0 || s->count == 0) return EVDB_E_UNSUPPORTED;
+    if (d != s->dim) return EVDB_E_DIM_MISMATCH;
+    const ShardLayout l = shard_layout(B, k, n_total);
+    if (B > gemm_max_batch() || !gemm_plan_supported(s, metric, B, l.KP) || (size_t)xw->world * l.KP > 2048 ||
+        l.win_words > xw->max_words || n_total > 0xFFFFFFF0ull)
+        return EVDB_E_UNSUPPORTED;
+    EVDB_TRY(set_device(s));
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    EVDB_TRY(ensure_bytes(&s->w_shard, &s->w_shard_cap, l.total));
+    int lists = 0;
+    const float *eps_q = nullptr;
+    RawCands raw;
+    s->last_plan = EVDB_PLAN_GEMM;
+    EVDB_TRY(launch_gemm_topk(s, (const double *)d_queries_f64, B, l.KP, metric, &lists, &eps_q, &raw, st));
+    EVDB_TRY(launch_shard_window(s, (const double *)d_queries_f64, &raw, lists, l.KP, B, l.kk, metric, eps_q, slot_base,
+                                 (uint64_t *)s->w_shard, st));
+    EVDB_TRY(exchange_push_words(xw, s->w_shard, l.win_words, st));
+    s->n_launches++;
+    s->n_searches += (uint64_t)B;
+    s->n_rows_scanned += (uint64_t)B * s->count;
+    return EVDB_OK;
+}
+
+int evdb_store_search_sharded_phase2(evdb_store *s, evdb_exchange *xw, evdb_exchange *xe, const void *d_queries_f64,
+                                     int B, int k, int metric, uint64_t n_total, void *stream) {
+    if (!s || !xw || !xe || !d_queries_f64) return EVDB_E_BAD_ARG;
+    const ShardLayout l = shard_layout(B, k, n_total);
+    if ((size_t)B * l.KP > xe->max_words) return EVDB_E_UNSUPPORTED;
+    EVDB_TRY(set_device(s));
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    uint8_t *w = (uint8_t *)s->w_shard;
+    EVDB_TRY(launch_shard_rerank(s, (const double *)d_queries_f64, B, l.KP, k, l.kk, metric, xw->rank, xw->world, n_total,
+                                 exchange_view(xw), (double *)(w + l.e_off), (uint64_t *)(w + l.g_off), w + l.m_off, st));
+    EVDB_TRY(exchange_push_words(xe, w + l.e_off, (size_t)B * l.KP, st));
+    s->n_launches++;
+    return EVDB_OK;
+}
+
+int evdb_store_search_sharded_phase3(evdb_store *s, evdb_exchange *xe, int B, int k, int metric, uint64_t n_total,
+                                     void *d_out_blob, void *stream) {
+    if (!s || !xe || !d_out_blob) return EVDB_E_BAD_ARG;
+    const ShardLayout l = shard_layout(B, k, n_total);
+    EVDB_TRY(set_device(s));
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    uint8_t *w = (uint8_t *)s->w_shard;
+    return launch_shard_final(s, B, l.KP, k, l.kk, metric, xe->rank, xe->world, n_total, exchange_view(xe),
+                              (const uint64_t *)(w + l.g_off), w + l.m_off, (uint64_t *)d_out_blob, st);
 }
 
 // ---- standalone codecs ------------------------------------------------------

@@ -171,6 +171,31 @@ class DeviceStore:
                 "evdb_store_search_dev")
 
 
+def gemm_window(k: int, n_total: int) -> int:
+    """Candidate window (KP) the tcgen05 plan uses for k results of an n_total-row store (mirrors store.cu)."""
+    kk = min(k, n_total)
+    want = max(kk + max(kk // 4, 6), 16)
+    kp = 1
+    while kp < want:
+        kp <<= 1
+    return 32 if kp <= 32 else (64 if kp <= 64 else (128 if kp <= 128 else kp))
+
+
+def sharded_phase1(store: "DeviceStore", xw: "Exchange", d_q, B, d, k, metric, slot_base, n_total, stream=0) -> int:
+    return N.lib().evdb_store_search_sharded_phase1(store.handle, xw._h, d_q, B, d, k, N.METRICS.get(metric, metric),
+                                                    slot_base, n_total, stream)
+
+
+def sharded_phase2(store, xw, xe, d_q, B, k, metric, n_total, stream=0):
+    N.check(N.lib().evdb_store_search_sharded_phase2(store.handle, xw._h, xe._h, d_q, B, k,
+                                                     N.METRICS.get(metric, metric), n_total, stream), "sharded_phase2")
+
+
+def sharded_phase3(store, xe, B, k, metric, n_total, d_out_blob, stream=0):
+    N.check(N.lib().evdb_store_search_sharded_phase3(store.handle, xe._h, B, k, N.METRICS.get(metric, metric),
+                                                     n_total, d_out_blob, stream), "sharded_phase3")
+
+
 def merge_topk_dev(device, d_ids, d_dists, d_counts, G, B, k, d_out_ids, d_out_dists, d_out_counts, stream=0):
     N.check(N.lib().evdb_merge_topk_dev(device, d_ids, d_dists, d_counts, G, B, k, d_out_ids, d_out_dists,
                                         d_out_counts, stream), "evdb_merge_topk_dev")

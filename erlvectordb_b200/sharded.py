@@ -22,7 +22,8 @@ import torch
 import torch.distributed as dist
 
 from . import _native as N
-from .device_store import DeviceStore, Exchange, merge_topk_packed_dev
+from .device_store import (DeviceStore, Exchange, gemm_window, merge_topk_packed_dev, sharded_phase1,
+                           sharded_phase2, sharded_phase3)
 
 
 def shard_bounds(n_total: int, world: int, rank: int) -> tuple[int, int]:
@@ -129,13 +130,13 @@ class ShardedStore:
                                  _stream_handle(q.device))
         # an empty shard keeps the zero counts the blob was created with
 
-    def _p2p(self, B: int, k: int, dev):
-        """The (B, k) exchange object, created and connected on first use (a collective call)."""
-        key = (B, k)
+    def _p2p(self, B: int, k: int, dev, words: int | None = None, tag: str = "blob"):
+        """An exchange object for (B, k), created and connected on first use (a collective call)."""
+        key = (B, k, tag)
         if key not in self._xchg:
             x = None
             try:
-                x = Exchange(dev.index or 0, self.rank, self.world, blob_words(B, k))
+                x = Exchange(dev.index or 0, self.rank, self.world, blob_words(B, k) if words is None else words)
                 mine = torch.tensor(list(bytes(x.handle_bytes)), dtype=torch.uint8, device=dev)
                 allh = torch.empty((self.world, 64), dtype=torch.uint8, device=dev)
                 dist.all_gather_into_tensor(allh.view(-1), mine, group=self.group)
@@ -157,10 +158,43 @@ class ShardedStore:
         merge_topk_packed_dev(dev.index or 0, gathered.data_ptr(), self.world, B, k, merged.data_ptr(),
                               _stream_handle(dev))
 
+    def _two_phase_ok(self, B: int, k: int, metric: str) -> bool:
+        """Decided from GLOBAL facts only, so that every rank takes the same path: the tcgen05 plan
+        must apply on every shard (F32, cosine/euclidean, a real batch, a window <= 128 keys, every
+        shard at least one corpus tile)."""
+        if self._merge is not None or self._local_search is not None or self.exchange != "p2p" or self.world < 2:
+            return False
+        per = (self.n_total + self.world - 1) // self.world
+        smallest = self.n_total - per * (self.world - 1)
+        return (self.dtype == "f32" and metric in ("cosine", "euclidean") and 16 <= B <= 8192 and
+                gemm_window(k, self.n_total) <= 128 and self.world * gemm_window(k, self.n_total) <= 2048 and
+                smallest >= 256 and self.n_total < 0xFFFFFFF0)
+
+    def _search_two_phase(self, q: torch.Tensor, k: int, metric: str):
+        """Query batches on the tcgen05 plan: approximate windows travel, owners re-rank (select.cu)."""
+        B, d = q.shape
+        kp = gemm_window(k, self.n_total)
+        xw = self._p2p(B, k, q.device, words=B * kp + B, tag="win")
+        xe = self._p2p(B, k, q.device, words=B * kp, tag="exact")
+        if xw is None or xe is None:
+            return None
+        merged, mv = self._buffers(B, k, q.device)[2], self._buffers(B, k, q.device)[4]
+        stream = _stream_handle(q.device)
+        rc = sharded_phase1(self._dev, xw, q.data_ptr(), B, d, k, metric, self.lo, self.n_total, stream)
+        if rc != N.OK:
+            raise N.EvdbError(rc, "sharded_phase1")   # the plan was agreed on from global facts: must not fail alone
+        sharded_phase2(self._dev, xw, xe, q.data_ptr(), B, k, metric, self.n_total, stream)
+        sharded_phase3(self._dev, xe, B, k, metric, self.n_total, merged.data_ptr(), stream)
+        return mv
+
     def search(self, q: torch.Tensor, k: int, metric: str = "cosine"):
         """q: (B, d) float64 on this rank's device (identical on every rank).
         Returns (ids (B,k) int64 global rows, dists (B,k) float64, counts (B,) int32, flags (B,))."""
         B = q.shape[0]
+        if self._two_phase_ok(B, k, metric):
+            r = self._search_two_phase(q, k, metric)
+            if r is not None:
+                return r
         local, gathered, merged, lv, mv, lptrs = self._buffers(B, k, q.device)
         if self._local_search is not None:      # injected (CPU tests): tensors in, packed here
             ids, dists, counts, flags = self._local_search(q, k, metric)

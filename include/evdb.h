@@ -200,6 +200,27 @@ int evdb_exchange_push(evdb_exchange *x, const void *d_local_blob, int B, int k,
 int evdb_exchange_merge(evdb_exchange *x, int B, int k, void *d_out_blob, void *stream);
 void evdb_exchange_destroy(evdb_exchange *x);
 
+/* ---- row-sharded query batches in two phases (tcgen05 GEMM plan, F32 stores) -----------------
+ * Re-ranking every shard's local top-k repeats the exact fp64 work on every rank.  Instead:
+ *   phase1: local GEMM + window selection; the approximate window (B x KP keys with global rows,
+ *           size, error bound) is pushed to every rank through exchange `xw`;
+ *   phase2: every rank merges the world windows into the same global window and re-ranks in exact
+ *           fp64 only the candidates it owns; those distances are pushed through exchange `xe`;
+ *   phase3: every rank orders the global candidates by the owners' exact distances, emits the
+ *           top k into d_out_blob (packed layout of evdb_merge_topk_packed_dev) and proves the window.
+ * All three only enqueue.  rank/world come from the exchanges (mailboxes of at least B*KP + B resp.
+ * B*KP words, KP <= 128).  EVDB_E_UNSUPPORTED (before anything is enqueued) when the plan does not
+ * apply -- callers decide from global facts (dtype, metric, B, k, smallest shard) so that every
+ * rank takes the same path.  n_total = rows of the whole store, slot_base = first global row here. */
+int evdb_store_search_sharded_phase1(evdb_store *s, evdb_exchange *xw, const void *d_queries_f64, int B,
+                                     int d, int k, int metric, uint64_t slot_base, uint64_t n_total,
+                                     void *stream);
+int evdb_store_search_sharded_phase2(evdb_store *s, evdb_exchange *xw, evdb_exchange *xe,
+                                     const void *d_queries_f64, int B, int k, int metric,
+                                     uint64_t n_total, void *stream);
+int evdb_store_search_sharded_phase3(evdb_store *s, evdb_exchange *xe, int B, int k, int metric,
+                                     uint64_t n_total, void *d_out_blob, void *stream);
+
 /* ---- codecs (vector_compression.erl:166-204), computed on the device ------
  * n rows of d fp64 -> codes (+ per-row fp64 min/max/scale).  ok[i] = 0 for a
  * row whose Max == Min (reference: badarith, caller stores it raw).          */

@@ -97,3 +97,59 @@ def test_peer_memory_exchange_equals_packed_merge(native, oracle):
         x.close()
     for st, _ in stores:
         st.close()
+
+
+@pytest.mark.parametrize("metric,n,d,B,k,G", [
+    ("cosine", 90_000, 128, 160, 10, 4),
+    ("cosine", 40_000, 768, 64, 10, 8),       # the bench shape, 8 shards
+    ("euclidean", 60_000, 64, 33, 100, 2),    # 128-key windows, ragged batch
+    ("cosine", 2_100, 32, 16, 10, 8),         # shards of ~262 rows: windows cover whole shards
+])
+def test_two_phase_sharded_search_equals_single_store(native, oracle, metric, n, d, B, k, G):
+    """Windows travel, owners re-rank (evdb_store_search_sharded_phase1/2/3): G ranks emulated on one
+    GPU with pointer-connected mailboxes; each phase is enqueued for ALL ranks before the next, so
+    no kernel ever waits.  Every rank's packed result must equal the single-store search bit for bit."""
+    import torch
+    from erlvectordb_b200.device_store import (DeviceStore, Exchange, gemm_window, sharded_phase1, sharded_phase2,
+                                               sharded_phase3)
+    from erlvectordb_b200.sharded import blob_views, blob_words, shard_bounds
+
+    dev = torch.device("cuda", 0)
+    kp = gemm_window(k, n)
+    stores, xws, xes = [], [], []
+    for g in range(G):
+        lo, hi = shard_bounds(n, G, g)
+        st = DeviceStore(dtype="f32", device=0)
+        st.fill_synthetic(oracle.SEED_CORPUS, hi - lo, d, row0=lo)
+        stores.append((st, lo))
+        xws.append(Exchange(0, g, G, B * kp + B))
+        xes.append(Exchange(0, g, G, B * kp))
+    for xs in (xws, xes):
+        boxes = [x.mailbox for x in xs]
+        for x in xs:
+            x.connect_ptrs(boxes)
+    one = DeviceStore(dtype="f32", device=0)
+    one.fill_synthetic(oracle.SEED_CORPUS, n, d)
+    for step in range(3):
+        qh = oracle.synth_f64(oracle.SEED_QUERY, step * B, B, d)
+        q = torch.from_numpy(qh).to(dev)
+        outs = [torch.zeros((blob_words(B, k),), dtype=torch.int64, device=dev) for _ in range(G)]
+        for g, (st, lo) in enumerate(stores):
+            assert sharded_phase1(st, xws[g], q.data_ptr(), B, d, k, metric, lo, n, 1) == 0
+        for g, (st, lo) in enumerate(stores):
+            sharded_phase2(st, xws[g], xes[g], q.data_ptr(), B, k, metric, n, 1)
+        for g, (st, lo) in enumerate(stores):
+            sharded_phase3(st, xes[g], B, k, metric, n, outs[g].data_ptr(), 1)
+        torch.cuda.synchronize()
+        s_ids, s_d, s_c = one.search(qh, k, metric)
+        for g in range(G):
+            ids, dd, cnt, flags = [t.cpu().numpy() for t in blob_views(outs[g], B, k)]
+            assert int(flags.sum()) == 0, (step, g)
+            assert np.array_equal(cnt, s_c)
+            assert np.array_equal(ids.astype(np.uint32), s_ids), (step, g)
+            assert np.array_equal(dd, s_d), (step, g)
+    for x in xws + xes:
+        x.close()
+    for st, _ in stores:
+        st.close()
+    one.close()
