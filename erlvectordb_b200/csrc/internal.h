@@ -163,9 +163,10 @@ int check_device_public(int dev);
 int launch_shard_window(evdb_store *s, const double *d_q64, const RawCands *raw, int L, int KP, int B, int kk,
                         int metric, const float *eps_q, uint64_t slot_base, uint64_t *win_blob, cudaStream_t st);
 size_t shard_gmeta_bytes(int B);
+int launch_shard_qnorm(evdb_store *s, const double *d_q64, int B, int rank, int world, uint64_t *qn_out, cudaStream_t st);
 int launch_shard_rerank(evdb_store *s, const double *d_q64, int B, int KP, int k, int kk, int metric, int rank,
                         int world, uint64_t n_total, const ExchangeView &win, double *e_out, uint64_t *g_out,
-                        void *g_meta, cudaStream_t st);
+                        void *g_meta, uint64_t *work, int *work_n, cudaStream_t st);
 int launch_shard_final(evdb_store *s, int B, int KP, int k, int kk, int metric, int rank, int world, uint64_t n_total,
                        const ExchangeView &ex, const uint64_t *g_out, const void *g_meta, uint64_t *out_blob,
                        cudaStream_t st);

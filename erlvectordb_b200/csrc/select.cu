@@ -859,6 +859,8 @@ struct ShardArgs {
     uint64_t n_total;
     ExchangeView win;     // phase 2 input: per rank [B*KP keys][B meta]
     double *e_out;        // phase 2 output: [B][KP] exact distances of the rows this rank owns (0 elsewhere)
+    uint64_t *work;       // phase 2a -> 2b: (b << 40 | j << 32 | local slot) of every candidate this rank re-ranks
+    int *work_n;          //   its length (zeroed before 2a)
     uint64_t *g_out;      // [B][KP] the global window (each rank's own copy, identical everywhere)
     GMeta *g_meta;        // [B]
     ExchangeView ex;      // phase 3 input: per rank [B][KP] exact distances
@@ -963,28 +965,117 @@ __global__ void __launch_bounds__(kShWarps * 32) shard_rerank_kernel(const Shard
         a.g_meta[b] = gm;
     }
 
-    // ---- exact fp64 distances of my rows ----
-    const double *q = a.q64 + (size_t)b * a.d;
+    // ---- my candidates go to the rank-wide work list: the fold kernel packs 32 ROWS OF ANY QUERIES per
+    // chain (a chain costs the fp64 unit the same for 1 row as for 32; per-query chains would make
+    // every rank pay B chains however few rows it owns) ----
+    int wbase_i = 0;
+    if (lane == 0 && no > 0) wbase_i = atomicAdd(a.work_n, no);
+    wbase_i = __shfl_sync(0xffffffffu, wbase_i, 0);
+    for (int i = lane; i < no; i += 32) {
+        const int j = olist[i];
+        a.work[wbase_i + i] = ((uint64_t)b << 40) | ((uint64_t)j << 32) | (uint32_t)((uint64_t)key_slot(ckeys[j]) - mylo);
+    }
+}
+
+// Mixed-query chain: lane r folds row (slot_r) against query b_r.  Products by all lanes, staged in
+// shared memory, one lane per row folds left to right (see sw_fold_chain).
+__device__ __forceinline__ double sw_fold_chain_mixed(const uint8_t *__restrict__ rows, size_t row_bytes,
+                                                      const double *__restrict__ q64, int d, int metric,
+                                                      uint8_t *stage, uint32_t my_slot, int my_b, int nr, int lane) {
+    double s = 0.0;
+    for (int kb = 0; kb < d; kb += kSwKC) {
+        const int cnt = d - kb < kSwKC ? d - kb : kSwKC;
+        const int unit = lane & 15, rsub = lane >> 4;
+        const int e0 = kb + 4 * unit;
+        __syncwarp();
+#pragma unroll 4
+        for (int r2 = 0; r2 < nr; r2 += 2) {
+            const int r = r2 + rsub;
+            const int rr = r < nr ? r : 0;
+            const uint32_t rslot = __shfl_sync(0xffffffffu, my_slot, rr);
+            const int rb = __shfl_sync(0xffffffffu, my_b, rr);
+            if (r >= nr) continue;
+            const double *q = q64 + (size_t)rb * d;
+            uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+            if ((size_t)e0 * 4 < row_bytes)
+                raw = __ldg(reinterpret_cast<const uint4 *>(rows + (size_t)rslot * row_bytes) + (e0 >> 2));
+            const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+            double t[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double qd = e0 + i < d ? __ldg(q + e0 + i) : 0.0;
+                const double x = widen_f32(w[i]);
+                if (metric == EVDB_COSINE) t[i] = __dmul_rn(qd, x);
+                else {
+                    const double df = __dsub_rn(qd, x);
+                    t[i] = metric == EVDB_EUCLIDEAN ? __dmul_rn(df, df) : fabs(df);
+                }
+            }
+            double2 *dst = reinterpret_cast<double2 *>(stage + (size_t)r * kSwProdStride) + 2 * unit;
+            dst[0] = make_double2(t[0], t[1]);
+            dst[1] = make_double2(t[2], t[3]);
+        }
+        __syncwarp();
+        if (lane < nr) {
+            const double2 *p = reinterpret_cast<const double2 *>(stage + (size_t)lane * kSwProdStride);
+            const int pairs = cnt >> 1;
+#pragma unroll 4
+            for (int i = 0; i < pairs; ++i) {
+                const double2 v = p[i];
+                s = __dadd_rn(s, v.x);
+                s = __dadd_rn(s, v.y);
+            }
+            if (cnt & 1) s = __dadd_rn(s, reinterpret_cast<const double *>(p)[cnt - 1]);
+        }
+    }
+    return s;
+}
+
+// phase 2b: the packed exact re-rank of this rank's work list
+__global__ void __launch_bounds__(kShWarps * 32) shard_fold_kernel(const ShardArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *stage = smem + (size_t)warp * (kSwRows * kSwProdStride);
+    const int total = *a.work_n;
+    const int nwarps = gridDim.x * kShWarps;
     const bool cosine = a.metric == EVDB_COSINE;
-    const int RC = cosine ? kSwRows - 1 : kSwRows;
-    for (int base = 0; base < no; base += RC) {
-        const int nr = no - base < RC ? no - base : RC;
+    for (int c = blockIdx.x * kShWarps + warp; c * 32 < total; c += nwarps) {
+        const int nr = total - c * 32 < 32 ? total - c * 32 : 32;
         const bool mine = lane < nr;
-        const int j = mine ? olist[base + lane] : 0;
-        const uint32_t slot = mine ? (uint32_t)((uint64_t)key_slot(ckeys[j]) - mylo) : 0u;
-        const double s = sw_fold_chain(a.rows, a.row_bytes, q, a.d, a.metric, stage, slot, nr, cosine, lane);
+        const uint64_t e = mine ? a.work[c * 32 + lane] : 0ull;
+        const int b = (int)(e >> 40), j = (int)((e >> 32) & 0xFF);
+        const uint32_t slot = (uint32_t)e;
+        const double s = sw_fold_chain_mixed(a.rows, a.row_bytes, a.q64, a.d, a.metric, stage, slot, b, nr, lane);
+        if (!mine) continue;
         double dist;
         if (cosine) {
-            const double sq = __shfl_sync(0xffffffffu, s, nr);
-            const double n1 = __dsqrt_rn(sq), n2 = mine ? a.norm64[slot] : 0.0;
+            // vector_norm(Query)^2, folded once per query by rank b % world in phase 1 and shipped with its window
+            const uint64_t *wo = a.win.slots + (size_t)(b % a.world) * a.win.stride + (size_t)a.B * a.KP + (size_t)a.B;
+            const double n1 = __dsqrt_rn(__longlong_as_double((long long)__ldcg(wo + b))), n2 = a.norm64[slot];
             dist = (n1 == 0.0 || n2 == 0.0) ? 1.0 : __dsub_rn(1.0, __ddiv_rn(s, __dmul_rn(n1, n2)));
         } else if (a.metric == EVDB_EUCLIDEAN) {
             dist = __dsqrt_rn(s);
         } else {
             dist = s;
         }
-        if (mine) a.e_out[(size_t)b * KP + j] = dist;
+        a.e_out[(size_t)b * a.KP + j] = dist;
     }
+}
+
+// phase 1b (cosine): the exact query norms, each folded ONCE in the whole group: rank r takes the
+// queries b = r (mod world), one lane per query, strictly left to right; results ride in the window blob.
+__global__ void __launch_bounds__(128) shard_qnorm_kernel(const double *__restrict__ q64, int B, int d, int rank,
+                                                          int world, uint64_t *__restrict__ qn_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = rank + i * world;
+    if (b >= B) return;
+    const double *q = q64 + (size_t)b * d;
+    double s = 0.0;
+    for (int t = 0; t < d; ++t) {
+        const double v = q[t];
+        s = __dadd_rn(s, __dmul_rn(v, v));
+    }
+    qn_out[b] = (uint64_t)__double_as_longlong(s);
 }
 
 __global__ void __launch_bounds__(kShWarps * 32) shard_final_kernel(const ShardArgs a) {
@@ -1056,6 +1147,17 @@ int launch_shard_window(evdb_store *s, const double *d_q64, const RawCands *raw,
     return launch_select_warp(a, B, st);
 }
 
+int launch_shard_qnorm(evdb_store *s, const double *d_q64, int B, int rank, int world, uint64_t *qn_out, cudaStream_t st) {
+    EVDB_CUDA(cudaMemsetAsync(qn_out, 0, sizeof(uint64_t) * (size_t)B, st));
+    const int mine = (B - rank + world - 1) / world;
+    if (mine > 0) {
+        shard_qnorm_kernel<<<(mine + 127) / 128, 128, 0, st>>>(d_q64, B, s->dim, rank, world, qn_out);
+        EVDB_CUDA(cudaGetLastError());
+        s->n_launches++;
+    }
+    return EVDB_OK;
+}
+
 static void fill_shard_args(ShardArgs *a, evdb_store *s, const double *d_q64, int B, int KP, int k, int kk, int metric,
                             int rank, int world, uint64_t n_total, double *e_out, uint64_t *g_out, void *g_meta) {
     memset(a, 0, sizeof(*a));
@@ -1069,15 +1171,27 @@ size_t shard_gmeta_bytes(int B) { return sizeof(GMeta) * (size_t)B; }
 
 int launch_shard_rerank(evdb_store *s, const double *d_q64, int B, int KP, int k, int kk, int metric, int rank,
                         int world, uint64_t n_total, const ExchangeView &win, double *e_out, uint64_t *g_out,
-                        void *g_meta, cudaStream_t st) {
+                        void *g_meta, uint64_t *work, int *work_n, cudaStream_t st) {
     ShardArgs a;
     fill_shard_args(&a, s, d_q64, B, KP, k, kk, metric, rank, world, n_total, e_out, g_out, g_meta);
     a.win = win;
+    a.work = work;
+    a.work_n = work_n;
+    EVDB_CUDA(cudaMemsetAsync(work_n, 0, sizeof(int), st));
     const size_t smem = (size_t)kShWarps * kShPerWarp;
     EVDB_TRY(ensure_func_smem((const void *)shard_rerank_kernel, smem));
     shard_rerank_kernel<<<(B + kShWarps - 1) / kShWarps, kShWarps * 32, smem, st>>>(a);
     EVDB_CUDA(cudaGetLastError());
-    s->n_launches++;
+    // 2b: chains of 32 rows; the list length is only known on the device, the grid covers the usual
+    // case in one wave and strides over the rest
+    const size_t smem_f = (size_t)kShWarps * kSwRows * kSwProdStride;
+    EVDB_TRY(ensure_func_smem((const void *)shard_fold_kernel, smem_f));
+    int grid = (int)(((size_t)B * 24 / (size_t)(world > 0 ? world : 1) + 32 * kShWarps - 1) / (32 * kShWarps));
+    if (grid < 8) grid = 8;
+    if (grid > s->sm_count * 3) grid = s->sm_count * 3;
+    shard_fold_kernel<<<grid, kShWarps * 32, smem_f, st>>>(a);
+    EVDB_CUDA(cudaGetLastError());
+    s->n_launches += 2;
     return EVDB_OK;
 }
 
