@@ -64,6 +64,19 @@ int exchange_push_words(evdb_exchange *x, const void *d_blob, size_t words, cuda
     return EVDB_OK;
 }
 
+PushTarget exchange_begin_push(evdb_exchange *x) {
+    x->epoch++;
+    const int parity = (int)(x->epoch & 1);
+    PushTarget t;
+    t.peer_box = x->d_peer_box;
+    t.slot_off = ((unsigned long long)parity * x->world + x->rank) * x->slot_words;
+    t.flag_off = 2ull * x->world * x->slot_words + (unsigned long long)parity * x->world + x->rank;
+    t.epoch = x->epoch;
+    t.counter = reinterpret_cast<unsigned int *>(x->mailbox + box_words(x) + 2 * (size_t)x->world) + 1;
+    t.world = x->world;
+    return t;
+}
+
 ExchangeView exchange_view(const evdb_exchange *x) {
     const int parity = (int)(x->epoch & 1);
     ExchangeView v;

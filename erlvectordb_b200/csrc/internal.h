@@ -102,6 +102,17 @@ struct ExchangeView {
     unsigned long long epoch;
 };
 int exchange_push_words(evdb_exchange *x, const void *d_blob, size_t words, cudaStream_t st);
+// Fused push: the PRODUCING kernel stores its output words straight into every peer's mailbox slot
+// (push_store) and its last warp publishes the epoch flags (push_arrive) -- no separate copy kernel.
+struct PushTarget {
+    uint64_t *const *peer_box;        // device array [world]
+    unsigned long long slot_off;      // word offset of my slot of this epoch's parity in every mailbox
+    unsigned long long flag_off;      // word offset of my flag there
+    unsigned long long epoch;
+    unsigned int *counter;            // local arrival counter (zero between uses)
+    int world;
+};
+PushTarget exchange_begin_push(evdb_exchange *x);   // starts the next epoch
 ExchangeView exchange_view(const evdb_exchange *x);
 
 struct ScanArgs {
@@ -161,12 +172,11 @@ int launch_merge_topk_packed(const uint64_t *blobs, size_t blob_stride, int G, i
 int check_device_public(int dev);
 // row-sharded two-phase GEMM search (select.cu)
 int launch_shard_window(evdb_store *s, const double *d_q64, const RawCands *raw, int L, int KP, int B, int kk,
-                        int metric, const float *eps_q, uint64_t slot_base, uint64_t *win_blob, cudaStream_t st);
+                        int metric, const float *eps_q, uint64_t slot_base, const PushTarget &push, cudaStream_t st);
 size_t shard_gmeta_bytes(int B);
-int launch_shard_qnorm(evdb_store *s, const double *d_q64, int B, int rank, int world, uint64_t *qn_out, cudaStream_t st);
 int launch_shard_rerank(evdb_store *s, const double *d_q64, int B, int KP, int k, int kk, int metric, int rank,
-                        int world, uint64_t n_total, const ExchangeView &win, double *e_out, uint64_t *g_out,
-                        void *g_meta, uint64_t *work, int *work_n, cudaStream_t st);
+                        int world, uint64_t n_total, const ExchangeView &win, const PushTarget &e_push, uint64_t *g_out,
+                        void *g_meta, cudaStream_t st);
 int launch_shard_final(evdb_store *s, int B, int KP, int k, int kk, int metric, int rank, int world, uint64_t n_total,
                        const ExchangeView &ex, const uint64_t *g_out, const void *g_meta, uint64_t *out_blob,
                        cudaStream_t st);

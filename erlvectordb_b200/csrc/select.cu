@@ -25,6 +25,26 @@ namespace evdb {
 
 constexpr int kSelSort = 4096;  // keys sorted / selected per merge round
 
+// ---- fused push (exchange.cu): store one word into my slot of EVERY rank's mailbox ----
+__device__ __forceinline__ void push_store(const PushTarget &t, size_t word, uint64_t v) {
+    for (int p = 0; p < t.world; ++p) t.peer_box[p][t.slot_off + word] = v;
+}
+// Every warp of the kernel calls this once after its last push_store (all 32 lanes): the warp that
+// arrives last publishes the epoch in every rank's mailbox.
+__device__ __forceinline__ void push_arrive(const PushTarget &t, unsigned int total_warps, int lane) {
+    __threadfence_system();
+    __syncwarp();
+    unsigned int prev = 0;
+    if (lane == 0) prev = atomicAdd(t.counter, 1u);
+    prev = __shfl_sync(0xffffffffu, prev, 0);
+    if (prev == total_warps - 1) {
+        __threadfence_system();
+        if (lane < t.world)
+            *reinterpret_cast<volatile unsigned long long *>(t.peer_box[lane] + t.flag_off) = t.epoch;
+        if (lane == 0) *t.counter = 0;
+    }
+}
+
 struct SelectArgs {
     const uint8_t *rows;
     size_t row_bytes;
@@ -40,8 +60,8 @@ struct SelectArgs {
     const float *eps_q;  // optional [B]: per-query absolute bound (GEMM plans)
     int squared;         // key scores are squared distances (euclidean GEMM plan)
     int variant;         // tuning: bit 0 = L1 prefetch pre-pass, bit 1 = pipelined fold, bit 2 = L2 prefetch instead
-    uint64_t *win_out;   // sharded search, phase 1: write the ascending window (keys with GLOBAL rows) + meta and stop
-    uint64_t *win_meta;  //   [B]: (eps bits << 32) | ncand
+    int win_mode;        // sharded search, phase 1: push the ascending window (keys with GLOBAL rows) + meta to every rank and stop
+    PushTarget push;     //   blob words: [B*KP keys][B meta = (eps bits << 32) | ncand]
     uint64_t slot_base;
     uint64_t *out_ids;
     double *out_dists;
@@ -715,7 +735,10 @@ __global__ void __launch_bounds__(kSwWarps * 32) select_warp_kernel(const Select
         __syncthreads();
         l0 = l1;
     }
-    if (b >= B) return;  // (after the last block barrier)
+    if (b >= B) {        // (after the last block barrier)
+        if (a.win_mode) push_arrive(a.push, gridDim.x * kSwWarps, lane);
+        return;
+    }
     uint8_t *stage = wbase;                                            // ... later: staged fp64 product rows
     uint64_t *ckeys = reinterpret_cast<uint64_t *>(wbase + LY::kUnion);  // [kSwMaxKP] the window, ascending
     uint64_t *dkey = ckeys + kSwMaxKP, *dslot = dkey + kSwMaxKP;
@@ -736,9 +759,10 @@ __global__ void __launch_bounds__(kSwWarps * 32) select_warp_kernel(const Select
     for (int i = lane; i < ncand; i += 32) ckeys[i] = keys[i];
     __syncwarp();
     const float bound = ncand > 0 ? key_score(ckeys[ncand - 1]) : 0.f;
-    if (a.win_out) {  // sharded search, phase 1: the window travels, the re-rank happens after the global merge
-        for (int i = lane; i < KP; i += 32) a.win_out[(size_t)b * KP + i] = i < ncand ? ckeys[i] + a.slot_base : kKeyMax;
-        if (lane == 0) a.win_meta[b] = ((uint64_t)__float_as_uint(eps_abs) << 32) | (uint32_t)ncand;
+    if (a.win_mode) {  // sharded search, phase 1: the window travels, the re-rank happens after the global merge
+        for (int i = lane; i < KP; i += 32) push_store(a.push, (size_t)b * KP + i, i < ncand ? ckeys[i] + a.slot_base : kKeyMax);
+        if (lane == 0) push_store(a.push, (size_t)B * KP + b, ((uint64_t)__float_as_uint(eps_abs) << 32) | (uint32_t)ncand);
+        push_arrive(a.push, gridDim.x * kSwWarps, lane);
         return;
     }
 
@@ -858,9 +882,7 @@ struct ShardArgs {
     int B, KP, kk, metric, squared, world, rank;
     uint64_t n_total;
     ExchangeView win;     // phase 2 input: per rank [B*KP keys][B meta]
-    double *e_out;        // phase 2 output: [B][KP] exact distances of the rows this rank owns (0 elsewhere)
-    uint64_t *work;       // phase 2a -> 2b: (b << 40 | j << 32 | local slot) of every candidate this rank re-ranks
-    int *work_n;          //   its length (zeroed before 2a)
+    PushTarget e_push;    // phase 2 output: [B][KP] exact distances of the rows this rank owns (0 elsewhere), pushed to every rank
     uint64_t *g_out;      // [B][KP] the global window (each rank's own copy, identical everywhere)
     GMeta *g_meta;        // [B]
     ExchangeView ex;      // phase 3 input: per rank [B][KP] exact distances
@@ -886,38 +908,60 @@ __device__ __forceinline__ void wait_flags(const unsigned long long *flags, unsi
 }
 
 constexpr int kShWarps = 4;
-constexpr int kShPerWarp = SwLayout::kUnion + kSwMaxKP * 8 * 2;   // keys / product staging + window copy + owned list
+constexpr int kShPerWarp = SwLayout::kUnion + kSwMaxKP * 8 * 3;   // keys / product staging + window copy + owned list + exact values
 
 __global__ void __launch_bounds__(kShWarps * 32) shard_rerank_kernel(const ShardArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.x * kShWarps + warp;
-    if (b >= a.B) return;
+    if (b >= a.B) {
+        push_arrive(a.e_push, gridDim.x * kShWarps, lane);
+        return;
+    }
     uint8_t *wbase = smem + (size_t)warp * kShPerWarp;
     uint64_t *keys = reinterpret_cast<uint64_t *>(wbase);
     uint8_t *stage = wbase;
     uint64_t *ckeys = reinterpret_cast<uint64_t *>(wbase + SwLayout::kUnion);   // [KP] global window
     int *olist = reinterpret_cast<int *>(ckeys + kSwMaxKP);                      // [KP] window positions this rank owns
+    double *evals = reinterpret_cast<double *>(ckeys + 2 * kSwMaxKP);            // [KP] exact distances of my rows, 0 elsewhere
     const int KP = a.KP;
     wait_flags(a.win.flags, a.win.epoch, a.world, lane);
 
-    // ---- merge the world windows ----
-    int T = 0, flag = 0, has_outside = 0;
+    // ---- merge the world windows (lane r reads rank r's header; then every key load is independent) ----
+    int flag = 0, has_outside = 0;
     float eps = 0.f, bstar = __int_as_float(0x7f800000);
-    for (int r = 0; r < a.world; ++r) {
-        const uint64_t *wr = a.win.slots + (size_t)r * a.win.stride;
+    int nc = 0;
+    if (lane < a.world) {
+        const uint64_t *wr = a.win.slots + (size_t)lane * a.win.stride;
         const uint64_t meta = __ldcg(wr + (size_t)a.B * KP + b);
-        const int nc = (int)(uint32_t)meta;
-        eps = fmaxf(eps, __uint_as_float((uint32_t)(meta >> 32)));
-        for (int j = lane; j < nc; j += 32) keys[T + j] = __ldcg(wr + (size_t)b * KP + j);
+        nc = (int)(uint32_t)meta;
+        eps = __uint_as_float((uint32_t)(meta >> 32));
         uint64_t lo, hi;
-        shard_range(a.n_total, a.world, r, &lo, &hi);
+        shard_range(a.n_total, a.world, lane, &lo, &hi);
         if ((uint64_t)nc < hi - lo) {          // rows of shard r exist outside its window
             has_outside = 1;
-            if (nc > 0) bstar = fminf(bstar, key_score(__ldcg(wr + (size_t)b * KP + nc - 1)));
+            if (nc > 0) bstar = key_score(__ldcg(wr + (size_t)b * KP + nc - 1));
             else flag = 1;                     // nothing admitted there: no bound to offer
         }
-        T += nc;
+    }
+    int incl = nc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    const int T = __shfl_sync(0xffffffffu, incl, 31);
+    const int excl = incl - nc;
+    for (int o = 16; o > 0; o >>= 1) {
+        eps = fmaxf(eps, __shfl_xor_sync(0xffffffffu, eps, o));
+        bstar = fminf(bstar, __shfl_xor_sync(0xffffffffu, bstar, o));
+        flag |= __shfl_xor_sync(0xffffffffu, flag, o);
+        has_outside |= __shfl_xor_sync(0xffffffffu, has_outside, o);
+    }
+    for (int idx = lane; idx < a.world * KP; idx += 32) {
+        const int r = idx / KP, j = idx - r * KP;
+        const int nr_ = __shfl_sync(0xffffffffu, nc, r), off = __shfl_sync(0xffffffffu, excl, r);
+        if (j < nr_) keys[off + j] = __ldcg(a.win.slots + (size_t)r * a.win.stride + (size_t)b * KP + j);
     }
     __syncwarp();
     int ng = T;
@@ -932,7 +976,7 @@ __global__ void __launch_bounds__(kShWarps * 32) shard_rerank_kernel(const Shard
         const uint64_t key = i < ng ? keys[i] : kKeyMax;
         ckeys[i] = key;
         a.g_out[(size_t)b * KP + i] = key;
-        a.e_out[(size_t)b * KP + i] = 0.0;
+        evals[i] = 0.0;
     }
     __syncwarp();
 
@@ -965,117 +1009,31 @@ __global__ void __launch_bounds__(kShWarps * 32) shard_rerank_kernel(const Shard
         a.g_meta[b] = gm;
     }
 
-    // ---- my candidates go to the rank-wide work list: the fold kernel packs 32 ROWS OF ANY QUERIES per
-    // chain (a chain costs the fp64 unit the same for 1 row as for 32; per-query chains would make
-    // every rank pay B chains however few rows it owns) ----
-    int wbase_i = 0;
-    if (lane == 0 && no > 0) wbase_i = atomicAdd(a.work_n, no);
-    wbase_i = __shfl_sync(0xffffffffu, wbase_i, 0);
-    for (int i = lane; i < no; i += 32) {
-        const int j = olist[i];
-        a.work[wbase_i + i] = ((uint64_t)b << 40) | ((uint64_t)j << 32) | (uint32_t)((uint64_t)key_slot(ckeys[j]) - mylo);
-    }
-}
-
-// Mixed-query chain: lane r folds row (slot_r) against query b_r.  Products by all lanes, staged in
-// shared memory, one lane per row folds left to right (see sw_fold_chain).
-__device__ __forceinline__ double sw_fold_chain_mixed(const uint8_t *__restrict__ rows, size_t row_bytes,
-                                                      const double *__restrict__ q64, int d, int metric,
-                                                      uint8_t *stage, uint32_t my_slot, int my_b, int nr, int lane) {
-    double s = 0.0;
-    for (int kb = 0; kb < d; kb += kSwKC) {
-        const int cnt = d - kb < kSwKC ? d - kb : kSwKC;
-        const int unit = lane & 15, rsub = lane >> 4;
-        const int e0 = kb + 4 * unit;
-        __syncwarp();
-#pragma unroll 4
-        for (int r2 = 0; r2 < nr; r2 += 2) {
-            const int r = r2 + rsub;
-            const int rr = r < nr ? r : 0;
-            const uint32_t rslot = __shfl_sync(0xffffffffu, my_slot, rr);
-            const int rb = __shfl_sync(0xffffffffu, my_b, rr);
-            if (r >= nr) continue;
-            const double *q = q64 + (size_t)rb * d;
-            uint4 raw = make_uint4(0u, 0u, 0u, 0u);
-            if ((size_t)e0 * 4 < row_bytes)
-                raw = __ldg(reinterpret_cast<const uint4 *>(rows + (size_t)rslot * row_bytes) + (e0 >> 2));
-            const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-            double t[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const double qd = e0 + i < d ? __ldg(q + e0 + i) : 0.0;
-                const double x = widen_f32(w[i]);
-                if (metric == EVDB_COSINE) t[i] = __dmul_rn(qd, x);
-                else {
-                    const double df = __dsub_rn(qd, x);
-                    t[i] = metric == EVDB_EUCLIDEAN ? __dmul_rn(df, df) : fabs(df);
-                }
-            }
-            double2 *dst = reinterpret_cast<double2 *>(stage + (size_t)r * kSwProdStride) + 2 * unit;
-            dst[0] = make_double2(t[0], t[1]);
-            dst[1] = make_double2(t[2], t[3]);
-        }
-        __syncwarp();
-        if (lane < nr) {
-            const double2 *p = reinterpret_cast<const double2 *>(stage + (size_t)lane * kSwProdStride);
-            const int pairs = cnt >> 1;
-#pragma unroll 4
-            for (int i = 0; i < pairs; ++i) {
-                const double2 v = p[i];
-                s = __dadd_rn(s, v.x);
-                s = __dadd_rn(s, v.y);
-            }
-            if (cnt & 1) s = __dadd_rn(s, reinterpret_cast<const double *>(p)[cnt - 1]);
-        }
-    }
-    return s;
-}
-
-// phase 2b: the packed exact re-rank of this rank's work list
-__global__ void __launch_bounds__(kShWarps * 32) shard_fold_kernel(const ShardArgs a) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint8_t *stage = smem + (size_t)warp * (kSwRows * kSwProdStride);
-    const int total = *a.work_n;
-    const int nwarps = gridDim.x * kShWarps;
+    // ---- exact fp64 distances of my rows ----
+    const double *q = a.q64 + (size_t)b * a.d;
     const bool cosine = a.metric == EVDB_COSINE;
-    for (int c = blockIdx.x * kShWarps + warp; c * 32 < total; c += nwarps) {
-        const int nr = total - c * 32 < 32 ? total - c * 32 : 32;
+    const int RC = cosine ? kSwRows - 1 : kSwRows;
+    for (int base = 0; base < no; base += RC) {
+        const int nr = no - base < RC ? no - base : RC;
         const bool mine = lane < nr;
-        const uint64_t e = mine ? a.work[c * 32 + lane] : 0ull;
-        const int b = (int)(e >> 40), j = (int)((e >> 32) & 0xFF);
-        const uint32_t slot = (uint32_t)e;
-        const double s = sw_fold_chain_mixed(a.rows, a.row_bytes, a.q64, a.d, a.metric, stage, slot, b, nr, lane);
-        if (!mine) continue;
+        const int j = mine ? olist[base + lane] : 0;
+        const uint32_t slot = mine ? (uint32_t)((uint64_t)key_slot(ckeys[j]) - mylo) : 0u;
+        const double s = sw_fold_chain(a.rows, a.row_bytes, q, a.d, a.metric, stage, slot, nr, cosine, lane);
         double dist;
         if (cosine) {
-            // vector_norm(Query)^2, folded once per query by rank b % world in phase 1 and shipped with its window
-            const uint64_t *wo = a.win.slots + (size_t)(b % a.world) * a.win.stride + (size_t)a.B * a.KP + (size_t)a.B;
-            const double n1 = __dsqrt_rn(__longlong_as_double((long long)__ldcg(wo + b))), n2 = a.norm64[slot];
+            const double sq = __shfl_sync(0xffffffffu, s, nr);
+            const double n1 = __dsqrt_rn(sq), n2 = mine ? a.norm64[slot] : 0.0;
             dist = (n1 == 0.0 || n2 == 0.0) ? 1.0 : __dsub_rn(1.0, __ddiv_rn(s, __dmul_rn(n1, n2)));
         } else if (a.metric == EVDB_EUCLIDEAN) {
             dist = __dsqrt_rn(s);
         } else {
             dist = s;
         }
-        a.e_out[(size_t)b * a.KP + j] = dist;
+        if (mine) evals[j] = dist;
     }
-}
-
-// phase 1b (cosine): the exact query norms, each folded ONCE in the whole group: rank r takes the
-// queries b = r (mod world), one lane per query, strictly left to right; results ride in the window blob.
-__global__ void __launch_bounds__(128) shard_qnorm_kernel(const double *__restrict__ q64, int B, int d, int rank,
-                                                          int world, uint64_t *__restrict__ qn_out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = rank + i * world;
-    if (b >= B) return;
-    const double *q = q64 + (size_t)b * d;
-    double s = 0.0;
-    for (int t = 0; t < d; ++t) {
-        const double v = q[t];
-        s = __dadd_rn(s, __dmul_rn(v, v));
-    }
-    qn_out[b] = (uint64_t)__double_as_longlong(s);
+    __syncwarp();
+    for (int i = lane; i < KP; i += 32) push_store(a.e_push, (size_t)b * KP + i, (uint64_t)__double_as_longlong(evals[i]));
+    push_arrive(a.e_push, gridDim.x * kShWarps, lane);
 }
 
 __global__ void __launch_bounds__(kShWarps * 32) shard_final_kernel(const ShardArgs a) {
@@ -1135,63 +1093,41 @@ __global__ void __launch_bounds__(kShWarps * 32) shard_final_kernel(const ShardA
 
 // phase 1: local window of every query -> win_blob ([B*KP keys][B meta])
 int launch_shard_window(evdb_store *s, const double *d_q64, const RawCands *raw, int L, int KP, int B, int kk,
-                        int metric, const float *eps_q, uint64_t slot_base, uint64_t *win_blob, cudaStream_t st) {
+                        int metric, const float *eps_q, uint64_t slot_base, const PushTarget &push, cudaStream_t st) {
     if (!raw || s->dtype != EVDB_F32 || KP > kSwMaxKP || L > kRawMaxLists) return EVDB_E_UNSUPPORTED;
     SelectArgs a;
     memset(&a, 0, sizeof(a));
     a.rows = s->rows; a.row_bytes = s->row_bytes; a.norm64 = s->norm64; a.qms64 = s->qms64;
     a.n = s->count; a.d = s->dim; a.q64 = d_q64; a.L = L; a.KP = KP; a.raw = *raw;
     a.kk = kk; a.kstride = kk; a.metric = metric; a.eps_q = eps_q; a.slot_base = slot_base;
-    a.win_out = win_blob; a.win_meta = win_blob + (size_t)B * KP;
+    a.win_mode = 1; a.push = push;
     s->n_launches++;
     return launch_select_warp(a, B, st);
 }
 
-int launch_shard_qnorm(evdb_store *s, const double *d_q64, int B, int rank, int world, uint64_t *qn_out, cudaStream_t st) {
-    EVDB_CUDA(cudaMemsetAsync(qn_out, 0, sizeof(uint64_t) * (size_t)B, st));
-    const int mine = (B - rank + world - 1) / world;
-    if (mine > 0) {
-        shard_qnorm_kernel<<<(mine + 127) / 128, 128, 0, st>>>(d_q64, B, s->dim, rank, world, qn_out);
-        EVDB_CUDA(cudaGetLastError());
-        s->n_launches++;
-    }
-    return EVDB_OK;
-}
-
 static void fill_shard_args(ShardArgs *a, evdb_store *s, const double *d_q64, int B, int KP, int k, int kk, int metric,
-                            int rank, int world, uint64_t n_total, double *e_out, uint64_t *g_out, void *g_meta) {
+                            int rank, int world, uint64_t n_total, uint64_t *g_out, void *g_meta) {
     memset(a, 0, sizeof(*a));
     a->rows = s->rows; a->row_bytes = s->row_bytes; a->norm64 = s->norm64; a->d = s->dim; a->q64 = d_q64;
     a->B = B; a->KP = KP; a->kk = kk; a->k = k; a->metric = metric; a->squared = metric == EVDB_EUCLIDEAN;
     a->world = world; a->rank = rank; a->n_total = n_total;
-    a->e_out = e_out; a->g_out = g_out; a->g_meta = (GMeta *)g_meta;
+    a->g_out = g_out; a->g_meta = (GMeta *)g_meta;
 }
 
 size_t shard_gmeta_bytes(int B) { return sizeof(GMeta) * (size_t)B; }
 
 int launch_shard_rerank(evdb_store *s, const double *d_q64, int B, int KP, int k, int kk, int metric, int rank,
-                        int world, uint64_t n_total, const ExchangeView &win, double *e_out, uint64_t *g_out,
-                        void *g_meta, uint64_t *work, int *work_n, cudaStream_t st) {
+                        int world, uint64_t n_total, const ExchangeView &win, const PushTarget &e_push, uint64_t *g_out,
+                        void *g_meta, cudaStream_t st) {
     ShardArgs a;
-    fill_shard_args(&a, s, d_q64, B, KP, k, kk, metric, rank, world, n_total, e_out, g_out, g_meta);
+    fill_shard_args(&a, s, d_q64, B, KP, k, kk, metric, rank, world, n_total, g_out, g_meta);
     a.win = win;
-    a.work = work;
-    a.work_n = work_n;
-    EVDB_CUDA(cudaMemsetAsync(work_n, 0, sizeof(int), st));
+    a.e_push = e_push;
     const size_t smem = (size_t)kShWarps * kShPerWarp;
     EVDB_TRY(ensure_func_smem((const void *)shard_rerank_kernel, smem));
     shard_rerank_kernel<<<(B + kShWarps - 1) / kShWarps, kShWarps * 32, smem, st>>>(a);
     EVDB_CUDA(cudaGetLastError());
-    // 2b: chains of 32 rows; the list length is only known on the device, the grid covers the usual
-    // case in one wave and strides over the rest
-    const size_t smem_f = (size_t)kShWarps * kSwRows * kSwProdStride;
-    EVDB_TRY(ensure_func_smem((const void *)shard_fold_kernel, smem_f));
-    int grid = (int)(((size_t)B * 24 / (size_t)(world > 0 ? world : 1) + 32 * kShWarps - 1) / (32 * kShWarps));
-    if (grid < 8) grid = 8;
-    if (grid > s->sm_count * 3) grid = s->sm_count * 3;
-    shard_fold_kernel<<<grid, kShWarps * 32, smem_f, st>>>(a);
-    EVDB_CUDA(cudaGetLastError());
-    s->n_launches += 2;
+    s->n_launches++;
     return EVDB_OK;
 }
 
@@ -1199,7 +1135,7 @@ int launch_shard_final(evdb_store *s, int B, int KP, int k, int kk, int metric, 
                        const ExchangeView &ex, const uint64_t *g_out, const void *g_meta, uint64_t *out_blob,
                        cudaStream_t st) {
     ShardArgs a;
-    fill_shard_args(&a, s, nullptr, B, KP, k, kk, metric, rank, world, n_total, nullptr, const_cast<uint64_t *>(g_out),
+    fill_shard_args(&a, s, nullptr, B, KP, k, kk, metric, rank, world, n_total, const_cast<uint64_t *>(g_out),
                     const_cast<void *>(g_meta));
     a.ex = ex;
     a.out_blob = out_blob;
@@ -1228,7 +1164,7 @@ int launch_select(evdb_store *s, const double *d_q64, const uint64_t *partial, c
     }
     a.kk = kk; a.kstride = kstride; a.metric = metric; a.eps_abs = eps_abs; a.eps_rel = eps_rel;
     a.eps_q = eps_q; a.squared = squared;
-    a.win_out = nullptr; a.win_meta = nullptr;
+    a.win_mode = 0;
     { static int v = -1; if (v < 0) { const char *e = getenv("EVDB_SEL_VARIANT"); v = e ? atoi(e) : 0; } a.variant = v; }
     a.slot_base = slot_base; a.out_ids = d_out_ids; a.out_dists = d_out_dists;
     a.out_counts = d_out_counts; a.out_flags = d_out_flags;

@@ -845,19 +845,16 @@ int evdb_merge_topk_packed_dev(int device, const void *d_blobs, int G, int B, in
 }
 
 // ---- row-sharded GEMM batches in two phases (select.cu: windows travel, owners re-rank) ----
-// window blob: [B*KP keys][B meta][B exact ||q||^2 bits (owner rank only)]
-struct ShardLayout { size_t win_words, e_off, g_off, m_off, w_off, c_off, total; int KP, kk; };
+struct ShardLayout { size_t win_words, e_off, g_off, m_off, total; int KP, kk; };
 static ShardLayout shard_layout(int B, int k, uint64_t n_total) {
     ShardLayout l;
     l.kk = (uint64_t)k < n_total ? k : (int)n_total;
     l.KP = gemm_kp(choose_kp(l.kk, 0));
-    l.win_words = (size_t)B * l.KP + 2 * (size_t)B;
+    l.win_words = (size_t)B * l.KP + (size_t)B;
     l.e_off = l.win_words * 8;
     l.g_off = l.e_off + (size_t)B * l.KP * 8;
     l.m_off = l.g_off + (size_t)B * l.KP * 8;
-    l.w_off = round_up64(l.m_off + shard_gmeta_bytes(B), 16);
-    l.c_off = l.w_off + (size_t)B * l.KP * 8;
-    l.total = l.c_off + 16;
+    l.total = l.m_off + shard_gmeta_bytes(B);
     return l;
 }
 
@@ -878,12 +875,9 @@ int evdb_store_search_sharded_phase1(evdb_store *s, evdb_exchange *xw, const voi
     RawCands raw;
     s->last_plan = EVDB_PLAN_GEMM;
     EVDB_TRY(launch_gemm_topk(s, (const double *)d_queries_f64, B, l.KP, metric, &lists, &eps_q, &raw, st));
+    // the window kernel stores straight into every rank's mailbox and publishes the epoch itself
     EVDB_TRY(launch_shard_window(s, (const double *)d_queries_f64, &raw, lists, l.KP, B, l.kk, metric, eps_q, slot_base,
-                                 (uint64_t *)s->w_shard, st));
-    if (metric == EVDB_COSINE)
-        EVDB_TRY(launch_shard_qnorm(s, (const double *)d_queries_f64, B, xw->rank, xw->world,
-                                    (uint64_t *)s->w_shard + (size_t)B * l.KP + (size_t)B, st));
-    EVDB_TRY(exchange_push_words(xw, s->w_shard, l.win_words, st));
+                                 exchange_begin_push(xw), st));
     s->n_launches++;
     s->n_searches += (uint64_t)B;
     s->n_rows_scanned += (uint64_t)B * s->count;
@@ -898,10 +892,9 @@ int evdb_store_search_sharded_phase2(evdb_store *s, evdb_exchange *xw, evdb_exch
     EVDB_TRY(set_device(s));
     cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
     uint8_t *w = (uint8_t *)s->w_shard;
+    const ExchangeView win = exchange_view(xw);
     EVDB_TRY(launch_shard_rerank(s, (const double *)d_queries_f64, B, l.KP, k, l.kk, metric, xw->rank, xw->world, n_total,
-                                 exchange_view(xw), (double *)(w + l.e_off), (uint64_t *)(w + l.g_off), w + l.m_off,
-                                 (uint64_t *)(w + l.w_off), (int *)(w + l.c_off), st));
-    EVDB_TRY(exchange_push_words(xe, w + l.e_off, (size_t)B * l.KP, st));
+                                 win, exchange_begin_push(xe), (uint64_t *)(w + l.g_off), w + l.m_off, st));
     s->n_launches++;
     return EVDB_OK;
 }

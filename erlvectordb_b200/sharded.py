@@ -174,7 +174,7 @@ class ShardedStore:
         """Query batches on the tcgen05 plan: approximate windows travel, owners re-rank (select.cu)."""
         B, d = q.shape
         kp = gemm_window(k, self.n_total)
-        xw = self._p2p(B, k, q.device, words=B * kp + 2 * B, tag="win")
+        xw = self._p2p(B, k, q.device, words=B * kp + B, tag="win")
         xe = self._p2p(B, k, q.device, words=B * kp, tag="exact")
         if xw is None or xe is None:
             return None

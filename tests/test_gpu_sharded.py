@@ -122,7 +122,7 @@ def test_two_phase_sharded_search_equals_single_store(native, oracle, metric, n,
         st = DeviceStore(dtype="f32", device=0)
         st.fill_synthetic(oracle.SEED_CORPUS, hi - lo, d, row0=lo)
         stores.append((st, lo))
-        xws.append(Exchange(0, g, G, B * kp + 2 * B))
+        xws.append(Exchange(0, g, G, B * kp + B))
         xes.append(Exchange(0, g, G, B * kp))
     for xs in (xws, xes):
         boxes = [x.mailbox for x in xs]
