@@ -38,6 +38,10 @@ for dtype, metric, n, d, B, k in [("f32", "cosine", 200_000, 128, 4, 10), ("f32"
     ok &= same
     print(f"rank {rank}: {dtype} {metric} n={n} d={d} B={B} k={k}: {'identical' if same else 'MISMATCH'}", flush=True)
     st.close(); one.close()
+t = torch.tensor([1 if ok else 0], device="cuda")
+dist.all_reduce(t, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("SHARDED_OK" if int(t.item()) == 1 else "SHARDED_MISMATCH", flush=True)
 dist.barrier()
 dist.destroy_process_group()
-sys.exit(0 if ok else 1)
+sys.exit(0 if int(t.item()) == 1 else 1)
