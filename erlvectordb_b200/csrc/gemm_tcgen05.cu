@@ -693,8 +693,13 @@ __global__ void __launch_bounds__(kSeedThreads) seed_threshold_kernel(const floa
                                                                       int S, int need, uint32_t *__restrict__ thr0) {
     __shared__ int s_cnt[6];
     __shared__ uint32_t s_lo, s_hi;
+    // blockIdx.y = group of <= 8192 pooled values: the `need`-th smallest of each group, maximum over
+    // the groups (atomicMax, thr0 zeroed before) -- with need = ceil(KP / groups) at least KP values
+    // of the whole sample are at or below that maximum, so it still bounds the KP-th best
     const int q = blockIdx.x;
-    const float *row = dump + (size_t)q * ld;
+    const int g0 = blockIdx.y * (kSeedThreads * kSeedMaxVpt);
+    const float *row = dump + (size_t)q * ld + g0;
+    S = S - g0 < kSeedThreads * kSeedMaxVpt ? S - g0 : kSeedThreads * kSeedMaxVpt;
     uint32_t v[kSeedVpt];
     uint32_t mn = 0xFFFFFFFFu, mx = 0u;
 #pragma unroll
@@ -740,7 +745,7 @@ __global__ void __launch_bounds__(kSeedThreads) seed_threshold_kernel(const floa
         ++it;
         __syncthreads();
     }
-    if (threadIdx.x == 0) thr0[q] = hi;
+    if (threadIdx.x == 0) atomicMax(thr0 + q, hi);
 }
 
 // ---- host side ------------------------------------------------------------------------------
@@ -966,7 +971,7 @@ int launch_gemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int metr
     // 32-row chunk pooled, KP-th smallest per query selected.  Kills the warm-up of the main sweep.
     const uint32_t *thr0 = nullptr;
     const char *noseed = getenv("EVDB_GEMM_NOSEED");
-    uint64_t S = 262144;
+    uint64_t S = (uint64_t)8192 * KP;   // admitted keys per query ~ count * KP / S: wider windows get a larger sample
     { const char *e = getenv("EVDB_GEMM_SAMPLE"); if (e && atoi(e) >= 1024) S = (uint64_t)atoi(e); }
     while (S * 16 > s->count && S > 1024) S >>= 1;
     if (S >= (uint64_t)64 * KP && S * 16 <= s->count && !(noseed && atoi(noseed))) {
@@ -984,10 +989,14 @@ int launch_gemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int metr
         p.n = S; p.nt = snt; p.NG = sNG; p.mode = 1; p.dump = dump; p.dump_ld = pooled;
         EVDB_TRY(launch_gemm_kernel(pair, MB * sNG, st, tmQ, tmVs, tmQt, tmVts, p));
         const int vpt = (pooled + kSeedThreads - 1) / kSeedThreads;
-        if (vpt <= 4) seed_threshold_kernel<4><<<Bpad, kSeedThreads, 0, st>>>(dump, pooled, pooled, KP, thr);
-        else if (vpt <= 8) seed_threshold_kernel<8><<<Bpad, kSeedThreads, 0, st>>>(dump, pooled, pooled, KP, thr);
-        else if (vpt <= 16) seed_threshold_kernel<16><<<Bpad, kSeedThreads, 0, st>>>(dump, pooled, pooled, KP, thr);
-        else seed_threshold_kernel<kSeedMaxVpt><<<Bpad, kSeedThreads, 0, st>>>(dump, pooled, pooled, KP, thr);
+        const int groups = (pooled + kSeedThreads * kSeedMaxVpt - 1) / (kSeedThreads * kSeedMaxVpt);
+        const int need = (KP + groups - 1) / groups;
+        const dim3 sgrid(Bpad, groups);
+        EVDB_CUDA(cudaMemsetAsync(thr, 0, sizeof(uint32_t) * (size_t)Bpad, st));
+        if (vpt <= 4) seed_threshold_kernel<4><<<sgrid, kSeedThreads, 0, st>>>(dump, pooled, pooled, need, thr);
+        else if (vpt <= 8) seed_threshold_kernel<8><<<sgrid, kSeedThreads, 0, st>>>(dump, pooled, pooled, need, thr);
+        else if (vpt <= 16) seed_threshold_kernel<16><<<sgrid, kSeedThreads, 0, st>>>(dump, pooled, pooled, need, thr);
+        else seed_threshold_kernel<kSeedMaxVpt><<<sgrid, kSeedThreads, 0, st>>>(dump, pooled, pooled, need, thr);
         EVDB_CUDA(cudaGetLastError());
         s->n_launches += 2;
         thr0 = thr;
