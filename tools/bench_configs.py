@@ -31,6 +31,7 @@ CASES = [
     ("cfg2 1M x768 f32 cosine k=10 B=1", 1_000_000, 768, "f32", "cosine", 10, 1, 768 * 4),
     ("cfg2 1M x768 f32 cosine k=10 B=1024", 1_000_000, 768, "f32", "cosine", 10, 1024, 768 * 4),
     ("cfg3 10M x128 f32 euclidean k=100 B=1", 10_000_000, 128, "f32", "euclidean", 100, 1, 128 * 4),
+    ("cfg3 10M x128 f32 euclidean k=100 B=4096 (tcgen05 GEMM + top-k epilogue)", 10_000_000, 128, "f32", "euclidean", 100, 4096, 128 * 4),
     ("cfg3' 10M x128 f32 cosine k=10 B=4096", 10_000_000, 128, "f32", "cosine", 10, 4096, 128 * 4),
     ("cfg4/8 12.5M x96 u8 cosine k=10 B=1", 12_500_000, 96, "u8", "cosine", 10, 1, 96 + 8),
     ("cfg5 1M x1536 f32 manhattan k=10 B=1", 1_000_000, 1536, "f32", "manhattan", 10, 1, 1536 * 4),
