@@ -159,53 +159,6 @@ __device__ __forceinline__ void load8(const uint8_t *row, int t8, double mn, dou
 // qlane), sum((q-v)^2) (euclidean), sum(|q-v|) (manhattan).  q: the fp64 query in global memory.
 template <int DTYPE>
 __device__ __forceinline__ double exact_fold_lane(const uint8_t *row, double mn, double sc,
-                                                  const double *__restrict__ q, int d, int metric, bool qlane) {
-    double s = 0.0;
-    const int full = d >> 3;
-    // software-pipelined by one step: the operands of the next 8 terms are in flight while the
-    // current 8 go through the (strictly sequential) add chain
-    double v[8], qq[8];
-    if (full > 0) {
-        load8<DTYPE>(row, 0, mn, sc, v);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) qq[i] = __ldg(q + i);  // same address in every lane: one broadcast each
-    }
-    for (int t8 = 0; t8 < full; ++t8) {
-        double nv[8], nq[8];
-        const int tn = t8 + 1 < full ? t8 + 1 : t8;
-        load8<DTYPE>(row, tn, mn, sc, nv);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) nq[i] = __ldg(q + 8 * tn + i);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const double x = qlane ? qq[i] : v[i];
-            double term;
-            if (metric == EVDB_COSINE) term = __dmul_rn(qq[i], x);
-            else {
-                const double t0 = __dsub_rn(qq[i], x);
-                term = metric == EVDB_EUCLIDEAN ? __dmul_rn(t0, t0) : fabs(t0);
-            }
-            s = __dadd_rn(s, term);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { v[i] = nv[i]; qq[i] = nq[i]; }
-    }
-    for (int t = full << 3; t < d; ++t) {
-        const double qv = q[t];
-        const double x = qlane ? qv : row_elem<DTYPE>(row, t, mn, sc);
-        double term;
-        if (metric == EVDB_COSINE) term = __dmul_rn(qv, x);
-        else {
-            const double t0 = __dsub_rn(qv, x);
-            term = metric == EVDB_EUCLIDEAN ? __dmul_rn(t0, t0) : fabs(t0);
-        }
-        s = __dadd_rn(s, term);
-    }
-    return s;
-}
-
-template <int DTYPE>
-__device__ __forceinline__ double exact_fold_lane_simple(const uint8_t *row, double mn, double sc,
                                                          const double *__restrict__ q, int d, int metric, bool qlane) {
     double s = 0.0;
     const int full = d >> 3;
@@ -238,10 +191,6 @@ __device__ __forceinline__ double exact_fold_lane_simple(const uint8_t *row, dou
         s = __dadd_rn(s, term);
     }
     return s;
-}
-
-__device__ __forceinline__ void prefetch_l1(const void *p) {
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
 
 }  // namespace evdb

@@ -59,7 +59,7 @@ struct SelectArgs {
     float eps_abs, eps_rel;
     const float *eps_q;  // optional [B]: per-query absolute bound (GEMM plans)
     int squared;         // key scores are squared distances (euclidean GEMM plan)
-    int variant;         // tuning: bit 0 = L1 prefetch pre-pass, bit 1 = pipelined fold, bit 2 = L2 prefetch instead
+    int variant;         // EVDB_SEL_VARIANT (measurement only): 16 = per-phase cycle counters, 32 = CTA-per-query kernel for GEMM batches too
     int win_mode;        // sharded search, phase 1: push the ascending window (keys with GLOBAL rows) + meta to every rank and stop
     PushTarget push;     //   blob words: [B*KP keys][B meta = (eps bits << 32) | ncand]
     uint64_t slot_base;
@@ -347,30 +347,11 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
         // Batches: the fold of one row is a strictly sequential fp64 chain (reference order), so candidates
         // are spread one per lane: cpw per warp, plus -- for cosine -- lane 31 of every working
         // warp folding the query's own squares.
-        // Pull the candidate rows (and the query) towards L1 first, with every thread of the CTA:
-        // each fold lane walks its row alone, and a DRAM miss per step would dominate the chain.
-        if (a.variant & 5) {
-            const int used = DTYPE == EVDB_F32 ? a.d * 4 : DTYPE == EVDB_BF16 ? a.d * 2 : DTYPE == EVDB_U8 ? a.d : (a.d + 1) / 2;
-            const int lines = (used + 127) >> 7;
-            for (int i = threadIdx.x; i < nrer * lines; i += blockDim.x) {
-                const int j = i / lines, l = i - j * lines;
-                const uint8_t *pp = a.rows + (size_t)key_slot(buf[j]) * a.row_bytes + (size_t)l * 128;
-                if (a.variant & 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
-                else prefetch_l1(pp);
-            }
-            const int qlines = (a.d * 8 + 127) >> 7;
-            for (int i = threadIdx.x; i < qlines; i += blockDim.x) prefetch_l1(reinterpret_cast<const uint8_t *>(q) + (size_t)i * 128);
-        }
         const bool cosine = a.metric == EVDB_COSINE;
         const int max_cpw = cosine ? 31 : 32;
-        // as few warps as possible: the fp64 pipe issues per warp instruction whatever the number of
-        // active lanes, and the chain is no shorter with fewer rows per warp (EVDB_SEL_VARIANT bit 3: old split)
-        int cpw = max_cpw;
-        if (a.variant & 8) {
-            cpw = (nrer + kSelWarps - 1) / kSelWarps;
-            if (cpw < 4) cpw = 4;
-            if (cpw > max_cpw) cpw = max_cpw;
-        }
+        // as few warps as possible: the fp64 unit issues per warp instruction whatever the number of
+        // active lanes, and the chain is no shorter with fewer rows per warp
+        const int cpw = max_cpw;
         for (int base = warp * cpw; base < nrer; base += kSelWarps * cpw) {
             const int j = base + lane;
             const bool mine = lane < cpw && j < nrer;
@@ -383,8 +364,7 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
                 mn = ms.x;
                 sc = ms.y;
             }
-            const double s = (a.variant & 2) ? exact_fold_lane<DTYPE>(row, mn, sc, q, a.d, a.metric, qlane)
-                                             : exact_fold_lane_simple<DTYPE>(row, mn, sc, q, a.d, a.metric, qlane);
+            const double s = exact_fold_lane<DTYPE>(row, mn, sc, q, a.d, a.metric, qlane);
             double dist;
             if (cosine) {
                 const double sq = __shfl_sync(0xffffffffu, s, 31);
