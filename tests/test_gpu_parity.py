@@ -478,3 +478,23 @@ def test_insert_batch_equals_sequential_inserts(native, oracle, fresh_name):
     finally:
         db.delete_store(a)
         db.delete_store(b)
+
+
+@pytest.mark.parametrize("k", [150, 600, 2000])
+@pytest.mark.parametrize("metric", ["cosine", "euclidean"])
+def test_batches_with_windows_wider_than_the_gemm_plan(native, oracle, k, metric):
+    """k = 150 / 600 need 256- / 1024-key windows (scan plan with the sorted-insert lists, CTA-per-query
+    select for the batch); k = 2000 exceeds every window and goes through the exhaustive fp64 plan.
+    A batch of 20 must equal the strict oracle query by query."""
+    n, d, B = 5000, 64, 20
+    st = _store(native, "f32")
+    st.fill_synthetic(oracle.SEED_CORPUS, n, d)
+    qs = oracle.synth_f64(oracle.SEED_QUERY, 0, B, d)
+    slots, dists, counts = st.search(qs, k, metric)
+    assert st.stats()["last_plan"] == (native.PLAN_EXACT if k == 2000 else native.PLAN_SCAN)
+    rows = oracle.synth_f64(oracle.SEED_CORPUS, 0, n, d)
+    for b in (0, 7, B - 1):
+        r, dd = oracle.search(rows, qs[b], k, metric)
+        assert counts[b] == k
+        assert slots[b].tolist() == r.tolist() and dists[b].tolist() == dd.tolist()
+    st.close()
