@@ -542,45 +542,52 @@ __device__ __forceinline__ void warp_select_inplace(uint64_t *keys, int T, int n
 __device__ __forceinline__ double sw_fold_chain(const uint8_t *__restrict__ rows, size_t row_bytes,
                                                 const double *__restrict__ q, int d, int metric, uint8_t *stage,
                                                 uint32_t my_slot, int nr, bool qrow, int lane) {
+    // The fold itself is cheap (a dependent DADD is ~9 cycles here, tools/micro/fp64_bench.cu); what
+    // a chain waits for is its operands: rows scattered over the store.  So the raw rows and the query
+    // values of chunk c+1 are loaded into registers BEFORE chunk c is folded.
     const int nrows = nr + (qrow ? 1 : 0);
+    const int unit = lane & 15, rsub = lane >> 4;   // a row chunk is 16 units of 4 elements: half a warp per row
+    constexpr int kIt = kSwRows / 2;                // row pairs per chunk
+    uint4 raw[kIt];
+    double qd[4];
+    auto load_chunk = [&](int kb) {
+        const int e0 = kb + 4 * unit;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) qd[i] = e0 + i < d ? __ldg(q + e0 + i) : 0.0;
+#pragma unroll
+        for (int it = 0; it < kIt; ++it) {
+            const int r = 2 * it + rsub;
+            const uint32_t rslot = __shfl_sync(0xffffffffu, my_slot, r < nr ? r : 0);
+            raw[it] = make_uint4(0u, 0u, 0u, 0u);
+            if (2 * it < nrows && r < nr && (size_t)e0 * 4 < row_bytes)
+                raw[it] = __ldg(reinterpret_cast<const uint4 *>(rows + (size_t)rslot * row_bytes) + (e0 >> 2));
+        }
+    };
     double s = 0.0;
+    load_chunk(0);
     for (int kb = 0; kb < d; kb += kSwKC) {
         const int cnt = d - kb < kSwKC ? d - kb : kSwKC;
-        // a row chunk is 16 units of 4 elements: half a warp per row, two rows per step
-        const int unit = lane & 15, rsub = lane >> 4;
-        const int e0 = kb + 4 * unit;
-        double qd[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) qd[i] = e0 + i < d ? q[e0 + i] : 0.0;
         __syncwarp();
-#pragma unroll 4
-        for (int r2 = 0; r2 < nrows; r2 += 2) {
-            const int r = r2 + rsub;
-            const uint32_t rslot = __shfl_sync(0xffffffffu, my_slot, r < nr ? r : 0);
-            if (r >= nrows) continue;
+#pragma unroll
+        for (int it = 0; it < kIt; ++it) {
+            const int r = 2 * it + rsub;
+            if (2 * it >= nrows || r >= nrows) continue;
+            const uint32_t w[4] = {raw[it].x, raw[it].y, raw[it].z, raw[it].w};
             double t[4];
-            if (r < nr) {
-                uint4 raw = make_uint4(0u, 0u, 0u, 0u);
-                if ((size_t)e0 * 4 < row_bytes)
-                    raw = __ldg(reinterpret_cast<const uint4 *>(rows + (size_t)rslot * row_bytes) + (e0 >> 2));
-                const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const double x = widen_f32(w[i]);
-                    if (metric == EVDB_COSINE) t[i] = __dmul_rn(qd[i], x);
-                    else {
-                        const double df = __dsub_rn(qd[i], x);
-                        t[i] = metric == EVDB_EUCLIDEAN ? __dmul_rn(df, df) : fabs(df);
-                    }
+            for (int i = 0; i < 4; ++i) {
+                const double x = r < nr ? widen_f32(w[i]) : qd[i];     // the last row: the query's own squares
+                if (metric == EVDB_COSINE) t[i] = __dmul_rn(qd[i], x);
+                else {
+                    const double df = __dsub_rn(qd[i], x);
+                    t[i] = metric == EVDB_EUCLIDEAN ? __dmul_rn(df, df) : fabs(df);
                 }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) t[i] = __dmul_rn(qd[i], qd[i]);
             }
             double2 *dst = reinterpret_cast<double2 *>(stage + (size_t)r * kSwProdStride) + 2 * unit;
             dst[0] = make_double2(t[0], t[1]);
             dst[1] = make_double2(t[2], t[3]);
         }
+        if (kb + kSwKC < d) load_chunk(kb + kSwKC);   // in flight during the fold below
         __syncwarp();
         if (lane < nrows) {
             const double2 *p = reinterpret_cast<const double2 *>(stage + (size_t)lane * kSwProdStride);
@@ -739,6 +746,16 @@ __global__ void __launch_bounds__(kSwWarps * 32) select_warp_kernel(const Select
     for (int i = lane; i < ncand; i += 32) ckeys[i] = keys[i];
     __syncwarp();
     const float bound = ncand > 0 ? key_score(ckeys[ncand - 1]) : 0.f;
+    if (!a.win_mode) {
+        // the rows most likely to be re-ranked start their trip from DRAM now (L2 prefetch): the fold
+        // below walks them 256 bytes at a time
+        const int npf = ncand < a.kk + 6 ? ncand : a.kk + 6;
+        const int lines = (int)((a.row_bytes + 127) >> 7);
+        for (int i = lane; i < npf * lines; i += 32) {
+            const int j = i / lines, l = i - j * lines;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.rows + (size_t)key_slot(ckeys[j]) * a.row_bytes + (size_t)l * 128));
+        }
+    }
     if (a.win_mode) {  // sharded search, phase 1: the window travels, the re-rank happens after the global merge
         for (int i = lane; i < KP; i += 32) push_store(a.push, (size_t)b * KP + i, i < ncand ? ckeys[i] + a.slot_base : kKeyMax);
         if (lane == 0) push_store(a.push, (size_t)B * KP + b, ((uint64_t)__float_as_uint(eps_abs) << 32) | (uint32_t)ncand);
