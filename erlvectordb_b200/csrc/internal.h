@@ -131,6 +131,10 @@ struct ScanArgs {
     int KP;
     int G;
     int B;
+    int tma_stages = 0;      // TMA-staged quantized scan: ring depth, bytes per stage, chunk rotation
+    int tma_stage_bytes = 0;
+    int bank_mul = 0;
+    int tma_wt = 8;          // consumer warps per tile
 };
 
 // Unsorted candidate buffers left by the tcgen05 GEMM plan: query q = (sweep c, block mb, thread et)

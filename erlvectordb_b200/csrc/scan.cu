@@ -13,6 +13,7 @@
 // (score, slot) keys in a sorted shared-memory list guarded by a register
 // threshold.  The CTA bitonic-merges its warps' lists and writes KP keys; the
 // select kernel (select.cu) merges CTAs and re-ranks exactly in fp64.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "internal.h"
@@ -91,9 +92,11 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const double *__restr
             int pos = i;
             if (dtype == EVDB_U4) {
                 // codes: byte j = (elem 2j << 4) | elem 2j+1.  (w >> 4) & 0x0F0F0F0F yields the
-                // even elements of a word, w & 0x0F0F0F0F the odd ones: lay the digits out to match.
+                // even elements of a word, w & 0x0F0F0F0F the odd ones: lay the digits out to match,
+                // even-element digits of all chunks first, then the odd ones (both halves are read
+                // at a 16-byte stride across lanes: no shared-memory bank conflicts).
                 int c = i >> 5, r = i & 31, w = r >> 3, e8 = r & 7;
-                pos = c * 32 + ((e8 & 1) ? 16 : 0) + w * 4 + (e8 >> 1);
+                pos = ((e8 & 1) ? (qdig_stride >> 1) : 0) + c * 16 + w * 4 + (e8 >> 1);
             }
             p0[pos] = (uint8_t)((Q >> 16) & 0xFF);  // signed high digit
             p1[pos] = (uint8_t)((Q >> 8) & 0xFF);
@@ -187,20 +190,21 @@ struct WarpCands {
         else evdb::offer(key, thr, mine, KP, lane);
     }
     // compact every warp's best <= KP keys to lists[w*KP ..], padded with kKeyMax (whole CTA calls)
-    __device__ __forceinline__ void finish(uint64_t *lists, int warp, int lane) {
+    // `active` = false for a warp that only takes part in the barrier (the TMA producer warp)
+    __device__ __forceinline__ void finish(uint64_t *lists, int warp, int lane, bool active = true) {
         if (!append) return;
-        if (cnt > KP) warp_buf_prune(mine, cnt, thr, KP, lane);
+        if (active && cnt > KP) warp_buf_prune(mine, cnt, thr, KP, lane);
         uint64_t e[kAppendMaxKP / 32];
 #pragma unroll
         for (int r = 0; r < kAppendMaxKP / 32; ++r) {
             const int i = r * 32 + lane;
-            e[r] = (i < cnt && i < KP) ? mine[i] : kKeyMax;
+            e[r] = (active && i < cnt && i < KP) ? mine[i] : kKeyMax;
         }
         __syncthreads();
 #pragma unroll
         for (int r = 0; r < kAppendMaxKP / 32; ++r) {
             const int i = r * 32 + lane;
-            if (i < KP) lists[(size_t)warp * KP + i] = e[r];
+            if (active && i < KP) lists[(size_t)warp * KP + i] = e[r];
         }
     }
 };
@@ -302,6 +306,64 @@ scan_float_kernel(const ScanArgs a) {
     cta_merge_and_store(lists, KP, a.partial + ((size_t)b * a.G + blockIdx.x) * KP);
 }
 
+// one 16-byte chunk (index c) of R rows against the three digit planes of the query
+template <int DTYPE, int R>
+__device__ __forceinline__ void quant_chunk(const uint4 (&v)[R], int c, const uint4 *sd, int plane_u4,
+                                            int (&A)[R], int (&Bm)[R], int (&Cl)[R]) {
+    if (DTYPE == EVDB_U8) {
+        const uint4 d0 = sd[c], d1 = sd[plane_u4 + c], d2 = sd[2 * plane_u4 + c];
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            A[j] = dp4a_su((int)d0.x, v[j].x, A[j]); A[j] = dp4a_su((int)d0.y, v[j].y, A[j]);
+            A[j] = dp4a_su((int)d0.z, v[j].z, A[j]); A[j] = dp4a_su((int)d0.w, v[j].w, A[j]);
+            Bm[j] = (int)dp4a_uu(d1.x, v[j].x, (uint32_t)Bm[j]); Bm[j] = (int)dp4a_uu(d1.y, v[j].y, (uint32_t)Bm[j]);
+            Bm[j] = (int)dp4a_uu(d1.z, v[j].z, (uint32_t)Bm[j]); Bm[j] = (int)dp4a_uu(d1.w, v[j].w, (uint32_t)Bm[j]);
+            Cl[j] = (int)dp4a_uu(d2.x, v[j].x, (uint32_t)Cl[j]); Cl[j] = (int)dp4a_uu(d2.y, v[j].y, (uint32_t)Cl[j]);
+            Cl[j] = (int)dp4a_uu(d2.z, v[j].z, (uint32_t)Cl[j]); Cl[j] = (int)dp4a_uu(d2.w, v[j].w, (uint32_t)Cl[j]);
+        }
+    } else {
+        const int half = plane_u4 >> 1;   // = chunks per row
+        const uint4 e0 = sd[c], o0 = sd[half + c];
+        const uint4 e1 = sd[plane_u4 + c], o1 = sd[plane_u4 + half + c];
+        const uint4 e2 = sd[2 * plane_u4 + c], o2 = sd[2 * plane_u4 + half + c];
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+            const uint32_t E0[4] = {e0.x, e0.y, e0.z, e0.w}, O0[4] = {o0.x, o0.y, o0.z, o0.w};
+            const uint32_t E1[4] = {e1.x, e1.y, e1.z, e1.w}, O1[4] = {o1.x, o1.y, o1.z, o1.w};
+            const uint32_t E2[4] = {e2.x, e2.y, e2.z, e2.w}, O2[4] = {o2.x, o2.y, o2.z, o2.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                uint32_t hi = (w[t] >> 4) & 0x0F0F0F0Fu, lo = w[t] & 0x0F0F0F0Fu;
+                A[j] = dp4a_su((int)E0[t], hi, A[j]); A[j] = dp4a_su((int)O0[t], lo, A[j]);
+                Bm[j] = (int)dp4a_uu(E1[t], hi, (uint32_t)Bm[j]); Bm[j] = (int)dp4a_uu(O1[t], lo, (uint32_t)Bm[j]);
+                Cl[j] = (int)dp4a_uu(E2[t], hi, (uint32_t)Cl[j]); Cl[j] = (int)dp4a_uu(O2[t], lo, (uint32_t)Cl[j]);
+            }
+        }
+    }
+}
+
+// reduce the three digit sums over the TPR lanes of a row and form the key (lane gl == 0 holds it)
+template <int TPR>
+__device__ __forceinline__ uint64_t quant_key(int sa, int sb, int sc, bool owner, float2 co, const QStat &qs,
+                                              uint64_t row) {
+#pragma unroll
+    for (int o = TPR / 2; o > 0; o >>= 1) {
+        sa += __shfl_xor_sync(0xffffffffu, sa, o);
+        sb += __shfl_xor_sync(0xffffffffu, sb, o);
+        sc += __shfl_xor_sync(0xffffffffu, sc, o);
+    }
+    uint64_t key = kKeyMax;
+    if (owner) {
+        long long S = ((long long)sa << 16) + ((long long)sb << 8) + (long long)sc;
+        float dotn = fmaf(co.x, __ll2float_rn(S) * qs.fx, co.y * qs.sum);
+        bool zero = (co.x == 0.f && co.y == 0.f) || qs.inv_norm == 0.f;
+        float score = zero ? 1.0f : 1.0f - dotn * qs.inv_norm;
+        key = make_key(score, (uint32_t)row);
+    }
+    return key;
+}
+
 // ----------------------------------------------------------------------------
 // u8 / packed-u4 codes: cosine of an unquantised query against Min + c*Scale
 //   q.y = Min*sum(q) + Scale*sum(q_i c_i);  sum(Q_i c_i) is an exact integer:
@@ -358,58 +420,195 @@ scan_quant_kernel(const ScanArgs a) {
             uint4 v[R];
 #pragma unroll
             for (int j = 0; j < R; ++j) v[j] = ldg_stream_u4(rp[j] + c);
-            if (DTYPE == EVDB_U8) {
-                const uint4 d0 = sd[c], d1 = sd[plane_u4 + c], d2 = sd[2 * plane_u4 + c];
-#pragma unroll
-                for (int j = 0; j < R; ++j) {
-                    A[j] = dp4a_su((int)d0.x, v[j].x, A[j]); A[j] = dp4a_su((int)d0.y, v[j].y, A[j]);
-                    A[j] = dp4a_su((int)d0.z, v[j].z, A[j]); A[j] = dp4a_su((int)d0.w, v[j].w, A[j]);
-                    Bm[j] = (int)dp4a_uu(d1.x, v[j].x, (uint32_t)Bm[j]); Bm[j] = (int)dp4a_uu(d1.y, v[j].y, (uint32_t)Bm[j]);
-                    Bm[j] = (int)dp4a_uu(d1.z, v[j].z, (uint32_t)Bm[j]); Bm[j] = (int)dp4a_uu(d1.w, v[j].w, (uint32_t)Bm[j]);
-                    Cl[j] = (int)dp4a_uu(d2.x, v[j].x, (uint32_t)Cl[j]); Cl[j] = (int)dp4a_uu(d2.y, v[j].y, (uint32_t)Cl[j]);
-                    Cl[j] = (int)dp4a_uu(d2.z, v[j].z, (uint32_t)Cl[j]); Cl[j] = (int)dp4a_uu(d2.w, v[j].w, (uint32_t)Cl[j]);
-                }
-            } else {
-                const uint4 e0 = sd[2 * c], o0 = sd[2 * c + 1];
-                const uint4 e1 = sd[plane_u4 + 2 * c], o1 = sd[plane_u4 + 2 * c + 1];
-                const uint4 e2 = sd[2 * plane_u4 + 2 * c], o2 = sd[2 * plane_u4 + 2 * c + 1];
-#pragma unroll
-                for (int j = 0; j < R; ++j) {
-                    const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-                    const uint32_t E0[4] = {e0.x, e0.y, e0.z, e0.w}, O0[4] = {o0.x, o0.y, o0.z, o0.w};
-                    const uint32_t E1[4] = {e1.x, e1.y, e1.z, e1.w}, O1[4] = {o1.x, o1.y, o1.z, o1.w};
-                    const uint32_t E2[4] = {e2.x, e2.y, e2.z, e2.w}, O2[4] = {o2.x, o2.y, o2.z, o2.w};
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        uint32_t hi = (w[t] >> 4) & 0x0F0F0F0Fu, lo = w[t] & 0x0F0F0F0Fu;
-                        A[j] = dp4a_su((int)E0[t], hi, A[j]); A[j] = dp4a_su((int)O0[t], lo, A[j]);
-                        Bm[j] = (int)dp4a_uu(E1[t], hi, (uint32_t)Bm[j]); Bm[j] = (int)dp4a_uu(O1[t], lo, (uint32_t)Bm[j]);
-                        Cl[j] = (int)dp4a_uu(E2[t], hi, (uint32_t)Cl[j]); Cl[j] = (int)dp4a_uu(O2[t], lo, (uint32_t)Cl[j]);
-                    }
-                }
-            }
+            quant_chunk<DTYPE, R>(v, c, sd, plane_u4, A, Bm, Cl);
         }
 #pragma unroll
         for (int j = 0; j < R; ++j) {
-            int sa = A[j], sb = Bm[j], sc = Cl[j];
-#pragma unroll
-            for (int o = TPR / 2; o > 0; o >>= 1) {
-                sa += __shfl_xor_sync(0xffffffffu, sa, o);
-                sb += __shfl_xor_sync(0xffffffffu, sb, o);
-                sc += __shfl_xor_sync(0xffffffffu, sc, o);
-            }
-            uint64_t key = kKeyMax;
-            if (valid[j] && gl == 0) {
-                long long S = ((long long)sa << 16) + ((long long)sb << 8) + (long long)sc;
-                float dotn = fmaf(co[j].x, __ll2float_rn(S) * qs.fx, co[j].y * qs.sum);
-                bool zero = (co[j].x == 0.f && co[j].y == 0.f) || qs.inv_norm == 0.f;
-                float score = zero ? 1.0f : 1.0f - dotn * qs.inv_norm;
-                key = make_key(score, (uint32_t)rix[j]);
-            }
+            uint64_t key = quant_key<TPR>(A[j], Bm[j], Cl[j], valid[j] && gl == 0, co[j], qs, rix[j]);
             wc.offer(key, lane);
         }
     }
     wc.finish(lists, warp, lane);
+    cta_merge_and_store(lists, KP, a.partial + ((size_t)b * a.G + blockIdx.x) * KP);
+}
+
+// ----------------------------------------------------------------------------
+// The same scan with the codes staged through shared memory by the TMA unit.
+//
+// The register-fed kernel above keeps at most (warps x rows x chunks) 16-byte loads in flight and
+// its dp4a work holds 128 registers, i.e. 16 warps per SM: memory latency and integer issue do
+// not overlap fully (75 % of the HBM peak).  Here a producer warp streams whole tiles of rows
+// (dense rows => one contiguous cp.async.bulk per tile, plus one for the tile's coefficients)
+// into a ring of `stages` shared-memory buffers, full/empty mbarriers per stage; the bytes in
+// flight are the ring, whatever the consumers are doing.  Eight consumer warps run the same
+// dp4a arithmetic out of shared memory.  Lane -> chunk assignment is rotated per row group
+// (`bank_mul`, chosen on the host) so that the 8 lanes of a quarter-warp hit 8 distinct 16-byte
+// bank groups even when the row pitch is a multiple of 128 bytes.
+// A tile is consumed by `tma_wt` warps (WT x 32/TPR x R rows): the 8 consumer warps form 8/WT groups
+// that take the CTA's tiles in turn, so a tile stays ~25 KB whatever the row length while every
+// warp still works on R = 2 rows at once (the query digits it reads from shared memory are
+// amortised over them: (3 + R)/R shared-memory bytes per row byte for u8, (6 + R)/R for u4).
+// The ring depth is a multiple of the group count, so a stage always belongs to one group.
+// Tiles are whole; the ragged tail of the store goes through the direct-load path in one CTA.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t s_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool sbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void sbar_wait(uint32_t bar, uint32_t parity) {  // bounded: a protocol bug traps
+    if (sbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!sbar_try_wait(bar, parity))
+        if (clock64() - t0 > 4000000000ll) __trap();
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+constexpr int kTmaMaxStages = 8;
+
+template <int DTYPE, int TPR, int R>
+__global__ void __launch_bounds__((kScanWarps + 1) * 32, 2)
+scan_quant_tma_kernel(const ScanArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int GPW = 32 / TPR;
+    constexpr int UPC = (DTYPE == EVDB_U8) ? 1 : 2;
+    const int WT = a.tma_wt, NG = kScanWarps / WT;     // warps per tile, consumer groups
+    const int TR = WT * GPW * R;                       // rows per tile
+    const int nch = a.nch, KP = a.KP, S = a.tma_stages;
+    const int plane_u4 = nch * UPC;
+    const uint32_t code_bytes = (uint32_t)TR * (uint32_t)a.row_bytes, coef_bytes = TR * 8u;
+    uint8_t *ring = smem;                              // [S][tma_stage_bytes]
+    uint4 *sd = reinterpret_cast<uint4 *>(smem + (size_t)S * a.tma_stage_bytes);
+    uint64_t *lists = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(sd) + (size_t)3 * plane_u4 * 16);
+    __shared__ __align__(8) uint64_t bars[2 * kTmaMaxStages];   // full[S], empty[S]
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool consumer = warp < kScanWarps;
+
+    const uint4 *dsrc = reinterpret_cast<const uint4 *>(a.qdig + (size_t)b * 3 * a.qdig_stride);
+    for (int i = threadIdx.x; i < 3 * plane_u4; i += blockDim.x) sd[i] = dsrc[i];
+    if (KP > kAppendMaxKP)
+        for (int i = threadIdx.x; i < kScanWarps * KP; i += blockDim.x) lists[i] = kKeyMax;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < S; ++i) {
+            sbar_init(s_u32(&bars[i]), 1);
+            sbar_init(s_u32(&bars[kTmaMaxStages + i]), WT);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    const QStat qs = a.qstat[b];
+    WarpCands wc;
+    wc.init(lists, KP, consumer ? warp : 0);
+
+    const uint64_t n_tiles = a.n / TR;
+    if (!consumer) {
+        if (lane == 0) {
+            uint32_t i = 0;
+            for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+                const uint32_t st = i % S, use = i / S;
+                if (use > 0) sbar_wait(s_u32(&bars[kTmaMaxStages + st]), (use - 1) & 1);
+                const uint32_t full = s_u32(&bars[st]);
+                const uint32_t dst = s_u32(ring + (size_t)st * a.tma_stage_bytes);
+                sbar_expect_tx(full, code_bytes + coef_bytes);
+                bulk_g2s(dst, a.rows + t * (uint64_t)code_bytes, code_bytes, full);
+                bulk_g2s(dst + code_bytes, a.qcoef + t * TR, coef_bytes, full);
+            }
+        }
+        __syncwarp();
+    } else {
+        const int g = lane / TPR, gl = lane % TPR;
+        int shift = (g * a.bank_mul) & 7;
+        if (shift >= nch) shift %= nch;
+        const int row_in_tile0 = (warp % WT) * GPW * R + g;
+        uint32_t i = warp / WT;                        // this group's first tile of the CTA's sequence
+        for (uint64_t t = blockIdx.x + (uint64_t)i * gridDim.x; t < n_tiles; t += (uint64_t)NG * gridDim.x, i += NG) {
+            const uint32_t st = i % S, use = i / S;
+            sbar_wait(s_u32(&bars[st]), use & 1);
+            const uint8_t *codes = ring + (size_t)st * a.tma_stage_bytes;
+            const float2 *cf = reinterpret_cast<const float2 *>(codes + code_bytes);
+            const uint4 *rp[R];
+            float2 co[R];
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                const int r = row_in_tile0 + j * GPW;
+                rp[j] = reinterpret_cast<const uint4 *>(codes + (size_t)r * a.row_bytes);
+                co[j] = gl == 0 ? cf[r] : make_float2(0.f, 0.f);
+            }
+            int A[R], Bm[R], Cl[R];
+#pragma unroll
+            for (int j = 0; j < R; ++j) A[j] = Bm[j] = Cl[j] = 0;
+#pragma unroll 2
+            for (int c0 = gl; c0 < nch; c0 += TPR) {
+                int c = c0 + shift;
+                if (c >= nch) c -= nch;
+                uint4 v[R];
+#pragma unroll
+                for (int j = 0; j < R; ++j) v[j] = rp[j][c];
+                quant_chunk<DTYPE, R>(v, c, sd, plane_u4, A, Bm, Cl);
+            }
+            __syncwarp();
+            if (lane == 0) sbar_arrive(s_u32(&bars[kTmaMaxStages + st]));   // this warp is done with the stage
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                const uint64_t row = t * TR + (uint64_t)(row_in_tile0 + j * GPW);
+                uint64_t key = quant_key<TPR>(A[j], Bm[j], Cl[j], gl == 0, co[j], qs, row);
+                wc.offer(key, lane);
+            }
+        }
+        // ragged tail (< TR rows): direct loads, in the CTA whose turn it would have been
+        if (blockIdx.x == (unsigned)(n_tiles % gridDim.x)) {
+            const uint64_t rows_per_wi = (uint64_t)GPW * R;
+            for (uint64_t base = n_tiles * TR + (uint64_t)warp * rows_per_wi; base < a.n;
+                 base += (uint64_t)kScanWarps * rows_per_wi) {
+                const uint4 *rp[R];
+                uint64_t rix[R];
+                bool valid[R];
+                float2 co[R];
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    uint64_t r = base + (uint64_t)j * GPW + g;
+                    valid[j] = r < a.n;
+                    rix[j] = r;
+                    rp[j] = reinterpret_cast<const uint4 *>(a.rows + (valid[j] ? r : a.n - 1) * a.row_bytes);
+                    co[j] = (valid[j] && gl == 0) ? __ldg(a.qcoef + r) : make_float2(0.f, 0.f);
+                }
+                int A[R], Bm[R], Cl[R];
+#pragma unroll
+                for (int j = 0; j < R; ++j) A[j] = Bm[j] = Cl[j] = 0;
+                for (int c = gl; c < nch; c += TPR) {
+                    uint4 v[R];
+#pragma unroll
+                    for (int j = 0; j < R; ++j) v[j] = ldg_stream_u4(rp[j] + c);
+                    quant_chunk<DTYPE, R>(v, c, sd, plane_u4, A, Bm, Cl);
+                }
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    uint64_t key = quant_key<TPR>(A[j], Bm[j], Cl[j], valid[j] && gl == 0, co[j], qs, rix[j]);
+                    wc.offer(key, lane);
+                }
+            }
+        }
+    }
+    wc.finish(lists, warp, lane, consumer);
     cta_merge_and_store(lists, KP, a.partial + ((size_t)b * a.G + blockIdx.x) * KP);
 }
 
@@ -451,15 +650,68 @@ static scan_fn_t pick_quant(int tpr) {
     }
 }
 
+constexpr int kTmaR = 2;   // rows per lane group in flight: 2 beat 4 on every shape measured (tools/sweep_quant.sh)
+template <int DTYPE>
+static scan_fn_t pick_quant_tma(int tpr) {
+    switch (tpr) {
+        case 1: return scan_quant_tma_kernel<DTYPE, 1, kTmaR>;
+        case 2: return scan_quant_tma_kernel<DTYPE, 2, kTmaR>;
+        case 4: return scan_quant_tma_kernel<DTYPE, 4, kTmaR>;
+        case 8: return scan_quant_tma_kernel<DTYPE, 8, kTmaR>;
+        case 16: return scan_quant_tma_kernel<DTYPE, 16, kTmaR>;
+        default: return scan_quant_tma_kernel<DTYPE, 32, kTmaR>;
+    }
+}
+
+// Shared-memory wavefronts of one warp's loads (row chunks + query digits) for a candidate chunk
+// rotation `m`: lane (g, gl) reads chunk (it*TPR + gl + ((g*m)&7)) mod nch of row g; an LDS.128
+// serves a quarter-warp per wavefront when its 8 lanes touch 8 distinct 16-byte bank groups.
+static int bank_cost(int nch, int tpr, int m, int R, int digit_loads) {
+    int cost = 0;
+    for (int it = 0; it * tpr < nch; ++it)
+        for (int q = 0; q < 4; ++q) {
+            int rowu[8] = {0}, sdu[8] = {0}, sd_addr[8][8], sd_n[8] = {0};
+            for (int l = 8 * q; l < 8 * q + 8; ++l) {
+                int g = l / tpr, gl = l % tpr, c0 = it * tpr + gl;
+                if (c0 >= nch) continue;
+                int sh = (g * m) & 7;
+                if (sh >= nch) sh %= nch;
+                int c = c0 + sh;
+                if (c >= nch) c -= nch;
+                rowu[(g * nch + c) & 7]++;
+                int u = c & 7;
+                bool seen = false;
+                for (int i = 0; i < sd_n[u]; ++i) seen |= sd_addr[u][i] == c;
+                if (!seen) { sd_addr[u][sd_n[u]++] = c; sdu[u]++; }
+            }
+            int mr = 0, ms = 0;
+            for (int u = 0; u < 8; ++u) { mr = rowu[u] > mr ? rowu[u] : mr; ms = sdu[u] > ms ? sdu[u] : ms; }
+            cost += R * mr + digit_loads * ms;
+        }
+    return cost;
+}
+
 struct ScanPlan {
     scan_fn_t fn;
     size_t smem;
-    int tpr, rows_per_wi;
+    int tpr, rows_per_wi, threads;
+    bool tma;
+    int stages, stage_bytes, bank_mul, tile_rows, wt;
 };
+
+static int scan_tma_mode() {   // EVDB_SCAN_TMA=0 forces the register-fed quantized scan (A/B measurements)
+    static int mode = -1;
+    if (mode < 0) { const char *e = getenv("EVDB_SCAN_TMA"); mode = e ? atoi(e) : 1; }
+    return mode;
+}
 
 static int make_scan_plan(evdb_store *s, int metric, int KP, ScanPlan *p) {
     int tpr = pick_tpr(s->nch, s->dtype);
     p->tpr = tpr;
+    p->threads = kScanWarps * 32;
+    p->tma = false;
+    p->stages = p->stage_bytes = p->bank_mul = p->tile_rows = 0;
+    p->wt = kScanWarps;
     int R = 4;
     size_t qbytes;
     switch (s->dtype) {
@@ -476,23 +728,77 @@ static int make_scan_plan(evdb_store *s, int metric, int KP, ScanPlan *p) {
             qbytes = (size_t)s->nch * 32;
             break;
         case EVDB_U8:
+        case EVDB_U4: {
             if (metric != EVDB_COSINE) return EVDB_E_UNSUPPORTED;
-            p->fn = pick_quant<EVDB_U8>(tpr);
-            qbytes = (size_t)s->nch * 16 * 3;
+            const bool u8 = s->dtype == EVDB_U8;
+            p->fn = u8 ? pick_quant<EVDB_U8>(tpr) : pick_quant<EVDB_U4>(tpr);
+            qbytes = (size_t)s->nch * (u8 ? 16 : 32) * 3;
             if (tpr == 32) R = 2;
+            // TMA-staged variant: whole tiles through a shared-memory ring (large stores only:
+            // a small one is latency-bound and spreads better one warp-iteration per warp)
+            if (scan_tma_mode() && s->row_bytes >= 64) {   // (32-byte rows: the register-fed kernel is level or better)
+                static int env_div = -1, env_wt = -1;
+                if (env_div < 0) { const char *e = getenv("EVDB_SCAN_TMA_DIV"); env_div = e && atoi(e) > 0 ? atoi(e) : 4; }
+                if (env_wt < 0) { const char *e = getenv("EVDB_SCAN_TMA_WT"); env_wt = e ? atoi(e) : 0; }
+                int t2 = 1;
+                while (t2 < 32 && (t2 < 2 ? s->nch >= 2 : t2 * 2 <= s->nch / env_div)) t2 <<= 1;
+                const int gpw = 32 / t2;
+                const size_t fixed = qbytes + scan_list_bytes(KP) + 1024;
+                const size_t half = 112 * 1024, whole = 224 * 1024;
+                int best_r = 0, best_wt = 0, best_s = 0;
+                size_t best_stage = 0;
+                // preference: two CTAs per SM, then the widest tile group.  A stage always belongs to
+                // the same group (stages % groups == 0: a group never waits on a barrier phase it
+                // did not see complete), and every group has a second stage in flight.
+                for (int pass = 0; pass < 2 && !best_r; ++pass)
+                    for (int wt = kScanWarps; wt >= 1 && !best_r; wt >>= 1) {
+                        if (env_wt && wt != env_wt) continue;
+                        const int ng = kScanWarps / wt;
+                        const size_t tile = (size_t)wt * gpw * kTmaR * (s->row_bytes + 8);
+                        const size_t stage = (tile + 127) / 128 * 128;
+                        const size_t room = pass == 0 ? half : whole;
+                        if (tile > 48 * 1024 || fixed + stage > room) continue;
+                        int stages = (int)((room - fixed) / stage);
+                        if (stages > kTmaMaxStages) stages = kTmaMaxStages;
+                        stages -= stages % ng;
+                        if (stages < (ng == 1 ? 3 : 2 * ng)) continue;
+                        best_r = kTmaR; best_wt = wt; best_s = stages; best_stage = stage;
+                    }
+                const uint64_t tile_rows = (uint64_t)best_wt * gpw * best_r;
+                if (best_r && s->count / tile_rows >= (uint64_t)4 * s->sm_count) {
+                    p->tma = true;
+                    tpr = t2;
+                    p->tpr = t2;
+                    p->fn = u8 ? pick_quant_tma<EVDB_U8>(t2) : pick_quant_tma<EVDB_U4>(t2);
+                    p->threads = (kScanWarps + 1) * 32;
+                    p->stages = best_s;
+                    p->stage_bytes = (int)best_stage;
+                    p->tile_rows = (int)tile_rows;
+                    p->wt = best_wt;
+                    R = best_r;
+                    int best = 0, best_cost = bank_cost(s->nch, t2, 0, R, u8 ? 3 : 6);
+                    if (t2 < 8)
+                        for (int m = 1; m < 8; ++m) {
+                            int c = bank_cost(s->nch, t2, m, R, u8 ? 3 : 6);
+                            if (c < best_cost) { best_cost = c; best = m; }
+                        }
+                    p->bank_mul = best;
+                    qbytes += (size_t)best_s * best_stage;
+                    static int dbg = -1;
+                    if (dbg < 0) { const char *e = getenv("EVDB_SCAN_DEBUG"); dbg = e && atoi(e) ? 1 : 0; }
+                    if (dbg)
+                        fprintf(stderr, "[evdb scan] tma plan: nch=%d tpr=%d R=%d wt=%d stages=%d stage=%zu B rotation=%d\n",
+                                s->nch, t2, best_r, best_wt, best_s, best_stage, best);
+                }
+            }
             break;
-        case EVDB_U4:
-            if (metric != EVDB_COSINE) return EVDB_E_UNSUPPORTED;
-            p->fn = pick_quant<EVDB_U4>(tpr);
-            qbytes = (size_t)s->nch * 32 * 3;
-            if (tpr == 32) R = 2;
-            break;
+        }
         default:
             return EVDB_E_BAD_ARG;
     }
     p->rows_per_wi = (32 / tpr) * R;
     p->smem = qbytes + scan_list_bytes(KP);
-    if (p->smem > 200 * 1024) return EVDB_E_UNSUPPORTED;
+    if (p->smem > 200 * 1024 && !p->tma) return EVDB_E_UNSUPPORTED;
     return EVDB_OK;
 }
 
@@ -502,24 +808,34 @@ int scan_grid_size(evdb_store *s, int metric, int KP, int *G_out) {
     if (p.smem > 48 * 1024)
         EVDB_TRY(ensure_func_smem((const void *)p.fn, p.smem));
     int occ = 1;
-    EVDB_TRY(cached_occupancy((const void *)p.fn, kScanWarps * 32, p.smem, &occ));
+    EVDB_TRY(cached_occupancy((const void *)p.fn, p.threads, p.smem, &occ));
     if (occ < 1) occ = 1;
     if (occ > 4) occ = 4;
-    uint64_t total_wi = (s->count + p.rows_per_wi - 1) / p.rows_per_wi;
-    // small stores are latency-bound: one warp-iteration per warp spreads them over the most SMs
-    uint64_t want = (total_wi + (uint64_t)kScanWarps - 1) / (uint64_t)kScanWarps;
     uint64_t cap = (uint64_t)s->sm_count * occ;
+    uint64_t want;
+    if (p.tma) {
+        want = s->count / p.tile_rows;   // one CTA per tile at most
+    } else {
+        uint64_t total_wi = (s->count + p.rows_per_wi - 1) / p.rows_per_wi;
+        // small stores are latency-bound: one warp-iteration per warp spreads them over the most SMs
+        want = (total_wi + (uint64_t)kScanWarps - 1) / (uint64_t)kScanWarps;
+    }
     uint64_t G = want < cap ? want : cap;
     if (G < 1) G = 1;
     *G_out = (int)G;
     return EVDB_OK;
 }
 
-int launch_scan(evdb_store *s, int metric, const ScanArgs &a, cudaStream_t st) {
+int launch_scan(evdb_store *s, int metric, const ScanArgs &a0, cudaStream_t st) {
     ScanPlan p;
-    EVDB_TRY(make_scan_plan(s, metric, a.KP, &p));
+    EVDB_TRY(make_scan_plan(s, metric, a0.KP, &p));
+    ScanArgs a = a0;
+    a.tma_stages = p.stages;
+    a.tma_stage_bytes = p.stage_bytes;
+    a.bank_mul = p.bank_mul;
+    a.tma_wt = p.wt;
     dim3 grid(a.G, a.B);
-    p.fn<<<grid, kScanWarps * 32, p.smem, st>>>(a);
+    p.fn<<<grid, p.threads, p.smem, st>>>(a);
     s->n_launches++;
     EVDB_CUDA(cudaGetLastError());
     return EVDB_OK;

@@ -498,3 +498,44 @@ def test_batches_with_windows_wider_than_the_gemm_plan(native, oracle, k, metric
         assert counts[b] == k
         assert slots[b].tolist() == r.tolist() and dists[b].tolist() == dd.tolist()
     st.close()
+
+
+@pytest.mark.parametrize("n,d,dtype", [
+    (200_003, 96, "u8"),      # cfg4 row shape: 2 lanes per row, ragged tail after 781 whole tiles
+    (170_000, 128, "u8"),     # row pitch = 128 B: the chunk rotation that keeps LDS.128 conflict-free
+    (300_001, 24, "u8"),      # two chunks per row
+    (160_001, 128, "u4"),     # 64-byte rows (the smallest that take this path)
+    (10_001, 6144, "u8"),     # 6 KB rows: two warps per tile, four consumer groups, one CTA per SM
+    (20_001, 1536, "u8"),     # 16 lanes per row, one row per lane group and tile
+    (40_000, 1536, "u4"),     # cfg5 row shape
+    (160_000, 100, "u8"),     # dimension not a multiple of 16: zero-padded last chunk
+])
+def test_tma_staged_quantized_scan_equals_exhaustive_plan(native, oracle, n, d, dtype):
+    """Stores with >= 4 * SMs whole tiles take the TMA-staged scan (scan.cu: scan_quant_tma_kernel).
+    Its result must be bit-equal to the exhaustive fp64 plan on the same store, and the winners'
+    distances bit-equal to the oracle's on the dequantised rows."""
+    st = _store(native, dtype)
+    st.fill_synthetic(oracle.SEED_CORPUS, n, d)
+    qs = oracle.synth_f64(oracle.SEED_QUERY, 0, 3, d)
+    k = 10
+    st.set_plan("scan")
+    ss, sd, sc = st.search(qs, k, "cosine")
+    assert st.stats()["last_plan"] == native.PLAN_SCAN
+    st.set_plan("exact")
+    es, ed, ec = st.search(qs, k, "cosine")
+    assert st.stats()["last_plan"] == native.PLAN_EXACT
+    assert np.array_equal(ss, es) and np.array_equal(sd, ed) and np.array_equal(sc, ec)
+    for b in range(3):
+        for j in (0, k - 1):
+            codes, mn, scale = st.get_codes(int(ss[b, j]))
+            row = oracle.dequantize_8bit(codes, mn, scale) if dtype == "u8" else \
+                oracle.dequantize_4bit(codes, d, mn, scale)
+            assert sd[b, j] == oracle.distance(qs[b], row, "cosine")
+    # k = 100 (128-key windows) and a 7-query batch (grid.y) through the same kernel
+    st.set_plan("scan")
+    q7 = oracle.synth_f64(oracle.SEED_QUERY, 3, 7, d)
+    s7, d7, _ = st.search(q7, 100, "cosine")
+    st.set_plan("exact")
+    e7, f7, _ = st.search(q7, 100, "cosine")
+    assert np.array_equal(s7, e7) and np.array_equal(d7, f7)
+    st.close()
