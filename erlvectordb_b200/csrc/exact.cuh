@@ -31,6 +31,34 @@ __device__ __forceinline__ double row_elem(const uint8_t *row, int i, double mn,
     }
 }
 
+// Left-to-right sum of cnt staged terms onto acc (one lane).  Terms come from shared memory 16 at
+// a time into registers of their own, the next 16 requested before the current 16 are added, so
+// the dependent DADD chain (8.6 cycles a step on B200) never waits for a load.
+__device__ __forceinline__ double fold_staged(double acc, const double *src, int cnt) {
+    constexpr int U = 16;
+    int i = 0;
+    if (cnt >= U) {
+        double t[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) t[k] = src[k];
+#pragma unroll 1
+        for (; i + 2 * U <= cnt; i += U) {
+            double n[U];
+#pragma unroll
+            for (int k = 0; k < U; ++k) n[k] = src[i + U + k];
+#pragma unroll
+            for (int k = 0; k < U; ++k) acc = __dadd_rn(acc, t[k]);
+#pragma unroll
+            for (int k = 0; k < U; ++k) t[k] = n[k];
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) acc = __dadd_rn(acc, t[k]);
+        i += U;
+    }
+    for (; i < cnt; ++i) acc = __dadd_rn(acc, src[i]);
+    return acc;
+}
+
 // vector_norm/1 of a stored row (src/vector_store.erl:251-252): returned to every lane.
 template <int DTYPE>
 __device__ double exact_norm_warp(const uint8_t *row, double mn, double sc, int d, double *sp,
@@ -43,10 +71,7 @@ __device__ double exact_norm_warp(const uint8_t *row, double mn, double sc, int 
             sp[t] = __dmul_rn(v, v);
         }
         __syncwarp();
-        if (lane == 0) {
-#pragma unroll 8
-            for (int i = 0; i < cnt; ++i) s = __dadd_rn(s, sp[i]);
-        }
+        if (lane == 0) s = fold_staged(s, sp, cnt);
         __syncwarp();
     }
     s = __shfl_sync(0xffffffffu, s, 0);
@@ -95,12 +120,10 @@ __device__ double exact_distance_warp(const uint8_t *row, double mn, double sc, 
             nq[i] = t < d ? q[t] : 0.0;
         }
         __syncwarp();
-        if (lane == 0) {
-#pragma unroll 8
-            for (int i = 0; i < cnt; ++i) s = __dadd_rn(s, sp[i]);
-        } else if (lane == 1 && metric == EVDB_COSINE) {
-#pragma unroll 8
-            for (int i = 0; i < cnt; ++i) sq = __dadd_rn(sq, sp2[i]);
+        // lane 0 folds the products, lane 1 (cosine) the query squares -- in the same instruction stream
+        if (lane < (metric == EVDB_COSINE ? 2 : 1)) {
+            const double r = fold_staged(lane == 0 ? s : sq, lane == 0 ? sp : sp2, cnt);
+            if (lane == 0) s = r; else sq = r;
         }
         __syncwarp();
     }

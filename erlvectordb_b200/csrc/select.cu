@@ -195,6 +195,7 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
         __syncthreads();
         SEL_MARK(0);
         int carried = 0, l0 = 0;
+        bool sorted = false;
         while (l0 < L) {
             // as many whole buffers as fit next to the carried keys (a buffer holds <= 256 keys)
             int lo = l0 + 1, hi = L;
@@ -203,17 +204,33 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
                 if (carried + s_off[mid] - s_off[l0] <= kSelSort) lo = mid; else hi = mid - 1;
             }
             const int l1 = lo;
-            for (int l = l0 + warp; l < l1; l += kSelWarps) {
-                const int n = s_off[l + 1] - s_off[l];
-                const uint64_t *src = rw.cand + list_index(l) * rw.cap * rw.gm + et;  // entry i at [i*gm]
-                uint64_t *dst = buf + carried + (s_off[l] - s_off[l0]);
-                for (int i = lane; i < n; i += 32) dst[i] = __ldcg(src + (size_t)i * rw.gm);
+            // one candidate per thread: the buffers hold a key or two each, walking them one after
+            // the other would put a memory latency on every buffer
+            const int e0 = s_off[l0], e1 = s_off[l1];
+            for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+                int a0 = l0, a1 = l1 - 1;           // largest l with s_off[l] <= e
+                while (a0 < a1) {
+                    const int mid = (a0 + a1 + 1) >> 1;
+                    if (s_off[mid] <= e) a0 = mid; else a1 = mid - 1;
+                }
+                const uint64_t *src = rw.cand + list_index(a0) * rw.cap * rw.gm + et;  // entry i at [i*gm]
+                buf[carried + (e - e0)] = __ldcg(src + (size_t)(e - s_off[a0]) * rw.gm);
             }
-            const int filled = carried + s_off[l1] - s_off[l0];
+            const int filled = carried + e1 - e0;
             __syncthreads();
             SEL_MARK(1);
             if (filled > KP) {
-                block_select_smallest(buf, filled, KP, dkey);
+                if (l1 == L && filled <= (int)blockDim.x) {
+                    // last round, one key per thread: a single sort selects and orders
+                    int np = KP;
+                    while (np < filled) np <<= 1;
+                    for (int i = filled + threadIdx.x; i < np; i += blockDim.x) buf[i] = kKeyMax;
+                    __syncthreads();
+                    block_bitonic_sort_fast(buf, np, dkey);
+                    sorted = true;
+                } else {
+                    block_select_smallest(buf, filled, KP, dkey);
+                }
                 carried = KP;
             } else {
                 carried = filled;
@@ -221,9 +238,11 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
             l0 = l1;
             SEL_MARK(2);
         }
-        for (int i = carried + threadIdx.x; i < KP; i += blockDim.x) buf[i] = kKeyMax;
-        __syncthreads();
-        block_bitonic_sort(buf, KP);
+        if (!sorted) {
+            for (int i = carried + threadIdx.x; i < KP; i += blockDim.x) buf[i] = kKeyMax;
+            __syncthreads();
+            block_bitonic_sort_fast(buf, KP, dkey);
+        }
     } else {
     // ---- 1b. scan plans: merge L ascending lists of KP keys into the KP smallest ----
     // Fast path: pool the first P = ceil(KP/L) keys of every list; the KP-th smallest of the pool
@@ -244,15 +263,22 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
             buf[i] = i < pool ? src[(size_t)(i / P) * KP + (i % P)] : kKeyMax;
         if (threadIdx.x == 0) s_cnt = 0;
         __syncthreads();
-        block_bitonic_sort(buf, Lp);
+        block_bitonic_sort_fast(buf, Lp, dkey);
         const uint64_t T = buf[KP - 1];  // >= KP keys are <= T (kKeyMax if the lists hold fewer)
         __syncthreads();
-        for (size_t i = threadIdx.x; i < total; i += blockDim.x) {
-            uint64_t key = src[i];
-            if (key <= T && key != kKeyMax) {
-                int p = atomicAdd(&s_cnt, 1);
-                if (p < kSelSort) buf[p] = key;
+        for (size_t i0 = threadIdx.x; i0 < total; i0 += (size_t)blockDim.x * 8) {
+            uint64_t kk[8];   // eight loads in flight per thread, then the filter
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const size_t i = i0 + (size_t)u * blockDim.x;
+                kk[u] = i < total ? __ldcg(src + i) : kKeyMax;
             }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (kk[u] <= T && kk[u] != kKeyMax) {
+                    int p = atomicAdd(&s_cnt, 1);
+                    if (p < kSelSort) buf[p] = kk[u];
+                }
         }
         __syncthreads();
         const int cnt = s_cnt;
@@ -261,7 +287,7 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
             while (nsort < cnt) nsort <<= 1;
             for (int i = cnt + threadIdx.x; i < nsort; i += blockDim.x) buf[i] = kKeyMax;
             __syncthreads();
-            block_bitonic_sort(buf, nsort);
+            block_bitonic_sort_fast(buf, nsort, dkey);
             merged = true;
         }
         __syncthreads();
@@ -278,7 +304,7 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
             for (int i = threadIdx.x; i < nsort - carried; i += blockDim.x)
                 buf[carried + i] = (size_t)i < take ? src[pos + i] : kKeyMax;
             __syncthreads();
-            block_bitonic_sort(buf, nsort);
+            block_bitonic_sort_fast(buf, nsort, dkey);
             pos += take;
             carried = KP;
             if (pos >= total) break;
@@ -389,7 +415,7 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
 
     // ---- 3. final order by (exact distance, slot); emit k; completeness proof ----
     SEL_MARK(5);
-    block_bitonic_sort_pairs(dkey, dslot, nsort);
+    block_bitonic_sort_pairs_fast(dkey, dslot, nsort, buf);
     for (int i = threadIdx.x; i < a.kstride; i += blockDim.x) {
         size_t o = (size_t)b * a.kstride + i;
         if (i < kout) {

@@ -178,7 +178,15 @@ static int search_core(evdb_store *s, const double *d_q64, int B, int k, int kst
     int squared = 0;
     int lists = 0;
     bool use_gemm = false;
-    if (plan == EVDB_PLAN_GEMM || (plan == EVDB_PLAN_AUTO && B >= 16))
+    // Auto: the tcgen05 plan reads the 2-byte operand column ONCE for the whole batch, the scan plan
+    // reads the 4-byte rows once PER QUERY -- so the GEMM plan also wins for a handful of queries,
+    // and even for a single one, as soon as the store is large enough to hide its extra launches
+    // (measured on B200, tools/sweep.py: 1 M x 768 B = 1: 0.30 vs 0.52 ms; B = 8: 0.36 vs 3.7 ms;
+    // 100 k x 128 B = 1: 0.068 vs 0.057 ms).  EVDB_GEMM_MIN_BYTES overrides the crossover.
+    static double gemm_min_bytes = -1.0;
+    if (gemm_min_bytes < 0.0) { const char *e = getenv("EVDB_GEMM_MIN_BYTES"); gemm_min_bytes = e ? atof(e) : 256e6; }
+    if (plan == EVDB_PLAN_GEMM ||
+        (plan == EVDB_PLAN_AUTO && (B >= 16 || (double)B * (double)s->count * (double)s->row_bytes >= gemm_min_bytes)))
         use_gemm = gemm_plan_supported(s, metric, B, gemm_kp(KP));
     if (plan == EVDB_PLAN_GEMM && !use_gemm) return EVDB_E_UNSUPPORTED;
 

@@ -68,6 +68,72 @@ __device__ __forceinline__ void block_bitonic_sort_pairs(uint64_t *keys, uint64_
     }
 }
 
+// Same result as block_bitonic_sort for n <= blockDim.x keys, one key per thread in a register:
+// compare-exchange distances below 32 are warp shuffles, only the wider ones go through shared
+// memory (ping-pong between buf and tmp: ONE barrier per such stage).  n = 1024 takes 15 barriers
+// instead of 55.  Larger n fall back to the in-place version.  tmp: n keys of scratch.
+__device__ __forceinline__ void block_bitonic_sort_fast(uint64_t *buf, int n, uint64_t *tmp) {
+    if (n > (int)blockDim.x) {
+        block_bitonic_sort(buf, n);
+        return;
+    }
+    const int i = threadIdx.x;
+    uint64_t v = i < n ? buf[i] : ~0ull;
+    uint64_t *cur = tmp;
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            uint64_t o;
+            if (j >= 32) {
+                if (i < n) cur[i] = v;
+                __syncthreads();
+                o = i < n ? cur[i ^ j] : ~0ull;
+                cur = cur == tmp ? buf : tmp;
+            } else {
+                o = __shfl_xor_sync(0xffffffffu, v, j);
+            }
+            const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
+            v = keep_min ? (v < o ? v : o) : (v > o ? v : o);
+        }
+    }
+    __syncthreads();
+    if (i < n) buf[i] = v;
+    __syncthreads();
+}
+
+// (key, payload) pairs ordered by (key, payload), n <= blockDim.x; tmp: 2n words of scratch.
+__device__ __forceinline__ void block_bitonic_sort_pairs_fast(uint64_t *keys, uint64_t *vals, int n, uint64_t *tmp) {
+    if (n > (int)blockDim.x) {
+        block_bitonic_sort_pairs(keys, vals, n);
+        return;
+    }
+    const int i = threadIdx.x;
+    uint64_t a = i < n ? keys[i] : ~0ull, va = i < n ? vals[i] : ~0ull;
+    uint64_t *ck = tmp, *cv = tmp + n;
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            uint64_t b, vb;
+            if (j >= 32) {
+                if (i < n) { ck[i] = a; cv[i] = va; }
+                __syncthreads();
+                b = i < n ? ck[i ^ j] : ~0ull;
+                vb = i < n ? cv[i ^ j] : ~0ull;
+                const bool first = ck == tmp;
+                ck = first ? keys : tmp;
+                cv = first ? vals : tmp + n;
+            } else {
+                b = __shfl_xor_sync(0xffffffffu, a, j);
+                vb = __shfl_xor_sync(0xffffffffu, va, j);
+            }
+            const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
+            const bool mine_less = a < b || (a == b && va < vb);
+            if (keep_min != mine_less && !(a == b && va == vb)) { a = b; va = vb; }
+        }
+    }
+    __syncthreads();
+    if (i < n) { keys[i] = a; vals[i] = va; }
+    __syncthreads();
+}
+
 // Selection without sorting: tau = the `need`-th smallest 32-bit score (orderable encoding, high
 // word of the key) among up to 256 keys held 8 per lane (kKeyMax pads), by 4-way search on the
 // value with warp-wide population counts.  Returns tau; *n_less = number of keys with score < tau.
