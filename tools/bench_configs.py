@@ -29,11 +29,13 @@ CASES = [
     # name, rows, dim, dtype, metric, k, batch, bytes_per_row
     ("cfg1 10k x128 f32 cosine k=10 B=1", 10_000, 128, "f32", "cosine", 10, 1, 128 * 4),
     ("cfg2 1M x768 f32 cosine k=10 B=1", 1_000_000, 768, "f32", "cosine", 10, 1, 768 * 4),
+    ("cfg2 1M x768 f32 cosine k=10 B=8", 1_000_000, 768, "f32", "cosine", 10, 8, 768 * 4),
     ("cfg2 1M x768 f32 cosine k=10 B=1024", 1_000_000, 768, "f32", "cosine", 10, 1024, 768 * 4),
     ("cfg3 10M x128 f32 euclidean k=100 B=1", 10_000_000, 128, "f32", "euclidean", 100, 1, 128 * 4),
     ("cfg3 10M x128 f32 euclidean k=100 B=4096 (tcgen05 GEMM + top-k epilogue)", 10_000_000, 128, "f32", "euclidean", 100, 4096, 128 * 4),
     ("cfg3' 10M x128 f32 cosine k=10 B=4096", 10_000_000, 128, "f32", "cosine", 10, 4096, 128 * 4),
     ("cfg4/8 12.5M x96 u8 cosine k=10 B=1", 12_500_000, 96, "u8", "cosine", 10, 1, 96 + 8),
+    ("cfg4' 12.5M x128 u8 cosine k=10 B=1", 12_500_000, 128, "u8", "cosine", 10, 1, 128 + 8),
     ("cfg5 1M x1536 f32 manhattan k=10 B=1", 1_000_000, 1536, "f32", "manhattan", 10, 1, 1536 * 4),
     ("cfg5 1M x1536 u4 cosine k=10 B=1", 1_000_000, 1536, "u4", "cosine", 10, 1, 1536 // 2 + 8),
     ("extra 1M x768 bf16 cosine k=10 B=1", 1_000_000, 768, "bf16", "cosine", 10, 1, 768 * 2),
@@ -62,7 +64,14 @@ for name, n, d, dtype, metric, k, B, bpr in CASES:
     kern = kms / max(ns, 1)
     rec = {"case": name, "plan": {1: "scan", 2: "gemm", 3: "exact"}.get(stt["last_plan"]), "step_ms": round(step, 4),
            "kernel_ms": round(kern, 4), "qps": round(B / step * 1e3, 1), "flagged": int(o[3].sum())}
-    if stt["last_plan"] == 2:
+    if stt["last_plan"] == 2 and B < 128:
+        # few queries: the tcgen05 candidate pass is bound by reading its 2-byte operand column once
+        col = float(n) * ((d + 63) // 64 * 64) * 2
+        gbs = col / (kern * 1e-3) / 1e9
+        rec.update({"bound": "hbm", "achieved_gbs": round(gbs, 1), "frac": round(gbs / PEAKS["hbm_gbs"], 3),
+                    "bytes": "fp16 operand column, read once for the batch",
+                    "fp32_rows_equivalent_gbs": round(float(n) * bpr * B / (kern * 1e-3) / 1e9, 1)})
+    elif stt["last_plan"] == 2:
         tf = 2.0 * n * d * B / (kern * 1e-3) / 1e12
         rec.update({"bound": "tensor", "achieved_tflops": round(tf, 1), "frac": round(tf / PEAKS["tf"], 3)})
     elif stt["last_plan"] == 1:
