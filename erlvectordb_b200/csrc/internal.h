@@ -51,6 +51,7 @@ struct evdb_store {
     float l2_sigma = 0.f;          // power-of-two scale: sigma * max||v|| in [64, 128)
     double max_norm = 0.0;         // upper bound on the largest row norm (valid when !max_norm_dirty)
     int max_norm_dirty = 1;
+    int gemm_oom = 0;            // the GEMM plan ran out of device memory once: AUTO stays on the scan plan
     void *d_scalar = nullptr;      // 64-byte device scratch (reductions)
 
     // ---- workspace (grown on demand) ----

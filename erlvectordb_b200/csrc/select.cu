@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
     if (a.raw.cand) {
         // ---- 1a. GEMM plan: gather this query's unsorted candidate buffers, keep the KP best ----
         __shared__ int s_off[kRawMaxLists + 1];  // exclusive prefix of the buffer fill counts
+        __shared__ int s_cut;
         const RawCands &rw = a.raw;
         const int L = a.L;                       // NG * parts buffers hold candidates of this query
         const int blk = b / rw.gm, et = b % rw.gm;
@@ -220,7 +221,42 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
             __syncthreads();
             SEL_MARK(1);
             if (filled > KP) {
-                if (l1 == L && filled <= (int)blockDim.x) {
+                if (KP <= 128 && filled >= 2 * (KP <= 64 ? 256 : 512)) {
+                    // Hundreds to thousands of keys of which KP are wanted (a full 1024-key sort costs
+                    // ~17 k cycles): the KP-th smallest of a strided subset bounds the KP-th smallest
+                    // overall, so only keys <= it can matter -- typically ~ filled * KP / subset of
+                    // them; one small sort finishes the round.
+                    uint64_t *sub = dslot;                 // 1024 keys of scratch (results come later)
+                    const int nsub = KP <= 64 ? 256 : 512;
+                    const int stride = filled / nsub;
+                    for (int i = threadIdx.x; i < nsub; i += blockDim.x) sub[i] = buf[i * stride];
+                    if (threadIdx.x == 0) s_cut = 0;
+                    __syncthreads();
+                    block_bitonic_sort_fast(sub, nsub, dkey);
+                    const uint64_t T = sub[KP - 1];
+                    __syncthreads();
+                    for (int i = threadIdx.x; i < filled; i += blockDim.x) {
+                        const uint64_t key = buf[i];
+                        if (key <= T) {
+                            const int p = atomicAdd(&s_cut, 1);
+                            if (p < 1024) sub[p] = key;
+                        }
+                    }
+                    __syncthreads();
+                    const int cnt = s_cut;
+                    if (cnt <= 1024) {
+                        int np = KP;
+                        while (np < cnt) np <<= 1;
+                        for (int i = cnt + threadIdx.x; i < np; i += blockDim.x) sub[i] = kKeyMax;
+                        __syncthreads();
+                        block_bitonic_sort_fast(sub, np, dkey);
+                        for (int i = threadIdx.x; i < KP; i += blockDim.x) buf[i] = sub[i];
+                        __syncthreads();
+                        sorted = l1 == L;
+                    } else {
+                        block_select_smallest(buf, filled, KP, dkey);
+                    }
+                } else if (l1 == L && filled <= (int)blockDim.x) {
                     // last round, one key per thread: a single sort selects and orders
                     int np = KP;
                     while (np < filled) np <<= 1;
@@ -259,8 +295,12 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
         const int pool = a.L * P;
         int Lp = 2;
         while (Lp < pool) Lp <<= 1;
+        // any KP keys bound the KP-th smallest: with many lists the heads of the first 256 do, and a
+        // 256-key sort is several times cheaper than a 1024-key one
+        const int pool_used = (Lp > 256 && P == 1 && KP <= 128) ? 256 : pool;
+        if (pool_used < pool) Lp = 256;
         for (int i = threadIdx.x; i < Lp; i += blockDim.x)
-            buf[i] = i < pool ? src[(size_t)(i / P) * KP + (i % P)] : kKeyMax;
+            buf[i] = i < pool_used ? src[(size_t)(i / P) * KP + (i % P)] : kKeyMax;
         if (threadIdx.x == 0) s_cnt = 0;
         __syncthreads();
         block_bitonic_sort_fast(buf, Lp, dkey);

@@ -186,7 +186,8 @@ static int search_core(evdb_store *s, const double *d_q64, int B, int k, int kst
     static double gemm_min_bytes = -1.0;
     if (gemm_min_bytes < 0.0) { const char *e = getenv("EVDB_GEMM_MIN_BYTES"); gemm_min_bytes = e ? atof(e) : 256e6; }
     if (plan == EVDB_PLAN_GEMM ||
-        (plan == EVDB_PLAN_AUTO && (B >= 16 || (double)B * (double)s->count * (double)s->row_bytes >= gemm_min_bytes)))
+        (plan == EVDB_PLAN_AUTO && !s->gemm_oom &&
+         (B >= 16 || (double)B * (double)s->count * (double)s->row_bytes >= gemm_min_bytes)))
         use_gemm = gemm_plan_supported(s, metric, B, gemm_kp(KP));
     if (plan == EVDB_PLAN_GEMM && !use_gemm) return EVDB_E_UNSUPPORTED;
 
@@ -202,13 +203,23 @@ static int search_core(evdb_store *s, const double *d_q64, int B, int k, int kst
         return EVDB_OK;
     }
     if (use_gemm) {
-        s->last_plan = EVDB_PLAN_GEMM;
-        KP = gemm_kp(KP);
         // the per-query error bound of the fp16 operands comes back in eps_q (device)
-        EVDB_TRY(launch_gemm_topk(s, d_q64, B, KP, metric, &lists, &eps_q, &raw, st));
-        have_raw = true;
-        squared = metric == EVDB_EUCLIDEAN;
-    } else {
+        const int rc = launch_gemm_topk(s, d_q64, B, gemm_kp(KP), metric, &lists, &eps_q, &raw, st);
+        if (rc == EVDB_E_OOM && plan == EVDB_PLAN_AUTO) {
+            // no room for the euclidean operand column / candidate buffers: the scan plan needs neither
+            (void)cudaGetLastError();
+            s->gemm_oom = 1;
+            use_gemm = false;
+            eps_q = nullptr;
+        } else {
+            EVDB_TRY(rc);
+            s->last_plan = EVDB_PLAN_GEMM;
+            KP = gemm_kp(KP);
+            have_raw = true;
+            squared = metric == EVDB_EUCLIDEAN;
+        }
+    }
+    if (!use_gemm) {
         EVDB_TRY(launch_prep_queries(s, d_q64, B, st));
         s->last_plan = EVDB_PLAN_SCAN;
         int G = 0;
