@@ -217,3 +217,27 @@ def test_batch_larger_than_one_launch_is_sliced(native, oracle):
         assert gs[b].tolist() == r.tolist() and gd[b].tolist() == dd.tolist(), b
     assert (gc == k).all()
     st.close()
+
+
+@pytest.mark.parametrize("metric,k", [("cosine", 10), ("euclidean", 100)])
+def test_auto_plan_uses_tcgen05_for_a_lone_query_on_a_large_store(native, oracle, metric, k):
+    """B * N * row_bytes >= 256 MB: AUTO answers even a single query through the tcgen05 candidate
+    pass (2-byte operand column read once) -- the result must not depend on that choice."""
+    n, d = 600_000, 128          # 307 MB of fp32 rows
+    st = _mk(native, n, d, seed=oracle.SEED_CORPUS)
+    qs = oracle.synth_f64(oracle.SEED_QUERY, 0, 3, d)
+    rows = oracle.synth_f64(oracle.SEED_CORPUS, 0, n, d)
+    for b in range(3):
+        gs, gd, gc = st.search(qs[b:b + 1], k, metric)
+        assert st.stats()["last_plan"] == native.PLAN_GEMM
+        r, dd = oracle.search(rows, qs[b], k, metric)
+        assert gs[0].tolist() == r.tolist() and gd[0].tolist() == dd.tolist()
+    st.set_plan("scan")
+    ss, sd, sc = st.search(qs, k, metric)
+    st.set_plan("auto")
+    gs, gd, gc = st.search(qs, k, metric)          # three queries: 921 MB, tcgen05 plan
+    assert st.stats()["last_plan"] == native.PLAN_GEMM
+    assert np.array_equal(gs, ss) and np.array_equal(gd, sd) and np.array_equal(gc, sc)
+    st.search(qs[:1], k, "manhattan")              # no GEMM form
+    assert st.stats()["last_plan"] == native.PLAN_SCAN
+    st.close()

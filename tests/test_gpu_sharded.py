@@ -14,6 +14,7 @@ pytestmark = pytest.mark.gpu
     ("f32", "euclidean", 60_000, 64, 64, 100, 2),  # euclidean GEMM plan, k = 100
     ("u8", "cosine", 50_000, 96, 2, 10, 8),        # BASELINE configs[3] shape scaled down: int8 scan, 8 shards
     ("f32", "cosine", 5, 16, 2, 10, 4),            # more shards than rows per shard: empty shards, k > N
+    ("f32", "cosine", 700_000, 128, 2, 10, 2),     # two queries, shards past the AUTO crossover: tcgen05 plan per shard
 ])
 def test_sharded_equals_single_store(native, oracle, dtype, metric, n, d, B, k, G):
     import torch
