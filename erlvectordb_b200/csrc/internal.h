@@ -12,6 +12,14 @@ struct QStat {
     float norm_sq;   // ||q||^2
 };
 
+// Quantized scans: the query sits on a fixed-point grid of 8*kQPlanes bits, one 8-bit digit plane per
+// dp4a.  Two planes: 1/3 less integer work per code; the coarser grid is covered by a per-query
+// error bound (scan.cu prep_queries_kernel), never by the result (exact fp64 re-rank).
+#ifndef EVDB_QPLANES
+#define EVDB_QPLANES 2
+#endif
+constexpr int kQPlanes = EVDB_QPLANES;
+static_assert(kQPlanes == 2 || kQPlanes == 3, "digit planes");
 constexpr int kMaxKP = 1024;   // widest candidate window the scan/select path carries
 constexpr int kMinKP = 16;
 constexpr int kScanWarps = 8;  // warps per scan CTA
@@ -61,6 +69,7 @@ struct evdb_store {
     void *w_seed = nullptr;    size_t w_seed_cap = 0;   // [Bpad][S] sampled scores + [Bpad] seeded thresholds (GEMM)
     void *w_qh = nullptr;      size_t w_qh_cap = 0;     // [Bpad][spitch] fp16 unit-norm queries (GEMM)
     evdb::QStat *w_qstat = nullptr; size_t w_qstat_cap = 0;
+    float *w_qeps = nullptr; size_t w_qeps_cap = 0;   // quantized scans: per-query bound of the query grid error
     uint64_t *w_partial = nullptr; size_t w_partial_cap = 0; // [B][G][KP]
     uint64_t *w_ids = nullptr;  size_t w_ids_cap = 0;   // [B][k]
     double *w_dists = nullptr;  size_t w_dists_cap = 0; // [B][k]

@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const double *__restr
                                                            float *__restrict__ q32, int q32_stride,
                                                            uint8_t *__restrict__ qdig,
                                                            int qdig_stride, int dtype,
-                                                           QStat *__restrict__ qstat) {
+                                                           QStat *__restrict__ qstat, float *__restrict__ qeps) {
     __shared__ double redd[8];
     __shared__ long long redl[8];
     const int b = blockIdx.x;
@@ -71,21 +71,22 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const double *__restr
     st.fx = 0.0f;
     if (dtype == EVDB_U8 || dtype == EVDB_U4) {
         mx = block_reduce<double>(mx, redd, true);
+        constexpr int kBits = 8 * kQPlanes;
         int e = 0;
         if (mx > 0.0) {
             int x;
-            frexp(mx, &x);  // mx = m * 2^x, m in [0.5,1)  =>  |q| * 2^(23-x) < 2^23
-            e = 23 - x;
+            frexp(mx, &x);  // mx = m * 2^x, m in [0.5,1)  =>  |q| * 2^(kBits-1-x) < 2^(kBits-1)
+            e = kBits - 1 - x;
         }
         double sc = ldexp(1.0, e);
-        uint8_t *p0 = qdig + (size_t)b * 3 * qdig_stride;
-        uint8_t *p1 = p0 + qdig_stride, *p2 = p1 + qdig_stride;
+        const double qmax = (double)((1 << (kBits - 1)) - 1), qmin = -(double)(1 << (kBits - 1));
+        uint8_t *p0 = qdig + (size_t)b * kQPlanes * qdig_stride;
         long long qsum = 0;
         for (int i = threadIdx.x; i < qdig_stride; i += blockDim.x) {
             int Q = 0;
             if (i < d) {
                 double t = rint(q[i] * sc);
-                t = fmin(fmax(t, -8388608.0), 8388607.0);
+                t = fmin(fmax(t, qmin), qmax);
                 Q = (int)t;
             }
             qsum += Q;
@@ -98,10 +99,14 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const double *__restr
                 int c = i >> 5, r = i & 31, w = r >> 3, e8 = r & 7;
                 pos = ((e8 & 1) ? (qdig_stride >> 1) : 0) + c * 16 + w * 4 + (e8 >> 1);
             }
-            p0[pos] = (uint8_t)((Q >> 16) & 0xFF);  // signed high digit
-            p1[pos] = (uint8_t)((Q >> 8) & 0xFF);
-            p2[pos] = (uint8_t)(Q & 0xFF);
+#pragma unroll
+            for (int pl = 0; pl < kQPlanes; ++pl)   // plane 0 = the signed high digit
+                p0[(size_t)pl * qdig_stride + pos] = (uint8_t)((Q >> (8 * (kQPlanes - 1 - pl))) & 0xFF);
         }
+        // |q_i - Q_i 2^-e| <= 2^-e (half a unit from rounding, up to one where the clamp bites) and
+        // max|q| 2^e >= 2^(kBits-2):  |dq . y| <= max|q| 2^-(kBits-2) ||y||_1 <= ... sqrt(d) ||y||
+        if (threadIdx.x == 0 && qeps)
+            qeps[b] = ss > 0.0 ? (float)(1.01 * ldexp(1.0, -(kBits - 2)) * sqrt((double)d) * mx / sqrt(ss)) : 0.f;
         qsum = block_reduce<long long>(qsum, redl, false);
         st.fx = (float)ldexp(1.0, -e);
         st.sum = (float)((double)qsum * ldexp(1.0, -e));
@@ -114,10 +119,13 @@ int launch_prep_queries(evdb_store *s, const double *d_q64, int B, cudaStream_t 
     int q32_stride = quant ? 0 : s->dpad;
     int qdig_stride = quant ? s->dpad : 0;
     if (!quant) EVDB_TRY(ensure_bytes((void **)&s->w_q32, &s->w_q32_cap, sizeof(float) * (size_t)B * q32_stride));
-    else EVDB_TRY(ensure_bytes((void **)&s->w_qdig, &s->w_qdig_cap, (size_t)B * 3 * qdig_stride));
+    else {
+        EVDB_TRY(ensure_bytes((void **)&s->w_qdig, &s->w_qdig_cap, (size_t)B * kQPlanes * qdig_stride));
+        EVDB_TRY(ensure_bytes((void **)&s->w_qeps, &s->w_qeps_cap, sizeof(float) * (size_t)B));
+    }
     EVDB_TRY(ensure_bytes((void **)&s->w_qstat, &s->w_qstat_cap, sizeof(QStat) * (size_t)B));
     prep_queries_kernel<<<B, 256, 0, st>>>(d_q64, s->dim, quant ? nullptr : s->w_q32, q32_stride,
-                                           s->w_qdig, qdig_stride, s->dtype, s->w_qstat);
+                                           s->w_qdig, qdig_stride, s->dtype, s->w_qstat, quant ? s->w_qeps : nullptr);
     s->n_launches++;
     EVDB_CUDA(cudaGetLastError());
     return EVDB_OK;
@@ -311,21 +319,25 @@ template <int DTYPE, int R>
 __device__ __forceinline__ void quant_chunk(const uint4 (&v)[R], int c, const uint4 *sd, int plane_u4,
                                             int (&A)[R], int (&Bm)[R], int (&Cl)[R]) {
     if (DTYPE == EVDB_U8) {
-        const uint4 d0 = sd[c], d1 = sd[plane_u4 + c], d2 = sd[2 * plane_u4 + c];
+        const uint4 d0 = sd[c], d1 = sd[plane_u4 + c];
+        const uint4 d2 = kQPlanes == 3 ? sd[2 * plane_u4 + c] : make_uint4(0, 0, 0, 0);
 #pragma unroll
         for (int j = 0; j < R; ++j) {
             A[j] = dp4a_su((int)d0.x, v[j].x, A[j]); A[j] = dp4a_su((int)d0.y, v[j].y, A[j]);
             A[j] = dp4a_su((int)d0.z, v[j].z, A[j]); A[j] = dp4a_su((int)d0.w, v[j].w, A[j]);
             Bm[j] = (int)dp4a_uu(d1.x, v[j].x, (uint32_t)Bm[j]); Bm[j] = (int)dp4a_uu(d1.y, v[j].y, (uint32_t)Bm[j]);
             Bm[j] = (int)dp4a_uu(d1.z, v[j].z, (uint32_t)Bm[j]); Bm[j] = (int)dp4a_uu(d1.w, v[j].w, (uint32_t)Bm[j]);
-            Cl[j] = (int)dp4a_uu(d2.x, v[j].x, (uint32_t)Cl[j]); Cl[j] = (int)dp4a_uu(d2.y, v[j].y, (uint32_t)Cl[j]);
-            Cl[j] = (int)dp4a_uu(d2.z, v[j].z, (uint32_t)Cl[j]); Cl[j] = (int)dp4a_uu(d2.w, v[j].w, (uint32_t)Cl[j]);
+            if (kQPlanes == 3) {
+                Cl[j] = (int)dp4a_uu(d2.x, v[j].x, (uint32_t)Cl[j]); Cl[j] = (int)dp4a_uu(d2.y, v[j].y, (uint32_t)Cl[j]);
+                Cl[j] = (int)dp4a_uu(d2.z, v[j].z, (uint32_t)Cl[j]); Cl[j] = (int)dp4a_uu(d2.w, v[j].w, (uint32_t)Cl[j]);
+            }
         }
     } else {
         const int half = plane_u4 >> 1;   // = chunks per row
+        const uint4 z4 = make_uint4(0, 0, 0, 0);
         const uint4 e0 = sd[c], o0 = sd[half + c];
         const uint4 e1 = sd[plane_u4 + c], o1 = sd[plane_u4 + half + c];
-        const uint4 e2 = sd[2 * plane_u4 + c], o2 = sd[2 * plane_u4 + half + c];
+        const uint4 e2 = kQPlanes == 3 ? sd[2 * plane_u4 + c] : z4, o2 = kQPlanes == 3 ? sd[2 * plane_u4 + half + c] : z4;
 #pragma unroll
         for (int j = 0; j < R; ++j) {
             const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
@@ -337,7 +349,9 @@ __device__ __forceinline__ void quant_chunk(const uint4 (&v)[R], int c, const ui
                 uint32_t hi = (w[t] >> 4) & 0x0F0F0F0Fu, lo = w[t] & 0x0F0F0F0Fu;
                 A[j] = dp4a_su((int)E0[t], hi, A[j]); A[j] = dp4a_su((int)O0[t], lo, A[j]);
                 Bm[j] = (int)dp4a_uu(E1[t], hi, (uint32_t)Bm[j]); Bm[j] = (int)dp4a_uu(O1[t], lo, (uint32_t)Bm[j]);
-                Cl[j] = (int)dp4a_uu(E2[t], hi, (uint32_t)Cl[j]); Cl[j] = (int)dp4a_uu(O2[t], lo, (uint32_t)Cl[j]);
+                if (kQPlanes == 3) {
+                    Cl[j] = (int)dp4a_uu(E2[t], hi, (uint32_t)Cl[j]); Cl[j] = (int)dp4a_uu(O2[t], lo, (uint32_t)Cl[j]);
+                }
             }
         }
     }
@@ -351,11 +365,12 @@ __device__ __forceinline__ uint64_t quant_key(int sa, int sb, int sc, bool owner
     for (int o = TPR / 2; o > 0; o >>= 1) {
         sa += __shfl_xor_sync(0xffffffffu, sa, o);
         sb += __shfl_xor_sync(0xffffffffu, sb, o);
-        sc += __shfl_xor_sync(0xffffffffu, sc, o);
+        if (kQPlanes == 3) sc += __shfl_xor_sync(0xffffffffu, sc, o);
     }
     uint64_t key = kKeyMax;
     if (owner) {
-        long long S = ((long long)sa << 16) + ((long long)sb << 8) + (long long)sc;
+        long long S = kQPlanes == 3 ? ((long long)sa << 16) + ((long long)sb << 8) + (long long)sc
+                                    : ((long long)sa << 8) + (long long)sb;
         float dotn = fmaf(co.x, __ll2float_rn(S) * qs.fx, co.y * qs.sum);
         bool zero = (co.x == 0.f && co.y == 0.f) || qs.inv_norm == 0.f;
         float score = zero ? 1.0f : 1.0f - dotn * qs.inv_norm;
@@ -377,13 +392,13 @@ scan_quant_kernel(const ScanArgs a) {
     constexpr int UPC = (DTYPE == EVDB_U8) ? 1 : 2;  // uint4 of digits per plane per row chunk
     const int nch = a.nch, KP = a.KP;
     const int plane_u4 = nch * UPC;                  // uint4 per plane
-    uint4 *sd = reinterpret_cast<uint4 *>(smem);     // [3][plane_u4]
-    uint64_t *lists = reinterpret_cast<uint64_t *>(smem + (size_t)3 * plane_u4 * 16);
+    uint4 *sd = reinterpret_cast<uint4 *>(smem);     // [kQPlanes][plane_u4]
+    uint64_t *lists = reinterpret_cast<uint64_t *>(smem + (size_t)kQPlanes * plane_u4 * 16);
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    const uint4 *dsrc = reinterpret_cast<const uint4 *>(a.qdig + (size_t)b * 3 * a.qdig_stride);
-    for (int i = threadIdx.x; i < 3 * plane_u4; i += blockDim.x) sd[i] = dsrc[i];
+    const uint4 *dsrc = reinterpret_cast<const uint4 *>(a.qdig + (size_t)b * kQPlanes * a.qdig_stride);
+    for (int i = threadIdx.x; i < kQPlanes * plane_u4; i += blockDim.x) sd[i] = dsrc[i];
     if (KP > kAppendMaxKP)
         for (int i = threadIdx.x; i < kScanWarps * KP; i += blockDim.x) lists[i] = kKeyMax;
     __syncthreads();
@@ -486,7 +501,7 @@ constexpr int kTmaMaxStages = 8;
 template <int DTYPE, int TPR, int R>
 __global__ void __launch_bounds__((kScanWarps + 1) * 32, 2)
 scan_quant_tma_kernel(const ScanArgs a) {
-    extern __shared__ __align__(128) uint8_t smem[];
+    extern __shared__ __align__(16) uint8_t smem[];   // (the runtime places dynamic shared memory on a >= 128-byte boundary; stages are multiples of 128 B)
     constexpr int GPW = 32 / TPR;
     constexpr int UPC = (DTYPE == EVDB_U8) ? 1 : 2;
     const int WT = a.tma_wt, NG = kScanWarps / WT;     // warps per tile, consumer groups
@@ -496,14 +511,14 @@ scan_quant_tma_kernel(const ScanArgs a) {
     const uint32_t code_bytes = (uint32_t)TR * (uint32_t)a.row_bytes, coef_bytes = TR * 8u;
     uint8_t *ring = smem;                              // [S][tma_stage_bytes]
     uint4 *sd = reinterpret_cast<uint4 *>(smem + (size_t)S * a.tma_stage_bytes);
-    uint64_t *lists = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(sd) + (size_t)3 * plane_u4 * 16);
+    uint64_t *lists = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(sd) + (size_t)kQPlanes * plane_u4 * 16);
     __shared__ __align__(8) uint64_t bars[2 * kTmaMaxStages];   // full[S], empty[S]
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool consumer = warp < kScanWarps;
 
-    const uint4 *dsrc = reinterpret_cast<const uint4 *>(a.qdig + (size_t)b * 3 * a.qdig_stride);
-    for (int i = threadIdx.x; i < 3 * plane_u4; i += blockDim.x) sd[i] = dsrc[i];
+    const uint4 *dsrc = reinterpret_cast<const uint4 *>(a.qdig + (size_t)b * kQPlanes * a.qdig_stride);
+    for (int i = threadIdx.x; i < kQPlanes * plane_u4; i += blockDim.x) sd[i] = dsrc[i];
     if (KP > kAppendMaxKP)
         for (int i = threadIdx.x; i < kScanWarps * KP; i += blockDim.x) lists[i] = kKeyMax;
     if (threadIdx.x == 0) {
@@ -732,7 +747,7 @@ static int make_scan_plan(evdb_store *s, int metric, int KP, ScanPlan *p) {
             if (metric != EVDB_COSINE) return EVDB_E_UNSUPPORTED;
             const bool u8 = s->dtype == EVDB_U8;
             p->fn = u8 ? pick_quant<EVDB_U8>(tpr) : pick_quant<EVDB_U4>(tpr);
-            qbytes = (size_t)s->nch * (u8 ? 16 : 32) * 3;
+            qbytes = (size_t)s->nch * (u8 ? 16 : 32) * kQPlanes;
             if (tpr == 32) R = 2;
             // TMA-staged variant: whole tiles through a shared-memory ring (large stores only:
             // a small one is latency-bound and spreads better one warp-iteration per warp)
@@ -776,10 +791,10 @@ static int make_scan_plan(evdb_store *s, int metric, int KP, ScanPlan *p) {
                     p->tile_rows = (int)tile_rows;
                     p->wt = best_wt;
                     R = best_r;
-                    int best = 0, best_cost = bank_cost(s->nch, t2, 0, R, u8 ? 3 : 6);
+                    int best = 0, best_cost = bank_cost(s->nch, t2, 0, R, (u8 ? 1 : 2) * kQPlanes);
                     if (t2 < 8)
                         for (int m = 1; m < 8; ++m) {
-                            int c = bank_cost(s->nch, t2, m, R, u8 ? 3 : 6);
+                            int c = bank_cost(s->nch, t2, m, R, (u8 ? 1 : 2) * kQPlanes);
                             if (c < best_cost) { best_cost = c; best = m; }
                         }
                     p->bank_mul = best;

@@ -243,7 +243,7 @@ static int search_core(evdb_store *s, const double *d_q64, int B, int k, int kst
         prof_end(s, st);
         lists = G;
         double depth = (double)s->dim / 64.0 + 24.0;
-        if (is_quant(s)) eps_abs = (float)((2.0 * sqrt((double)s->dim) + 24.0) * u);
+        if (is_quant(s)) { eps_abs = (float)(24.0 * u); eps_q = s->w_qeps; }   // + the query-grid bound, per query
         else if (metric == EVDB_COSINE) eps_abs = (float)(depth * u);
         else { eps_rel = (float)(depth * u); eps_abs = 1e-37f; }
     }
@@ -602,7 +602,7 @@ void evdb_store_destroy(evdb_store *s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     cudaFree(s->rows); cudaFree(s->norm64); cudaFree(s->inv_norm); cudaFree(s->norm_sq);
     cudaFree(s->qcoef); cudaFree(s->qms64); cudaFree(s->shadow); cudaFree(s->shadow_l2); cudaFree(s->l2_tail); cudaFree(s->d_scalar);
-    cudaFree(s->w_q64); cudaFree(s->w_q32); cudaFree(s->w_qdig); cudaFree(s->w_qh); cudaFree(s->w_seed); cudaFree(s->w_qstat);
+    cudaFree(s->w_q64); cudaFree(s->w_q32); cudaFree(s->w_qdig); cudaFree(s->w_qh); cudaFree(s->w_seed); cudaFree(s->w_qstat); cudaFree(s->w_qeps);
     cudaFree(s->w_partial); cudaFree(s->w_ids); cudaFree(s->w_dists); cudaFree(s->w_counts);
     cudaFree(s->w_tmp); cudaFree(s->w_shard);
     if (s->h_pin) cudaFreeHost(s->h_pin);
