@@ -40,7 +40,7 @@ __device__ __forceinline__ T block_reduce(T v, T *red, bool is_max) {
 }
 
 // One CTA per query: narrow to fp32 (zero padded), norms, and -- for quantized
-// stores -- the 24-bit fixed-point query split into three 8-bit digit planes so
+// stores -- the fixed-point query (8*kQPlanes bits) split into 8-bit digit planes so
 // that sum(Q_i * c_i) is an exact integer computed with dp4a.
 __global__ void __launch_bounds__(256) prep_queries_kernel(const double *__restrict__ q64, int d,
                                                            float *__restrict__ q32, int q32_stride,
@@ -382,7 +382,7 @@ __device__ __forceinline__ uint64_t quant_key(int sa, int sb, int sc, bool owner
 // ----------------------------------------------------------------------------
 // u8 / packed-u4 codes: cosine of an unquantised query against Min + c*Scale
 //   q.y = Min*sum(q) + Scale*sum(q_i c_i);  sum(Q_i c_i) is an exact integer:
-//   Q = a*2^16 + b*2^8 + c (a signed, b,c unsigned digits), three dp4a per word.
+//   Q = a*2^8 + b (a signed, b unsigned digit; a third digit with EVDB_QPLANES=3), one dp4a per digit and word.
 // ----------------------------------------------------------------------------
 template <int DTYPE, int TPR, int R>
 __global__ void __launch_bounds__(kScanWarps * 32, 2)
