@@ -167,9 +167,7 @@ static int search_core(evdb_store *s, const double *d_q64, int B, int k, int kst
         return exact_plan_search(s, d_q64, B, kk, kstride, metric, slot_base, d_ids, d_dists,
                                  d_counts, d_flags, st);
     }
-    if ((uint64_t)KP > s->count) {
-        // the whole store fits in the window: keep KP a power of two, lists pad with kKeyMax
-    }
+    // (a window wider than the store is fine: KP stays a power of two, lists pad with kKeyMax)
     const double u = 5.9604644775390625e-08;  // 2^-24
     float eps_abs = 0.f, eps_rel = 0.f;
     const float *eps_q = nullptr;
