@@ -141,8 +141,113 @@ __device__ void block_select_smallest(uint64_t *buf, int n, int need, uint64_t *
     __syncthreads();
 }
 
+// Lone-query re-rank (1024 threads, <= 30 candidates to re-rank): warp r forms the products of
+// candidate r chunk by chunk (one more warp the query's squares for cosine) into a double-buffered
+// stage, and ONE warp folds all rows in lock-step -- lane r adds row r's terms left to right, in
+// the reference order.  One fp64 chain instruction stream for all candidates: the chains no longer
+// contend for the SM's fp64 pipe, and staging chunk c+1 overlaps folding chunk c.
+constexpr int kFoldStride = kExactChunk + 1;   // doubles per staged row: lanes r, r+16 share a bank, no others
+constexpr int kFoldRows = 31;                  // producer warps 0..30, folder = warp 31
+template <int DTYPE>
+__device__ __forceinline__ void lone_rerank(const SelectArgs &a, const uint64_t *buf, int nrer, int nsort,
+                                            const double *__restrict__ q, double *stage, uint64_t *dkey,
+                                            uint64_t *dslot, int warp, int lane) {
+    const int d = a.d, metric = a.metric;
+    const bool cosine = metric == EVDB_COSINE;
+    const int nrows = nrer + (cosine ? 1 : 0);
+    const int nchunks = (d + kExactChunk - 1) / kExactChunk;
+    constexpr int kPer = kExactChunk / kWarp;
+    const bool producer = warp < nrows;
+    const bool qrow = cosine && warp == nrer;
+    const bool folder = warp == kFoldRows;
+    const uint8_t *row = a.rows;
+    double mn = 0.0, sc = 0.0;
+    if (producer && !qrow) {
+        const uint32_t slot = key_slot(buf[warp]);
+        row = a.rows + (size_t)slot * a.row_bytes;
+        if (DTYPE == EVDB_U8 || DTYPE == EVDB_U4) {
+            const double2 ms = a.qms64[slot];
+            mn = ms.x;
+            sc = ms.y;
+        }
+        // the whole row into L2 now: a DRAM round trip (~2 k cycles) is longer than folding one
+        // chunk, so loading chunk c+1 from DRAM while chunk c folds would stall every chunk
+        const int lines = (int)((a.row_bytes + 254) / 128);
+        for (int l = lane; l < lines; l += 32)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(row + (size_t)l * 128));
+    }
+    uint32_t fslot = 0;
+    double vnorm = 0.0;
+    if (folder && lane < nrer) {
+        fslot = key_slot(buf[lane]);
+        if (cosine) vnorm = a.norm64[fslot];
+    }
+    double nv[kPer], nq[kPer];
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+        const int t = i * kWarp + lane;
+        nq[i] = (producer && t < d) ? q[t] : 0.0;
+        nv[i] = (producer && !qrow && t < d) ? row_elem<DTYPE>(row, t, mn, sc) : nq[i];
+    }
+    double acc = 0.0;
+    for (int c = 0; c <= nchunks; ++c) {
+        if (producer && c < nchunks) {
+            double *dst = stage + (size_t)((c & 1) * kFoldRows + warp) * kFoldStride;
+            const int base = c * kExactChunk;
+            const int cnt = min(kExactChunk, d - base);
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) {
+                const int t = i * kWarp + lane;
+                const double v = nv[i], qq = nq[i];
+                if (t < cnt) {
+                    if (cosine) {
+                        dst[t] = __dmul_rn(qq, v);           // dot_product X*Y; the q row: v == qq, X*X
+                    } else if (metric == EVDB_EUCLIDEAN) {
+                        const double t0 = __dsub_rn(qq, v);  // vector_subtract
+                        dst[t] = __dmul_rn(t0, t0);
+                    } else {
+                        dst[t] = fabs(__dsub_rn(qq, v));     // abs(X - Y)
+                    }
+                }
+            }
+            const int nb = base + kExactChunk;
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) {
+                const int t = nb + i * kWarp + lane;
+                nq[i] = t < d ? q[t] : 0.0;
+                nv[i] = (!qrow && t < d) ? row_elem<DTYPE>(row, t, mn, sc) : nq[i];
+            }
+        }
+        if (folder && c > 0 && lane < nrows) {
+            const int base = (c - 1) * kExactChunk;
+            acc = fold_staged(acc, stage + (size_t)(((c - 1) & 1) * kFoldRows + lane) * kFoldStride,
+                              min(kExactChunk, d - base));
+        }
+        __syncthreads();
+    }
+    if (folder) {
+        double dist;
+        if (cosine) {
+            const double sq = __shfl_sync(0xffffffffu, acc, nrer);
+            const double n1 = __dsqrt_rn(sq), n2 = vnorm;
+            dist = (n1 == 0.0 || n2 == 0.0) ? 1.0 : __dsub_rn(1.0, __ddiv_rn(acc, __dmul_rn(n1, n2)));
+        } else if (metric == EVDB_EUCLIDEAN) {
+            dist = __dsqrt_rn(acc);
+        } else {
+            dist = acc;
+        }
+        if (lane < nrer) {
+            dkey[lane] = f64_orderable(dist);
+            dslot[lane] = fslot;
+        } else if (lane < nsort) {
+            dkey[lane] = kKeyMax;
+            dslot[lane] = kKeyMax;
+        }
+    }
+}
+
 // EVDB_SEL_VARIANT bit 4 (tuning aid): cycles per phase, summed over CTAs
-__device__ unsigned long long g_sel_dbg[8];
+__device__ unsigned long long g_sel_dbg[10];
 #define SEL_MARK(i) do { if ((a.variant & 16) && threadIdx.x == 0) { long long _t = clock64(); atomicAdd(&g_sel_dbg[i], (unsigned long long)(_t - t_mark)); t_mark = _t; } } while (0)
 
 // THREADS = 1024 for a lone query (latency), 256 for batches (more CTAs per SM, cheaper barriers).
@@ -220,6 +325,7 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
             const int filled = carried + e1 - e0;
             __syncthreads();
             SEL_MARK(1);
+            if ((a.variant & 16) && threadIdx.x == 0) atomicAdd(&g_sel_dbg[8], (unsigned long long)(e1 - e0));
             if (filled > KP) {
                 if (KP <= 128 && filled >= 2 * (KP <= 64 ? 256 : 512)) {
                     // Hundreds to thousands of keys of which KP are wanted (a full 1024-key sort costs
@@ -385,8 +491,10 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
     int nsort = 2;
     while (nsort < nrer) nsort <<= 1;
     const double *q = a.q64 + (size_t)b * a.d;
-    if (THREADS == 1024) {
-        // Lone query: latency matters, not fp64-pipe occupancy.  One warp per candidate: 32 lanes
+    if (THREADS == 1024 && nrer + (a.metric == EVDB_COSINE ? 1 : 0) <= kFoldRows && nrer > 0 && !(a.variant & 64)) {
+        lone_rerank<DTYPE>(a, buf, nrer, nsort, q, sp_all, dkey, dslot, warp, lane);
+    } else if (THREADS == 1024) {
+        // Many candidates to re-rank (or EVDB_SEL_VARIANT bit 6): one warp per candidate, 32 lanes
         // form the independent products, one lane folds them in the reference order.
         double *sp = sp_all + warp * 2 * kExactChunk;
         for (int j = warp; j < nsort; j += kSelWarps) {
@@ -915,7 +1023,7 @@ static int launch_select_warp(const SelectArgs &a, int B, cudaStream_t st) {
     EVDB_CUDA(cudaGetLastError());
     if (a.variant & 16) {
         cudaStreamSynchronize(st);
-        unsigned long long h[8], z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        unsigned long long h[10], z[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         cudaMemcpyFromSymbol(h, g_sel_dbg, sizeof(h));
         cudaMemcpyToSymbol(g_sel_dbg, z, sizeof(z));
         fprintf(stderr, "[select-warp dbg] cycles/query: gather(slow path)=%.0f select=%.0f sort+window=%.0f fold=%.0f final=%.0f  keys=%.0f nrer=%.1f\n",
@@ -1252,12 +1360,12 @@ int launch_select(evdb_store *s, const double *d_q64, const uint64_t *partial, c
     EVDB_CUDA(cudaGetLastError());
     if (a.variant & 16) {
         cudaStreamSynchronize(st);
-        unsigned long long h[8], z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        unsigned long long h[10], z[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         cudaMemcpyFromSymbol(h, g_sel_dbg, sizeof(h));
         cudaMemcpyToSymbol(g_sel_dbg, z, sizeof(z));
-        fprintf(stderr, "[select dbg] cycles/CTA: counts+scan=%.0f gather=%.0f select=%.0f sort=%.0f ncand=%.0f fold=%.0f final=%.0f nrer=%.1f\n",
+        fprintf(stderr, "[select dbg] cycles/CTA: counts+scan=%.0f gather=%.0f select=%.0f sort=%.0f ncand=%.0f fold=%.0f final=%.0f nrer=%.1f keys=%.0f\n",
                 (double)h[0] / B, (double)h[1] / B, (double)h[2] / B, (double)h[3] / B, (double)h[4] / B, (double)h[5] / B,
-                (double)h[6] / B, (double)h[7] / B);
+                (double)h[6] / B, (double)h[7] / B, (double)h[8] / B);
     }
     return EVDB_OK;
 }

@@ -200,6 +200,16 @@ static int search_core(evdb_store *s, const double *d_q64, int B, int k, int kst
         }
         return EVDB_OK;
     }
+    constexpr int kScanMaxBatch = 32768;   // the scan kernels put the query index in gridDim.y (<= 65535)
+    if (!use_gemm && B > kScanMaxBatch) {
+        for (int b0 = 0; b0 < B; b0 += kScanMaxBatch) {
+            const int nb = B - b0 < kScanMaxBatch ? B - b0 : kScanMaxBatch;
+            EVDB_TRY(search_core(s, d_q64 + (size_t)b0 * s->dim, nb, k, kstride, metric, kp_min, plan, slot_base,
+                                 d_ids + (size_t)b0 * kstride, d_dists + (size_t)b0 * kstride, d_counts + b0,
+                                 d_flags ? d_flags + b0 : nullptr, st));
+        }
+        return EVDB_OK;
+    }
     if (use_gemm) {
         // the per-query error bound of the fp16 operands comes back in eps_q (device)
         const int rc = launch_gemm_topk(s, d_q64, B, gemm_kp(KP), metric, &lists, &eps_q, &raw, st);

@@ -78,21 +78,25 @@ __device__ __forceinline__ void block_bitonic_sort_fast(uint64_t *buf, int n, ui
         return;
     }
     const int i = threadIdx.x;
+    const bool live = (i & ~31) < n;   // warps without a key only keep the barriers company: the network
+                                       // is issue-bound, 32 warps stepping through it cost 4x what 8 do
     uint64_t v = i < n ? buf[i] : ~0ull;
     uint64_t *cur = tmp;
     for (int k = 2; k <= n; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            uint64_t o;
+            uint64_t o = ~0ull;
             if (j >= 32) {
                 if (i < n) cur[i] = v;
                 __syncthreads();
-                o = i < n ? cur[i ^ j] : ~0ull;
+                if (i < n) o = cur[i ^ j];
                 cur = cur == tmp ? buf : tmp;
-            } else {
+            } else if (live) {
                 o = __shfl_xor_sync(0xffffffffu, v, j);
             }
-            const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
-            v = keep_min ? (v < o ? v : o) : (v > o ? v : o);
+            if (live) {
+                const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
+                v = keep_min ? (v < o ? v : o) : (v > o ? v : o);
+            }
         }
     }
     __syncthreads();
@@ -107,26 +111,28 @@ __device__ __forceinline__ void block_bitonic_sort_pairs_fast(uint64_t *keys, ui
         return;
     }
     const int i = threadIdx.x;
+    const bool live = (i & ~31) < n;
     uint64_t a = i < n ? keys[i] : ~0ull, va = i < n ? vals[i] : ~0ull;
     uint64_t *ck = tmp, *cv = tmp + n;
     for (int k = 2; k <= n; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            uint64_t b, vb;
+            uint64_t b = ~0ull, vb = ~0ull;
             if (j >= 32) {
                 if (i < n) { ck[i] = a; cv[i] = va; }
                 __syncthreads();
-                b = i < n ? ck[i ^ j] : ~0ull;
-                vb = i < n ? cv[i ^ j] : ~0ull;
+                if (i < n) { b = ck[i ^ j]; vb = cv[i ^ j]; }
                 const bool first = ck == tmp;
                 ck = first ? keys : tmp;
                 cv = first ? vals : tmp + n;
-            } else {
+            } else if (live) {
                 b = __shfl_xor_sync(0xffffffffu, a, j);
                 vb = __shfl_xor_sync(0xffffffffu, va, j);
             }
-            const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
-            const bool mine_less = a < b || (a == b && va < vb);
-            if (keep_min != mine_less && !(a == b && va == vb)) { a = b; va = vb; }
+            if (live) {
+                const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
+                const bool mine_less = a < b || (a == b && va < vb);
+                if (keep_min != mine_less && !(a == b && va == vb)) { a = b; va = vb; }
+            }
         }
     }
     __syncthreads();

@@ -539,3 +539,58 @@ def test_tma_staged_quantized_scan_equals_exhaustive_plan(native, oracle, n, d, 
     e7, f7, _ = st.search(q7, 100, "cosine")
     assert np.array_equal(s7, e7) and np.array_equal(d7, f7)
     st.close()
+
+
+def test_scan_batch_larger_than_the_grid_limit_is_sliced(native, oracle):
+    """The scan kernels carry the query index in gridDim.y: more than 32768 queries on a store
+    without a GEMM plan (here: quantized) go through in slices, every slice in its own rows."""
+    n, d, B, k = 3000, 32, 32768 + 700, 5
+    st = _store(native, "u8")
+    st.fill_synthetic(oracle.SEED_CORPUS, n, d)
+    qs = oracle.synth_f64(oracle.SEED_QUERY, 0, B, d)
+    slots, dists, counts = st.search(qs, k, "cosine")
+    assert st.stats()["last_plan"] == native.PLAN_SCAN
+    assert (counts == k).all()
+    rows = np.stack([oracle.dequantize_8bit(*st.get_codes(r)) for r in range(n)])
+    for b in (0, 32767, 32768, B - 1):
+        r, dd = oracle.search(rows, qs[b], k, "cosine")
+        assert slots[b].tolist() == r.tolist() and dists[b].tolist() == dd.tolist(), b
+    st.close()
+
+
+def test_tma_staged_scan_after_mutations_and_with_wide_windows(native, oracle):
+    """The tile schedule follows the live row count: deletes (swap-with-last), an overwrite and an
+    append batch between searches, then k = 300 (512-key windows: the sorted-insert lists instead
+    of the append buffers) -- always bit-equal to the exhaustive plan on the same store."""
+    n, d = 200_000, 96
+    st = _store(native, "u8")
+    st.fill_synthetic(oracle.SEED_CORPUS, n, d)
+    qs = oracle.synth_f64(oracle.SEED_QUERY, 0, 2, d)
+
+    def check(k):
+        st.set_plan("scan")
+        a = st.search(qs, k, "cosine")
+        assert st.stats()["last_plan"] == native.PLAN_SCAN
+        st.set_plan("exact")
+        b = st.search(qs, k, "cosine")
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+        return a
+
+    s0, d0, _ = check(10)
+    best = int(s0[0, 0])
+    moved = st.delete(best)                       # the winner goes away, the last row takes its slot
+    assert moved == n - 1
+    for _ in range(300):                          # the count drops below a tile multiple
+        st.delete(st.count - 1)
+    s1, d1, _ = check(10)
+    assert d1[0, 0] >= d0[0, 0] and not (s1[0, 0] == best and d1[0, 0] == d0[0, 0])
+    target = qs[1] * 0.5 + 0.01                   # a row (nearly) parallel to query 1
+    assert st.upsert(12345, target) == 0
+    first = st.append(np.tile(qs[0], (3, 1)) * np.array([[1.0], [2.0], [0.25]]))
+    assert first == st.count - 3
+    s2, d2, _ = check(10)
+    assert s2[1, 0] == 12345
+    assert set(s2[0, :3].tolist()) == {first, first + 1, first + 2}
+    check(300)
+    st.close()
