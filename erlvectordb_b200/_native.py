@@ -93,6 +93,7 @@ SYMBOLS = [
     ("evdb_quantize_4bit", _i, [_i, _pd, _u64, _i, _pu8, _pd, _pd, _pd, _pu8]),
     ("evdb_dequantize_8bit", _i, [_i, _pu8, _pd, _pd, _u64, _i, _pd]),
     ("evdb_dequantize_4bit", _i, [_i, _pu8, _pd, _pd, _u64, _i, _pd]),
+    ("evdb_debug_scan_tile_plan", _i, [_i, _i, _i, _u64, _i, _pi32]),
 ]
 
 _lib = None

@@ -706,6 +706,65 @@ static int bank_cost(int nch, int tpr, int m, int R, int digit_loads) {
     return cost;
 }
 
+// Tile plan of the TMA-staged quantized scan: pure host arithmetic (no device state), exported for
+// the CPU tests as evdb_debug_scan_tile_plan.  Returns false when the register-fed kernel should run.
+struct TmaTilePlan {
+    int tpr, wt, stages, stage_bytes, tile_rows, bank_mul;
+    size_t smem;   // dynamic shared memory of the launch: ring + query digits + candidate lists
+};
+
+static bool choose_tma_tile_plan(int dtype, int nch, size_t row_bytes, int KP, uint64_t count, int sm_count,
+                                 TmaTilePlan *o) {
+    const bool u8 = dtype == EVDB_U8;
+    if (!u8 && dtype != EVDB_U4) return false;
+    if (row_bytes < 64) return false;   // 32-byte rows: the register-fed kernel is level or better
+    static int env_div = -1, env_wt = -1;
+    if (env_div < 0) { const char *e = getenv("EVDB_SCAN_TMA_DIV"); env_div = e && atoi(e) > 0 ? atoi(e) : 4; }
+    if (env_wt < 0) { const char *e = getenv("EVDB_SCAN_TMA_WT"); env_wt = e ? atoi(e) : 0; }
+    int t2 = 1;
+    while (t2 < 32 && (t2 < 2 ? nch >= 2 : t2 * 2 <= nch / env_div)) t2 <<= 1;
+    const int gpw = 32 / t2;
+    const size_t qbytes = (size_t)nch * (u8 ? 16 : 32) * kQPlanes;
+    const size_t fixed = qbytes + scan_list_bytes(KP) + 1024;
+    const size_t half = 112 * 1024, whole = 224 * 1024;
+    int best_wt = 0, best_s = 0;
+    size_t best_stage = 0;
+    // preference: two CTAs per SM, then the widest tile group.  A stage always belongs to the same
+    // group (stages % groups == 0: a group never waits on a barrier phase it did not see complete),
+    // and every group has a second stage in flight.
+    for (int pass = 0; pass < 2 && !best_wt; ++pass)
+        for (int wt = kScanWarps; wt >= 1 && !best_wt; wt >>= 1) {
+            if (env_wt && wt != env_wt) continue;
+            const int ng = kScanWarps / wt;
+            const size_t tile = (size_t)wt * gpw * kTmaR * (row_bytes + 8);
+            const size_t stage = (tile + 127) / 128 * 128;
+            const size_t room = pass == 0 ? half : whole;
+            if (tile > 48 * 1024 || fixed + stage > room) continue;
+            int stages = (int)((room - fixed) / stage);
+            if (stages > kTmaMaxStages) stages = kTmaMaxStages;
+            stages -= stages % ng;
+            if (stages < (ng == 1 ? 3 : 2 * ng)) continue;
+            best_wt = wt; best_s = stages; best_stage = stage;
+        }
+    if (!best_wt) return false;
+    const uint64_t tile_rows = (uint64_t)best_wt * gpw * kTmaR;
+    if (count / tile_rows < (uint64_t)4 * sm_count) return false;
+    int best = 0, best_cost = bank_cost(nch, t2, 0, kTmaR, (u8 ? 1 : 2) * kQPlanes);
+    if (t2 < 8)
+        for (int m = 1; m < 8; ++m) {
+            const int c = bank_cost(nch, t2, m, kTmaR, (u8 ? 1 : 2) * kQPlanes);
+            if (c < best_cost) { best_cost = c; best = m; }
+        }
+    o->tpr = t2;
+    o->wt = best_wt;
+    o->stages = best_s;
+    o->stage_bytes = (int)best_stage;
+    o->tile_rows = (int)tile_rows;
+    o->bank_mul = best;
+    o->smem = qbytes + scan_list_bytes(KP) + (size_t)best_s * best_stage;
+    return true;
+}
+
 struct ScanPlan {
     scan_fn_t fn;
     size_t smem;
@@ -751,60 +810,25 @@ static int make_scan_plan(evdb_store *s, int metric, int KP, ScanPlan *p) {
             if (tpr == 32) R = 2;
             // TMA-staged variant: whole tiles through a shared-memory ring (large stores only:
             // a small one is latency-bound and spreads better one warp-iteration per warp)
-            if (scan_tma_mode() && s->row_bytes >= 64) {   // (32-byte rows: the register-fed kernel is level or better)
-                static int env_div = -1, env_wt = -1;
-                if (env_div < 0) { const char *e = getenv("EVDB_SCAN_TMA_DIV"); env_div = e && atoi(e) > 0 ? atoi(e) : 4; }
-                if (env_wt < 0) { const char *e = getenv("EVDB_SCAN_TMA_WT"); env_wt = e ? atoi(e) : 0; }
-                int t2 = 1;
-                while (t2 < 32 && (t2 < 2 ? s->nch >= 2 : t2 * 2 <= s->nch / env_div)) t2 <<= 1;
-                const int gpw = 32 / t2;
-                const size_t fixed = qbytes + scan_list_bytes(KP) + 1024;
-                const size_t half = 112 * 1024, whole = 224 * 1024;
-                int best_r = 0, best_wt = 0, best_s = 0;
-                size_t best_stage = 0;
-                // preference: two CTAs per SM, then the widest tile group.  A stage always belongs to
-                // the same group (stages % groups == 0: a group never waits on a barrier phase it
-                // did not see complete), and every group has a second stage in flight.
-                for (int pass = 0; pass < 2 && !best_r; ++pass)
-                    for (int wt = kScanWarps; wt >= 1 && !best_r; wt >>= 1) {
-                        if (env_wt && wt != env_wt) continue;
-                        const int ng = kScanWarps / wt;
-                        const size_t tile = (size_t)wt * gpw * kTmaR * (s->row_bytes + 8);
-                        const size_t stage = (tile + 127) / 128 * 128;
-                        const size_t room = pass == 0 ? half : whole;
-                        if (tile > 48 * 1024 || fixed + stage > room) continue;
-                        int stages = (int)((room - fixed) / stage);
-                        if (stages > kTmaMaxStages) stages = kTmaMaxStages;
-                        stages -= stages % ng;
-                        if (stages < (ng == 1 ? 3 : 2 * ng)) continue;
-                        best_r = kTmaR; best_wt = wt; best_s = stages; best_stage = stage;
-                    }
-                const uint64_t tile_rows = (uint64_t)best_wt * gpw * best_r;
-                if (best_r && s->count / tile_rows >= (uint64_t)4 * s->sm_count) {
-                    p->tma = true;
-                    tpr = t2;
-                    p->tpr = t2;
-                    p->fn = u8 ? pick_quant_tma<EVDB_U8>(t2) : pick_quant_tma<EVDB_U4>(t2);
-                    p->threads = (kScanWarps + 1) * 32;
-                    p->stages = best_s;
-                    p->stage_bytes = (int)best_stage;
-                    p->tile_rows = (int)tile_rows;
-                    p->wt = best_wt;
-                    R = best_r;
-                    int best = 0, best_cost = bank_cost(s->nch, t2, 0, R, (u8 ? 1 : 2) * kQPlanes);
-                    if (t2 < 8)
-                        for (int m = 1; m < 8; ++m) {
-                            int c = bank_cost(s->nch, t2, m, R, (u8 ? 1 : 2) * kQPlanes);
-                            if (c < best_cost) { best_cost = c; best = m; }
-                        }
-                    p->bank_mul = best;
-                    qbytes += (size_t)best_s * best_stage;
-                    static int dbg = -1;
-                    if (dbg < 0) { const char *e = getenv("EVDB_SCAN_DEBUG"); dbg = e && atoi(e) ? 1 : 0; }
-                    if (dbg)
-                        fprintf(stderr, "[evdb scan] tma plan: nch=%d tpr=%d R=%d wt=%d stages=%d stage=%zu B rotation=%d\n",
-                                s->nch, t2, best_r, best_wt, best_s, best_stage, best);
-                }
+            TmaTilePlan tp;
+            if (scan_tma_mode() && choose_tma_tile_plan(s->dtype, s->nch, s->row_bytes, KP, s->count, s->sm_count, &tp)) {
+                p->tma = true;
+                tpr = tp.tpr;
+                p->tpr = tp.tpr;
+                p->fn = u8 ? pick_quant_tma<EVDB_U8>(tp.tpr) : pick_quant_tma<EVDB_U4>(tp.tpr);
+                p->threads = (kScanWarps + 1) * 32;
+                p->stages = tp.stages;
+                p->stage_bytes = tp.stage_bytes;
+                p->tile_rows = tp.tile_rows;
+                p->wt = tp.wt;
+                p->bank_mul = tp.bank_mul;
+                R = kTmaR;
+                qbytes += (size_t)tp.stages * tp.stage_bytes;
+                static int dbg = -1;
+                if (dbg < 0) { const char *e = getenv("EVDB_SCAN_DEBUG"); dbg = e && atoi(e) ? 1 : 0; }
+                if (dbg)
+                    fprintf(stderr, "[evdb scan] tma plan: nch=%d tpr=%d R=%d wt=%d stages=%d stage=%d B rotation=%d\n",
+                            s->nch, tp.tpr, kTmaR, tp.wt, tp.stages, tp.stage_bytes, tp.bank_mul);
             }
             break;
         }
@@ -857,3 +881,20 @@ int launch_scan(evdb_store *s, int metric, const ScanArgs &a0, cudaStream_t st) 
 }
 
 }  // namespace evdb
+
+// Diagnostics (CPU tests): the tile plan the TMA-staged quantized scan would use for a store of this
+// shape.  Returns 1 and fills out[8] = {lanes per row, warps per tile, stages, stage bytes, rows per
+// tile, chunk rotation, dynamic shared memory, consumer groups}, 0 if the register-fed kernel would
+// run, a negative EVDB_E_* for bad arguments.  Touches no device.
+extern "C" int evdb_debug_scan_tile_plan(int dtype, int dim, int window, uint64_t count, int sm_count, int32_t *out) {
+    if (!out || dim <= 0 || window <= 0 || sm_count <= 0) return EVDB_E_BAD_ARG;
+    if (dtype != EVDB_U8 && dtype != EVDB_U4) return EVDB_E_BAD_ARG;
+    const int dpad = dtype == EVDB_U8 ? (dim + 15) / 16 * 16 : (dim + 31) / 32 * 32;
+    const int nch = dtype == EVDB_U8 ? dpad / 16 : dpad / 32;
+    const size_t row_bytes = dtype == EVDB_U8 ? (size_t)dpad : (size_t)dpad / 2;
+    evdb::TmaTilePlan tp;
+    if (!evdb::choose_tma_tile_plan(dtype, nch, row_bytes, window, count, sm_count, &tp)) return 0;
+    out[0] = tp.tpr; out[1] = tp.wt; out[2] = tp.stages; out[3] = tp.stage_bytes;
+    out[4] = tp.tile_rows; out[5] = tp.bank_mul; out[6] = (int32_t)tp.smem; out[7] = evdb::kScanWarps / tp.wt;
+    return 1;
+}

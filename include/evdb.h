@@ -233,6 +233,16 @@ int evdb_dequantize_8bit(int device, const uint8_t *codes, const double *mins,
 int evdb_dequantize_4bit(int device, const uint8_t *packed, const double *mins,
                          const double *scales, uint64_t n, int d, double *out);
 
+/* ---- diagnostics -----------------------------------------------------------
+ * Host arithmetic only (touches no device): the tile plan the TMA-staged scan over
+ * quantization_8bit / _4bit codes (csrc/scan.cu, replaces the maps:fold of
+ * src/vector_store.erl:227-231 for compressed stores) would use for a store of `count` rows of
+ * `dim` elements with a `window`-key candidate window on a GPU with `sm_count` SMs.
+ * Returns 1 and out[8] = {lanes per row, warps per tile, ring stages, bytes per stage, rows per tile,
+ * chunk rotation, dynamic shared memory bytes, consumer groups}; 0 when the register-fed scan
+ * would run instead; a negative EVDB_E_* for bad arguments.                              */
+int evdb_debug_scan_tile_plan(int dtype, int dim, int window, uint64_t count, int sm_count, int32_t *out);
+
 #ifdef __cplusplus
 }
 #endif
