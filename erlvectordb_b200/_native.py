@@ -37,7 +37,12 @@ class EvdbError(RuntimeError):
 
 class Opts(C.Structure):
     _fields_ = [("device", C.c_int32), ("dtype", C.c_int32), ("dim", C.c_int32),
-                ("gemm_shadow", C.c_int32), ("capacity_hint", C.c_uint64)]
+                ("gemm_shadow", C.c_int32), ("capacity_hint", C.c_uint64),
+                ("n_shards", C.c_int32), ("devices", C.c_int32 * 16)]
+
+
+class SearchOpts(C.Structure):
+    _fields_ = [("plan", C.c_int32), ("kp_min", C.c_int32), ("slot_base", C.c_uint64), ("slot_stride", C.c_uint64)]
 
 
 class Stats(C.Structure):
@@ -45,7 +50,10 @@ class Stats(C.Structure):
                 ("device", C.c_int32), ("last_plan", C.c_int32), ("capacity", C.c_uint64),
                 ("device_bytes", C.c_uint64), ("searches", C.c_uint64),
                 ("rows_scanned", C.c_uint64), ("escalations", C.c_uint64),
-                ("kernel_launches", C.c_uint64), ("last_search_ms", C.c_double)]
+                ("kernel_launches", C.c_uint64), ("last_search_ms", C.c_double),
+                ("n_shards", C.c_int32), ("gemm_disabled", C.c_int32), ("shadow_bytes", C.c_uint64),
+                ("upserts", C.c_uint64), ("deletes", C.c_uint64), ("last_h2d_ms", C.c_double),
+                ("last_device_ms", C.c_double), ("last_d2h_ms", C.c_double)]
 
 
 # every symbol include/evdb.h declares: (name, restype, argtypes)
@@ -77,6 +85,7 @@ SYMBOLS = [
     ("evdb_store_search_f64", _i, [_vp, _pd, _i, _i, _i, _i, _pu32, _pd, _pi32]),
     ("evdb_store_search_f32", _i, [_vp, _pf, _i, _i, _i, _i, _pu32, _pd, _pi32]),
     ("evdb_store_search_dev", _i, [_vp, _vp, _i, _i, _i, _i, _u64, _vp, _vp, _vp, _vp, _vp]),
+    ("evdb_store_search_dev_ex", _i, [_vp, _vp, _i, _i, _i, _i, C.POINTER(SearchOpts), _vp, _vp, _vp, _vp, _vp]),
     ("evdb_merge_topk_dev", _i, [_i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     ("evdb_merge_topk_packed_dev", _i, [_i, _vp, _i, _i, _i, _vp, _vp]),
     ("evdb_exchange_create", _i, [_i, _i, _i, _u64, C.POINTER(_vp), _vp]),

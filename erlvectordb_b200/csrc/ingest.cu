@@ -83,11 +83,11 @@ int launch_finalize_rows(evdb_store *s, uint64_t slot0, uint64_t n, cudaStream_t
 struct RowSrc {
     const double *r64;
     const float *r32;
-    uint64_t seed, row0;
+    uint64_t seed, row0, rstride;
     int synth;
     int d;
     __device__ __forceinline__ double at(uint64_t r, int c) const {
-        if (synth) return (double)synth_value(seed, (row0 + r) * (uint64_t)d + (uint64_t)c);
+        if (synth) return (double)synth_value(seed, (row0 + r * rstride) * (uint64_t)d + (uint64_t)c);
         if (r64) return r64[r * (uint64_t)d + c];
         return (double)r32[r * (uint64_t)d + c];
     }
@@ -146,7 +146,7 @@ int launch_quantize_rows(int dtype, const double *d_rows64, const float *d_rows3
                          uint8_t *codes, size_t code_row_bytes, double2 *ms64, double *maxs,
                          uint8_t *ok, cudaStream_t st) {
     if (n == 0) return EVDB_OK;
-    RowSrc src{d_rows64, d_rows32, 0, 0, 0, d};
+    RowSrc src{d_rows64, d_rows32, 0, 0, 1, 0, d};
     uint64_t blocks = (n + 7) / 8;
     int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
     if (dtype == EVDB_U8) quantize_rows_kernel<EVDB_U8><<<grid, 256, 0, st>>>(src, n, d, codes, code_row_bytes, ms64, maxs, ok);
@@ -187,27 +187,27 @@ int launch_dequantize_rows(int dtype, const uint8_t *codes, size_t code_row_byte
 template <int DTYPE>
 __global__ void __launch_bounds__(256) fill_float_kernel(uint8_t *__restrict__ rows, size_t row_bytes,
                                                          int d, int dpad, uint64_t seed,
-                                                         uint64_t row0, uint64_t n) {
+                                                         uint64_t row0, uint64_t rstride, uint64_t n) {
     const uint64_t total = n * (uint64_t)dpad;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t r = i / dpad;
         int c = (int)(i % dpad);
-        float v = c < d ? synth_value(seed, (row0 + r) * (uint64_t)d + (uint64_t)c) : 0.0f;
+        float v = c < d ? synth_value(seed, (row0 + r * rstride) * (uint64_t)d + (uint64_t)c) : 0.0f;
         if (DTYPE == EVDB_F32) reinterpret_cast<float *>(rows + r * row_bytes)[c] = v;
         else reinterpret_cast<__nv_bfloat16 *>(rows + r * row_bytes)[c] = __float2bfloat16_rn(v);
     }
 }
 
-int launch_fill_synthetic(evdb_store *s, uint64_t seed, uint64_t row0, uint64_t n, cudaStream_t st) {
+int launch_fill_synthetic(evdb_store *s, uint64_t seed, uint64_t row0, uint64_t rstride, uint64_t n, cudaStream_t st) {
     if (n == 0) return EVDB_OK;
     if (s->dtype == EVDB_F32 || s->dtype == EVDB_BF16) {
         uint64_t blocks = (n * (uint64_t)s->dpad + 255) / 256;
         int grid = (int)(blocks < (uint64_t)s->sm_count * 16 ? blocks : (uint64_t)s->sm_count * 16);
-        if (s->dtype == EVDB_F32) fill_float_kernel<EVDB_F32><<<grid, 256, 0, st>>>(s->rows, s->row_bytes, s->dim, s->dpad, seed, row0, n);
-        else fill_float_kernel<EVDB_BF16><<<grid, 256, 0, st>>>(s->rows, s->row_bytes, s->dim, s->dpad, seed, row0, n);
+        if (s->dtype == EVDB_F32) fill_float_kernel<EVDB_F32><<<grid, 256, 0, st>>>(s->rows, s->row_bytes, s->dim, s->dpad, seed, row0, rstride, n);
+        else fill_float_kernel<EVDB_BF16><<<grid, 256, 0, st>>>(s->rows, s->row_bytes, s->dim, s->dpad, seed, row0, rstride, n);
     } else {
-        RowSrc src{nullptr, nullptr, seed, row0, 1, s->dim};
+        RowSrc src{nullptr, nullptr, seed, row0, rstride, 1, s->dim};
         uint64_t blocks = (n + 7) / 8;
         int grid = (int)(blocks < (uint64_t)s->sm_count * 8 ? blocks : (uint64_t)s->sm_count * 8);
         if (s->dtype == EVDB_U8) quantize_rows_kernel<EVDB_U8><<<grid, 256, 0, st>>>(src, n, s->dim, s->rows, s->row_bytes, s->qms64, nullptr, nullptr);

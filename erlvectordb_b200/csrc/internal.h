@@ -27,8 +27,11 @@ constexpr int kProfMax = 512;
 
 }  // namespace evdb
 
+namespace evdb { struct MStore; }
+
 // Device-resident store.  One owner thread at a time (the store's gen_server).
 struct evdb_store {
+    evdb::MStore *multi = nullptr;   // n_shards > 1: this handle only fronts the shard stores (mstore.cu)
     int device = 0;
     int dtype = EVDB_F32;
     int dim = 0;    // 0 = undefined (reference: dimension :: undefined)
@@ -40,7 +43,7 @@ struct evdb_store {
     int gemm_shadow = 0;
     uint64_t count = 0, capacity = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;   // host search: start, end, after H2D, before D2H
 
     // ---- columns (all [capacity]) ----
     uint8_t *rows = nullptr;       // F32: f32[dpad]; BF16: bf16[dpad]; U8: u8[dpad]; U4: u8[dpad/2]
@@ -59,6 +62,7 @@ struct evdb_store {
     float l2_sigma = 0.f;          // power-of-two scale: sigma * max||v|| in [64, 128)
     double max_norm = 0.0;         // upper bound on the largest row norm (valid when !max_norm_dirty)
     int max_norm_dirty = 1;
+    uint64_t slot_mul = 1;        // returned id = slot_base + slot * slot_mul (> 1: round-robin shard of a multi-device store)
     int gemm_oom = 0;            // the GEMM plan ran out of device memory once: AUTO stays on the scan plan
     void *d_scalar = nullptr;      // 64-byte device scratch (reductions)
 
@@ -84,7 +88,8 @@ struct evdb_store {
     cudaStream_t prof_stream = nullptr;
 
     // ---- counters ----
-    uint64_t n_searches = 0, n_rows_scanned = 0, n_escalations = 0, n_launches = 0;
+    uint64_t n_searches = 0, n_rows_scanned = 0, n_escalations = 0, n_launches = 0, n_upserts = 0, n_deletes = 0;
+    double last_h2d_ms = 0.0, last_device_ms = 0.0, last_d2h_ms = 0.0;
     int last_plan = 0;
     double last_search_ms = 0.0;
 };
@@ -158,7 +163,7 @@ struct RawCands {
 constexpr int kRawMaxLists = 640;  // NG * parts <= 148 * 4
 
 // ---- launchers (each returns EVDB_OK or an error; all async on `st`) ----
-int launch_prep_queries(evdb_store *s, const double *d_q64, int B, cudaStream_t st);
+int launch_prep_queries(evdb_store *s, const double *d_q64, int B, int metric, cudaStream_t st);
 int scan_grid_size(evdb_store *s, int metric, int KP, int *G_out);
 int launch_scan(evdb_store *s, int metric, const ScanArgs &a, cudaStream_t st);
 // eps_q: optional per-query absolute bound added to eps_abs; squared: key scores are squared
@@ -168,7 +173,7 @@ int launch_select(evdb_store *s, const double *d_q64, const uint64_t *partial, c
                   const float *eps_q, int squared, uint64_t slot_base, uint64_t *d_out_ids, double *d_out_dists,
                   int32_t *d_out_counts, int32_t *d_out_flags, cudaStream_t st);
 int launch_finalize_rows(evdb_store *s, uint64_t slot0, uint64_t n, cudaStream_t st);
-int launch_fill_synthetic(evdb_store *s, uint64_t seed, uint64_t row0, uint64_t n, cudaStream_t st);
+int launch_fill_synthetic(evdb_store *s, uint64_t seed, uint64_t row0, uint64_t rstride, uint64_t n, cudaStream_t st);
 int launch_quantize_rows(int dtype, const double *d_rows64, const float *d_rows32, uint64_t n,
                          int d, uint8_t *codes, size_t code_row_bytes, double2 *ms64,
                          double *maxs, uint8_t *ok, cudaStream_t st);
@@ -201,6 +206,34 @@ int gemm_max_batch();
 int launch_gemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int metric, int *lists_per_query,
                      const float **d_eps_q, RawCands *raw, cudaStream_t st);
 int launch_l2_shadow_rows(evdb_store *s, uint64_t slot0, uint64_t n, cudaStream_t st);
+
+// store.cu internals shared with the multi-device store (mstore.cu)
+int choose_kp(int kk, int kp_min);
+int search_core(evdb_store *s, const double *d_q64, int B, int k, int kstride, int metric, int kp_min, int plan,
+                uint64_t slot_base, uint64_t *d_ids, double *d_dists, int32_t *d_counts, int32_t *d_flags, cudaStream_t st);
+int store_put_rows(evdb_store *s, uint64_t slot0, const void *rows, bool is_f64, uint64_t n, size_t pitch, int d);
+int store_load_codes(evdb_store *s, const uint8_t *codes, size_t code_pitch, const double *mins, const double *scales,
+                     size_t ms_stride, uint64_t n, int d);
+int store_fill_synthetic(evdb_store *s, uint64_t seed, uint64_t row0, uint64_t row_stride, uint64_t n, int d);
+void store_drop_last(evdb_store *s);
+int store_refinalize(evdb_store *s, uint64_t slot0, uint64_t n, cudaStream_t st);
+int store_ensure_capacity(evdb_store *s, uint64_t need);
+uint64_t store_device_bytes(const evdb_store *s);
+// one handle, N devices (mstore.cu); `owner` mirrors count / dimension for the ABI's argument checks
+int mstore_create(evdb_store *owner, const evdb_opts *o);
+void mstore_destroy(MStore *m);
+int m_put(MStore *m, uint64_t slot0, const void *rows, bool is_f64, uint64_t n, int d, bool replace_all);
+int m_bulk_codes(MStore *m, const uint8_t *codes, const double *mins, const double *scales, uint64_t n, int d);
+int m_delete(MStore *m, uint32_t slot, int64_t *moved_from);
+int m_get_f64(MStore *m, uint32_t slot, double *out, int d);
+int m_get_codes(MStore *m, uint32_t slot, uint8_t *codes, double *mn, double *scale);
+int m_fill_synthetic(MStore *m, uint64_t seed, uint64_t row0, uint64_t n, int d);
+int m_stats(MStore *m, evdb_stats *out);
+int m_set_plan(MStore *m, int plan);
+int m_profile(MStore *m, int enable);
+int m_profile_read(MStore *m, int32_t *n_samples, double *total_ms);
+int m_search_host(MStore *m, const void *queries, bool is_f64, int B, int d, int k, int metric, uint32_t *out_slots,
+                  double *out_dists, int32_t *out_counts);
 
 int ensure_bytes(void **p, size_t *cap, size_t need, bool pinned = false);
 int ensure_func_smem(const void *fn, size_t smem);                        // cached cudaFuncSetAttribute(MaxDynamicSharedMemorySize)

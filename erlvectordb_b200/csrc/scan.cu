@@ -45,7 +45,7 @@ __device__ __forceinline__ T block_reduce(T v, T *red, bool is_max) {
 __global__ void __launch_bounds__(256) prep_queries_kernel(const double *__restrict__ q64, int d,
                                                            float *__restrict__ q32, int q32_stride,
                                                            uint8_t *__restrict__ qdig,
-                                                           int qdig_stride, int dtype,
+                                                           int qdig_stride, int dtype, int metric,
                                                            QStat *__restrict__ qstat, float *__restrict__ qeps) {
     __shared__ double redd[8];
     __shared__ long long redl[8];
@@ -62,7 +62,32 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const double *__restr
     sm = block_reduce<double>(sm, redd, false);
     if (q32) {
         float *o = q32 + (size_t)b * q32_stride;
-        for (int i = threadIdx.x; i < q32_stride; i += blockDim.x) o[i] = i < d ? (float)q[i] : 0.0f;
+        // The float scans see q narrowed to fp32.  For euclidean / manhattan that moves every score by
+        // up to the narrowing residual (triangle inequality: | ||q32-v|| - ||q-v|| | <= ||q-q32||_2,
+        // | |q32-v|_1 - |q-v|_1 | <= |q-q32|_1) -- an ABSOLUTE error the relative arithmetic bound does
+        // not cover when rows lie much closer to the query than ||q||.  It becomes the query's eps_q
+        // (0 for a query that is exact in fp32; cosine's absolute bound already covers 2^-24 ||q||).
+        double r2 = 0.0, r1 = 0.0;
+        for (int i = threadIdx.x; i < q32_stride; i += blockDim.x) {
+            const float f = i < d ? (float)q[i] : 0.0f;
+            o[i] = f;
+            if (i < d) {
+                const double df = fabs(q[i] - (double)f);
+                r2 += df * df;
+                r1 += df;
+            }
+        }
+        if (qeps) {
+            r2 = block_reduce<double>(r2, redd, false);
+            r1 = block_reduce<double>(r1, redd, false);
+            if (threadIdx.x == 0) {
+                float e = 0.f;
+                if (metric == EVDB_EUCLIDEAN) e = (float)(sqrt(r2) * 1.0000002);
+                else if (metric == EVDB_MANHATTAN) e = (float)(r1 * 1.0000002);
+                if (e > 0.f) e = nextafterf(e, __int_as_float(0x7f800000));   // the casts round to nearest: never below the bound
+                qeps[b] = e;
+            }
+        }
     }
     QStat st;
     st.norm_sq = (float)ss;
@@ -114,18 +139,16 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const double *__restr
     if (threadIdx.x == 0) qstat[b] = st;
 }
 
-int launch_prep_queries(evdb_store *s, const double *d_q64, int B, cudaStream_t st) {
+int launch_prep_queries(evdb_store *s, const double *d_q64, int B, int metric, cudaStream_t st) {
     bool quant = s->dtype == EVDB_U8 || s->dtype == EVDB_U4;
     int q32_stride = quant ? 0 : s->dpad;
     int qdig_stride = quant ? s->dpad : 0;
     if (!quant) EVDB_TRY(ensure_bytes((void **)&s->w_q32, &s->w_q32_cap, sizeof(float) * (size_t)B * q32_stride));
-    else {
-        EVDB_TRY(ensure_bytes((void **)&s->w_qdig, &s->w_qdig_cap, (size_t)B * kQPlanes * qdig_stride));
-        EVDB_TRY(ensure_bytes((void **)&s->w_qeps, &s->w_qeps_cap, sizeof(float) * (size_t)B));
-    }
+    else EVDB_TRY(ensure_bytes((void **)&s->w_qdig, &s->w_qdig_cap, (size_t)B * kQPlanes * qdig_stride));
+    EVDB_TRY(ensure_bytes((void **)&s->w_qeps, &s->w_qeps_cap, sizeof(float) * (size_t)B));
     EVDB_TRY(ensure_bytes((void **)&s->w_qstat, &s->w_qstat_cap, sizeof(QStat) * (size_t)B));
     prep_queries_kernel<<<B, 256, 0, st>>>(d_q64, s->dim, quant ? nullptr : s->w_q32, q32_stride,
-                                           s->w_qdig, qdig_stride, s->dtype, s->w_qstat, quant ? s->w_qeps : nullptr);
+                                           s->w_qdig, qdig_stride, s->dtype, metric, s->w_qstat, s->w_qeps);
     s->n_launches++;
     EVDB_CUDA(cudaGetLastError());
     return EVDB_OK;

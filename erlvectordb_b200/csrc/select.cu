@@ -62,7 +62,8 @@ struct SelectArgs {
     int variant;         // EVDB_SEL_VARIANT (measurement only): 16 = per-phase cycle counters, 32 = CTA-per-query kernel for GEMM batches too
     int win_mode;        // sharded search, phase 1: push the ascending window (keys with GLOBAL rows) + meta to every rank and stop
     PushTarget push;     //   blob words: [B*KP keys][B meta = (eps bits << 32) | ncand]
-    uint64_t slot_base;
+    uint64_t slot_base;  // returned id = slot_base + slot * slot_mul (slot_mul > 1: round-robin shard of a multi-device store)
+    uint64_t slot_mul;
     uint64_t *out_ids;
     double *out_dists;
     int32_t *out_counts;
@@ -570,7 +571,7 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
             uint64_t ob = dkey[i];
             uint64_t bits = ob ^ ((ob >> 63) ? 0x8000000000000000ull : 0xFFFFFFFFFFFFFFFFull);
             a.out_dists[o] = __longlong_as_double((long long)bits);
-            a.out_ids[o] = a.slot_base + dslot[i];
+            a.out_ids[o] = a.slot_base + dslot[i] * a.slot_mul;
         } else {
             a.out_dists[o] = 0.0;
             a.out_ids[o] = kKeyMax;
@@ -931,7 +932,7 @@ __global__ void __launch_bounds__(kSwWarps * 32) select_warp_kernel(const Select
         }
     }
     if (a.win_mode) {  // sharded search, phase 1: the window travels, the re-rank happens after the global merge
-        for (int i = lane; i < KP; i += 32) push_store(a.push, (size_t)b * KP + i, i < ncand ? ckeys[i] + a.slot_base : kKeyMax);
+        for (int i = lane; i < KP; i += 32) push_store(a.push, (size_t)b * KP + i, i < ncand ? (ckeys[i] & 0xFFFFFFFF00000000ull) | (a.slot_base + (ckeys[i] & 0xFFFFFFFFull) * a.slot_mul) : kKeyMax);
         if (lane == 0) push_store(a.push, (size_t)B * KP + b, ((uint64_t)__float_as_uint(eps_abs) << 32) | (uint32_t)ncand);
         push_arrive(a.push, gridDim.x * kSwWarps, lane);
         return;
@@ -991,7 +992,7 @@ __global__ void __launch_bounds__(kSwWarps * 32) select_warp_kernel(const Select
             const uint64_t ob = dkey[i];
             const uint64_t bits = ob ^ ((ob >> 63) ? 0x8000000000000000ull : 0xFFFFFFFFFFFFFFFFull);
             a.out_dists[o] = __longlong_as_double((long long)bits);
-            a.out_ids[o] = a.slot_base + dslot[i];
+            a.out_ids[o] = a.slot_base + dslot[i] * a.slot_mul;
         } else {
             a.out_dists[o] = 0.0;
             a.out_ids[o] = kKeyMax;
@@ -1051,6 +1052,7 @@ struct GMeta { int nrer, kout, flag, has_outside; float bound, eps; };
 struct ShardArgs {
     const uint8_t *rows; size_t row_bytes; const double *norm64; int d; const double *q64;
     int B, KP, kk, metric, squared, world, rank;
+    int strided;          // 0: rank r owns the contiguous block shard_range(r); 1: rank r owns the rows == r (mod world)
     uint64_t n_total;
     ExchangeView win;     // phase 2 input: per rank [B*KP keys][B meta]
     PushTarget e_push;    // phase 2 output: [B][KP] exact distances of the rows this rank owns (0 elsewhere), pushed to every rank
@@ -1065,6 +1067,13 @@ __device__ __forceinline__ void shard_range(uint64_t n, int world, int r, uint64
     const uint64_t per = (n + world - 1) / world;
     *lo = (uint64_t)r * per < n ? (uint64_t)r * per : n;
     *hi = *lo + per < n ? *lo + per : n;
+}
+// rows of the whole store that live on rank r
+__device__ __forceinline__ uint64_t shard_rows(uint64_t n, int world, int r, int strided) {
+    if (strided) return n > (uint64_t)r ? (n - r + world - 1) / world : 0;
+    uint64_t lo, hi;
+    shard_range(n, world, r, &lo, &hi);
+    return hi - lo;
 }
 
 __device__ __forceinline__ void wait_flags(const unsigned long long *flags, unsigned long long epoch, int world, int lane) {
@@ -1107,9 +1116,7 @@ __global__ void __launch_bounds__(kShWarps * 32) shard_rerank_kernel(const Shard
         const uint64_t meta = __ldcg(wr + (size_t)a.B * KP + b);
         nc = (int)(uint32_t)meta;
         eps = __uint_as_float((uint32_t)(meta >> 32));
-        uint64_t lo, hi;
-        shard_range(a.n_total, a.world, lane, &lo, &hi);
-        if ((uint64_t)nc < hi - lo) {          // rows of shard r exist outside its window
+        if ((uint64_t)nc < shard_rows(a.n_total, a.world, lane, a.strided)) {   // rows of shard r exist outside its window
             has_outside = 1;
             if (nc > 0) bstar = key_score(__ldcg(wr + (size_t)b * KP + nc - 1));
             else flag = 1;                     // nothing admitted there: no bound to offer
@@ -1168,7 +1175,7 @@ __global__ void __launch_bounds__(kShWarps * 32) shard_rerank_kernel(const Shard
     for (int base = 0; base < nrer; base += 32) {
         const int j = base + lane;
         const uint64_t row = j < nrer ? (uint64_t)key_slot(ckeys[j]) : ~0ull;
-        const bool own = j < nrer && row >= mylo && row < myhi;
+        const bool own = j < nrer && (a.strided ? row % (uint64_t)a.world == (uint64_t)a.rank : row >= mylo && row < myhi);
         const unsigned m = __ballot_sync(0xffffffffu, own);
         if (own) olist[no + __popc(m & ((1u << lane) - 1u))] = j;
         no += __popc(m);
@@ -1188,7 +1195,8 @@ __global__ void __launch_bounds__(kShWarps * 32) shard_rerank_kernel(const Shard
         const int nr = no - base < RC ? no - base : RC;
         const bool mine = lane < nr;
         const int j = mine ? olist[base + lane] : 0;
-        const uint32_t slot = mine ? (uint32_t)((uint64_t)key_slot(ckeys[j]) - mylo) : 0u;
+        const uint64_t grow = mine ? (uint64_t)key_slot(ckeys[j]) : 0ull;
+        const uint32_t slot = mine ? (uint32_t)(a.strided ? grow / (uint64_t)a.world : grow - mylo) : 0u;
         const double s = sw_fold_chain(a.rows, a.row_bytes, q, a.d, a.metric, stage, slot, nr, cosine, lane);
         double dist;
         if (cosine) {
@@ -1223,7 +1231,7 @@ __global__ void __launch_bounds__(kShWarps * 32) shard_final_kernel(const ShardA
         uint64_t key = kKeyMax, id = kKeyMax;
         if (j < gm.nrer) {
             id = (uint64_t)key_slot(a.g_out[(size_t)b * KP + j]);
-            const int owner = (int)(id / per);
+            const int owner = a.strided ? (int)(id % (uint64_t)a.world) : (int)(id / per);
             key = f64_orderable(__ldcg(reinterpret_cast<const double *>(a.ex.slots + (size_t)owner * a.ex.stride) +
                                        (size_t)b * KP + j));
         }
@@ -1270,7 +1278,7 @@ int launch_shard_window(evdb_store *s, const double *d_q64, const RawCands *raw,
     memset(&a, 0, sizeof(a));
     a.rows = s->rows; a.row_bytes = s->row_bytes; a.norm64 = s->norm64; a.qms64 = s->qms64;
     a.n = s->count; a.d = s->dim; a.q64 = d_q64; a.L = L; a.KP = KP; a.raw = *raw;
-    a.kk = kk; a.kstride = kk; a.metric = metric; a.eps_q = eps_q; a.slot_base = slot_base;
+    a.kk = kk; a.kstride = kk; a.metric = metric; a.eps_q = eps_q; a.slot_base = slot_base; a.slot_mul = s->slot_mul;
     a.win_mode = 1; a.push = push;
     s->n_launches++;
     return launch_select_warp(a, B, st);
@@ -1281,7 +1289,7 @@ static void fill_shard_args(ShardArgs *a, evdb_store *s, const double *d_q64, in
     memset(a, 0, sizeof(*a));
     a->rows = s->rows; a->row_bytes = s->row_bytes; a->norm64 = s->norm64; a->d = s->dim; a->q64 = d_q64;
     a->B = B; a->KP = KP; a->kk = kk; a->k = k; a->metric = metric; a->squared = metric == EVDB_EUCLIDEAN;
-    a->world = world; a->rank = rank; a->n_total = n_total;
+    a->world = world; a->rank = rank; a->n_total = n_total; a->strided = s->slot_mul > 1;
     a->g_out = g_out; a->g_meta = (GMeta *)g_meta;
 }
 
@@ -1337,7 +1345,7 @@ int launch_select(evdb_store *s, const double *d_q64, const uint64_t *partial, c
     a.eps_q = eps_q; a.squared = squared;
     a.win_mode = 0;
     { static int v = -1; if (v < 0) { const char *e = getenv("EVDB_SEL_VARIANT"); v = e ? atoi(e) : 0; } a.variant = v; }
-    a.slot_base = slot_base; a.out_ids = d_out_ids; a.out_dists = d_out_dists;
+    a.slot_base = slot_base; a.slot_mul = s->slot_mul; a.out_ids = d_out_ids; a.out_dists = d_out_dists;
     a.out_counts = d_out_counts; a.out_flags = d_out_flags;
     if (raw && B >= 8 && KP <= kSwMaxKP && s->dtype == EVDB_F32 && !(a.variant & 32)) {  // GEMM plan, query batch
         s->n_launches++;
@@ -1401,14 +1409,14 @@ __global__ void __launch_bounds__(256) exact_all_kernel(const uint8_t *__restric
 }
 
 __global__ void emit_sorted_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ slots,
-                                   int kout, int kstride, uint64_t slot_base, uint64_t *out_ids,
+                                   int kout, int kstride, uint64_t slot_base, uint64_t slot_mul, uint64_t *out_ids,
                                    double *out_dists, int32_t *out_count, int32_t *out_flag) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kstride; i += gridDim.x * blockDim.x) {
         if (i < kout) {
             uint64_t ob = keys[i];
             uint64_t bits = ob ^ ((ob >> 63) ? 0x8000000000000000ull : 0xFFFFFFFFFFFFFFFFull);
             out_dists[i] = __longlong_as_double((long long)bits);
-            out_ids[i] = slot_base + slots[i];
+            out_ids[i] = slot_base + slots[i] * slot_mul;
         } else {
             out_dists[i] = 0.0;
             out_ids[i] = kKeyMax;
@@ -1448,7 +1456,7 @@ int exact_plan_search(evdb_store *s, const double *d_q64, int B, int kk, int kst
         // LSD radix sort is stable: equal distances keep ascending slot order
         EVDB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, k0, k1, s0, s1, (int64_t)n, 0, 64, st));
         emit_sorted_kernel<<<(kstride + 255) / 256 > 0 ? (kstride + 255) / 256 : 1, 256, 0, st>>>(
-            k1, s1, kout, kstride, slot_base, d_out_ids + (size_t)b * kstride,
+            k1, s1, kout, kstride, slot_base, s->slot_mul, d_out_ids + (size_t)b * kstride,
             d_out_dists + (size_t)b * kstride, d_out_counts + b, d_out_flags ? d_out_flags + b : nullptr);
         EVDB_CUDA(cudaGetLastError());
         s->n_launches += 3;
@@ -1530,6 +1538,68 @@ __global__ void __launch_bounds__(1024) merge_topk_kernel(const uint64_t *__rest
     }
 }
 
+// Lists too long for one CTA's shared memory (G * k keys > 8192: K in the thousands): every list is
+// already ascending by (distance, id) and ids are unique, so the merged position of an element is
+// its own index plus, for every other list, the number of elements there that precede it -- one
+// binary search each.  No scratch, no sort; one thread per element.
+__global__ void __launch_bounds__(256) merge_rank_kernel(const uint64_t *__restrict__ ids, const double *__restrict__ dists,
+                                                         const int32_t *__restrict__ counts, const int32_t *__restrict__ flags,
+                                                         size_t stride8, size_t stride4, int G, int B, int k,
+                                                         uint64_t *__restrict__ out_ids, double *__restrict__ out_dists,
+                                                         int32_t *__restrict__ out_counts, int32_t *__restrict__ out_flags,
+                                                         const unsigned long long *arrived, unsigned long long epoch) {
+    const int b = blockIdx.y;
+    if (arrived) {
+        if ((int)threadIdx.x < G) {
+            const volatile unsigned long long *f = arrived + threadIdx.x;
+            const long long t0 = clock64();
+            while (*f < epoch)
+                if (clock64() - t0 > 8000000000ll) __trap();
+        }
+        __threadfence_system();
+        __syncthreads();
+    }
+    int total = 0, flag = 0;
+    for (int g = 0; g < G; ++g) {
+        total += __ldcg(counts + (size_t)g * stride4 + b);
+        if (flags) flag |= __ldcg(flags + (size_t)g * stride4 + b);
+    }
+    const int kout = total < k ? total : k;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < G * k) {
+        const int g = e / k, j = e % k;
+        if (j < __ldcg(counts + (size_t)g * stride4 + b)) {
+            const size_t o = (size_t)g * stride8 + (size_t)b * k + j;
+            const double dv = __ldcg(dists + o);
+            const uint64_t key = f64_orderable(dv), id = __ldcg(ids + o);
+            int rank = j;
+            for (int g2 = 0; g2 < G && rank < kout; ++g2) {
+                if (g2 == g) continue;
+                const size_t o2 = (size_t)g2 * stride8 + (size_t)b * k;
+                int lo = 0, hi = __ldcg(counts + (size_t)g2 * stride4 + b);   // first element of list g2 that does NOT precede (key, id)
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    const uint64_t k2 = f64_orderable(__ldcg(dists + o2 + mid)), i2 = __ldcg(ids + o2 + mid);
+                    if (k2 < key || (k2 == key && i2 < id)) lo = mid + 1; else hi = mid;
+                }
+                rank += lo;
+            }
+            if (rank < kout) {
+                out_dists[(size_t)b * k + rank] = dv;
+                out_ids[(size_t)b * k + rank] = id;
+            }
+        }
+    }
+    if (e >= kout && e < k) {
+        out_dists[(size_t)b * k + e] = 0.0;
+        out_ids[(size_t)b * k + e] = kKeyMax;
+    }
+    if (e == 0) {
+        out_counts[b] = kout;
+        if (out_flags) out_flags[b] = flag;
+    }
+}
+
 static int merge_launch(const uint64_t *ids, const double *dists, const int32_t *counts, const int32_t *flags,
                         size_t stride8, size_t stride4, int G, int B, int k, uint64_t *out_ids,
                         double *out_dists, int32_t *out_counts, int32_t *out_flags, cudaStream_t st,
@@ -1538,7 +1608,14 @@ static int merge_launch(const uint64_t *ids, const double *dists, const int32_t 
     int nsort = next_pow2(G * k);
     if (nsort < 2) nsort = 2;
     size_t smem = (size_t)nsort * 16;
-    if (smem > 200 * 1024) return EVDB_E_UNSUPPORTED;
+    if (smem > 128 * 1024) {
+        if (B > 65535) return EVDB_E_UNSUPPORTED;
+        const dim3 grid((unsigned)(((size_t)G * k + 255) / 256), (unsigned)B);
+        merge_rank_kernel<<<grid, 256, 0, st>>>(ids, dists, counts, flags, stride8, stride4, G, B, k, out_ids, out_dists,
+                                                out_counts, out_flags, arrived, epoch);
+        EVDB_CUDA(cudaGetLastError());
+        return EVDB_OK;
+    }
     EVDB_TRY(ensure_func_smem((const void *)merge_topk_kernel, smem));
     const int threads = nsort >= 2048 ? 1024 : (nsort >= 512 ? 256 : 128);
     merge_topk_kernel<<<B, threads, smem, st>>>(ids, dists, counts, flags, stride8, stride4, G, B, k, nsort,

@@ -146,7 +146,7 @@ static uint64_t device_bytes(const evdb_store *s) {
 // ----------------------------------------------------------------------------
 // search orchestration (device side, asynchronous on `st`)
 // ----------------------------------------------------------------------------
-static int choose_kp(int kk, int kp_min) {
+int choose_kp(int kk, int kp_min) {
     int slack = kk / 4 > 6 ? kk / 4 : 6;
     int want = kk + slack;
     if (want < kp_min) want = kp_min;
@@ -155,7 +155,7 @@ static int choose_kp(int kk, int kp_min) {
 }
 
 // d_q64: [B][dim] fp64 on the device.  Outputs [B][kstride].
-static int search_core(evdb_store *s, const double *d_q64, int B, int k, int kstride, int metric,
+int search_core(evdb_store *s, const double *d_q64, int B, int k, int kstride, int metric,
                        int kp_min, int plan, uint64_t slot_base, uint64_t *d_ids, double *d_dists,
                        int32_t *d_counts, int32_t *d_flags, cudaStream_t st) {
     const int kk = (uint64_t)k < s->count ? k : (int)s->count;
@@ -228,7 +228,7 @@ static int search_core(evdb_store *s, const double *d_q64, int B, int k, int kst
         }
     }
     if (!use_gemm) {
-        EVDB_TRY(launch_prep_queries(s, d_q64, B, st));
+        EVDB_TRY(launch_prep_queries(s, d_q64, B, metric, st));
         s->last_plan = EVDB_PLAN_SCAN;
         int G = 0;
         int rc = scan_grid_size(s, metric, KP, &G);
@@ -253,7 +253,7 @@ static int search_core(evdb_store *s, const double *d_q64, int B, int k, int kst
         double depth = (double)s->dim / 64.0 + 24.0;
         if (is_quant(s)) { eps_abs = (float)(24.0 * u); eps_q = s->w_qeps; }   // + the query-grid bound, per query
         else if (metric == EVDB_COSINE) eps_abs = (float)(depth * u);
-        else { eps_rel = (float)(depth * u); eps_abs = 1e-37f; }
+        else { eps_rel = (float)(depth * u); eps_abs = 1e-37f; eps_q = s->w_qeps; }   // + the fp32 narrowing residual of the query
     }
     // EVDB_PROF_SELECT=1 (tuning aid): the profiling bracket times the select kernel instead of the scan/GEMM
     static int prof_sel = -1;
@@ -303,6 +303,10 @@ static int search_host(evdb_store *s, const void *queries, bool is_f64, int B, i
         return EVDB_OK;
     }
     if (d != s->dim) return EVDB_E_DIM_MISMATCH;
+    if (s->multi) {
+        if (k == 0) { for (int b = 0; b < B; ++b) out_counts[b] = 0; return all_finite(queries, is_f64, (size_t)B * d) ? EVDB_OK : EVDB_E_BAD_VECTOR; }
+        return m_search_host(s->multi, queries, is_f64, B, d, k, metric, out_slots, out_dists, out_counts);
+    }
     size_t nq = (size_t)B * d;
     // validate_vector/2 (lists:all(is_number)): a small query is checked before anything is
     // enqueued; a large batch is checked on the host WHILE the device works on it (the result is
@@ -331,8 +335,10 @@ static int search_host(evdb_store *s, const void *queries, bool is_f64, int B, i
         EVDB_CUDA(cudaGetLastError());
     }
     int32_t *d_counts = s->w_counts, *d_flags = s->w_counts + B;
+    EVDB_CUDA(cudaEventRecord(s->ev2, st));
     EVDB_TRY(search_core(s, s->w_q64, B, k, kstride, metric, 0, EVDB_PLAN_AUTO, 0, s->w_ids,
                          s->w_dists, d_counts, d_flags, st));
+    EVDB_CUDA(cudaEventRecord(s->ev3, st));
     size_t nk = (size_t)B * kstride;
     size_t pin_need = nk * (sizeof(uint64_t) + sizeof(double)) + sizeof(int32_t) * 2 * (size_t)B;
     EVDB_TRY(ensure_bytes(&s->h_pin, &s->h_pin_cap, pin_need, true));
@@ -349,6 +355,9 @@ static int search_host(evdb_store *s, const void *queries, bool is_f64, int B, i
     float ms = 0.f;
     cudaEventElapsedTime(&ms, s->ev0, s->ev1);
     s->last_search_ms = ms;
+    cudaEventElapsedTime(&ms, s->ev0, s->ev2); s->last_h2d_ms = ms;
+    cudaEventElapsedTime(&ms, s->ev2, s->ev3); s->last_device_ms = ms;
+    cudaEventElapsedTime(&ms, s->ev3, s->ev1); s->last_d2h_ms = ms;
     s->n_searches += (uint64_t)B;
 
     // escalate queries whose candidate window could not be proven complete
@@ -394,21 +403,29 @@ static int search_host(evdb_store *s, const void *queries, bool is_f64, int B, i
 // ----------------------------------------------------------------------------
 // ingest helpers
 // ----------------------------------------------------------------------------
-static int check_dim(evdb_store *s, int d) {
+// validate_vector/2 (reference src/vector_store.erl:213-225): the length is compared first, the
+// dimension of an empty store is fixed only by a vector that passed every check (:128-131)
+static int check_dim(const evdb_store *s, int d) {
     if (d <= 0) return EVDB_E_BAD_VECTOR;
-    if (s->dim == 0) {
-        set_dim(s, d);
-        return EVDB_OK;
-    }
+    if (s->dim == 0) return EVDB_OK;
     return d == s->dim ? EVDB_OK : EVDB_E_DIM_MISMATCH;
+}
+static void fix_dim(evdb_store *s, int d) { if (s->dim == 0) set_dim(s, d); }
+
+template <typename T>
+static bool rows_finite(const T *rows, uint64_t n) {
+    for (uint64_t i = 0; i < n; ++i) if (!isfinite((double)rows[i])) return false;
+    return true;
 }
 
 int launch_narrow_rows(evdb_store *s, uint64_t dst0, const void *src, bool is_f64, uint64_t n,
                        cudaStream_t st);
 
-// rows: n x d host values (fp64 or fp32) -> slots [slot0, slot0+n)
-static int ingest_rows(evdb_store *s, uint64_t slot0, const void *rows, bool is_f64, uint64_t n) {
+// rows: n host rows of d values (fp64 or fp32), `pitch` elements apart (pitch == d: dense; a
+// multi-device store hands every shard each S-th row of the caller's array) -> slots [slot0, slot0+n)
+static int ingest_rows(evdb_store *s, uint64_t slot0, const void *rows, bool is_f64, uint64_t n, size_t pitch = 0) {
     const int d = s->dim;
+    if (pitch == 0) pitch = (size_t)d;
     cudaStream_t st = s->stream;
     const size_t esz = is_f64 ? sizeof(double) : sizeof(float);
     // chunk so that staging stays <= 256 MiB
@@ -416,10 +433,10 @@ static int ingest_rows(evdb_store *s, uint64_t slot0, const void *rows, bool is_
     if (chunk < 1) chunk = 1;
     for (uint64_t r0 = 0; r0 < n; r0 += chunk) {
         uint64_t cnt = n - r0 < chunk ? n - r0 : chunk;
-        const uint8_t *src = (const uint8_t *)rows + r0 * (size_t)d * esz;
+        const uint8_t *src = (const uint8_t *)rows + r0 * pitch * esz;
         uint64_t dst0 = slot0 + r0;
         if (s->dtype == EVDB_F32 && !is_f64) {
-            EVDB_CUDA(cudaMemcpy2DAsync(s->rows + dst0 * s->row_bytes, s->row_bytes, src, (size_t)d * 4,
+            EVDB_CUDA(cudaMemcpy2DAsync(s->rows + dst0 * s->row_bytes, s->row_bytes, src, pitch * 4,
                                         (size_t)d * 4, cnt, cudaMemcpyHostToDevice, st));
             if (s->dpad != d)
                 EVDB_CUDA(cudaMemset2DAsync(s->rows + dst0 * s->row_bytes + (size_t)d * 4, s->row_bytes, 0,
@@ -427,7 +444,9 @@ static int ingest_rows(evdb_store *s, uint64_t slot0, const void *rows, bool is_
         } else {
             size_t bytes = cnt * (size_t)d * esz;
             EVDB_TRY(ensure_bytes(&s->w_tmp, &s->w_tmp_cap, bytes));
-            EVDB_CUDA(cudaMemcpyAsync(s->w_tmp, src, bytes, cudaMemcpyHostToDevice, st));
+            if (pitch == (size_t)d) EVDB_CUDA(cudaMemcpyAsync(s->w_tmp, src, bytes, cudaMemcpyHostToDevice, st));
+            else EVDB_CUDA(cudaMemcpy2DAsync(s->w_tmp, (size_t)d * esz, src, pitch * esz, (size_t)d * esz, cnt,
+                                             cudaMemcpyHostToDevice, st));
             if (is_quant(s)) {
                 EVDB_TRY(launch_quantize_rows(s->dtype, is_f64 ? (const double *)s->w_tmp : nullptr,
                                               is_f64 ? nullptr : (const float *)s->w_tmp, cnt, d,
@@ -480,21 +499,31 @@ template <typename T>
 static int upsert_any(evdb_store *s, uint32_t slot, const T *vec, int d, bool is_f64) {
     if (!s || !vec) return EVDB_E_BAD_ARG;
     EVDB_TRY(check_dim(s, d));
-    for (int i = 0; i < d; ++i) if (!isfinite((double)vec[i])) return EVDB_E_BAD_VECTOR;
+    if (!rows_finite(vec, (uint64_t)d)) return EVDB_E_BAD_VECTOR;
     if ((uint64_t)slot > s->count) return EVDB_E_BAD_ARG;
+    if (s->multi) return m_put(s->multi, slot, vec, is_f64, 1, d, false);
+    fix_dim(s, d);
     EVDB_TRY(set_device(s));
     EVDB_TRY(ensure_capacity(s, (uint64_t)slot + 1));
     EVDB_TRY(ingest_rows(s, slot, vec, is_f64, 1));
     if ((uint64_t)slot == s->count) s->count++;
+    s->n_upserts++;
     return EVDB_OK;
 }
 
 template <typename T>
 static int bulk_any(evdb_store *s, const T *rows, uint64_t n, int d, bool is_f64) {
     if (!s || (n > 0 && !rows)) return EVDB_E_BAD_ARG;
-    if (n == 0) { s->count = 0; s->shadow_valid = 0; s->l2_valid = 0; return EVDB_OK; }
+    if (n == 0) {
+        if (s->multi) return m_put(s->multi, 0, nullptr, is_f64, 0, s->dim, true);
+        s->count = 0; s->shadow_valid = 0; s->l2_valid = 0;
+        return EVDB_OK;
+    }
     EVDB_TRY(check_dim(s, d));
     if (n > 0xFFFFFFF0ull) return EVDB_E_BAD_ARG;
+    if (!rows_finite(rows, n * (uint64_t)d)) return EVDB_E_BAD_VECTOR;
+    if (s->multi) return m_put(s->multi, 0, rows, is_f64, n, d, true);
+    fix_dim(s, d);
     EVDB_TRY(set_device(s));
     EVDB_TRY(ensure_capacity(s, n));
     s->count = 0;
@@ -502,6 +531,7 @@ static int bulk_any(evdb_store *s, const T *rows, uint64_t n, int d, bool is_f64
     s->l2_valid = 0;
     EVDB_TRY(ingest_rows(s, 0, rows, is_f64, n));
     s->count = n;
+    s->n_upserts += n;
     return EVDB_OK;
 }
 
@@ -513,13 +543,75 @@ static int append_any(evdb_store *s, const T *rows, uint64_t n, int d, bool is_f
     if (n == 0) return EVDB_OK;
     EVDB_TRY(check_dim(s, d));
     if (s->count + n > 0xFFFFFFF0ull) return EVDB_E_BAD_ARG;
-    for (uint64_t i = 0; i < n * (uint64_t)d; ++i) if (!isfinite((double)rows[i])) return EVDB_E_BAD_VECTOR;
+    if (!rows_finite(rows, n * (uint64_t)d)) return EVDB_E_BAD_VECTOR;
+    if (s->multi) return m_put(s->multi, s->count, rows, is_f64, n, d, false);
+    fix_dim(s, d);
     EVDB_TRY(set_device(s));
     EVDB_TRY(ensure_capacity(s, s->count + n));
     EVDB_TRY(ingest_rows(s, s->count, rows, is_f64, n));
     s->count += n;
+    s->n_upserts += n;
     return EVDB_OK;
 }
+
+// validated rows -> slots [slot0, slot0 + n) of one device store (a shard of a multi-device store
+// gets every S-th row of the caller's array: `pitch` elements between consecutive source rows)
+int store_put_rows(evdb_store *s, uint64_t slot0, const void *rows, bool is_f64, uint64_t n, size_t pitch, int d) {
+    if (n == 0) return EVDB_OK;
+    if (slot0 > s->count || slot0 + n > 0xFFFFFFF0ull) return EVDB_E_BAD_ARG;
+    EVDB_TRY(check_dim(s, d));
+    fix_dim(s, d);
+    EVDB_TRY(set_device(s));
+    EVDB_TRY(ensure_capacity(s, slot0 + n));
+    EVDB_TRY(ingest_rows(s, slot0, rows, is_f64, n, pitch));
+    if (slot0 + n > s->count) s->count = slot0 + n;
+    s->n_upserts += n;
+    return EVDB_OK;
+}
+
+// compressed records -> slots [0, n): codes `code_pitch` bytes apart, mins / scales `ms_stride` doubles apart
+int store_load_codes(evdb_store *s, const uint8_t *codes, size_t code_pitch, const double *mins, const double *scales,
+                     size_t ms_stride, uint64_t n, int d) {
+    if (n == 0) { s->count = 0; return EVDB_OK; }
+    EVDB_TRY(check_dim(s, d));
+    fix_dim(s, d);
+    EVDB_TRY(set_device(s));
+    EVDB_TRY(ensure_capacity(s, n));
+    s->count = 0;
+    cudaStream_t st = s->stream;
+    const size_t src_row = s->dtype == EVDB_U8 ? (size_t)d : (size_t)(d + 1) / 2;
+    EVDB_CUDA(cudaMemset2DAsync(s->rows, s->row_bytes, 0, s->row_bytes, n, st));
+    EVDB_CUDA(cudaMemcpy2DAsync(s->rows, s->row_bytes, codes, code_pitch, src_row, n, cudaMemcpyHostToDevice, st));
+    // interleave {min, scale} on the host (n pairs), one H2D
+    EVDB_TRY(ensure_bytes(&s->h_pin, &s->h_pin_cap, n * sizeof(double2), true));
+    double2 *hp = (double2 *)s->h_pin;
+    for (uint64_t i = 0; i < n; ++i) { hp[i].x = mins[i * ms_stride]; hp[i].y = scales[i * ms_stride]; }
+    EVDB_CUDA(cudaMemcpyAsync(s->qms64, hp, n * sizeof(double2), cudaMemcpyHostToDevice, st));
+    EVDB_TRY(launch_finalize_rows(s, 0, n, st));
+    EVDB_CUDA(cudaStreamSynchronize(st));
+    s->count = n;
+    s->max_norm_dirty = 1;
+    return EVDB_OK;
+}
+
+// drop the last row (the tail of a swap-with-last delete whose hole was filled from elsewhere)
+void store_drop_last(evdb_store *s) {
+    if (s->count == 0) return;
+    s->count--;
+    if (s->shadow_valid > s->count) s->shadow_valid = s->count;
+    if (s->l2_valid > s->count) s->l2_valid = s->count;
+}
+
+// refresh the cached per-row values of slots [slot0, slot0 + n) after their raw columns were written
+int store_refinalize(evdb_store *s, uint64_t slot0, uint64_t n, cudaStream_t st) {
+    EVDB_TRY(launch_finalize_rows(s, slot0, n, st));
+    EVDB_TRY(launch_l2_shadow_rows(s, slot0, n, st));
+    s->max_norm_dirty = 1;
+    return EVDB_OK;
+}
+
+int store_ensure_capacity(evdb_store *s, uint64_t need) { EVDB_TRY(set_device(s)); return ensure_capacity(s, need); }
+uint64_t store_device_bytes(const evdb_store *s) { return device_bytes(s); }
 
 }  // namespace evdb
 
@@ -580,6 +672,21 @@ int evdb_store_create(const evdb_opts *opts, evdb_store **out) {
     if (!opts || !out) return EVDB_E_BAD_ARG;
     *out = nullptr;
     if (opts->dtype < EVDB_F32 || opts->dtype > EVDB_U4 || opts->dim < 0) return EVDB_E_BAD_ARG;
+    if (opts->n_shards < 0 || opts->n_shards > EVDB_MAX_SHARDS) return EVDB_E_BAD_ARG;
+    if (opts->n_shards > 1) {
+        // ONE handle, n_shards devices: the owner carries count / dimension / dtype for validation,
+        // the rows live in the shard stores behind s->multi (mstore.cu)
+        for (int i = 0; i < opts->n_shards; ++i) EVDB_TRY(check_device(opts->devices[i]));
+        evdb_store *s = new (std::nothrow) evdb_store();
+        if (!s) return EVDB_E_OOM;
+        s->device = opts->devices[0];
+        s->dtype = opts->dtype;
+        s->gemm_shadow = opts->gemm_shadow;
+        const int rc = mstore_create(s, opts);
+        if (rc != EVDB_OK) { delete s; return rc; }
+        *out = s;
+        return EVDB_OK;
+    }
     EVDB_TRY(check_device(opts->device));
     evdb_store *s = new (std::nothrow) evdb_store();
     if (!s) return EVDB_E_OOM;
@@ -593,7 +700,8 @@ int evdb_store_create(const evdb_opts *opts, evdb_store **out) {
         cudaGetDeviceProperties(&p, s->device);
         s->sm_count = p.multiProcessorCount;
         if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = EVDB_E_CUDA; break; }
-        if (cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess) { rc = EVDB_E_CUDA; break; }
+        if (cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess ||
+            cudaEventCreate(&s->ev2) != cudaSuccess || cudaEventCreate(&s->ev3) != cudaSuccess) { rc = EVDB_E_CUDA; break; }
         if (opts->dim > 0) {
             set_dim(s, opts->dim);
             if (opts->capacity_hint) rc = ensure_capacity(s, opts->capacity_hint);
@@ -606,6 +714,7 @@ int evdb_store_create(const evdb_opts *opts, evdb_store **out) {
 
 void evdb_store_destroy(evdb_store *s) {
     if (!s) return;
+    if (s->multi) { mstore_destroy(s->multi); s->multi = nullptr; delete s; return; }
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     cudaFree(s->rows); cudaFree(s->norm64); cudaFree(s->inv_norm); cudaFree(s->norm_sq);
@@ -616,6 +725,8 @@ void evdb_store_destroy(evdb_store *s) {
     if (s->h_pin) cudaFreeHost(s->h_pin);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->ev2) cudaEventDestroy(s->ev2);
+    if (s->ev3) cudaEventDestroy(s->ev3);
     if (s->prof_ev) {
         for (int i = 0; i < 2 * kProfMax; ++i) if (s->prof_ev[i]) cudaEventDestroy(s->prof_ev[i]);
         free(s->prof_ev);
@@ -628,6 +739,7 @@ void evdb_store_destroy(evdb_store *s) {
 int evdb_store_stats(evdb_store *s, evdb_stats *out) {
     if (!s || !out) return EVDB_E_BAD_ARG;
     memset(out, 0, sizeof(*out));
+    if (s->multi) return m_stats(s->multi, out);
     out->count = s->count;
     out->dimension = s->dim;
     out->dtype = s->dtype;
@@ -640,17 +752,28 @@ int evdb_store_stats(evdb_store *s, evdb_stats *out) {
     out->escalations = s->n_escalations;
     out->kernel_launches = s->n_launches;
     out->last_search_ms = s->last_search_ms;
+    out->n_shards = 1;
+    out->gemm_disabled = s->gemm_oom;
+    out->shadow_bytes = (s->shadow ? s->capacity * (uint64_t)s->spitch * 2 : 0) +
+                        (s->shadow_l2 ? s->l2_cap * (uint64_t)(s->l2_pitch + 16) * 2 : 0);
+    out->upserts = s->n_upserts;
+    out->deletes = s->n_deletes;
+    out->last_h2d_ms = s->last_h2d_ms;
+    out->last_device_ms = s->last_device_ms;
+    out->last_d2h_ms = s->last_d2h_ms;
     return EVDB_OK;
 }
 
 int evdb_store_set_plan(evdb_store *s, int plan) {
     if (!s || plan < EVDB_PLAN_AUTO || plan > EVDB_PLAN_EXACT) return EVDB_E_BAD_ARG;
+    if (s->multi) return m_set_plan(s->multi, plan);
     s->plan = plan;
     return EVDB_OK;
 }
 
 int evdb_store_profile(evdb_store *s, int enable) {
     if (!s) return EVDB_E_BAD_ARG;
+    if (s->multi) return m_profile(s->multi, enable);
     EVDB_TRY(set_device(s));
     if (enable && !s->prof_ev) {
         s->prof_ev = (cudaEvent_t *)calloc(2 * kProfMax, sizeof(cudaEvent_t));
@@ -666,6 +789,7 @@ int evdb_store_profile_read(evdb_store *s, int32_t *n_samples, double *total_ms)
     if (!s || !n_samples || !total_ms) return EVDB_E_BAD_ARG;
     *n_samples = 0;
     *total_ms = 0.0;
+    if (s->multi) return m_profile_read(s->multi, n_samples, total_ms);
     if (!s->prof_ev || s->prof_n == 0) return EVDB_OK;
     EVDB_TRY(set_device(s));
     EVDB_CUDA(cudaEventSynchronize(s->prof_ev[2 * s->prof_n - 1]));
@@ -704,32 +828,21 @@ int evdb_store_append_f32(evdb_store *s, const float *rows, uint64_t n, int d, u
 int evdb_store_bulk_load_codes(evdb_store *s, const uint8_t *codes, const double *mins,
                                const double *scales, uint64_t n, int d) {
     if (!s || !is_quant(s)) return EVDB_E_BAD_ARG;
-    if (n == 0) { s->count = 0; return EVDB_OK; }
-    if (!codes || !mins || !scales) return EVDB_E_BAD_ARG;
-    EVDB_TRY(check_dim(s, d));
+    if (n > 0 && (!codes || !mins || !scales)) return EVDB_E_BAD_ARG;
     if (n > 0xFFFFFFF0ull) return EVDB_E_BAD_ARG;
-    EVDB_TRY(set_device(s));
-    EVDB_TRY(ensure_capacity(s, n));
-    s->count = 0;
-    cudaStream_t st = s->stream;
-    size_t src_row = s->dtype == EVDB_U8 ? (size_t)d : (size_t)(d + 1) / 2;
-    EVDB_CUDA(cudaMemset2DAsync(s->rows, s->row_bytes, 0, s->row_bytes, n, st));
-    EVDB_CUDA(cudaMemcpy2DAsync(s->rows, s->row_bytes, codes, src_row, src_row, n, cudaMemcpyHostToDevice, st));
-    // interleave {min, scale} on the host (n pairs), one H2D
-    EVDB_TRY(ensure_bytes(&s->h_pin, &s->h_pin_cap, n * sizeof(double2), true));
-    double2 *hp = (double2 *)s->h_pin;
-    for (uint64_t i = 0; i < n; ++i) { hp[i].x = mins[i]; hp[i].y = scales[i]; }
-    EVDB_CUDA(cudaMemcpyAsync(s->qms64, hp, n * sizeof(double2), cudaMemcpyHostToDevice, st));
-    EVDB_TRY(launch_finalize_rows(s, 0, n, st));
-    EVDB_CUDA(cudaStreamSynchronize(st));
-    s->count = n;
-    return EVDB_OK;
+    if (n > 0) {
+        EVDB_TRY(check_dim(s, d));
+        if (!rows_finite(mins, n) || !rows_finite(scales, n)) return EVDB_E_BAD_VECTOR;
+    }
+    if (s->multi) return m_bulk_codes(s->multi, codes, mins, scales, n, d);
+    return store_load_codes(s, codes, s->dtype == EVDB_U8 ? (size_t)d : (size_t)(d + 1) / 2, mins, scales, 1, n, d);
 }
 
 int evdb_store_delete(evdb_store *s, uint32_t slot, int64_t *moved_from) {
     if (!s) return EVDB_E_BAD_ARG;
     if (moved_from) *moved_from = -1;
     if ((uint64_t)slot >= s->count) return EVDB_E_BAD_ARG;
+    if (s->multi) return m_delete(s->multi, slot, moved_from);
     EVDB_TRY(set_device(s));
     uint64_t last = s->count - 1;
     cudaStream_t st = s->stream;
@@ -757,6 +870,7 @@ int evdb_store_delete(evdb_store *s, uint32_t slot, int64_t *moved_from) {
         if (moved_from) *moved_from = (int64_t)last;
     }
     s->count = last;
+    s->n_deletes++;
     if (s->shadow_valid > s->count) s->shadow_valid = s->count;
     if (s->l2_valid > s->count) s->l2_valid = s->count;
     return EVDB_OK;
@@ -766,6 +880,7 @@ int evdb_store_get_f64(evdb_store *s, uint32_t slot, double *out, int d) {
     if (!s || !out) return EVDB_E_BAD_ARG;
     if ((uint64_t)slot >= s->count) return EVDB_E_BAD_ARG;
     if (d != s->dim) return EVDB_E_DIM_MISMATCH;
+    if (s->multi) return m_get_f64(s->multi, slot, out, d);
     EVDB_TRY(set_device(s));
     cudaStream_t st = s->stream;
     EVDB_TRY(ensure_bytes(&s->h_pin, &s->h_pin_cap, s->row_bytes + sizeof(double2) + (size_t)d * sizeof(double), true));
@@ -797,6 +912,7 @@ int evdb_store_get_f64(evdb_store *s, uint32_t slot, double *out, int d) {
 int evdb_store_get_codes(evdb_store *s, uint32_t slot, uint8_t *codes, double *mn, double *scale) {
     if (!s || !codes || !is_quant(s)) return EVDB_E_BAD_ARG;
     if ((uint64_t)slot >= s->count) return EVDB_E_BAD_ARG;
+    if (s->multi) return m_get_codes(s->multi, slot, codes, mn, scale);
     EVDB_TRY(set_device(s));
     size_t nb = s->dtype == EVDB_U8 ? (size_t)s->dim : (size_t)(s->dim + 1) / 2;
     double2 ms;
@@ -812,18 +928,28 @@ int evdb_store_fill_synthetic(evdb_store *s, uint64_t seed, uint64_t row0, uint6
     if (!s) return EVDB_E_BAD_ARG;
     EVDB_TRY(check_dim(s, d));
     if (n > 0xFFFFFFF0ull) return EVDB_E_BAD_ARG;
+    if (s->multi) return m_fill_synthetic(s->multi, seed, row0, n, d);
+    return store_fill_synthetic(s, seed, row0, 1, n, d);
+}
+}  // extern "C"
+namespace evdb {
+// local row i = global row row0 + i * row_stride of the synthetic corpus
+int store_fill_synthetic(evdb_store *s, uint64_t seed, uint64_t row0, uint64_t row_stride, uint64_t n, int d) {
+    fix_dim(s, d);
     EVDB_TRY(set_device(s));
     EVDB_TRY(ensure_capacity(s, n));
     s->count = 0;
     s->shadow_valid = 0;
     s->l2_valid = 0;
     s->max_norm_dirty = 1;
-    EVDB_TRY(launch_fill_synthetic(s, seed, row0, n, s->stream));
+    EVDB_TRY(launch_fill_synthetic(s, seed, row0, row_stride, n, s->stream));
     EVDB_TRY(launch_finalize_rows(s, 0, n, s->stream));
     EVDB_CUDA(cudaStreamSynchronize(s->stream));
     s->count = n;
     return EVDB_OK;
 }
+}  // namespace evdb
+extern "C" {
 
 int evdb_store_search_f64(evdb_store *s, const double *queries, int B, int d, int k, int metric,
                           uint32_t *out_slots, double *out_dists, int32_t *out_counts) {
@@ -837,6 +963,7 @@ int evdb_store_search_f32(evdb_store *s, const float *queries, int B, int d, int
 int evdb_store_search_dev(evdb_store *s, const void *d_queries_f64, int B, int d, int k, int metric,
                           uint64_t slot_base, void *d_out_ids_u64, void *d_out_dists_f64,
                           void *d_out_counts_i32, void *d_out_flags_i32, void *stream) {
+    if (s && s->multi) return EVDB_E_UNSUPPORTED;   // one handle, N devices: host entry points only
     if (!s || !d_queries_f64 || B <= 0 || k <= 0 || metric < 0 || metric > 2) return EVDB_E_BAD_ARG;
     if (!d_out_ids_u64 || !d_out_dists_f64 || !d_out_counts_i32) return EVDB_E_BAD_ARG;
     if (s->dim == 0 || s->count == 0) return EVDB_E_BAD_ARG;
@@ -846,6 +973,28 @@ int evdb_store_search_dev(evdb_store *s, const void *d_queries_f64, int B, int d
     EVDB_TRY(search_core(s, (const double *)d_queries_f64, B, k, k, metric, 0, EVDB_PLAN_AUTO,
                          slot_base, (uint64_t *)d_out_ids_u64, (double *)d_out_dists_f64,
                          (int32_t *)d_out_counts_i32, (int32_t *)d_out_flags_i32, st));
+    s->n_searches += (uint64_t)B;
+    return EVDB_OK;
+}
+
+int evdb_store_search_dev_ex(evdb_store *s, const void *d_queries_f64, int B, int d, int k, int metric,
+                             const evdb_search_opts *o, void *d_out_ids_u64, void *d_out_dists_f64,
+                             void *d_out_counts_i32, void *d_out_flags_i32, void *stream) {
+    if (s && s->multi) return EVDB_E_UNSUPPORTED;   // one handle, N devices: host entry points only
+    if (!s || !o || !d_queries_f64 || B <= 0 || k <= 0 || metric < 0 || metric > 2) return EVDB_E_BAD_ARG;
+    if (!d_out_ids_u64 || !d_out_dists_f64 || !d_out_counts_i32) return EVDB_E_BAD_ARG;
+    if (o->plan < EVDB_PLAN_AUTO || o->plan > EVDB_PLAN_EXACT || o->kp_min < 0) return EVDB_E_BAD_ARG;
+    if (s->dim == 0 || s->count == 0) return EVDB_E_BAD_ARG;
+    if (d != s->dim) return EVDB_E_DIM_MISMATCH;
+    EVDB_TRY(set_device(s));
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    const uint64_t keep_mul = s->slot_mul;
+    s->slot_mul = o->slot_stride > 1 ? o->slot_stride : 1;
+    const int rc = search_core(s, (const double *)d_queries_f64, B, k, k, metric, o->kp_min, o->plan, o->slot_base,
+                               (uint64_t *)d_out_ids_u64, (double *)d_out_dists_f64, (int32_t *)d_out_counts_i32,
+                               (int32_t *)d_out_flags_i32, st);
+    s->slot_mul = keep_mul;
+    EVDB_TRY(rc);
     s->n_searches += (uint64_t)B;
     return EVDB_OK;
 }
@@ -887,11 +1036,13 @@ static ShardLayout shard_layout(int B, int k, uint64_t n_total) {
 
 int evdb_store_search_sharded_phase1(evdb_store *s, evdb_exchange *xw, const void *d_queries_f64, int B, int d, int k,
                                      int metric, uint64_t slot_base, uint64_t n_total, void *stream) {
+    if (s && s->multi) return EVDB_E_UNSUPPORTED;
     if (!s || !xw || !d_queries_f64 || B <= 0 || k <= 0) return EVDB_E_BAD_ARG;
     if (s->dim == 0 || s->count == 0) return EVDB_E_UNSUPPORTED;
     if (d != s->dim) return EVDB_E_DIM_MISMATCH;
     const ShardLayout l = shard_layout(B, k, n_total);
-    if (B > gemm_max_batch() || !gemm_plan_supported(s, metric, B, l.KP) || (size_t)xw->world * l.KP > 2048 ||
+    if (B > gemm_max_batch() || !gemm_plan_supported(s, metric, B, l.KP) || (size_t)xw->world * l.KP > 2048 || xw->world > 32 ||   // the phase kernels map one lane per rank
+       
         l.win_words > xw->max_words || n_total > 0xFFFFFFF0ull)
         return EVDB_E_UNSUPPORTED;
     EVDB_TRY(set_device(s));
@@ -913,6 +1064,7 @@ int evdb_store_search_sharded_phase1(evdb_store *s, evdb_exchange *xw, const voi
 
 int evdb_store_search_sharded_phase2(evdb_store *s, evdb_exchange *xw, evdb_exchange *xe, const void *d_queries_f64,
                                      int B, int k, int metric, uint64_t n_total, void *stream) {
+    if (s && s->multi) return EVDB_E_UNSUPPORTED;
     if (!s || !xw || !xe || !d_queries_f64) return EVDB_E_BAD_ARG;
     const ShardLayout l = shard_layout(B, k, n_total);
     if ((size_t)B * l.KP > xe->max_words) return EVDB_E_UNSUPPORTED;
@@ -928,6 +1080,7 @@ int evdb_store_search_sharded_phase2(evdb_store *s, evdb_exchange *xw, evdb_exch
 
 int evdb_store_search_sharded_phase3(evdb_store *s, evdb_exchange *xe, int B, int k, int metric, uint64_t n_total,
                                      void *d_out_blob, void *stream) {
+    if (s && s->multi) return EVDB_E_UNSUPPORTED;
     if (!s || !xe || !d_out_blob) return EVDB_E_BAD_ARG;
     const ShardLayout l = shard_layout(B, k, n_total);
     EVDB_TRY(set_device(s));

@@ -18,11 +18,18 @@ def _p(a, ct):
 
 
 class DeviceStore:
-    def __init__(self, dtype="f32", dim=0, device=0, capacity_hint=0, gemm_shadow=True):
+    def __init__(self, dtype="f32", dim=0, device=0, capacity_hint=0, gemm_shadow=True, devices=None):
+        """devices: a list of CUDA ordinals = ONE store spread over several GPUs of this process behind
+        this one handle (evdb_opts.n_shards; the same ordinal may repeat: several shards on one GPU)."""
         L = N.lib()
         self._h = C.c_void_p()
         opts = N.Opts(device=device, dtype=N.DTYPES.get(dtype, dtype), dim=dim,
                       gemm_shadow=1 if gemm_shadow else 0, capacity_hint=capacity_hint)
+        if devices is not None and len(devices) > 1:
+            opts.n_shards = len(devices)
+            for i, dv in enumerate(devices):
+                opts.devices[i] = dv
+            device = devices[0]
         N.check(L.evdb_store_create(C.byref(opts), C.byref(self._h)), "evdb_store_create")
         self.device = device
         self.dtype = N.DTYPES.get(dtype, dtype)
@@ -169,6 +176,15 @@ class DeviceStore:
         N.check(N.lib().evdb_store_search_dev(self._h, d_queries_ptr, B, d, k, N.METRICS.get(metric, metric),
                                               slot_base, d_ids, d_dists, d_counts, d_flags, stream),
                 "evdb_store_search_dev")
+
+
+    def search_dev_ex(self, d_queries_ptr, B, d, k, metric, d_ids, d_dists, d_counts, d_flags, stream=0, *,
+                      plan="auto", kp_min=0, slot_base=0, slot_stride=1):
+        """search_dev with an explicit plan / minimum window (escalation of flagged queries)."""
+        o = N.SearchOpts(plan=N.PLANS.get(plan, plan), kp_min=kp_min, slot_base=slot_base, slot_stride=slot_stride)
+        N.check(N.lib().evdb_store_search_dev_ex(self._h, d_queries_ptr, B, d, k, N.METRICS.get(metric, metric),
+                                                 C.byref(o), d_ids, d_dists, d_counts, d_flags, stream),
+                "evdb_store_search_dev_ex")
 
 
 def gemm_window(k: int, n_total: int) -> int:

@@ -93,6 +93,7 @@ class ShardedStore:
         self.lo = self.hi = 0
         self.n_total = 0
         self.dim = 0
+        self.n_escalations = 0
 
     # -- ingest --------------------------------------------------------------------
     def fill_synthetic(self, seed: int, n_total: int, d: int):
@@ -122,12 +123,16 @@ class ShardedStore:
             self._bufs[key] = (local, gathered, merged, lv, mv, tuple(t.data_ptr() for t in lv))
         return self._bufs[key]
 
-    def _cuda_local_search(self, q: torch.Tensor, k: int, metric: str, ptrs):
+    def _cuda_local_search(self, q: torch.Tensor, k: int, metric: str, ptrs, plan="auto", kp_min=0):
         """The library writes this shard's result straight into the packed blob (ptrs: its four views)."""
         B, d = q.shape
         if self.hi > self.lo:
-            self._dev.search_dev(q.data_ptr(), B, d, k, metric, self.lo, ptrs[0], ptrs[1], ptrs[2], ptrs[3],
-                                 _stream_handle(q.device))
+            if plan == "auto" and kp_min == 0:
+                self._dev.search_dev(q.data_ptr(), B, d, k, metric, self.lo, ptrs[0], ptrs[1], ptrs[2], ptrs[3],
+                                     _stream_handle(q.device))
+            else:
+                self._dev.search_dev_ex(q.data_ptr(), B, d, k, metric, ptrs[0], ptrs[1], ptrs[2], ptrs[3],
+                                        _stream_handle(q.device), plan=plan, kp_min=kp_min, slot_base=self.lo)
         # an empty shard keeps the zero counts the blob was created with
 
     def _p2p(self, B: int, k: int, dev, words: int | None = None, tag: str = "blob"):
@@ -168,6 +173,7 @@ class ShardedStore:
         smallest = self.n_total - per * (self.world - 1)
         return (self.dtype == "f32" and metric in ("cosine", "euclidean") and 16 <= B <= 8192 and
                 gemm_window(k, self.n_total) <= 128 and self.world * gemm_window(k, self.n_total) <= 2048 and
+                self.world <= 32 and      # the phase kernels map one lane per rank
                 smallest >= 256 and self.n_total < 0xFFFFFFF0)
 
     def _search_two_phase(self, q: torch.Tensor, k: int, metric: str):
@@ -187,20 +193,49 @@ class ShardedStore:
         sharded_phase3(self._dev, xe, B, k, metric, self.n_total, merged.data_ptr(), stream)
         return mv
 
-    def search(self, q: torch.Tensor, k: int, metric: str = "cosine"):
+    def search(self, q: torch.Tensor, k: int, metric: str = "cosine", escalate: bool = True):
         """q: (B, d) float64 on this rank's device (identical on every rank).
-        Returns (ids (B,k) int64 global rows, dists (B,k) float64, counts (B,) int32, flags (B,))."""
+        Returns (ids (B,k) int64 global rows, dists (B,k) float64, counts (B,) int32, flags (B,)).
+
+        A query whose candidate window could not be proven complete comes back flagged by the device
+        path (evdb.h: evdb_store_search_dev).  With `escalate` (the default) no such result leaves
+        this call: flagged queries are re-issued on EVERY rank -- the flags are identical everywhere
+        (every rank merges the same blobs), so the decision needs no extra collective -- first with a
+        256-key window on the scan plan, then through the exhaustive fp64 plan: the ladder
+        evdb_store_search_f64 climbs on one GPU (store.cu search_host).  Costs one flag read-back
+        per call; escalate=False only enqueues (callers then own the flags)."""
+        out = self._search_once(q, k, metric)
+        if not escalate:
+            return out
+        ids, dists, counts, flags = out
+        if int(flags.max().item()) == 0:
+            return out
+        idx = torch.nonzero(flags).flatten()
+        self.n_escalations += int(idx.numel())
+        for plan, kp_min in (("scan", 256), ("exact", 0)):
+            r = self._search_once(q[idx].contiguous(), k, metric, plan=plan, kp_min=kp_min)
+            ids[idx] = r[0]; dists[idx] = r[1]; counts[idx] = r[2]; flags[idx] = r[3]
+            idx = idx[r[3].to(torch.bool)]
+            if idx.numel() == 0:
+                break
+        return out
+
+    def _search_once(self, q: torch.Tensor, k: int, metric: str, plan: str = "auto", kp_min: int = 0):
         B = q.shape[0]
-        if self._two_phase_ok(B, k, metric):
+        forced = plan != "auto" or kp_min != 0
+        if not forced and self._two_phase_ok(B, k, metric):
             r = self._search_two_phase(q, k, metric)
             if r is not None:
                 return r
         local, gathered, merged, lv, mv, lptrs = self._buffers(B, k, q.device)
         if self._local_search is not None:      # injected (CPU tests): tensors in, packed here
-            ids, dists, counts, flags = self._local_search(q, k, metric)
+            if forced:
+                ids, dists, counts, flags = self._local_search(q, k, metric, plan=plan, kp_min=kp_min)
+            else:
+                ids, dists, counts, flags = self._local_search(q, k, metric)
             lv[0].copy_(ids); lv[1].copy_(dists); lv[2].copy_(counts); lv[3].copy_(flags)
         else:
-            self._cuda_local_search(q, k, metric, lptrs)
+            self._cuda_local_search(q, k, metric, lptrs, plan, kp_min)
         if self.world == 1:
             return lv
         if self._merge is None and self.exchange == "p2p":
@@ -244,6 +279,7 @@ class ReplicaGroup:
         self._dev = None if local_search else DeviceStore(dtype=dtype, device=device)
         self._bufs = {}
         self.n_total = 0
+        self.n_escalations = 0
 
     def fill_synthetic(self, seed: int, n_total: int, d: int):
         self.n_total = n_total
@@ -255,9 +291,10 @@ class ReplicaGroup:
         if self._dev is not None:
             self._dev.bulk_load(rows)
 
-    def search(self, q: torch.Tensor, k: int, metric: str = "cosine"):
+    def search(self, q: torch.Tensor, k: int, metric: str = "cosine", escalate: bool = True):
         """q: (B, d) float64, identical on every rank; rank r answers queries [r*per, (r+1)*per).
-        Returns the same tuple as ShardedStore.search, for all B queries, on every rank."""
+        Returns the same tuple as ShardedStore.search, for all B queries, on every rank; flagged
+        queries are escalated by the replica that answers them (see ShardedStore.search)."""
         B, d = q.shape
         per = (B + self.world - 1) // self.world
         key = (B, k, q.device)
@@ -277,6 +314,26 @@ class ReplicaGroup:
             else:
                 self._dev.search_dev(qb.data_ptr(), nb, d, k, metric, 0, lv[0].data_ptr(), lv[1].data_ptr(),
                                      lv[2].data_ptr(), lv[3].data_ptr(), _stream_handle(q.device))
+            if escalate and int(lv[3][:nb].max().item()) != 0:
+                # a replica owns the whole store: its flagged queries climb the ladder locally
+                idx = torch.nonzero(lv[3][:nb]).flatten()
+                self.n_escalations += int(idx.numel())
+                for plan, kp_min in (("scan", 256), ("exact", 0)):
+                    qs = qb[idx].contiguous()
+                    if self._local_search is not None:
+                        r = self._local_search(qs, k, metric, plan=plan, kp_min=kp_min)
+                    else:
+                        r = (torch.empty((idx.numel(), k), dtype=torch.int64, device=q.device),
+                             torch.empty((idx.numel(), k), dtype=torch.float64, device=q.device),
+                             torch.zeros((idx.numel(),), dtype=torch.int32, device=q.device),
+                             torch.zeros((idx.numel(),), dtype=torch.int32, device=q.device))
+                        self._dev.search_dev_ex(qs.data_ptr(), idx.numel(), d, k, metric, r[0].data_ptr(), r[1].data_ptr(),
+                                                r[2].data_ptr(), r[3].data_ptr(), _stream_handle(q.device),
+                                                plan=plan, kp_min=kp_min)
+                    lv[0][idx] = r[0]; lv[1][idx] = r[1]; lv[2][idx] = r[2]; lv[3][idx] = r[3]
+                    idx = idx[r[3].to(torch.bool)]
+                    if idx.numel() == 0:
+                        break
         if self.world == 1:
             return tuple(t[:B] for t in lv)
         gather_blobs(local, self.world, self.group, out=gathered)

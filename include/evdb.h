@@ -41,7 +41,8 @@
 extern "C" {
 #endif
 
-#define EVDB_ABI_VERSION 1
+#define EVDB_ABI_VERSION 2
+#define EVDB_MAX_SHARDS 16
 
 typedef struct evdb_store evdb_store;
 
@@ -66,11 +67,20 @@ enum {
 };
 
 typedef struct evdb_opts {
-    int32_t device;         /* CUDA device ordinal */
+    int32_t device;         /* CUDA device ordinal (n_shards <= 1) */
     int32_t dtype;          /* EVDB_F32 | EVDB_BF16 | EVDB_U8 | EVDB_U4 */
     int32_t dim;            /* 0 = fixed by the first upsert/bulk load (reference :213-217) */
-    int32_t gemm_shadow;    /* F32 stores: keep a bf16 shadow column for the tcgen05 path */
+    int32_t gemm_shadow;    /* F32 stores: keep the fp16 operand column for the tcgen05 path */
     uint64_t capacity_hint; /* rows to reserve up front (0 = grow by doubling) */
+    /* ONE store behind ONE handle on n_shards GPUs of this process (the BEAM is one OS process with
+     * one gen_server per store, reference src/vector_store.erl:38-39): slot g lives on shard
+     * g % n_shards at local slot g / n_shards, so appends and swap-with-last deletes keep every shard
+     * dense and balanced.  Searches fan out on one host thread + stream per device, candidates meet
+     * over peer memory (NVLink), the merged result comes back through the same host entry points.
+     * 0 or 1 = a single-device store on `device`.  The same ordinal may be listed more than once
+     * (several shards on one GPU: tests on a one-GPU box).                                        */
+    int32_t n_shards;
+    int32_t devices[EVDB_MAX_SHARDS];
 } evdb_opts;
 
 typedef struct evdb_stats {
@@ -86,6 +96,16 @@ typedef struct evdb_stats {
     uint64_t escalations;    /* candidate windows that had to be widened */
     uint64_t kernel_launches;/* CUDA kernels launched by this store      */
     double last_search_ms;   /* device time of the last search call      */
+    /* ---- ABI 2 ---- */
+    int32_t n_shards;        /* devices behind this handle (1 = single)  */
+    int32_t gemm_disabled;   /* AUTO gave up the tcgen05 plan for this store: its operand column or
+                                candidate buffers did not fit in device memory (scan plan from then on) */
+    uint64_t shadow_bytes;   /* HBM held by the fp16 operand columns      */
+    uint64_t upserts;        /* rows written by upsert/append/bulk load   */
+    uint64_t deletes;
+    double last_h2d_ms;      /* last host search: query copy, device work, result copy */
+    double last_device_ms;
+    double last_d2h_ms;
 } evdb_stats;
 
 /* ---- process / device ---------------------------------------------------- */
@@ -170,6 +190,19 @@ int evdb_store_search_dev(evdb_store *s, const void *d_queries_f64, int B, int d
                           int metric, uint64_t slot_base, void *d_out_ids_u64,
                           void *d_out_dists_f64, void *d_out_counts_i32,
                           void *d_out_flags_i32, void *stream);
+
+/* The same with the knobs an escalation needs (a sharded caller re-issues flagged queries on every
+ * rank: first with a wider window on the scan plan, then through the exhaustive fp64 plan -- the
+ * ladder evdb_store_search_f64 climbs by itself, src of the rule: DESIGN.md section 4).          */
+typedef struct evdb_search_opts {
+    int32_t plan;         /* EVDB_PLAN_*; AUTO = the store's own plan                              */
+    int32_t kp_min;       /* smallest candidate window to use (0 = default)                        */
+    uint64_t slot_base;   /* returned id = slot_base + slot * slot_stride                          */
+    uint64_t slot_stride; /* 0 or 1 = contiguous block; S = this store holds every S-th global row */
+} evdb_search_opts;
+int evdb_store_search_dev_ex(evdb_store *s, const void *d_queries_f64, int B, int d, int k, int metric,
+                             const evdb_search_opts *o, void *d_out_ids_u64, void *d_out_dists_f64,
+                             void *d_out_counts_i32, void *d_out_flags_i32, void *stream);
 
 /* G-way merge of per-shard results (the step after the NCCL allgather):
  * in: G lists per query, laid out [G][B][k] (ids u64, dists fp64, counts

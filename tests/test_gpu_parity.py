@@ -594,3 +594,33 @@ def test_tma_staged_scan_after_mutations_and_with_wide_windows(native, oracle):
     assert set(s2[0, :3].tolist()) == {first, first + 1, first + 2}
     check(300)
     st.close()
+
+
+@pytest.mark.parametrize("metric", ["euclidean", "manhattan"])
+def test_near_duplicate_cluster_with_an_unrepresentable_query(native, oracle, metric):
+    """Rows much closer to the query than ||q||, and a query that is NOT exact in fp32: the scan sees
+    q narrowed to fp32, which moves every score by up to ||q - q32|| -- far more than the relative
+    arithmetic bound when distances are ~1e-7 ||q||.  The per-query narrowing residual
+    (scan.cu prep_queries_kernel) must enter the window proof so that the result is still exact."""
+    n, d, k = 20000, 128, 10
+    rng = np.random.default_rng(11)
+    q = rng.standard_normal(d) * (1.0 + 1e-9 * rng.standard_normal(d))     # full fp64 mantissas
+    assert not np.array_equal(q, q.astype(np.float32).astype(np.float64))
+    rows = oracle.synth_f64(oracle.SEED_CORPUS, 0, n, d).astype(np.float32)
+    for i in range(600):
+        rows[7 + 31 * i] = (q * (1.0 + 2e-7 * rng.standard_normal(d))).astype(np.float32)
+    st = _store(native)
+    try:
+        st.bulk_load(rows)
+        st.set_plan("scan")
+        slots, dists, counts = st.search(q, k, metric)
+        r, dd = oracle.search(rows.astype(np.float64), q, k, metric)
+        assert slots[0].tolist() == r.tolist()
+        assert dists[0].tolist() == dd.tolist()
+        # an fp32-exact query has no residual: same store, same plan, still exact
+        q32 = q.astype(np.float32).astype(np.float64)
+        slots, dists, counts = st.search(q32, k, metric)
+        r, dd = oracle.search(rows.astype(np.float64), q32, k, metric)
+        assert slots[0].tolist() == r.tolist() and dists[0].tolist() == dd.tolist()
+    finally:
+        st.close()

@@ -41,18 +41,30 @@ def _worker(rank, world, port, n, d, k, out_q):
     lo, hi = shard_bounds(n, world, rank)
     rows = O.synth_f64(O.SEED_CORPUS, lo, hi - lo, d) if hi > lo else np.zeros((0, d))
 
-    def local_search(q, kk, metric):
+    q_all = torch.from_numpy(O.synth_f64(O.SEED_QUERY, 0, 3, d))
+    calls = []
+
+    def local_search(q, kk, metric, plan="auto", kp_min=0):
+        # Stands in for the device path INCLUDING its contract on unproven windows: rank 1 cannot prove
+        # query 1 on the first pass nor with the wider window (it returns a wrong, flagged result), only
+        # the exhaustive plan settles it -- ShardedStore.search must climb the ladder on every rank.
         B = q.shape[0]
+        calls.append((plan, kp_min, B))
         ids = torch.full((B, kk), -1, dtype=torch.int64)
         dd = torch.zeros((B, kk), dtype=torch.float64)
         cnt = torch.zeros((B,), dtype=torch.int32)
+        flg = torch.zeros((B,), dtype=torch.int32)
         for b in range(B):
             if hi > lo:
                 r, dist_ = O.search(rows, q[b].numpy(), kk, metric)
+                unproven = rank == world - 1 and plan != "exact" and torch.equal(q[b], q_all[1])
+                if unproven:
+                    r, dist_ = r[::-1].copy(), dist_[::-1] + 1.0
+                    flg[b] = 1
                 ids[b, :len(r)] = torch.from_numpy(r + lo)
                 dd[b, :len(r)] = torch.from_numpy(dist_)
                 cnt[b] = len(r)
-        return ids, dd, cnt, torch.zeros((B,), dtype=torch.int32)
+        return ids, dd, cnt, flg
 
     def merge(g_ids, g_d, g_c, kk):  # same contract as evdb_merge_topk_dev
         G, B = g_c.shape
@@ -71,28 +83,36 @@ def _worker(rank, world, port, n, d, k, out_q):
     st = ShardedStore(rank=rank, world=world, local_search=local_search, merge=merge)
     st.fill_synthetic(O.SEED_CORPUS, n, d)
     assert (st.lo, st.hi) == (lo, hi)
-    q = torch.from_numpy(O.synth_f64(O.SEED_QUERY, 0, 3, d))
+    q = q_all
     ids, dd, cnt, flags = st.search(q, k, "cosine")
+    assert int(flags.sum()) == 0 and st.n_escalations == 1
+    # the ladder: everything once, then the flagged query alone with a 256-key scan window, then exact
+    assert calls == [("auto", 0, 3), ("scan", 256, 1), ("exact", 0, 1)], calls
+    raw = st.search(q, k, "cosine", escalate=False)
+    assert raw[3].tolist() == [0, 1, 0]          # without the ladder the flag reaches the caller
 
     # replica group: every rank holds the whole store and answers a disjoint block of the queries
     from erlvectordb_b200.sharded import ReplicaGroup
     all_rows = O.synth_f64(O.SEED_CORPUS, 0, n, d)
 
-    def replica_search(qb, kk, metric):
+    def replica_search(qb, kk, metric, plan="auto", kp_min=0):
         B = qb.shape[0]
         r_ids = torch.full((B, kk), -1, dtype=torch.int64)
         r_dd = torch.zeros((B, kk), dtype=torch.float64)
         r_cnt = torch.zeros((B,), dtype=torch.int32)
+        r_flg = torch.zeros((B,), dtype=torch.int32)
         for b in range(B):
             r, dist_ = O.search(all_rows, qb[b].numpy(), kk, metric)
+            if plan == "auto" and torch.equal(qb[b], q_all[2]):   # unproven on the first pass only
+                r, dist_, r_flg[b] = r[::-1].copy(), dist_[::-1] + 1.0, 1
             r_ids[b, :len(r)] = torch.from_numpy(r)
             r_dd[b, :len(r)] = torch.from_numpy(dist_)
             r_cnt[b] = len(r)
-        return r_ids, r_dd, r_cnt, torch.zeros((B,), dtype=torch.int32)
+        return r_ids, r_dd, r_cnt, r_flg
 
     rg = ReplicaGroup(rank=rank, world=world, local_search=replica_search)
-    g_ids, g_dd, g_cnt, _ = rg.search(q, k, "cosine")
-    assert torch.equal(g_ids, ids) and torch.equal(g_dd, dd) and torch.equal(g_cnt, cnt)
+    g_ids, g_dd, g_cnt, g_flg = rg.search(q, k, "cosine")
+    assert torch.equal(g_ids, ids) and torch.equal(g_dd, dd) and torch.equal(g_cnt, cnt) and int(g_flg.sum()) == 0
     out_q.put((rank, ids.numpy(), dd.numpy(), cnt.numpy()))
     dist.barrier()
     dist.destroy_process_group()
