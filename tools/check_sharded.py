@@ -66,7 +66,7 @@ for dtype, metric, n, d, B, k, cluster in CASES:
         st2.close()
     s_ids, s_d, s_c = one.search(qh, k, metric)
     same = np.array_equal(ids.cpu().numpy().astype(np.uint32), s_ids) and np.array_equal(dd.cpu().numpy(), s_d)
-    if cluster:
+    if cluster and B >= 16:   # the tcgen05 pass cannot separate the cluster: the ladder must have been climbed
         same = same and st.n_escalations > 0
     ok &= same
     print(f"rank {rank}/{world}: {dtype} {metric} n={n} d={d} B={B} k={k}{' near-duplicate cluster' if cluster else ''}: "
