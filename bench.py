@@ -6,24 +6,32 @@
 
 Workload (BASELINE.json configs[1]): 1,000,000 x 768 fp32 synthetic corpus, cosine, k = 10,
 query batch 1024 (the headline `value`, tensor-bound) and batch 1 (reported under "batch1",
-HBM-bound).  A step is one search call over one batch.  N > 1 row-shards the SAME corpus over
-the ranks (strong scaling): each GPU searches its shard, candidates are all-gathered over
-NCCL and merged on every rank.
+HBM-bound).  A step is one search call over one batch; consecutive steps use DIFFERENT query
+batches (a pool of 4).  N > 1 row-shards the SAME corpus over the ranks (strong scaling), one
+process per GPU: each GPU searches its shard, candidates meet over peer memory (NVLink).
 
-`value`   : device-timed (CUDA events), queries already resident in HBM.
-`e2e`     : the same metric through the reference-facing call with HOST buffers -- the C-ABI
-            entry evdb_store_search_f64 at N = 1 (ShardedStore.search + copies at N > 1) -- with
-            the host->device query copy and the device->host result copy inside the timed region.
+`value`   : device-timed (CUDA events), queries already resident in HBM, max over ranks.
+`e2e`     : the same metric through the reference-facing C-ABI call evdb_store_search_f64 with
+            PAGEABLE host buffers (what a NIF binary is): host->device query copy and
+            device->host result copy inside the timed region.  N = 1: the rank's own store; N > 1:
+            ONE handle over all N devices (evdb_opts.n_shards, mstore.cu) driven by rank 0's
+            process -- the way one BEAM process would drive the box.
 `roofline`: dominant kernel (scan: HBM bytes; tcgen05 GEMM: flops) timed with CUDA events on its
             launching stream inside the timed region, against MEASURED_PEAKS.json.
 `cpu_baseline`: the CPU oracle (a port of the reference's Erlang arithmetic: full fp64 scan with
             the query norm recomputed per row + full sort) on a bounded sample, rank 0, N = 1.
-The corpus (3.07 GB; 1.5 GB bf16 shadow) is far larger than the 126 MB L2, so consecutive steps
-cannot be served from cache ("inputs larger than L2").
+`config.result_check`: after the timed region the results of every batch size are compared bit for
+            bit with a single-device store's on rank 0 and their digest is printed -- the same digest
+            must appear at N = 1, 2, 4, 8.
+`configs` : the other BASELINE.json configurations (cfg1, cfg3, cfg4_weak, cfg5) as secondary lines,
+            each with its roofline and result digest (skipped with --no-extra).
+The corpus (3.07 GB; 1.5 GB fp16 operand column) is far larger than the 126 MB L2, so consecutive
+steps cannot be served from cache ("inputs larger than L2").
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -37,7 +45,9 @@ sys.path.insert(0, ROOT)
 
 N_ROWS, DIM, K = 1_000_000, 768, 10
 BATCH_MAIN, BATCH_ONE = 1024, 1
+POOL = 4   # distinct query batches rotated through the timed steps
 METRIC_NAME = "QPS (k=10, 1Mx768 cosine, batch 1024)"
+BPR = {"f32": lambda d: 4 * d, "bf16": lambda d: 2 * d, "u8": lambda d: d + 8, "u4": lambda d: (d + 1) // 2 + 8}
 
 
 def peaks():
@@ -99,7 +109,6 @@ class ClockSampler:
 # reference arm: the reference's algorithm (CPU oracle port) on the host cores
 # ---------------------------------------------------------------------------------------
 def cpu_reference_qps(threads: int, sample_rows: int, steps: int, warmup: int):
-    import numpy as np
     from oracle import oracle as O
     rows = O.synth_f32(O.SEED_CORPUS, 0, sample_rows, DIM, threads=threads)
     qs = O.synth_f64(O.SEED_QUERY, 0, threads * (steps + warmup), DIM)
@@ -147,12 +156,23 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------
+def digest(ids, dists) -> str:
+    import numpy as np
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(ids).astype(np.uint32).tobytes())
+    h.update(np.ascontiguousarray(dists, dtype=np.float64).tobytes())
+    return h.hexdigest()[:16]
+
+
 def run_ours(args):
+    import ctypes as C
+
     import numpy as np
     import torch
     import torch.distributed as dist
     from erlvectordb_b200 import _native as N
     from erlvectordb_b200 import synth
+    from erlvectordb_b200.device_store import DeviceStore
     from erlvectordb_b200.sharded import ShardedStore
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -162,29 +182,78 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; erlvectordb_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        # a HOST barrier for the sections where only rank 0 drives the GPUs (an NCCL barrier would park a
+        # spinning kernel on every other GPU for the whole measurement)
+        cpu_group = dist.new_group(backend="gloo")
     rc = N.lib().evdb_init(None, 0)
     if rc != 0:
         raise SystemExit(f"evdb_init: {N.lib().evdb_strerror(rc).decode()}")
-
-    st = ShardedStore(dtype="f32", device=local, rank=rank, world=world)
-    st.fill_synthetic(synth.SEED_CORPUS, N_ROWS, DIM)
     pk = peaks()
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the committed ncu --set full captures
+    if os.path.exists(tp):
+        traffic = json.load(open(tp))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(batch: int, steps: int, warmup: int, sample_clocks: bool):
-        qh = torch.from_numpy(synth.synth(synth.SEED_QUERY, 0, batch, DIM)).pin_memory()
-        qd = qh.to(dev)
-        for _ in range(warmup):
-            out = st.search(qd, K, "cosine")
+    def host_barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=cpu_group)
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def c_abi_search(store: DeviceStore, qn, k, metric, slots, dists, counts):
+        N.check(N.lib().evdb_store_search_f64(
+            store.handle, qn.ctypes.data_as(C.POINTER(C.c_double)), qn.shape[0], qn.shape[1], k, N.METRICS[metric],
+            slots.ctypes.data_as(C.POINTER(C.c_uint32)), dists.ctypes.data_as(C.POINTER(C.c_double)),
+            counts.ctypes.data_as(C.POINTER(C.c_int32))), "evdb_store_search_f64")
+
+    def roofline(plan, kernel_ms, batch, rows_local, d, dtype, tkey=None):
+        if kernel_ms is None or kernel_ms <= 0:
+            return None
+        tr = traffic.get(tkey) if (tkey and world == 1) else None
+        if plan == N.PLAN_GEMM and batch < 128:
+            # a handful of queries: 2*B flop per operand byte is far below the machine balance, the
+            # tcgen05 candidate pass is bound by reading its 2-byte operand column once
+            byts = float(rows_local) * ((d + 63) // 64 * 64) * 2
+            ach = byts / (kernel_ms * 1e-3) / 1e9
+            return {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                    "traffic": tr, "algorithmic_bytes": byts, "peak_source": pk["src"] + " copy bandwidth",
+                    "frac_of_8TBs_nominal": ach / 8000.0,
+                    "kernel": "gemm_topk_kernel (fp16 operand column read once; candidates re-ranked in fp64 from the fp32 rows)",
+                    "kernel_ms": kernel_ms,
+                    "fp32_row_bytes_equivalent_gbs": float(rows_local) * d * 4 / (kernel_ms * 1e-3) / 1e9}
+        if plan == N.PLAN_GEMM:
+            flops = 2.0 * rows_local * d * batch
+            ach = flops / (kernel_ms * 1e-3) / 1e12
+            return {"bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                    "frac": ach / pk["tf_sustained"], "traffic": tr, "algorithmic_flops": flops,
+                    "peak_source": pk["src"] + " bf16 sustained", "frac_of_burst": ach / pk["tf_burst"],
+                    "kernel": "gemm_topk_kernel (tcgen05 kind::f16, fp32 accumulate in TMEM)", "kernel_ms": kernel_ms}
+        byts = float(rows_local) * BPR[dtype](d)   # one corpus pass serves the whole launch
+        ach = byts / (kernel_ms * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                "traffic": tr, "algorithmic_bytes": byts, "peak_source": pk["src"] + " copy bandwidth",
+                "frac_of_8TBs_nominal": ach / 8000.0, "kernel": "scan kernel of the plan", "kernel_ms": kernel_ms}
+
+    def device_timed(st: ShardedStore, n_rows, d, k, metric, batch, steps, warmup, sample_clocks=False, phases=False):
+        """K steps of st.search over rotating resident query batches, CUDA events, max over ranks."""
+        qd = [torch.from_numpy(synth.synth(synth.SEED_QUERY, i * batch, batch, d)).to(dev) for i in range(POOL)]
+        for i in range(warmup):
+            st.search(qd[i % POOL], k, metric, escalate=False)
         barrier()
-        st._dev.profile(True)
-        l0 = st._dev.stats()["kernel_launches"]
         sampler = ClockSampler(local)
         if sample_clocks:
             # nvidia-smi samples every 200 ms and the timed region may last only tens of ms: the
@@ -193,138 +262,208 @@ def run_ours(args):
             # the steady (power-capped) state rather than from a cold burst
             sampler.start()
             t_probe = time.perf_counter()
+            i = 0
             while time.perf_counter() - t_probe < 0.6:
                 for _ in range(8):
-                    st.search(qd, K, "cosine")
+                    st.search(qd[i % POOL], k, metric, escalate=False)
+                    i += 1
                 torch.cuda.synchronize()
+        if st._dev is not None:
+            st._dev.profile(True)
+        l0 = st._dev.stats()["kernel_launches"]
+        if phases:
+            st.phase_events = []
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
-        for _ in range(steps):
-            out = st.search(qd, K, "cosine")
+        for i in range(steps):
+            # enqueue only: the per-call flag read-back of the escalating API would put a host round trip
+            # between steps; every distinct batch goes through that API in result_check below
+            st.search(qd[i % POOL], k, metric, escalate=False)
         e1.record()
         barrier()
-        ms = e0.elapsed_time(e1)
+        ms = max_over_ranks(e0.elapsed_time(e1))
         clocks = sampler.stop() if sample_clocks else None
         nsamp, kms = st._dev.profile_read()
         st._dev.profile(False)
-        launches = st._dev.stats()["kernel_launches"] - l0 + (steps if world > 1 else 0)  # + merge kernel
-        plan = st._dev.stats()["last_plan"]
-        flagged = int(out[3].sum().item())
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        ph = None
+        if phases and st.phase_events:
+            acc = [0.0, 0.0, 0.0]
+            for ev in st.phase_events:
+                for j in range(3):
+                    acc[j] += ev[j].elapsed_time(ev[j + 1])
+            n = len(st.phase_events)
+            ph = {"phase1_prep_seed_gemm_window_push_us": max_over_ranks(acc[0] / n * 1e3),
+                  "phase2_merge_rerank_push_us": max_over_ranks(acc[1] / n * 1e3),
+                  "phase3_final_us": max_over_ranks(acc[2] / n * 1e3),
+                  "gemm_kernel_us": max_over_ranks((kms / nsamp) * 1e3 if nsamp else 0.0),
+                  "how": "CUDA events between the phases on the real GPUs, mean over the timed steps, max over ranks"}
+        st.phase_events = None
+        stt = st._dev.stats()
+        launches = stt["kernel_launches"] - l0 + (steps if (world > 1 and ph is None) else 0)  # + the merge kernel
+        # every distinct batch through the escalating API: nothing unproven may be left
+        esc0 = st.n_escalations
+        for i in range(POOL):
+            out = st.search(qd[i], k, metric)
+            assert int(out[3].sum().item()) == 0
+        return {"ms_per_step": ms / steps, "qps": batch * steps / (ms / 1e3),
+                "kernel_ms": (kms / nsamp) if nsamp else None, "plan": stt["last_plan"], "launches": launches,
+                "clocks": clocks, "phases": ph, "escalated": st.n_escalations - esc0, "qd": qd}
 
-        # ---- end to end: host buffers in, host results out, copies inside the timed region ----
-        h_ids = torch.empty((batch, K), dtype=torch.int64).pin_memory()
-        h_d = torch.empty((batch, K), dtype=torch.float64).pin_memory()
-        if world == 1:
-            import ctypes as C
-            qn = qh.numpy()
-            slots = np.empty((batch, K), dtype=np.uint32)
-            dists = np.empty((batch, K), dtype=np.float64)
-            counts = np.empty(batch, dtype=np.int32)
-
-            def e2e_step():
-                N.check(N.lib().evdb_store_search_f64(
-                    st._dev.handle, qn.ctypes.data_as(C.POINTER(C.c_double)), batch, DIM, K, N.COSINE,
-                    slots.ctypes.data_as(C.POINTER(C.c_uint32)), dists.ctypes.data_as(C.POINTER(C.c_double)),
-                    counts.ctypes.data_as(C.POINTER(C.c_int32))), "evdb_store_search_f64")
-        else:
-            def e2e_step():
-                q2 = qh.to(dev, non_blocking=True)
-                o = st.search(q2, K, "cosine")
-                h_ids.copy_(o[0], non_blocking=True)
-                h_d.copy_(o[1], non_blocking=True)
-                torch.cuda.synchronize()
-        for _ in range(min(warmup, 3)):
-            e2e_step()
-        barrier()
-        lat = []
+    def e2e_timed(store: DeviceStore, d, k, metric, batch, steps, warmup):
+        """The C-ABI host call with pageable numpy buffers, wall clock, rank 0's process."""
+        qn = [np.array(synth.synth(synth.SEED_QUERY, i * batch, batch, d)) for i in range(POOL)]   # pageable
+        slots = np.empty((batch, k), dtype=np.uint32)
+        dists = np.empty((batch, k), dtype=np.float64)
+        counts = np.empty(batch, dtype=np.int32)
+        for i in range(max(3, min(warmup, 5))):
+            c_abi_search(store, qn[i % POOL], k, metric, slots, dists, counts)
+        lat, h2d, dv, d2h = [], [], [], []
         t0 = time.perf_counter()
-        for _ in range(steps):
+        for i in range(steps):
             t1 = time.perf_counter()
-            e2e_step()
+            c_abi_search(store, qn[i % POOL], k, metric, slots, dists, counts)
             lat.append(time.perf_counter() - t1)
-        barrier()
-        e2e_s = time.perf_counter() - t0
+        total = time.perf_counter() - t0
+        for i in range(min(steps, 8)):   # the library's own event split of a call (not in the timed loop)
+            c_abi_search(store, qn[i % POOL], k, metric, slots, dists, counts)
+            s = store.stats()
+            h2d.append(s["last_h2d_ms"]); dv.append(s["last_device_ms"]); d2h.append(s["last_d2h_ms"])
         lat.sort()
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        return {"qps": batch * steps / total, "ms_per_step": total / steps * 1e3,
+                "p50_ms": lat[len(lat) // 2] * 1e3, "p99_ms": lat[min(len(lat) - 1, int(len(lat) * 0.99))] * 1e3,
+                "h2d": batch * d * 8, "d2h": batch * k * 12 + batch * 4,
+                "breakdown_ms": {"h2d": statistics.mean(h2d), "device": statistics.mean(dv), "d2h": statistics.mean(d2h),
+                                 "how": "CUDA events inside the library around the query copy, the device work and the result copy"}}
+
+    def check_results(st: ShardedStore, single: DeviceStore | None, multi: DeviceStore | None, d, k, metric, batch):
+        """Sharded result of pool batch 0 (escalating API) == single-device store == one-handle multi-device store."""
+        qh = np.array(synth.synth(synth.SEED_QUERY, 0, batch, d))
+        out = st.search(torch.from_numpy(qh).to(dev), k, metric)
+        ids, dd = out[0].cpu().numpy(), out[1].cpu().numpy()
+        mine = digest(ids, dd)
+        digs = [mine]
         if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-        return {"ms_total": ms, "ms_per_step": ms / steps, "qps": batch * steps / (ms / 1e3),
-                "kernel_ms": (kms / nsamp) if nsamp else None, "kernel_samples": nsamp, "plan": plan,
-                "launches": launches, "clocks": clocks, "flagged": flagged,
-                "e2e_qps": batch * steps / e2e_s, "e2e_ms_per_step": e2e_s / steps * 1e3,
-                "lat_p50_ms": lat[len(lat) // 2] * 1e3, "lat_p99_ms": lat[min(len(lat) - 1, int(len(lat) * 0.99))] * 1e3,
-                "h2d": batch * DIM * 8, "d2h": batch * K * 16 + batch * 8}
+            digs = [None] * world
+            dist.all_gather_object(digs, mine)
+        res = {"digest": mine, "all_ranks_equal": len(set(digs)) == 1}
+        if rank == 0 and single is not None:
+            s_ids, s_d, _ = single.search(qh, k, metric)
+            res["single_gpu_digest"] = digest(s_ids, s_d)
+            res["identical_to_single_gpu"] = bool(np.array_equal(ids.astype(np.uint32), s_ids) and np.array_equal(dd, s_d))
+        if rank == 0 and multi is not None:
+            m_ids, m_d, _ = multi.search(qh, k, metric)
+            res["one_handle_multi_device_digest"] = digest(m_ids, m_d)
+        return res
 
-    traffic = {}
-    tp = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the committed ncu --set full captures
-    if os.path.exists(tp):
-        traffic = json.load(open(tp))
+    # ================================ headline: configs[1] ================================
+    st = ShardedStore(dtype="f32", device=local, rank=rank, world=world)
+    st.fill_synthetic(synth.SEED_CORPUS, N_ROWS, DIM)
+    rows_local = st.hi - st.lo
+    main = device_timed(st, N_ROWS, DIM, K, "cosine", args.batch, args.steps, args.warmup, sample_clocks=True,
+                        phases=world > 1)
+    one = None
+    if args.batch != BATCH_ONE:
+        one = device_timed(st, N_ROWS, DIM, K, "cosine", BATCH_ONE, max(args.steps * 10, 50), max(args.warmup, 5))
 
-    def roofline(r, batch):
-        rows_local = st.hi - st.lo
-        if r["kernel_ms"] is None:
-            return None
-        if r["plan"] == N.PLAN_GEMM and batch < 128:
-            # a handful of queries: 2*B flop per operand byte is far below the machine balance, the
-            # tcgen05 candidate pass is bound by reading its 2-byte operand column once
-            byts = float(rows_local) * ((DIM + 63) // 64 * 64) * 2
-            ach = byts / (r["kernel_ms"] * 1e-3) / 1e9
-            return {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                    "frac": ach / pk["hbm_gbs"], "traffic": traffic.get("gemm_topk_kernel_b1") if world == 1 else None,
-                    "algorithmic_bytes": byts, "peak_source": pk["src"] + " copy bandwidth",
-                    "frac_of_8TBs_nominal": ach / 8000.0,
-                    "kernel": "gemm_topk_kernel (fp16 operand column read once; candidates re-ranked in fp64 from the fp32 rows)",
-                    "kernel_ms": r["kernel_ms"],
-                    "fp32_row_bytes_equivalent_gbs": float(rows_local) * DIM * 4 / (r["kernel_ms"] * 1e-3) / 1e9}
-        if r["plan"] == N.PLAN_GEMM:
-            flops = 2.0 * rows_local * DIM * batch
-            ach = flops / (r["kernel_ms"] * 1e-3) / 1e12
-            return {"bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / pk["tf_sustained"], "traffic": traffic.get("gemm_topk_kernel") if world == 1 else None,
-                    "algorithmic_flops": flops, "peak_source": pk["src"] + " bf16 sustained",
-                    "frac_of_burst": ach / pk["tf_burst"], "kernel": "gemm_topk_kernel (tcgen05 kind::f16, fp32 accumulate in TMEM)",
-                    "kernel_ms": r["kernel_ms"]}
-        byts = float(rows_local) * DIM * 4 * batch  # one corpus pass per query in the scan plan
-        ach = byts / (r["kernel_ms"] * 1e-3) / 1e9
-        return {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": ach / pk["hbm_gbs"], "traffic": traffic.get("scan_float_kernel") if world == 1 else None,
-                "algorithmic_bytes": byts, "peak_source": pk["src"] + " copy bandwidth",
-                "frac_of_8TBs_nominal": ach / 8000.0, "kernel": "scan_float_kernel", "kernel_ms": r["kernel_ms"]}
-
-    main = timed(args.batch, args.steps, args.warmup, sample_clocks=True)
-    one = timed(BATCH_ONE, max(args.steps * 10, 50), max(args.warmup, 5), sample_clocks=False) \
-        if args.batch != BATCH_ONE else None
+    # the stores the reference-facing call is measured on (and the results are checked against)
+    single = multi = None
+    if rank == 0:
+        if world == 1:
+            single = st._dev
+        else:
+            single = DeviceStore(dtype="f32", device=local)
+            single.fill_synthetic(synth.SEED_CORPUS, N_ROWS, DIM)
+            multi = DeviceStore(dtype="f32", devices=list(range(world)))
+            multi.fill_synthetic(synth.SEED_CORPUS, N_ROWS, DIM)
+    host_barrier()
+    e2e_main = e2e_one = None
+    if rank == 0:
+        host_store = single if world == 1 else multi
+        e2e_main = e2e_timed(host_store, DIM, K, "cosine", args.batch, args.steps, args.warmup)
+        if one is not None:
+            e2e_one = e2e_timed(host_store, DIM, K, "cosine", BATCH_ONE, max(args.steps * 10, 50), 5)
+    host_barrier()
+    chk_main = check_results(st, single, multi, DIM, K, "cosine", args.batch)
+    chk_one = check_results(st, single, multi, DIM, K, "cosine", BATCH_ONE) if one is not None else None
 
     # secondary (N > 1): whole-store replicas answering disjoint query blocks (SURVEY 8f-4, the
     # reference's own scale-out model) -- the throughput alternative to row sharding for a store
     # that fits one GPU.  Reported beside the row-sharded headline, never instead of it.
     replicas = None
-    if world > 1:
+    if world > 1 and not args.no_extra:
         from erlvectordb_b200.sharded import ReplicaGroup
         rg = ReplicaGroup(dtype="f32", device=local, rank=rank, world=world)
         rg.fill_synthetic(synth.SEED_CORPUS, N_ROWS, DIM)
-        qd = torch.from_numpy(synth.synth(synth.SEED_QUERY, 0, args.batch, DIM)).to(dev)
-        for _ in range(args.warmup):
-            rg.search(qd, K, "cosine")
+        qd = main["qd"]
+        for i in range(args.warmup):
+            rg.search(qd[i % POOL], K, "cosine", escalate=False)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(args.steps):
-            rg.search(qd, K, "cosine")
+        for i in range(args.steps):
+            rg.search(qd[i % POOL], K, "cosine", escalate=False)
         e1.record()
         barrier()
-        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        r = rg.search(qd[0], K, "cosine")
         replicas = {"value": args.batch * args.steps / (ms / 1e3), "unit": "queries/s", "ms_per_step": ms / args.steps,
+                    "digest": digest(r[0].cpu().numpy(), r[1].cpu().numpy()),
                     "note": f"{world} whole-store replicas, batch {args.batch} split into disjoint blocks, results all-gathered"}
         rg.close()
+    if multi is not None:
+        multi.close()
+    if single is not None and world > 1:
+        single.close()
+    st.close()
+    del st
+    torch.cuda.empty_cache()
+
+    # ================================ the other BASELINE configurations ================================
+    def extra(name, n_total, d, dtype, metric, k, batch, steps, note, weak=False):
+        s2 = ShardedStore(dtype=dtype, device=local, rank=rank, world=world)
+        s2.fill_synthetic(synth.SEED_CORPUS, n_total, d)
+        r = device_timed(s2, n_total, d, k, metric, batch, steps, 3)
+        ref = None
+        if rank == 0:
+            ref = s2._dev if world == 1 else DeviceStore(dtype=dtype, device=local)
+            if world > 1:
+                ref.fill_synthetic(synth.SEED_CORPUS, n_total, d)
+        chk = check_results(s2, ref, None, d, k, metric, batch)
+        e2e = None
+        if rank == 0 and batch == 1:
+            e2e = e2e_timed(ref, d, k, metric, 1, max(steps, 50), 5)
+        rl = roofline(r["plan"], r["kernel_ms"], batch, s2.hi - s2.lo, d, dtype)
+        rec = {"workload": name, "rows": n_total, "dim": d, "dtype": dtype, "metric": metric, "k": k, "batch": batch,
+               "scaling": "weak" if weak else "strong", "value": r["qps"], "unit": "queries/s", "ms_per_step": r["ms_per_step"],
+               "plan": {1: "scan", 2: "gemm", 3: "exact"}.get(r["plan"]), "roofline": rl, "result_check": chk,
+               "escalated_queries": r["escalated"], "note": note}
+        if e2e is not None:
+            rec["latency_ms_single_gpu_c_abi"] = {"p50": e2e["p50_ms"], "p99": e2e["p99_ms"]}
+        if rank == 0 and world > 1:
+            ref.close()
+        s2.close()
+        del s2
+        torch.cuda.empty_cache()
+        return rec
+
+    configs = None
+    if not args.no_extra:
+        configs = {
+            "cfg1": extra("configs[0]: 10k x128 cosine k=10, batch 1 (the reference's own CPU-runnable case)",
+                          10_000, 128, "f32", "cosine", 10, 1, 200, "L2-resident, latency-bound: no roofline claim"),
+            "cfg3": extra("configs[2]: 10M x128 euclidean k=100, batch 4096 (tcgen05 GEMM + top-k epilogue)",
+                          10_000_000, 128, "f32", "euclidean", 100, 4096, max(3, min(args.steps, 6)),
+                          "row norms ride in the K dimension; fp64 re-rank of the squared-distance candidates"),
+            "cfg4_weak": extra(f"configs[3]: {12.5 * world:g}M x96 quantization_8bit over {world} GPU(s), 12.5M rows per GPU, batch 1",
+                               12_500_000 * world, 96, "u8", "cosine", 10, 1, 100,
+                               "int8 dp4a scan on TMA-staged tiles + peer-memory exchange + merge; weak scaling: north_star's 100M point is N = 8",
+                               weak=True),
+            "cfg5_manhattan": extra("configs[4]: 1M x1536 manhattan k=10, batch 1", 1_000_000, 1536, "f32", "manhattan", 10, 1, 50,
+                                    "bandwidth-bound fp32 scan"),
+            "cfg5_u4": extra("configs[4]: 1M x1536 quantization_4bit cosine k=10, batch 1", 1_000_000, 1536, "u4", "cosine", 10, 1, 100,
+                             "bandwidth-bound packed-nibble scan"),
+        }
 
     cpu = None
     if world == 1 and rank == 0 and not args.no_cpu:
@@ -347,28 +486,36 @@ def run_ours(args):
             "config": {"workload": "1Mx768 fp32 cosine k=10 (BASELINE.json configs[1])", "rows": N_ROWS,
                        "dim": DIM, "k": K, "batch": args.batch, "plan": {1: "scan", 2: "gemm", 3: "exact"}.get(main["plan"]),
                        "sharding": f"rows/{world}" if world > 1 else "none",
+                       "queries": f"{POOL} distinct batches rotated through the steps",
                        "cache": "inputs larger than L2 (3.07 GB fp32 corpus, 126 MB L2)",
-                       "result_check": "candidates re-ranked in exact fp64 on device; ids+distances bit-equal to the oracle in tests/"},
+                       "result_check": chk_main},
             "clocks": main["clocks"],
-            "e2e": {"value": main["e2e_qps"], "unit": "queries/s", "h2d_bytes_per_step": main["h2d"],
-                    "d2h_bytes_per_step": main["d2h"], "ms_per_step": main["e2e_ms_per_step"]},
+            "e2e": {"value": e2e_main["qps"], "unit": "queries/s", "h2d_bytes_per_step": e2e_main["h2d"],
+                    "d2h_bytes_per_step": e2e_main["d2h"], "ms_per_step": e2e_main["ms_per_step"],
+                    "breakdown_ms": e2e_main["breakdown_ms"],
+                    "through": "evdb_store_search_f64, pageable host buffers" +
+                               ("" if world == 1 else f", one handle over {world} devices (evdb_opts.n_shards) in rank 0's process")},
             "gpu_launches": main["launches"],
-            "roofline": roofline(main, args.batch),
+            "roofline": roofline(main["plan"], main["kernel_ms"], args.batch, rows_local, DIM, "f32", "gemm_topk_kernel"),
             "cpu_baseline": cpu,
-            "escalated_queries": main["flagged"],
+            "escalated_queries": main["escalated"],
         }
+        if main["phases"]:
+            out["phases"] = main["phases"]
         if replicas is not None:
             out["replica_groups"] = replicas
         if one is not None:
             out["batch1"] = {"value": one["qps"], "unit": "queries/s", "ms_per_step": one["ms_per_step"],
-                             "latency_ms": {"p50": one["lat_p50_ms"], "p99": one["lat_p99_ms"],
-                                            "how": "wall clock around the host-buffer call"},
-                             "e2e": {"value": one["e2e_qps"], "unit": "queries/s",
-                                     "h2d_bytes_per_step": one["h2d"], "d2h_bytes_per_step": one["d2h"]},
-                             "roofline": roofline(one, BATCH_ONE), "gpu_launches": one["launches"],
-                             "steps": max(args.steps * 10, 50)}
+                             "latency_ms": {"p50": e2e_one["p50_ms"], "p99": e2e_one["p99_ms"],
+                                            "how": "wall clock around the host-buffer C-ABI call"},
+                             "e2e": {"value": e2e_one["qps"], "unit": "queries/s", "h2d_bytes_per_step": e2e_one["h2d"],
+                                     "d2h_bytes_per_step": e2e_one["d2h"], "breakdown_ms": e2e_one["breakdown_ms"]},
+                             "roofline": roofline(one["plan"], one["kernel_ms"], BATCH_ONE, rows_local, DIM, "f32",
+                                                  "gemm_topk_kernel_b1" if one["plan"] == N.PLAN_GEMM else "scan_float_kernel"),
+                             "gpu_launches": one["launches"], "steps": max(args.steps * 10, 50), "result_check": chk_one}
+        if configs is not None:
+            out["configs"] = configs
         print(json.dumps(out))
-    st.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -382,6 +529,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_MAIN)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary BASELINE configurations")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

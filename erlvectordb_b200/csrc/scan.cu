@@ -402,6 +402,62 @@ __device__ __forceinline__ uint64_t quant_key(int sa, int sb, int sc, bool owner
     return key;
 }
 
+// Diagnostics (evdb_debug_quant_dots): the integer digit-plane sums of chosen rows, formed by the SAME
+// quant_chunk arithmetic the scans run, so a test can compare them with integer arithmetic on the host.
+template <int DTYPE>
+__global__ void __launch_bounds__(256) quant_dots_debug_kernel(const uint8_t *__restrict__ rows, size_t row_bytes, int nch,
+                                                               const uint8_t *__restrict__ qdig, int qdig_stride,
+                                                               const uint32_t *__restrict__ slots, int n,
+                                                               long long *__restrict__ out_S, int *__restrict__ out_planes,
+                                                               int *__restrict__ out_csum) {
+    constexpr int UPC = (DTYPE == EVDB_U8) ? 1 : 2;
+    const int lane = threadIdx.x & 31, w = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (w >= n) return;
+    const uint4 *sd = reinterpret_cast<const uint4 *>(qdig);
+    const int plane_u4 = nch * UPC;
+    const uint4 *rp = reinterpret_cast<const uint4 *>(rows + (size_t)slots[w] * row_bytes);
+    int A[1] = {0}, Bm[1] = {0}, Cl[1] = {0};
+    uint32_t cs = 0;
+    for (int c = lane; c < nch; c += 32) {
+        uint4 v[1] = {rp[c]};
+        quant_chunk<DTYPE, 1>(v, c, sd, plane_u4, A, Bm, Cl);
+        const uint32_t ww[4] = {v[0].x, v[0].y, v[0].z, v[0].w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            if (DTYPE == EVDB_U8) cs = dp4a_uu(0x01010101u, ww[t], cs);
+            else { cs = dp4a_uu(0x01010101u, (ww[t] >> 4) & 0x0F0F0F0Fu, cs); cs = dp4a_uu(0x01010101u, ww[t] & 0x0F0F0F0Fu, cs); }
+        }
+    }
+    int sa = A[0], sb = Bm[0], sc = Cl[0];
+    for (int o = 16; o > 0; o >>= 1) {
+        sa += __shfl_xor_sync(0xffffffffu, sa, o);
+        sb += __shfl_xor_sync(0xffffffffu, sb, o);
+        sc += __shfl_xor_sync(0xffffffffu, sc, o);
+        cs += __shfl_xor_sync(0xffffffffu, cs, o);
+    }
+    if (lane == 0) {
+        out_S[w] = kQPlanes == 3 ? ((long long)sa << 16) + ((long long)sb << 8) + (long long)sc : ((long long)sa << 8) + (long long)sb;
+        out_planes[3 * w] = sa; out_planes[3 * w + 1] = sb; out_planes[3 * w + 2] = sc;
+        out_csum[w] = (int)cs;
+    }
+}
+
+int debug_quant_dots(evdb_store *s, const double *d_q64, const uint32_t *d_slots, int n, long long *d_S, int *d_planes,
+                     int *d_csum, float *h_fx, cudaStream_t st) {
+    EVDB_TRY(launch_prep_queries(s, d_q64, 1, EVDB_COSINE, st));
+    const int grid = (n + 7) / 8;
+    if (s->dtype == EVDB_U8)
+        quant_dots_debug_kernel<EVDB_U8><<<grid, 256, 0, st>>>(s->rows, s->row_bytes, s->nch, s->w_qdig, s->dpad, d_slots, n, d_S, d_planes, d_csum);
+    else
+        quant_dots_debug_kernel<EVDB_U4><<<grid, 256, 0, st>>>(s->rows, s->row_bytes, s->nch, s->w_qdig, s->dpad, d_slots, n, d_S, d_planes, d_csum);
+    EVDB_CUDA(cudaGetLastError());
+    QStat qs;
+    EVDB_CUDA(cudaMemcpyAsync(&qs, s->w_qstat, sizeof(qs), cudaMemcpyDeviceToHost, st));
+    EVDB_CUDA(cudaStreamSynchronize(st));
+    *h_fx = qs.fx;
+    return EVDB_OK;
+}
+
 // ----------------------------------------------------------------------------
 // u8 / packed-u4 codes: cosine of an unquantised query against Min + c*Scale
 //   q.y = Min*sum(q) + Scale*sum(q_i c_i);  sum(Q_i c_i) is an exact integer:

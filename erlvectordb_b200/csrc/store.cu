@@ -1090,6 +1090,34 @@ int evdb_store_search_sharded_phase3(evdb_store *s, evdb_exchange *xe, int B, in
                               (const uint64_t *)(w + l.g_off), w + l.m_off, (uint64_t *)d_out_blob, st);
 }
 
+// ---- diagnostics: integer digit-plane sums of the quantized scan -------------------------------
+int evdb_debug_quant_dots(evdb_store *s, const double *query, int d, const uint32_t *slots, int n, int64_t *out_sum,
+                          int32_t *out_planes, int32_t *out_code_sum, int32_t *out_shift) {
+    if (!s || s->multi || !is_quant(s) || !query || !slots || n <= 0 || !out_sum || !out_planes || !out_code_sum || !out_shift)
+        return EVDB_E_BAD_ARG;
+    if (d != s->dim) return EVDB_E_DIM_MISMATCH;
+    for (int i = 0; i < n; ++i) if ((uint64_t)slots[i] >= s->count) return EVDB_E_BAD_ARG;
+    EVDB_TRY(set_device(s));
+    cudaStream_t st = s->stream;
+    const size_t qb = round_up64((size_t)d * 8, 256), sb = round_up64((size_t)n * 4, 256), Sb = round_up64((size_t)n * 8, 256),
+                 pb = round_up64((size_t)n * 12, 256);
+    EVDB_TRY(ensure_bytes(&s->w_tmp, &s->w_tmp_cap, qb + 2 * sb + Sb + pb));
+    uint8_t *w = (uint8_t *)s->w_tmp;
+    double *d_q = (double *)w; uint32_t *d_slots = (uint32_t *)(w + qb); long long *d_S = (long long *)(w + qb + sb);
+    int *d_pl = (int *)(w + qb + sb + Sb), *d_cs = (int *)(w + qb + sb + Sb + pb);
+    EVDB_CUDA(cudaMemcpyAsync(d_q, query, (size_t)d * 8, cudaMemcpyHostToDevice, st));
+    EVDB_CUDA(cudaMemcpyAsync(d_slots, slots, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    float fx = 0.f;
+    EVDB_TRY(debug_quant_dots(s, d_q, d_slots, n, d_S, d_pl, d_cs, &fx, st));
+    EVDB_CUDA(cudaMemcpy(out_sum, d_S, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    EVDB_CUDA(cudaMemcpy(out_planes, d_pl, (size_t)n * 12, cudaMemcpyDeviceToHost));
+    EVDB_CUDA(cudaMemcpy(out_code_sum, d_cs, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    int e = 0;
+    frexp((double)fx, &e);     // fx = 2^-shift = 0.5 * 2^(1-shift)
+    *out_shift = 1 - e;
+    return EVDB_OK;
+}
+
 // ---- standalone codecs ------------------------------------------------------
 static int codec_quantize(int device, int dtype, const double *rows, uint64_t n, int d, uint8_t *codes,
                           double *mins, double *maxs, double *scales, uint8_t *ok) {

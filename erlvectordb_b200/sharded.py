@@ -94,6 +94,7 @@ class ShardedStore:
         self.n_total = 0
         self.dim = 0
         self.n_escalations = 0
+        self.phase_events = None   # a list: the two-phase search records 4 CUDA events per call into it
 
     # -- ingest --------------------------------------------------------------------
     def fill_synthetic(self, seed: int, n_total: int, d: int):
@@ -186,11 +187,22 @@ class ShardedStore:
             return None
         merged, mv = self._buffers(B, k, q.device)[2], self._buffers(B, k, q.device)[4]
         stream = _stream_handle(q.device)
+        ev = None
+        if self.phase_events is not None:   # measurement aid (bench.py): CUDA events between the phases
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
         rc = sharded_phase1(self._dev, xw, q.data_ptr(), B, d, k, metric, self.lo, self.n_total, stream)
         if rc != N.OK:
             raise N.EvdbError(rc, "sharded_phase1")   # the plan was agreed on from global facts: must not fail alone
+        if ev:
+            ev[1].record()
         sharded_phase2(self._dev, xw, xe, q.data_ptr(), B, k, metric, self.n_total, stream)
+        if ev:
+            ev[2].record()
         sharded_phase3(self._dev, xe, B, k, metric, self.n_total, merged.data_ptr(), stream)
+        if ev:
+            ev[3].record()
+            self.phase_events.append(ev)
         return mv
 
     def search(self, q: torch.Tensor, k: int, metric: str = "cosine", escalate: bool = True):

@@ -275,6 +275,16 @@ int evdb_dequantize_4bit(int device, const uint8_t *packed, const double *mins,
  * chunk rotation, dynamic shared memory bytes, consumer groups}; 0 when the register-fed scan
  * would run instead; a negative EVDB_E_* for bad arguments.                              */
 int evdb_debug_scan_tile_plan(int dtype, int dim, int window, uint64_t count, int sm_count, int32_t *out);
+/* The INTEGER part of the quantized scan (replaces dot_product/2 over decompressed lists, reference
+ * src/vector_store.erl:248-249 after src/vector_compression.erl:180-183,201-204), observable: for
+ * each of n slots of a U8/U4 store, out_sum = sum_i Q_i * c_i where c are the row's codes and
+ * Q_i = clamp(rint(query_i * 2^shift)) is the query on the scan's 16-bit fixed-point grid
+ * (*out_shift); out_planes[3*i..] = the signed high-digit and unsigned low-digit dp4a sums the
+ * kernels accumulate (third = 0 with two planes), out_code_sum = sum_i c_i.  Exact integers: a test
+ * compares them with int64 arithmetic on the host (north_star: "integer quantized-code dot
+ * products are bit-exact").                                                                  */
+int evdb_debug_quant_dots(evdb_store *s, const double *query, int d, const uint32_t *slots, int n,
+                          int64_t *out_sum, int32_t *out_planes, int32_t *out_code_sum, int32_t *out_shift);
 
 #ifdef __cplusplus
 }

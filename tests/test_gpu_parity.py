@@ -624,3 +624,44 @@ def test_near_duplicate_cluster_with_an_unrepresentable_query(native, oracle, me
         assert slots[0].tolist() == r.tolist() and dists[0].tolist() == dd.tolist()
     finally:
         st.close()
+
+
+@pytest.mark.parametrize("dtype,d", [("u8", 96), ("u8", 100), ("u4", 1536), ("u4", 77)])
+def test_integer_digit_plane_sums_are_bit_exact(native, oracle, dtype, d):
+    """north_star: "the integer quantized-code dot products are bit-exact".  The dp4a digit-plane sums
+    the quantized scans accumulate (scan.cu quant_chunk) are read back for chosen rows and compared
+    with int64 arithmetic on the codes the reference codec produces (vector_compression.erl:167-199)."""
+    import ctypes as C
+    n = 3000
+    rows = oracle.synth_f64(oracle.SEED_CORPUS, 0, n, d)
+    st = _store(native, dtype)
+    try:
+        st.bulk_load(rows)
+        rng = np.random.default_rng(5)
+        slots = np.array(sorted(set(rng.integers(0, n, 64).tolist()) | {0, n - 1}), dtype=np.uint32)
+        for qi in range(3):
+            q = oracle.synth_f64(oracle.SEED_QUERY, qi, 1, d)[0] * (1.0 if qi < 2 else 37.5)
+            m = len(slots)
+            S = np.zeros(m, dtype=np.int64); planes = np.zeros((m, 3), dtype=np.int32)
+            csum = np.zeros(m, dtype=np.int32); shift = C.c_int32(0)
+            native.check(native.lib().evdb_debug_quant_dots(
+                st.handle, q.ctypes.data_as(C.POINTER(C.c_double)), d, slots.ctypes.data_as(C.POINTER(C.c_uint32)), m,
+                S.ctypes.data_as(C.POINTER(C.c_int64)), planes.ctypes.data_as(C.POINTER(C.c_int32)),
+                csum.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(shift)), "evdb_debug_quant_dots")
+            e = shift.value
+            assert 2.0 ** 14 <= np.max(np.abs(q)) * 2.0 ** e < 2.0 ** 15       # 16-bit grid, top bit used
+            Q = np.clip(np.rint(q * 2.0 ** e), -32768, 32767).astype(np.int64)
+            hi, lo = Q >> 8, Q & 255                                            # signed high digit, unsigned low digit
+            for i, slot in enumerate(slots):
+                if dtype == "u8":
+                    codes, _, _, _ = oracle.quantize_8bit(rows[slot])
+                    c = np.asarray(codes, dtype=np.int64)
+                else:
+                    packed, _, _, _ = oracle.quantize_4bit(rows[slot])
+                    b = np.asarray(packed, dtype=np.int64)
+                    c = np.stack([b >> 4, b & 15], axis=1).reshape(-1)[:d]
+                assert S[i] == int(np.dot(Q, c)), (dtype, d, slot)
+                assert planes[i, 0] == int(np.dot(hi, c)) and planes[i, 1] == int(np.dot(lo, c))
+                assert csum[i] == int(c.sum())
+    finally:
+        st.close()
