@@ -40,6 +40,7 @@ int enif_get_int64(ErlNifEnv *, ERL_NIF_TERM, ErlNifSInt64 *);
 int enif_get_uint64(ErlNifEnv *, ERL_NIF_TERM, ErlNifUInt64 *);
 int enif_inspect_binary(ErlNifEnv *, ERL_NIF_TERM, ErlNifBinary *);
 int enif_is_identical(ERL_NIF_TERM, ERL_NIF_TERM);
+int enif_is_number(ErlNifEnv *, ERL_NIF_TERM);
 #define ERL_NIF_INIT(NAME, FUNCS, LOAD, RELOAD, UPGRADE, UNLOAD) \
     const ErlNifFunc *evdb_nif_init_##NAME(void) { (void)(LOAD); return (FUNCS); }
 #endif

@@ -29,7 +29,7 @@
 
 static ErlNifResourceType *STORE_RT;
 static ERL_NIF_TERM a_ok, a_error, a_none, a_dimension_mismatch, a_invalid_vector_format, a_cosine,
-    a_euclidean, a_manhattan;
+    a_euclidean, a_manhattan, a_enomem;
 
 typedef struct { evdb_store *s; } store_res;
 
@@ -60,6 +60,12 @@ static int list_to_doubles(ErlNifEnv *env, ERL_NIF_TERM list, double **out, unsi
         if (!enif_get_list_cell(env, tail, &head, &tail)) { free(v); return 0; }
         if (enif_get_double(env, head, &d)) v[i] = d;
         else if (enif_get_int64(env, head, &i64)) v[i] = (double)i64;
+        else if (enif_is_number(env, head)) {
+            /* a bignum: is_number/1 accepts it (reference :213-225); its magnitude is >= 2^63, which as a
+             * vector element can only overflow the arithmetic (the reference store would crash with
+             * badarith) -- passed on as an infinity, which the library rejects as invalid_vector_format */
+            v[i] = 1.0 / 0.0;
+        }
         else { free(v); return 0; }
     }
     *out = v;
@@ -76,15 +82,25 @@ static int get_metric(ErlNifEnv *env, ERL_NIF_TERM t, int *m) {
     return 1;
 }
 
-/* new(#{device => I, dtype => 0..3, gemm_shadow => 0|1}) -> {ok, Ref} */
+/* new([Device, ...], Dtype 0..3, GemmShadow 0|1) -> {ok, Ref}
+ * one ordinal = a single-device store; several = ONE store behind one handle on those GPUs
+ * (evdb_opts.n_shards: the BEAM is one OS process, reference src/vector_store.erl:38-39)      */
 static ERL_NIF_TERM nif_new(ErlNifEnv *env, int argc, const ERL_NIF_TERM argv[]) {
-    int device = 0, dtype = EVDB_F32, shadow = 1;
-    if (argc != 3 || !enif_get_int(env, argv[0], &device) || !enif_get_int(env, argv[1], &dtype) ||
-        !enif_get_int(env, argv[2], &shadow))
+    int dtype = EVDB_F32, shadow = 1;
+    unsigned ndev = 0;
+    if (argc != 3 || !enif_get_list_length(env, argv[0], &ndev) || ndev < 1 || ndev > EVDB_MAX_SHARDS ||
+        !enif_get_int(env, argv[1], &dtype) || !enif_get_int(env, argv[2], &shadow))
         return enif_make_badarg(env);
     evdb_opts o;
     memset(&o, 0, sizeof(o));
-    o.device = device;
+    ERL_NIF_TERM head, tail = argv[0];
+    for (unsigned i = 0; i < ndev; ++i) {
+        int dv;
+        if (!enif_get_list_cell(env, tail, &head, &tail) || !enif_get_int(env, head, &dv)) return enif_make_badarg(env);
+        o.devices[i] = dv;
+    }
+    o.device = o.devices[0];
+    o.n_shards = ndev > 1 ? (int)ndev : 0;
     o.dtype = dtype;
     o.gemm_shadow = shadow;
     evdb_store *s = NULL;
@@ -151,8 +167,14 @@ static ERL_NIF_TERM nif_bulk_load_codes(ErlNifEnv *env, int argc, const ERL_NIF_
     if (argc != 6 || !enif_get_resource(env, argv[0], STORE_RT, (void **)&r) ||
         !enif_inspect_binary(env, argv[1], &codes) || !enif_inspect_binary(env, argv[2], &mins) ||
         !enif_inspect_binary(env, argv[3], &scales) || !enif_get_uint64(env, argv[4], &n) ||
-        !enif_get_int(env, argv[5], &d) || mins.size != n * sizeof(double) || scales.size != n * sizeof(double))
+        !enif_get_int(env, argv[5], &d) || d <= 0 || mins.size != n * sizeof(double) || scales.size != n * sizeof(double))
         return enif_make_badarg(env);
+    {   /* the code binary must hold n rows of d bytes (8-bit) or (d+1)/2 bytes (4-bit): a short one would be read past its end */
+        evdb_stats st;
+        if (evdb_store_stats(r->s, &st) != EVDB_OK) return enif_make_badarg(env);
+        const size_t row = st.dtype == EVDB_U8 ? (size_t)d : ((size_t)d + 1) / 2;
+        if ((st.dtype != EVDB_U8 && st.dtype != EVDB_U4) || codes.size != n * row) return enif_make_badarg(env);
+    }
     int rc = evdb_store_bulk_load_codes(r->s, codes.data, (const double *)mins.data,
                                         (const double *)scales.data, n, d);
     return rc == EVDB_OK ? a_ok : mk_error(env, rc);
@@ -171,6 +193,13 @@ static ERL_NIF_TERM nif_delete(ErlNifEnv *env, int argc, const ERL_NIF_TERM argv
     return enif_make_tuple2(env, a_ok, moved < 0 ? a_none : enif_make_int64(env, moved));
 }
 
+/* K > N returns all N rows (lists:sublist/2): the result buffers never need more than count places */
+static int clamp_k(evdb_store *s, int k) {
+    evdb_stats st;
+    if (evdb_store_stats(s, &st) != EVDB_OK) return 0;
+    return (uint64_t)k > st.count ? (int)st.count : k;
+}
+
 /* search(Ref, [number()], K, Metric) -> {ok, [{Distance, Slot}]} ascending by (Distance, Slot) */
 static ERL_NIF_TERM nif_search(ErlNifEnv *env, int argc, const ERL_NIF_TERM argv[]) {
     store_res *r;
@@ -181,8 +210,10 @@ static ERL_NIF_TERM nif_search(ErlNifEnv *env, int argc, const ERL_NIF_TERM argv
         !enif_get_int(env, argv[2], &k) || k < 0 || !get_metric(env, argv[3], &metric))
         return enif_make_badarg(env);
     if (!list_to_doubles(env, argv[1], &q, &n)) return enif_make_tuple2(env, a_error, a_invalid_vector_format);
+    k = clamp_k(r->s, k);   /* lists:sublist/2 tolerates any K: never size buffers from the caller's number */
     uint32_t *slots = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(k ? k : 1));
     double *dists = (double *)malloc(sizeof(double) * (size_t)(k ? k : 1));
+    if (!slots || !dists) { free(q); free(slots); free(dists); return enif_make_tuple2(env, a_error, a_enomem); }
     int32_t count = 0;
     int rc = evdb_store_search_f64(r->s, q, 1, (int)n, k, metric, slots, dists, &count);
     ERL_NIF_TERM out;
@@ -209,10 +240,12 @@ static ERL_NIF_TERM nif_search_batch(ErlNifEnv *env, int argc, const ERL_NIF_TER
         !enif_get_int(env, argv[3], &d) || !enif_get_int(env, argv[4], &k) || k < 0 || B < 0 ||
         !get_metric(env, argv[5], &metric) || qb.size != (size_t)B * (size_t)d * sizeof(double))
         return enif_make_badarg(env);
+    k = clamp_k(r->s, k);
     size_t nk = (size_t)B * (size_t)(k ? k : 1);
     uint32_t *slots = (uint32_t *)malloc(sizeof(uint32_t) * (nk ? nk : 1));
     double *dists = (double *)malloc(sizeof(double) * (nk ? nk : 1));
     int32_t *counts = (int32_t *)calloc((size_t)(B ? B : 1), sizeof(int32_t));
+    if (!slots || !dists || !counts) { free(slots); free(dists); free(counts); return enif_make_tuple2(env, a_error, a_enomem); }
     int rc = evdb_store_search_f64(r->s, (const double *)qb.data, B, d, k, metric, slots, dists, counts);
     ERL_NIF_TERM out;
     if (rc != EVDB_OK) {
@@ -241,6 +274,7 @@ static ERL_NIF_TERM nif_get(ErlNifEnv *env, int argc, const ERL_NIF_TERM argv[])
         !enif_get_uint(env, argv[1], &slot) || !enif_get_int(env, argv[2], &d) || d <= 0)
         return enif_make_badarg(env);
     double *v = (double *)malloc(sizeof(double) * (size_t)d);
+    if (!v) return enif_make_tuple2(env, a_error, a_enomem);
     int rc = evdb_store_get_f64(r->s, slot, v, d);
     ERL_NIF_TERM out;
     if (rc != EVDB_OK) {
@@ -278,6 +312,7 @@ static int load(ErlNifEnv *env, void **priv, ERL_NIF_TERM info) {
     a_cosine = enif_make_atom(env, "cosine");
     a_euclidean = enif_make_atom(env, "euclidean");
     a_manhattan = enif_make_atom(env, "manhattan");
+    a_enomem = enif_make_atom(env, "enomem");
     return evdb_init(NULL, 0) == EVDB_OK ? 0 : -1;  /* no GPU -> the NIF refuses to load: no CPU fallback */
 }
 

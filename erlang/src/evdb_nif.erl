@@ -14,7 +14,8 @@ init() ->
     %% there is deliberately no CPU fallback behind this module
     erlang:load_nif(filename:join(Dir, "evdb_nif"), 0).
 
-new(_Device, _Dtype, _Shadow) -> erlang:nif_error(nif_not_loaded).
+%% Devices :: [non_neg_integer()] -- one ordinal = a single-device store; several = one handle over N GPUs
+new(_Devices, _Dtype, _Shadow) -> erlang:nif_error(nif_not_loaded).
 upsert(_Ref, _Slot, _Vector) -> erlang:nif_error(nif_not_loaded).
 bulk_load(_Ref, _F32Bin, _N, _D) -> erlang:nif_error(nif_not_loaded).
 append(_Ref, _F64Bin, _N, _D) -> erlang:nif_error(nif_not_loaded).

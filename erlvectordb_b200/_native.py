@@ -102,6 +102,7 @@ SYMBOLS = [
     ("evdb_quantize_4bit", _i, [_i, _pd, _u64, _i, _pu8, _pd, _pd, _pd, _pu8]),
     ("evdb_dequantize_8bit", _i, [_i, _pu8, _pd, _pd, _u64, _i, _pd]),
     ("evdb_dequantize_4bit", _i, [_i, _pu8, _pd, _pd, _u64, _i, _pd]),
+    ("evdb_vector_utils_f64", _i, [_i, _i, _pd, _pd, _u64, _i, _pd]),
     ("evdb_debug_scan_tile_plan", _i, [_i, _i, _i, _u64, _i, _pi32]),
     ("evdb_debug_quant_dots", _i, [_vp, _pd, _i, _pu32, _i, _pi64, _pi32, _pi32, _pi32]),
 ]

@@ -49,7 +49,8 @@ def _stale(target: str, deps: list[str]) -> bool:
 
 
 def _compile(nvcc: str, src: str, obj: str) -> None:
-    cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+    extra = os.environ.get("EVDB_NVCC_EXTRA", "").split()   # e.g. -DEVDB_MW_DEBUG for an instrumented A/B build
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")

@@ -218,4 +218,58 @@ int launch_fill_synthetic(evdb_store *s, uint64_t seed, uint64_t row0, uint64_t 
     return EVDB_OK;
 }
 
+// ----------------------------------------------------------------------------
+// vector_utils (reference src/vector_utils.erl:28-57): pairwise functions of two fp64 vectors, one
+// warp per pair, in the reference's operation order (independent products, strictly sequential
+// lists:sum folds, no FMA).  Lane 0 folds the cross terms, lanes 1 / 2 the squares of a / b.
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) vector_utils_kernel(int op, const double *__restrict__ a, const double *__restrict__ b,
+                                                           uint64_t n, int d, double *__restrict__ out) {
+    __shared__ double sp_all[8 * 3 * kExactChunk];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *sp = sp_all + warp * 3 * kExactChunk;
+    for (uint64_t p = (uint64_t)blockIdx.x * 8 + warp; p < n; p += (uint64_t)gridDim.x * 8) {
+        const double *x = a + p * (uint64_t)d, *y = b ? b + p * (uint64_t)d : x;
+        double s = 0.0;   // lane 0: cross terms; lane 1: sum x*x; lane 2: sum y*y
+        for (int base = 0; base < d; base += kExactChunk) {
+            const int cnt = min(kExactChunk, d - base);
+            for (int t = lane; t < cnt; t += kWarp) {
+                const double u = x[base + t], v = y[base + t];
+                double c;
+                if (op == EVDB_VU_EUCLIDEAN) { const double df = __dsub_rn(u, v); c = __dmul_rn(df, df); }   // vector_subtract, then X*X
+                else if (op == EVDB_VU_MANHATTAN) c = fabs(__dsub_rn(u, v));
+                else c = __dmul_rn(u, v);
+                sp[t] = c;
+                sp[kExactChunk + t] = __dmul_rn(u, u);
+                sp[2 * kExactChunk + t] = __dmul_rn(v, v);
+            }
+            __syncwarp();
+            if (lane < 3) s = fold_staged(s, sp + lane * kExactChunk, cnt);
+            __syncwarp();
+        }
+        const double cross = __shfl_sync(0xffffffffu, s, 0), xx = __shfl_sync(0xffffffffu, s, 1), yy = __shfl_sync(0xffffffffu, s, 2);
+        if (lane == 0) {
+            double r;
+            const double n1 = __dsqrt_rn(xx), n2 = __dsqrt_rn(yy);
+            switch (op) {
+                case EVDB_VU_COSINE_SIMILARITY: r = (n1 == 0.0 || n2 == 0.0) ? 0.0 : __ddiv_rn(cross, __dmul_rn(n1, n2)); break;
+                case EVDB_VU_COSINE_DISTANCE: r = (n1 == 0.0 || n2 == 0.0) ? 1.0 : __dsub_rn(1.0, __ddiv_rn(cross, __dmul_rn(n1, n2))); break;
+                case EVDB_VU_EUCLIDEAN: r = __dsqrt_rn(cross); break;
+                case EVDB_VU_MANHATTAN: r = cross; break;
+                case EVDB_VU_DOT: r = cross; break;
+                default: r = n1; break;   // EVDB_VU_NORM
+            }
+            out[p] = r;
+        }
+    }
+}
+
+int launch_vector_utils(int op, const double *d_a, const double *d_b, uint64_t n, int d, double *d_out, cudaStream_t st) {
+    if (n == 0) return EVDB_OK;
+    const uint64_t blocks = (n + 7) / 8;
+    vector_utils_kernel<<<(int)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, st>>>(op, d_a, d_b, n, d, d_out);
+    EVDB_CUDA(cudaGetLastError());
+    return EVDB_OK;
+}
+
 }  // namespace evdb

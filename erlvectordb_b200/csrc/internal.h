@@ -181,6 +181,7 @@ int launch_quantize_rows(int dtype, const double *d_rows64, const float *d_rows3
                          double *maxs, uint8_t *ok, cudaStream_t st);
 int launch_dequantize_rows(int dtype, const uint8_t *codes, size_t code_row_bytes,
                            const double2 *ms64, uint64_t n, int d, double *out, cudaStream_t st);
+int launch_vector_utils(int op, const double *d_a, const double *d_b, uint64_t n, int d, double *d_out, cudaStream_t st);
 int exact_plan_search(evdb_store *s, const double *d_q64, int B, int kk, int kstride, int metric,
                       uint64_t slot_base, uint64_t *d_out_ids, double *d_out_dists,
                       int32_t *d_out_counts, int32_t *d_out_flags, cudaStream_t st);

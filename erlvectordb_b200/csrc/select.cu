@@ -660,7 +660,66 @@ __device__ __forceinline__ void warp_bitonic_smem_pairs(uint64_t *k, uint64_t *v
 }
 
 // keep the `need` smallest of keys[0, T) (need < T), compacted in place to keys[0, need)
+// Returns the need-th smallest of the kSub = 32 * VPL scores a warp holds in registers (VPL per lane).
+template <int VPL>
+__device__ __forceinline__ uint32_t warp_nth_of_regs(const uint32_t (&v)[VPL], int need) {
+    uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) { mn = min(mn, v[i]); mx = max(mx, v[i]); }
+    uint32_t lo = __reduce_min_sync(0xffffffffu, mn), hi = __reduce_max_sync(0xffffffffu, mx);
+    while (lo < hi) {  // invariant: count(v <= hi) >= need > count(v < lo)
+        const uint32_t span = hi - lo, qd = span >> 2;
+        const uint32_t p2 = lo + (span >> 1), p1 = qd ? lo + qd : p2, p3 = qd ? p2 + qd : p2;
+        int c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            c1 += v[i] <= p1 ? 1 : 0;
+            c2 += v[i] <= p2 ? 1 : 0;
+            c3 += v[i] <= p3 ? 1 : 0;
+        }
+        c1 = __reduce_add_sync(0xffffffffu, c1);
+        c2 = __reduce_add_sync(0xffffffffu, c2);
+        c3 = __reduce_add_sync(0xffffffffu, c3);
+        if (c1 >= need) hi = p1;
+        else if (c2 >= need) { lo = p1 + 1; hi = p2; }
+        else if (c3 >= need) { lo = p2 + 1; hi = p3; }
+        else lo = p3 + 1;
+    }
+    return lo;
+}
+
+// Many more keys than wanted (the GEMM plan leaves ~30 x KP per query): the need-th smallest score of a
+// strided SUBSET bounds the need-th smallest overall, so only keys at or below it can matter --
+// about T * need / subset of them.  The subset lives in registers (no shared-memory passes per
+// bisection round); one compaction pass, then the exact selection runs on what is left.
+__device__ __forceinline__ int warp_precut_inplace(uint64_t *keys, int T, int need, int lane) {
+    constexpr int VPL = 8;                       // 256-key subset
+    const uint32_t *hi32 = reinterpret_cast<const uint32_t *>(keys) + 1;
+    const int stride = T / (32 * VPL);
+    uint32_t v[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) v[i] = hi32[2 * ((i * 32 + lane) * stride)];
+    const uint32_t cut = warp_nth_of_regs<VPL>(v, need);
+    int out = 0;
+    const unsigned below = (1u << lane) - 1u;
+    for (int base = 0; base < T; base += 32) {    // in order: the write cursor never passes the read cursor
+        const int i = base + lane;
+        const uint64_t key = i < T ? keys[i] : kKeyMax;
+        const bool keep = i < T && (uint32_t)(key >> 32) <= cut;
+        const unsigned mk = __ballot_sync(0xffffffffu, keep);
+        __syncwarp();
+        if (keep) keys[out + __popc(mk & below)] = key;
+        out += __popc(mk);
+        __syncwarp();
+    }
+    return out;   // >= need
+}
+
 __device__ __forceinline__ void warp_select_inplace(uint64_t *keys, int T, int need, int lane) {
+    if (need <= 64 && T >= 8 * need && T >= 512) {
+        T = warp_precut_inplace(keys, T, need, lane);
+        if (T == need) return;
+    }
     const uint32_t *hi32 = reinterpret_cast<const uint32_t *>(keys) + 1;  // score word of key i at hi32[2*i]
     uint32_t mn = 0xFFFFFFFFu, mx = 0u;
     for (int i = lane; i < T; i += 32) {
@@ -779,11 +838,152 @@ __device__ __forceinline__ double sw_fold_chain(const uint8_t *__restrict__ rows
     return s;
 }
 
-// F32 stores only (the GEMM plan's precondition).
-__global__ void __launch_bounds__(kSwWarps * 32) select_warp_kernel(const SelectArgs a, int B) {
+// ---- the same fold by a GROUP of warps (one query): a leader and kMwProducers producer warps --------
+// One warp per query is bound by its own instruction latency: ~500 instructions per 64-element chunk,
+// each waiting ~5 cycles for the previous one, 12 chunks at d = 768 -- 89 k cycles for a chain whose
+// dependent DADDs need 6.6 k (r02 EVDB_SEL_VARIANT=16 counters).  Here the producer warps form the
+// products of chunk c (two rows per warp instruction, row pairs dealt round-robin) into one half of
+// a double-buffered stage WHILE the leader's lanes fold chunk c-1 out of the other half, one group
+// barrier (bar.sync on the group's own id) per chunk.  At most kMwRows rows are staged per round.
+constexpr int kMwProducers = 3;
+constexpr int kMwGroup = 1 + kMwProducers;         // warps per query
+constexpr int kMwRows = 16;                        // staged rows per round: 2 buffers x 16 rows == the single-warp stage
+constexpr int kMwIt = (kMwRows / 2 + kMwProducers - 1) / kMwProducers;   // row pairs per producer warp and chunk
+static_assert(2 * kMwRows * kSwProdStride <= SwLayout::kUnion, "the double-buffered stage must fit the key buffer it reuses");
+
+__device__ __forceinline__ void group_bar(int id) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kMwGroup * 32) : "memory");
+}
+
+// role 0: the leader (lane r < nrows folds row r and gets its sum back); role 1..kMwProducers: producers.
+// slots: shared memory, the nr row slots of this round (written by the leader before the group's barrier).
+template <int METRIC>
+__device__ __forceinline__ double mw_fold_m(const uint8_t *__restrict__ rows, size_t row_bytes, const double *__restrict__ q,
+                                            int d, uint8_t *stage, const uint32_t *slots, int nr, bool qrow,
+                                            int role, int lane, int bar_id) {
+    constexpr int metric = METRIC;
+    const int nrows = nr + (qrow ? 1 : 0);
+    const int npairs = (nrows + 1) >> 1;
+    const int unit = lane & 15, rsub = lane >> 4;   // a row chunk is 16 units of 4 elements: half a warp per row
+    const int nchunks = (d + kSwKC - 1) / kSwKC;
+    const int nu = (int)(row_bytes >> 4);          // 16-byte units per stored row
+    // producers: the raw rows of one chunk into registers
+    auto load_raw = [&](int kb, uint4 (&raw)[kMwIt]) {
+        const int u = (kb >> 2) + unit;
+#pragma unroll
+        for (int j = 0; j < kMwIt; ++j) {
+            const int it = (role - 1) + kMwProducers * j, r = 2 * it + rsub;
+            raw[j] = make_uint4(0u, 0u, 0u, 0u);
+            if (it < npairs && r < nr && u < nu)
+                raw[j] = __ldg(reinterpret_cast<const uint4 *>(rows + (size_t)slots[r] * row_bytes) + u);
+        }
+    };
+    auto produce = [&](int c, const uint4 (&raw)[kMwIt]) {
+        uint8_t *st = stage + (size_t)(c & 1) * kMwRows * kSwProdStride;
+        const int e0 = c * kSwKC + 4 * unit;
+        double qd[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) qd[i] = e0 + i < d ? __ldg(q + e0 + i) : 0.0;   // L1 hits: the group shares q
+#pragma unroll
+        for (int j = 0; j < kMwIt; ++j) {
+            const int it = (role - 1) + kMwProducers * j, r = 2 * it + rsub;
+            if (it >= npairs || r >= nrows) continue;
+            const uint32_t w[4] = {raw[j].x, raw[j].y, raw[j].z, raw[j].w};
+            double t[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                // F2F.F64.F32 (exact, subnormals included): one issue slot per element; the conversion unit's
+                // 16 lanes/clk/SM (tools/micro/cvt_bench.cu: 2.0 cycles per warp conversion, the same as the
+                // ~8-instruction integer widening) sit idle otherwise
+                const double x = r < nr ? (double)__uint_as_float(w[i]) : qd[i];   // the last row: the query's own squares
+                if (metric == EVDB_COSINE) t[i] = __dmul_rn(qd[i], x);
+                else {
+                    const double df = __dsub_rn(qd[i], x);
+                    t[i] = metric == EVDB_EUCLIDEAN ? __dmul_rn(df, df) : fabs(df);
+                }
+            }
+            double2 *dst = reinterpret_cast<double2 *>(st + (size_t)r * kSwProdStride) + 2 * unit;
+            dst[0] = make_double2(t[0], t[1]);
+            dst[1] = make_double2(t[2], t[3]);
+        }
+    };
+    auto fold = [&](int c, double s) -> double {   // leader: lane r adds the staged terms of chunk c to row r's sum, left to right
+        const int kb = c * kSwKC;
+        const int cnt = d - kb < kSwKC ? d - kb : kSwKC;
+        const double2 *p = reinterpret_cast<const double2 *>(stage + (size_t)(c & 1) * kMwRows * kSwProdStride +
+                                                             (size_t)lane * kSwProdStride);
+        const int pairs = cnt >> 1;
+        // the chain waits 8.6 cycles per DADD whatever else happens: the staged terms of the NEXT four
+        // pairs are requested before the current four are added, so no shared-memory latency joins it
+        double2 v0 = make_double2(0.0, 0.0), v1 = v0, v2 = v0, v3 = v0;
+        if (pairs >= 4) { v0 = p[0]; v1 = p[1]; v2 = p[2]; v3 = p[3]; }
+        int i = 0;
+        for (; i + 4 <= pairs; i += 4) {
+            double2 n0 = v0, n1 = v1, n2 = v2, n3 = v3;
+            if (i + 8 <= pairs) { n0 = p[i + 4]; n1 = p[i + 5]; n2 = p[i + 6]; n3 = p[i + 7]; }
+            s = __dadd_rn(s, v0.x); s = __dadd_rn(s, v0.y);
+            s = __dadd_rn(s, v1.x); s = __dadd_rn(s, v1.y);
+            s = __dadd_rn(s, v2.x); s = __dadd_rn(s, v2.y);
+            s = __dadd_rn(s, v3.x); s = __dadd_rn(s, v3.y);
+            v0 = n0; v1 = n1; v2 = n2; v3 = n3;
+        }
+        for (; i < pairs; ++i) {
+            const double2 v = p[i];
+            s = __dadd_rn(s, v.x);
+            s = __dadd_rn(s, v.y);
+        }
+        if (cnt & 1) s = __dadd_rn(s, reinterpret_cast<const double *>(p)[cnt - 1]);
+        return s;
+    };
+    double s = 0.0;
+    if (role > 0) {
+        // (two register sets -- the loads of chunk c+1 issued before chunk c is worked on -- were tried with
+        // 2 producers per query: the kernel then needs > 80 registers at 768 threads and spills; slower)
+        uint4 ra[kMwIt];
+        load_raw(0, ra);
+        for (int c = 0; c <= nchunks; ++c) {
+            if (c < nchunks) produce(c, ra);
+            if (c + 1 < nchunks) load_raw((c + 1) * kSwKC, ra);   // in flight across the barrier
+            group_bar(bar_id);
+        }
+    } else {
+        for (int c = 0; c <= nchunks; ++c) {
+            if (c > 0 && lane < nrows) s = fold(c - 1, s);
+            group_bar(bar_id);
+        }
+    }
+    return s;
+}
+
+__device__ __forceinline__ double mw_fold(const uint8_t *__restrict__ rows, size_t row_bytes, const double *__restrict__ q,
+                                          int d, int metric, uint8_t *stage, const uint32_t *slots, int nr, bool qrow,
+                                          int role, int lane, int bar_id) {
+    if (metric == EVDB_COSINE) return mw_fold_m<EVDB_COSINE>(rows, row_bytes, q, d, stage, slots, nr, qrow, role, lane, bar_id);
+    if (metric == EVDB_EUCLIDEAN) return mw_fold_m<EVDB_EUCLIDEAN>(rows, row_bytes, q, d, stage, slots, nr, qrow, role, lane, bar_id);
+    return mw_fold_m<EVDB_MANHATTAN>(rows, row_bytes, q, d, stage, slots, nr, qrow, role, lane, bar_id);
+}
+
+// Producer side of a query group: wait for the leader's rounds until it posts nr == 0.
+__device__ __forceinline__ void mw_produce(const uint8_t *rows, size_t row_bytes, const double *q, int d, int metric,
+                                           uint8_t *stage, const uint32_t *slots, const volatile int *ctl, bool qrow,
+                                           int role, int lane, int bar_id) {
+    while (true) {
+        group_bar(bar_id);
+        const int nr = ctl[0];
+        if (nr <= 0) return;
+        mw_fold(rows, row_bytes, q, d, metric, stage, slots, nr, qrow, role, lane, bar_id);
+    }
+}
+
+// F32 stores only (the GEMM plan's precondition).  A CTA serves kSwWarps consecutive queries with
+// kMwGroup warps each: warp w < kSwWarps leads query w (gather, selection, order, fold, proof), warps
+// kSwWarps + kMwProducers*w + {0..} are its producers.
+__global__ void __launch_bounds__(kSwWarps * kMwGroup * 32) select_warp_kernel(const SelectArgs a, int B) {
     using LY = SwLayout;
     extern __shared__ __align__(16) uint8_t smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int role = wid < kSwWarps ? 0 : 1 + (wid - kSwWarps) % kMwProducers;
+    const int warp = wid < kSwWarps ? wid : (wid - kSwWarps) / kMwProducers;   // the query of the CTA this warp works for
     const int b0 = blockIdx.x * kSwWarps;
     const int b = b0 + warp;
     uint8_t *wbase = smem + (size_t)warp * LY::kPerWarp;
@@ -793,6 +993,8 @@ __global__ void __launch_bounds__(kSwWarps * 32) select_warp_kernel(const Select
     int *s_off = reinterpret_cast<int *>(s_cnt + (size_t)(L + 1) * kSwWarps);                // [L+1][8] exclusive prefix of each query's counts
     int *s_moff = s_off + (size_t)(L + 1) * kSwWarps;                                         // [L+1] prefix of max-over-queries counts
     __shared__ int s_car[kSwWarps];
+    __shared__ uint32_t s_slots[kSwWarps][kMwRows];   // the rows of the current fold round, per query group
+    __shared__ int s_nr[kSwWarps];
     // ---- 1. gather: the CTA's 8 consecutive queries together ----
     // The GEMM epilogue leaves thread t's i-th key of a buffer at [i][t]: 8 consecutive queries'
     // keys are 64 contiguous bytes, so one pair of sectors serves all 8 warps (reading each query
@@ -819,7 +1021,7 @@ __global__ void __launch_bounds__(kSwWarps * 32) select_warp_kernel(const Select
     }
     if (threadIdx.x == 0) s_moff[0] = 0;
     __syncthreads();
-    {   // warp w: exclusive prefix of its query's counts; warp 0 also the prefix of the row maxima
+    if (role == 0) {   // leader w: exclusive prefix of its query's counts; warp 0 also the prefix of the row maxima
         int carry = 0;
         for (int l0 = 0; l0 < L; l0 += 32) {
             const int l = l0 + lane;
@@ -890,12 +1092,22 @@ __global__ void __launch_bounds__(kSwWarps * 32) select_warp_kernel(const Select
         __syncthreads();
         pos = carried + s_off[l1 * 8 + warp] - s_off[l0 * 8 + warp];
         if (l1 < L) {  // more to come: reduce to the KP best so the next range fits
-            if (pos > KP) { warp_select_inplace(keys, pos, KP, lane); carried = KP; } else carried = pos;
-            __syncwarp();
-            if (lane == 0) s_car[warp] = carried;
+            if (role == 0) {
+                if (pos > KP) { warp_select_inplace(keys, pos, KP, lane); carried = KP; } else carried = pos;
+                __syncwarp();
+                if (lane == 0) s_car[warp] = carried;
+            } else {
+                carried = pos > KP ? KP : pos;
+            }
         }
         __syncthreads();
         l0 = l1;
+    }
+    if (role > 0) {      // producers: nothing to do for a padding query or when only the window travels
+        if (b >= B || a.win_mode) return;
+        mw_produce(a.rows, a.row_bytes, a.q64 + (size_t)b * a.d, a.d, a.metric, wbase, s_slots[warp], &s_nr[warp],
+                   a.metric == EVDB_COSINE, role, lane, 1 + warp);
+        return;
     }
     if (b >= B) {        // (after the last block barrier)
         if (a.win_mode) push_arrive(a.push, gridDim.x * kSwWarps, lane);
@@ -957,12 +1169,16 @@ __global__ void __launch_bounds__(kSwWarps * 32) select_warp_kernel(const Select
     // strictly left to right.  For cosine one more staged row holds q*q (vector_norm(Query)).
     const double *q = a.q64 + (size_t)b * a.d;
     const bool cosine = a.metric == EVDB_COSINE;
-    const int RC = cosine ? kSwRows - 1 : kSwRows;   // candidates per round
+    const int RC = cosine ? kMwRows - 1 : kMwRows;   // candidates per round
     for (int base = 0; base < nrer; base += RC) {
         const int nr = nrer - base < RC ? nrer - base : RC;
         const bool mine = lane < nr;
         const uint32_t slot = mine ? key_slot(ckeys[base + lane]) : 0u;
-        const double s = sw_fold_chain(a.rows, a.row_bytes, q, a.d, a.metric, stage, slot, nr, cosine, lane);
+        if (mine) s_slots[warp][lane] = slot;
+        if (lane == 0) s_nr[warp] = nr;
+        __syncwarp();
+        group_bar(1 + warp);
+        const double s = mw_fold(a.rows, a.row_bytes, q, a.d, a.metric, stage, s_slots[warp], nr, cosine, 0, lane, 1 + warp);
         double dist;
         if (cosine) {
             const double sq = __shfl_sync(0xffffffffu, s, nr);
@@ -978,6 +1194,9 @@ __global__ void __launch_bounds__(kSwWarps * 32) select_warp_kernel(const Select
             dslot[base + lane] = slot;
         }
     }
+    if (lane == 0) s_nr[warp] = 0;   // no more rounds: the producers leave
+    __syncwarp();
+    group_bar(1 + warp);
     int nsort = 2;
     while (nsort < nrer) nsort <<= 1;
     for (int j = nrer + lane; j < nsort; j += 32) { dkey[j] = kKeyMax; dslot[j] = kKeyMax; }
@@ -1020,7 +1239,7 @@ static int launch_select_warp(const SelectArgs &a, int B, cudaStream_t st) {
     const size_t smem = (size_t)kSwWarps * SwLayout::kPerWarp + (size_t)(a.L + 1) * kSwWarps * 6 + (size_t)(a.L + 1) * 4 + 16;
     if (smem > 220 * 1024) return EVDB_E_UNSUPPORTED;
     EVDB_TRY(ensure_func_smem((const void *)select_warp_kernel, smem));
-    select_warp_kernel<<<(B + kSwWarps - 1) / kSwWarps, kSwWarps * 32, smem, st>>>(a, B);
+    select_warp_kernel<<<(B + kSwWarps - 1) / kSwWarps, kSwWarps * kMwGroup * 32, smem, st>>>(a, B);
     EVDB_CUDA(cudaGetLastError());
     if (a.variant & 16) {
         cudaStreamSynchronize(st);
@@ -1090,10 +1309,21 @@ __device__ __forceinline__ void wait_flags(const unsigned long long *flags, unsi
 constexpr int kShWarps = 4;
 constexpr int kShPerWarp = SwLayout::kUnion + kSwMaxKP * 8 * 3;   // keys / product staging + window copy + owned list + exact values
 
-__global__ void __launch_bounds__(kShWarps * 32) shard_rerank_kernel(const ShardArgs a) {
+// kShWarps queries per CTA, kMwGroup warps each (a leader + the fold's producers, see mw_fold)
+__global__ void __launch_bounds__(kShWarps * kMwGroup * 32) shard_rerank_kernel(const ShardArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ uint32_t s_slots[kShWarps][kMwRows];
+    __shared__ int s_nr[kShWarps];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int role = wid < kShWarps ? 0 : 1 + (wid - kShWarps) % kMwProducers;
+    const int warp = wid < kShWarps ? wid : (wid - kShWarps) / kMwProducers;
     const int b = blockIdx.x * kShWarps + warp;
+    if (role > 0) {
+        if (b < a.B)
+            mw_produce(a.rows, a.row_bytes, a.q64 + (size_t)b * a.d, a.d, a.metric, smem + (size_t)warp * kShPerWarp,
+                       s_slots[warp], &s_nr[warp], a.metric == EVDB_COSINE, role, lane, 1 + warp);
+        return;
+    }
     if (b >= a.B) {
         push_arrive(a.e_push, gridDim.x * kShWarps, lane);
         return;
@@ -1190,14 +1420,18 @@ __global__ void __launch_bounds__(kShWarps * 32) shard_rerank_kernel(const Shard
     // ---- exact fp64 distances of my rows ----
     const double *q = a.q64 + (size_t)b * a.d;
     const bool cosine = a.metric == EVDB_COSINE;
-    const int RC = cosine ? kSwRows - 1 : kSwRows;
+    const int RC = cosine ? kMwRows - 1 : kMwRows;
     for (int base = 0; base < no; base += RC) {
         const int nr = no - base < RC ? no - base : RC;
         const bool mine = lane < nr;
         const int j = mine ? olist[base + lane] : 0;
         const uint64_t grow = mine ? (uint64_t)key_slot(ckeys[j]) : 0ull;
         const uint32_t slot = mine ? (uint32_t)(a.strided ? grow / (uint64_t)a.world : grow - mylo) : 0u;
-        const double s = sw_fold_chain(a.rows, a.row_bytes, q, a.d, a.metric, stage, slot, nr, cosine, lane);
+        if (mine) s_slots[warp][lane] = slot;
+        if (lane == 0) s_nr[warp] = nr;
+        __syncwarp();
+        group_bar(1 + warp);
+        const double s = mw_fold(a.rows, a.row_bytes, q, a.d, a.metric, stage, s_slots[warp], nr, cosine, 0, lane, 1 + warp);
         double dist;
         if (cosine) {
             const double sq = __shfl_sync(0xffffffffu, s, nr);
@@ -1210,7 +1444,9 @@ __global__ void __launch_bounds__(kShWarps * 32) shard_rerank_kernel(const Shard
         }
         if (mine) evals[j] = dist;
     }
+    if (lane == 0) s_nr[warp] = 0;   // the producers leave
     __syncwarp();
+    group_bar(1 + warp);
     for (int i = lane; i < KP; i += 32) push_store(a.e_push, (size_t)b * KP + i, (uint64_t)__double_as_longlong(evals[i]));
     push_arrive(a.e_push, gridDim.x * kShWarps, lane);
 }
@@ -1304,7 +1540,7 @@ int launch_shard_rerank(evdb_store *s, const double *d_q64, int B, int KP, int k
     a.e_push = e_push;
     const size_t smem = (size_t)kShWarps * kShPerWarp;
     EVDB_TRY(ensure_func_smem((const void *)shard_rerank_kernel, smem));
-    shard_rerank_kernel<<<(B + kShWarps - 1) / kShWarps, kShWarps * 32, smem, st>>>(a);
+    shard_rerank_kernel<<<(B + kShWarps - 1) / kShWarps, kShWarps * kMwGroup * 32, smem, st>>>(a);
     EVDB_CUDA(cudaGetLastError());
     s->n_launches++;
     return EVDB_OK;

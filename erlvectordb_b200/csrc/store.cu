@@ -1090,6 +1090,32 @@ int evdb_store_search_sharded_phase3(evdb_store *s, evdb_exchange *xe, int B, in
                               (const uint64_t *)(w + l.g_off), w + l.m_off, (uint64_t *)d_out_blob, st);
 }
 
+// ---- vector_utils pairwise functions ----------------------------------------------------------
+int evdb_vector_utils_f64(int device, int op, const double *a, const double *b, uint64_t n, int d, double *out) {
+    if (!a || !out || d <= 0 || op < EVDB_VU_COSINE_SIMILARITY || op > EVDB_VU_NORM) return EVDB_E_BAD_ARG;
+    if (!b && op != EVDB_VU_NORM) return EVDB_E_BAD_ARG;
+    if (n == 0) return EVDB_OK;
+    if (!rows_finite(a, n * (uint64_t)d) || (b && !rows_finite(b, n * (uint64_t)d))) return EVDB_E_BAD_VECTOR;
+    EVDB_TRY(check_device(device));
+    EVDB_CUDA(cudaSetDevice(device));
+    const size_t bytes = n * (size_t)d * sizeof(double);
+    double *d_a = nullptr, *d_b = nullptr, *d_o = nullptr;
+    int rc = EVDB_OK;
+#define VU(expr) do { if ((expr) != cudaSuccess) { set_cuda_error(cudaGetLastError(), __FILE__, __LINE__); rc = EVDB_E_CUDA; goto done; } } while (0)
+    VU(cudaMalloc((void **)&d_a, bytes));
+    if (b) VU(cudaMalloc((void **)&d_b, bytes));
+    VU(cudaMalloc((void **)&d_o, n * sizeof(double)));
+    VU(cudaMemcpy(d_a, a, bytes, cudaMemcpyHostToDevice));
+    if (b) VU(cudaMemcpy(d_b, b, bytes, cudaMemcpyHostToDevice));
+    rc = launch_vector_utils(op, d_a, d_b, n, d, d_o, 0);
+    if (rc != EVDB_OK) goto done;
+    VU(cudaMemcpy(out, d_o, n * sizeof(double), cudaMemcpyDeviceToHost));
+done:
+#undef VU
+    cudaFree(d_a); cudaFree(d_b); cudaFree(d_o);
+    return rc;
+}
+
 // ---- diagnostics: integer digit-plane sums of the quantized scan -------------------------------
 int evdb_debug_quant_dots(evdb_store *s, const double *query, int d, const uint32_t *slots, int n, int64_t *out_sum,
                           int32_t *out_planes, int32_t *out_code_sum, int32_t *out_shift) {

@@ -266,6 +266,15 @@ int evdb_dequantize_8bit(int device, const uint8_t *codes, const double *mins,
 int evdb_dequantize_4bit(int device, const uint8_t *packed, const double *mins,
                          const double *scales, uint64_t n, int d, double *out);
 
+/* ---- vector_utils (reference src/vector_utils.erl:28-57), computed on the device ----------------
+ * n pairs (a[i], b[i]) of d fp64 numbers -> out[i], in the reference's operation order (independent
+ * products, left-to-right lists:sum, no FMA): bit-equal to the Erlang result.  cosine_similarity/2 is
+ * Dot/(|a||b|) and 0.0 on a zero norm (:28-36) -- similarity, NOT the distance search uses;
+ * EVDB_VU_NORM ignores b (may be NULL).                                                          */
+enum { EVDB_VU_COSINE_SIMILARITY = 0, EVDB_VU_COSINE_DISTANCE = 1, EVDB_VU_EUCLIDEAN = 2, EVDB_VU_MANHATTAN = 3,
+       EVDB_VU_DOT = 4, EVDB_VU_NORM = 5 };
+int evdb_vector_utils_f64(int device, int op, const double *a, const double *b, uint64_t n, int d, double *out);
+
 /* ---- diagnostics -----------------------------------------------------------
  * Host arithmetic only (touches no device): the tile plan the TMA-staged scan over
  * quantization_8bit / _4bit codes (csrc/scan.cu, replaces the maps:fold of

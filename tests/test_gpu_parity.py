@@ -665,3 +665,30 @@ def test_integer_digit_plane_sums_are_bit_exact(native, oracle, dtype, d):
                 assert csum[i] == int(c.sum())
     finally:
         st.close()
+
+
+def test_vector_utils_pairwise_functions_are_bit_exact(native, oracle):
+    """reference src/vector_utils.erl:28-57 (cosine_similarity/2 is row a11 of SURVEY 8a): the device
+    results equal the oracle's strict left-fold restatement bit for bit, zero-norm cases included."""
+    import ctypes as C
+    from erlvectordb_b200 import vector_utils as vu
+    L = oracle.lib()
+    dp = C.POINTER(C.c_double)
+    rng = np.random.default_rng(2)
+    for d in (1, 3, 127, 128, 129, 768, 1000):
+        a = rng.standard_normal((17, d)) * rng.uniform(0.1, 30.0)
+        b = rng.standard_normal((17, d))
+        a[3] = 0.0                      # zero norm -> similarity 0.0
+        b[5] = 0.0
+        sim, eu, ma, dot, nrm = (vu.cosine_similarity(a, b), vu.euclidean_distance(a, b), vu.manhattan_distance(a, b),
+                                 vu.dot_product(a, b), vu.vector_norm(a))
+        for i in range(17):
+            pa, pb = a[i].ctypes.data_as(dp), b[i].ctypes.data_as(dp)
+            assert sim[i] == L.evo_cosine_similarity(pa, pb, d)
+            assert eu[i] == L.evo_euclidean_distance(pa, pb, d)
+            assert ma[i] == L.evo_manhattan_distance(pa, pb, d)
+            assert dot[i] == L.evo_dot(pa, pb, d)
+            assert nrm[i] == L.evo_norm(pa, d)
+        assert sim[3] == 0.0 and sim[5] == 0.0
+    # the documented fixture of SURVEY 8c: [2,3,4] against itself is 1 - (-2.2e-16) away from 1
+    assert vu.cosine_similarity([2.0, 3.0, 4.0], [2.0, 3.0, 4.0]) == 1.0000000000000002

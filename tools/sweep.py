@@ -36,7 +36,7 @@ for spec in sys.argv[1:]:
     st._dev.set_plan(plan)
     q = torch.from_numpy(synth.synth(synth.SEED_QUERY, 0, B, d)).cuda()
     for _ in range(3):
-        o = st.search(q, k, metric)
+        o = st.search(q, k, metric, escalate=False)
     torch.cuda.synchronize()
     st._dev.profile(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -44,7 +44,7 @@ for spec in sys.argv[1:]:
     e0.record()
     t0 = time.perf_counter()
     for _ in range(iters):
-        o = st.search(q, k, metric)
+        o = st.search(q, k, metric, escalate=False)
     host_us = (time.perf_counter() - t0) / iters * 1e6   # host time to ENQUEUE one search (no sync)
     e1.record()
     torch.cuda.synchronize()
