@@ -24,7 +24,7 @@ def test_header_symbols_are_exported_and_bound():
     for s in syms:
         assert hasattr(L, s), f"libevdb_b200.so does not export {s}"
         assert s in bound, f"_native.py does not bind {s}"
-    assert L.evdb_abi_version() == 1
+    assert L.evdb_abi_version() == 2   # EVDB_ABI_VERSION: n_shards / devices in evdb_opts, the ABI-2 tail of evdb_stats
 
 
 def test_error_strings_map_to_reference_atoms():
