@@ -465,6 +465,42 @@ def run_ours(args):
                              "bandwidth-bound packed-nibble scan"),
         }
 
+    # ---- f-3: inserts and deletes at rate through the C ABI (rank 0, one device) ----
+    ingest = None
+    if rank == 0 and not args.no_extra:
+        ing = DeviceStore(dtype="f32", device=local, capacity_hint=70_000)
+        base = np.array(synth.synth(synth.SEED_CORPUS, 0, 4096, DIM))             # pageable fp64 rows, as a NIF sees them
+        ptrs = [base[i].ctypes.data_as(C.POINTER(C.c_double)) for i in range(4096)]   # (the ctypes casts are not the product)
+        up, de = N.lib().evdb_store_upsert_f64, N.lib().evdb_store_delete
+        for i in range(64):                                                        # warm-up: ring, workspaces
+            up(ing.handle, i, ptrs[i], DIM)
+        ing.append(base); ing.flush()
+        c0 = ing.stats()["count"]
+        n_up = 20_000
+        t0 = time.perf_counter()
+        for i in range(n_up):
+            up(ing.handle, c0 + i, ptrs[i & 4095], DIM)
+        ing.flush()
+        t_up = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for i in range(10):
+            ing.append(base)
+        ing.flush()
+        t_app = time.perf_counter() - t0
+        n_del = 20_000
+        cnt = ing.stats()["count"]
+        moved = C.c_int64()
+        t0 = time.perf_counter()
+        for i in range(n_del):
+            de(ing.handle, (i * 7919) % (cnt - i), C.byref(moved))
+        ing.flush()
+        t_del = time.perf_counter() - t0
+        ingest = {"upserts_per_s": n_up / t_up, "append_rows_per_s": 40960 / t_app, "deletes_per_s": n_del / t_del,
+                  "rows": "768 x fp64 from pageable host memory, fp32 store with the fp16 operand column",
+                  "how": "evdb_store_upsert_f64 one row per call (enqueue only: pinned staging ring, narrow + finalize kernels), "
+                         "evdb_store_append_f64 4096 rows per call, evdb_store_delete (one swap kernel); flushed at the end of each leg"}
+        ing.close()
+
     cpu = None
     if world == 1 and rank == 0 and not args.no_cpu:
         threads = os.cpu_count() or 1
@@ -515,6 +551,8 @@ def run_ours(args):
                              "gpu_launches": one["launches"], "steps": max(args.steps * 10, 50), "result_check": chk_one}
         if configs is not None:
             out["configs"] = configs
+        if ingest is not None:
+            out["ingest"] = ingest
         print(json.dumps(out))
     if world > 1:
         dist.barrier()

@@ -69,6 +69,7 @@ SYMBOLS = [
     ("evdb_store_destroy", None, [_vp]),
     ("evdb_store_stats", _i, [_vp, C.POINTER(Stats)]),
     ("evdb_store_set_plan", _i, [_vp, _i]),
+    ("evdb_store_flush", _i, [_vp]),
     ("evdb_store_profile", _i, [_vp, _i]),
     ("evdb_store_profile_read", _i, [_vp, _pi32, _pd]),
     ("evdb_store_upsert_f64", _i, [_vp, _u32, _pd, _i]),

@@ -21,13 +21,25 @@ __global__ void __launch_bounds__(256) finalize_rows_kernel(uint8_t *__restrict_
                                                             float *__restrict__ norm_sq,
                                                             float2 *__restrict__ qcoef,
                                                             const double2 *__restrict__ qms64,
-                                                            __half *__restrict__ shadow) {
+                                                            __half *__restrict__ shadow,
+                                                            const double *__restrict__ src64,
+                                                            const float *__restrict__ src32, int dpad) {
     __shared__ double sp_all[8 * kExactChunk];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *sp = sp_all + warp * kExactChunk;
     for (uint64_t i = (uint64_t)blockIdx.x * 8 + warp; i < n; i += (uint64_t)gridDim.x * 8) {
         const uint64_t r = slot0 + i;
         const uint8_t *row = rows + r * row_bytes;
+        if ((DTYPE == EVDB_F32 || DTYPE == EVDB_BF16) && (src64 || src32)) {
+            // fused ingest of float stores: the staged source row is narrowed into place by this warp first
+            // (one launch per upsert instead of two), then read back below for the cached values
+            for (int c = lane; c < dpad; c += 32) {
+                const float v = c < d ? (src64 ? (float)src64[i * (uint64_t)d + c] : src32[i * (uint64_t)d + c]) : 0.0f;
+                if (DTYPE == EVDB_F32) reinterpret_cast<float *>(rows + r * row_bytes)[c] = v;
+                else reinterpret_cast<__nv_bfloat16 *>(rows + r * row_bytes)[c] = __float2bfloat16_rn(v);
+            }
+            __syncwarp();
+        }
         double mn = 0.0, sc = 0.0;
         if (DTYPE == EVDB_U8 || DTYPE == EVDB_U4) {
             double2 ms = qms64[r];
@@ -54,15 +66,17 @@ __global__ void __launch_bounds__(256) finalize_rows_kernel(uint8_t *__restrict_
     }
 }
 
-int launch_finalize_rows(evdb_store *s, uint64_t slot0, uint64_t n, cudaStream_t st) {
+int launch_finalize_rows(evdb_store *s, uint64_t slot0, uint64_t n, cudaStream_t st, const void *d_src, bool src_f64) {
     if (n == 0) return EVDB_OK;
+    const double *src64 = d_src && src_f64 ? (const double *)d_src : nullptr;
+    const float *src32 = d_src && !src_f64 ? (const float *)d_src : nullptr;
     uint64_t blocks = (n + 7) / 8;
     uint64_t cap = (uint64_t)s->sm_count * 8;
     int grid = (int)(blocks < cap ? blocks : cap);
 #define EVDB_FIN(DT)                                                                              \
     finalize_rows_kernel<DT><<<grid, 256, 0, st>>>(s->rows, s->row_bytes, s->dim, s->spitch, slot0, \
                                                    n, s->norm64, s->inv_norm, s->norm_sq,         \
-                                                   s->qcoef, s->qms64, s->shadow)
+                                                   s->qcoef, s->qms64, s->shadow, src64, src32, s->dpad)
     switch (s->dtype) {
         case EVDB_F32: EVDB_FIN(EVDB_F32); break;
         case EVDB_BF16: EVDB_FIN(EVDB_BF16); break;

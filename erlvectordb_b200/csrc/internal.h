@@ -81,6 +81,13 @@ struct evdb_store {
     void *w_tmp = nullptr;      size_t w_tmp_cap = 0;   // ingest staging / exact plan
     void *w_shard = nullptr;    size_t w_shard_cap = 0; // sharded two-phase search: window blob, exact blob, global window, meta
     void *h_pin = nullptr;      size_t h_pin_cap = 0;   // pinned host staging
+    // ingest at rate: pinned + device staging ring (two halves), enqueue-only upserts / deletes
+    uint8_t *h_ring = nullptr, *d_ring = nullptr;
+    cudaEvent_t ring_ev[2] = {nullptr, nullptr}, ev_ing = nullptr;
+    int ring_busy[2] = {0, 0};
+    uint64_t ring_pos = 0;
+    size_t ring_off = 0;        // bytes of the current half already handed to the stream
+    int ingest_pending = 0;     // work enqueued on `stream` since the last flush
 
     // ---- dominant-kernel profiling (evdb_store_profile) ----
     int prof_on = 0, prof_n = 0;
@@ -174,7 +181,8 @@ int launch_select(evdb_store *s, const double *d_q64, const uint64_t *partial, c
                   int KP, int B, int kk, int kstride, int metric, float eps_abs, float eps_rel,
                   const float *eps_q, int squared, uint64_t slot_base, uint64_t *d_out_ids, double *d_out_dists,
                   int32_t *d_out_counts, int32_t *d_out_flags, cudaStream_t st);
-int launch_finalize_rows(evdb_store *s, uint64_t slot0, uint64_t n, cudaStream_t st);
+// d_src != NULL (float stores): rows [slot0, slot0+n) are first narrowed from the staged n x dim source (fused ingest)
+int launch_finalize_rows(evdb_store *s, uint64_t slot0, uint64_t n, cudaStream_t st, const void *d_src = nullptr, bool src_f64 = false);
 int launch_fill_synthetic(evdb_store *s, uint64_t seed, uint64_t row0, uint64_t rstride, uint64_t n, cudaStream_t st);
 int launch_quantize_rows(int dtype, const double *d_rows64, const float *d_rows32, uint64_t n,
                          int d, uint8_t *codes, size_t code_row_bytes, double2 *ms64,
@@ -233,6 +241,7 @@ int m_get_codes(MStore *m, uint32_t slot, uint8_t *codes, double *mn, double *sc
 int m_fill_synthetic(MStore *m, uint64_t seed, uint64_t row0, uint64_t n, int d);
 int m_stats(MStore *m, evdb_stats *out);
 int m_set_plan(MStore *m, int plan);
+int m_flush(MStore *m);
 int m_profile(MStore *m, int enable);
 int m_profile_read(MStore *m, int32_t *n_samples, double *total_ms);
 int m_search_host(MStore *m, const void *queries, bool is_f64, int B, int d, int k, int metric, uint32_t *out_slots,

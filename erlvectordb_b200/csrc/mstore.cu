@@ -123,6 +123,8 @@ struct MStore {
     std::mutex mu;
     std::condition_variable cv_go, cv_done;
     uint64_t seq = 0;
+    std::atomic<uint64_t> seq_pub{0};   // == seq, readable without the mutex (the workers' spin phase)
+    std::atomic<int> ndone_pub{0};
     int ndone = 0;
     bool quit = false;
     MJob job;
@@ -171,6 +173,10 @@ static int step_stage(MStore *m, int j, const MJob &jb) {
     MShard &h = m->sh[j];
     EVDB_TRY(set_dev(h.dev));
     cudaStream_t st = shard_stream(m, j);
+    if (h.st->ingest_pending && st != h.st->stream && h.st->ev_ing) {   // serial mode: the shard's ingest ran on its own stream
+        EVDB_CUDA(cudaEventRecord(h.st->ev_ing, h.st->stream));
+        EVDB_CUDA(cudaStreamWaitEvent(st, h.st->ev_ing, 0));
+    }
     const int per = (jb.B + m->S - 1) / m->S;
     const int b0 = j * per < jb.B ? j * per : jb.B;
     const int nb = jb.B - b0 < per ? jb.B - b0 : per;
@@ -181,17 +187,20 @@ static int step_stage(MStore *m, int j, const MJob &jb) {
         const size_t esz = jb.is_f64 ? 8 : 4;
         // validate_vector/2 (lists:all(is_number)) and the copy into pinned memory in one pass over my slice
         EVDB_TRY(ensure_bytes(&h.h_stage, &h.h_stage_cap, nq * esz, true));
-        bool ok = true;
+        // (exponent-field tests on the raw words: the loop vectorises, a per-element isfinite() does not)
+        const uint8_t *srcb = (const uint8_t *)jb.queries + (size_t)b0 * jb.d * esz;
+        memcpy(h.h_stage, srcb, nq * esz);
+        uint32_t bad = 0;
         if (jb.is_f64) {
-            const double *src = (const double *)jb.queries + (size_t)b0 * jb.d;
-            double *dst = (double *)h.h_stage;
-            for (size_t i = 0; i < nq; ++i) { const double v = src[i]; const bool f = isfinite(v); ok &= f; dst[i] = f ? v : 0.0; }
+            const uint64_t *w = (const uint64_t *)h.h_stage;
+            for (size_t i = 0; i < nq; ++i) bad |= (uint32_t)(((w[i] >> 52) & 0x7FFu) == 0x7FFu);
         } else {
-            const float *src = (const float *)jb.queries + (size_t)b0 * jb.d;
-            float *dst = (float *)h.h_stage;
-            for (size_t i = 0; i < nq; ++i) { const float v = src[i]; const bool f = isfinite(v); ok &= f; dst[i] = f ? v : 0.0f; }
+            const uint32_t *w = (const uint32_t *)h.h_stage;
+            for (size_t i = 0; i < nq; ++i) bad |= (uint32_t)(((w[i] >> 23) & 0xFFu) == 0xFFu);
         }
-        h.bad_query = !ok;   // the protocol still completes (peers wait for this slice); the caller discards the result
+        // a bad slice still goes through the protocol (peers wait for it) as zeros; the caller discards the result
+        if (bad) memset(h.h_stage, 0, nq * esz);
+        h.bad_query = bad != 0;
         double *mine = h.qbuf + (size_t)b0 * jb.d;
         if (jb.is_f64) {
             EVDB_CUDA(cudaMemcpyAsync(mine, h.h_stage, nq * 8, cudaMemcpyHostToDevice, st));
@@ -315,6 +324,13 @@ static void worker_main(MStore *m, int j) {
     while (true) {
         MJob jb;
         {
+            // searches come in bursts: watch the sequence number for a little while before sleeping on the
+            // condition variable (a futex wake-up costs more than a lone query's device time allows)
+            for (int spin = 0; spin < 20000 && m->seq_pub.load(std::memory_order_acquire) == seen && !m->quit; ++spin) {
+#if defined(__x86_64__)
+                __builtin_ia32_pause();
+#endif
+            }
             std::unique_lock<std::mutex> lk(m->mu);
             m->cv_go.wait(lk, [&] { return m->quit || m->seq != seen; });
             if (m->quit) return;
@@ -327,7 +343,9 @@ static void worker_main(MStore *m, int j) {
         {
             std::lock_guard<std::mutex> lk(m->mu);
             m->sh[j].rc = rc;
-            if (++m->ndone == m->S) m->cv_done.notify_one();
+            ++m->ndone;
+            m->ndone_pub.store(m->ndone, std::memory_order_release);
+            if (m->ndone == m->S) m->cv_done.notify_one();
         }
     }
 }
@@ -349,9 +367,16 @@ static int dispatch(MStore *m, const MJob &jb) {
         std::lock_guard<std::mutex> lk(m->mu);
         m->job = jb;
         m->ndone = 0;
+        m->ndone_pub.store(0, std::memory_order_relaxed);
         m->seq++;
+        m->seq_pub.store(m->seq, std::memory_order_release);
     }
     m->cv_go.notify_all();
+    for (int spin = 0; spin < 200000 && m->ndone_pub.load(std::memory_order_acquire) != m->S; ++spin) {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
     {
         std::unique_lock<std::mutex> lk(m->mu);
         m->cv_done.wait(lk, [&] { return m->ndone == m->S; });
@@ -555,6 +580,10 @@ int m_stats(MStore *m, evdb_stats *out) {
 int m_set_plan(MStore *m, int plan) {
     for (int j = 0; j < m->S; ++j) EVDB_TRY(evdb_store_set_plan(m->sh[j].st, plan));
     m->owner->plan = plan;
+    return EVDB_OK;
+}
+int m_flush(MStore *m) {
+    for (int j = 0; j < m->S; ++j) EVDB_TRY(evdb_store_flush(m->sh[j].st));
     return EVDB_OK;
 }
 int m_profile(MStore *m, int enable) { return evdb_store_profile(m->sh[0].st, enable); }

@@ -279,15 +279,17 @@ static int ensure_out(evdb_store *s, int B, int kstride) {
     return EVDB_OK;
 }
 
+// exponent-field test on the raw words, accumulated without an early exit: the loop vectorises
 static bool all_finite(const void *v, bool is_f64, size_t n) {
+    uint32_t bad = 0;
     if (is_f64) {
-        const double *q = (const double *)v;
-        for (size_t i = 0; i < n; ++i) if (!isfinite(q[i])) return false;
+        const uint64_t *w = (const uint64_t *)v;
+        for (size_t i = 0; i < n; ++i) bad |= (uint32_t)(((w[i] >> 52) & 0x7FFu) == 0x7FFu);
     } else {
-        const float *q = (const float *)v;
-        for (size_t i = 0; i < n; ++i) if (!isfinite(q[i])) return false;
+        const uint32_t *w = (const uint32_t *)v;
+        for (size_t i = 0; i < n; ++i) bad |= (uint32_t)(((w[i] >> 23) & 0xFFu) == 0xFFu);
     }
-    return true;
+    return bad == 0;
 }
 
 // Host-facing search: H2D queries, search, D2H results, escalate flagged queries.
@@ -413,19 +415,15 @@ static int check_dim(const evdb_store *s, int d) {
 static void fix_dim(evdb_store *s, int d) { if (s->dim == 0) set_dim(s, d); }
 
 template <typename T>
-static bool rows_finite(const T *rows, uint64_t n) {
-    for (uint64_t i = 0; i < n; ++i) if (!isfinite((double)rows[i])) return false;
-    return true;
-}
+static bool rows_finite(const T *rows, uint64_t n) { return all_finite(rows, sizeof(T) == 8, (size_t)n); }
 
 int launch_narrow_rows(evdb_store *s, uint64_t dst0, const void *src, bool is_f64, uint64_t n,
                        cudaStream_t st);
 
 // rows: n host rows of d values (fp64 or fp32), `pitch` elements apart (pitch == d: dense; a
 // multi-device store hands every shard each S-th row of the caller's array) -> slots [slot0, slot0+n)
-static int ingest_rows(evdb_store *s, uint64_t slot0, const void *rows, bool is_f64, uint64_t n, size_t pitch = 0) {
+static int ingest_rows_big(evdb_store *s, uint64_t slot0, const void *rows, bool is_f64, uint64_t n, size_t pitch) {
     const int d = s->dim;
-    if (pitch == 0) pitch = (size_t)d;
     cudaStream_t st = s->stream;
     const size_t esz = is_f64 ? sizeof(double) : sizeof(float);
     // chunk so that staging stays <= 256 MiB
@@ -463,6 +461,102 @@ static int ingest_rows(evdb_store *s, uint64_t slot0, const void *rows, bool is_
     }
     s->max_norm_dirty = 1;
     return EVDB_OK;
+}
+
+// Inserts at rate (reference handle_call({insert,..}), src/vector_store.erl:113-141: one call per vector).
+// The rows are copied into a PINNED staging ring (two halves, an event each), so the caller's buffer
+// is free when the call returns, the host->device copy and the row kernels are only ENQUEUED on the
+// store's stream, and nothing waits: a later search on that stream is ordered behind them, a half
+// is waited for only when it comes round again while still in flight.  evdb_store_flush drains.
+constexpr size_t kRingHalf = 4u << 20;
+static int ensure_ring(evdb_store *s) {
+    if (s->h_ring) return EVDB_OK;
+    EVDB_CUDA(cudaMallocHost((void **)&s->h_ring, 2 * kRingHalf));
+    EVDB_CUDA(cudaMalloc((void **)&s->d_ring, 2 * kRingHalf));
+    for (int i = 0; i < 2; ++i) EVDB_CUDA(cudaEventCreateWithFlags(&s->ring_ev[i], cudaEventDisableTiming));
+    EVDB_CUDA(cudaEventCreateWithFlags(&s->ev_ing, cudaEventDisableTiming));
+    return EVDB_OK;
+}
+
+static int ingest_rows(evdb_store *s, uint64_t slot0, const void *rows, bool is_f64, uint64_t n, size_t pitch = 0) {
+    const int d = s->dim;
+    if (pitch == 0) pitch = (size_t)d;
+    const size_t esz = is_f64 ? sizeof(double) : sizeof(float), rowb = (size_t)d * esz;
+    // loads of many megabytes keep the chunked synchronous path (the wait is amortised, no second host copy)
+    if (rowb > kRingHalf || n * rowb >= ((size_t)64 << 20)) return ingest_rows_big(s, slot0, rows, is_f64, n, pitch);
+    EVDB_TRY(ensure_ring(s));
+    cudaStream_t st = s->stream;
+    for (uint64_t r0 = 0; r0 < n;) {
+        // consecutive small upserts share a half (at growing offsets); a half that is full is handed over
+        // with an event and waited for only when the ring comes round to it again
+        int h = (int)(s->ring_pos & 1);
+        if (s->ring_off + rowb > kRingHalf) {
+            EVDB_CUDA(cudaEventRecord(s->ring_ev[h], st));
+            s->ring_busy[h] = 1;
+            s->ring_pos++;
+            s->ring_off = 0;
+            h ^= 1;
+            if (s->ring_busy[h]) { EVDB_CUDA(cudaEventSynchronize(s->ring_ev[h])); s->ring_busy[h] = 0; }
+        }
+        const uint64_t room = (kRingHalf - s->ring_off) / rowb;
+        const uint64_t cnt = n - r0 < room ? n - r0 : room;
+        const size_t off = (size_t)h * kRingHalf + s->ring_off;
+        uint8_t *hp = s->h_ring + off, *dp = s->d_ring + off;
+        const uint8_t *src = (const uint8_t *)rows + r0 * pitch * esz;
+        if (pitch == (size_t)d) memcpy(hp, src, cnt * rowb);
+        else for (uint64_t i = 0; i < cnt; ++i) memcpy(hp + i * rowb, src + i * pitch * esz, rowb);
+        EVDB_CUDA(cudaMemcpyAsync(dp, hp, cnt * rowb, cudaMemcpyHostToDevice, st));
+        const uint64_t dst0 = slot0 + r0;
+        if (is_quant(s)) {
+            EVDB_TRY(launch_quantize_rows(s->dtype, is_f64 ? (const double *)dp : nullptr, is_f64 ? nullptr : (const float *)dp,
+                                          cnt, d, s->rows + dst0 * s->row_bytes, s->row_bytes, s->qms64 + dst0, nullptr, nullptr, st));
+            s->n_launches++;
+            EVDB_TRY(launch_finalize_rows(s, dst0, cnt, st));
+        } else {
+            EVDB_TRY(launch_finalize_rows(s, dst0, cnt, st, dp, is_f64));   // narrows the staged rows into place first
+        }
+        EVDB_TRY(launch_l2_shadow_rows(s, dst0, cnt, st));
+        s->ring_off += (cnt * rowb + 255) & ~(size_t)255;
+        r0 += cnt;
+    }
+    s->ingest_pending = 1;
+    s->max_norm_dirty = 1;
+    return EVDB_OK;
+}
+
+// device work enqueued on the store's own stream (ingest, delete) must precede a search on a caller's stream
+static int order_after_ingest(evdb_store *s, cudaStream_t st) {
+    if (!s->ingest_pending || st == s->stream || !s->ev_ing) return EVDB_OK;
+    EVDB_CUDA(cudaEventRecord(s->ev_ing, s->stream));
+    EVDB_CUDA(cudaStreamWaitEvent(st, s->ev_ing, 0));
+    return EVDB_OK;
+}
+
+// swap-with-last delete in ONE launch: every column of row `last` -> row `slot`
+__global__ void __launch_bounds__(256) delete_swap_kernel(uint8_t *rows, size_t row_bytes, double *norm64, float *inv_norm,
+                                                          float *norm_sq, float2 *qcoef, double2 *qms64, __half *shadow,
+                                                          int spitch, __half *shadow_l2, __half *l2_tail, int l2_pitch,
+                                                          uint64_t slot, uint64_t last) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(rows + last * row_bytes);
+    uint4 *dst = reinterpret_cast<uint4 *>(rows + slot * row_bytes);
+    for (size_t i = threadIdx.x; i < row_bytes / 16; i += blockDim.x) dst[i] = src[i];
+    if (shadow) {
+        const uint4 *s2 = reinterpret_cast<const uint4 *>(shadow + last * (size_t)spitch);
+        uint4 *d2 = reinterpret_cast<uint4 *>(shadow + slot * (size_t)spitch);
+        for (int i = threadIdx.x; i < spitch / 8; i += blockDim.x) d2[i] = s2[i];
+    }
+    if (shadow_l2) {
+        const uint4 *s3 = reinterpret_cast<const uint4 *>(shadow_l2 + last * (size_t)l2_pitch);
+        uint4 *d3 = reinterpret_cast<uint4 *>(shadow_l2 + slot * (size_t)l2_pitch);
+        for (int i = threadIdx.x; i < l2_pitch / 8; i += blockDim.x) d3[i] = s3[i];
+        if (threadIdx.x < 2) reinterpret_cast<uint4 *>(l2_tail + slot * 16)[threadIdx.x] = reinterpret_cast<const uint4 *>(l2_tail + last * 16)[threadIdx.x];
+    }
+    if (threadIdx.x == 0) {
+        norm64[slot] = norm64[last];
+        inv_norm[slot] = inv_norm[last];
+        norm_sq[slot] = norm_sq[last];
+        if (qcoef) { qcoef[slot] = qcoef[last]; qms64[slot] = qms64[last]; }
+    }
 }
 
 template <typename SRC, int DTYPE>
@@ -723,6 +817,10 @@ void evdb_store_destroy(evdb_store *s) {
     cudaFree(s->w_partial); cudaFree(s->w_ids); cudaFree(s->w_dists); cudaFree(s->w_counts);
     cudaFree(s->w_tmp); cudaFree(s->w_shard);
     if (s->h_pin) cudaFreeHost(s->h_pin);
+    if (s->h_ring) cudaFreeHost(s->h_ring);
+    cudaFree(s->d_ring);
+    for (int i = 0; i < 2; ++i) if (s->ring_ev[i]) cudaEventDestroy(s->ring_ev[i]);
+    if (s->ev_ing) cudaEventDestroy(s->ev_ing);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->ev2) cudaEventDestroy(s->ev2);
@@ -761,6 +859,18 @@ int evdb_store_stats(evdb_store *s, evdb_stats *out) {
     out->last_h2d_ms = s->last_h2d_ms;
     out->last_device_ms = s->last_device_ms;
     out->last_d2h_ms = s->last_d2h_ms;
+    return EVDB_OK;
+}
+
+int evdb_store_flush(evdb_store *s) {
+    if (!s) return EVDB_E_BAD_ARG;
+    if (s->multi) return m_flush(s->multi);
+    EVDB_TRY(set_device(s));
+    EVDB_CUDA(cudaStreamSynchronize(s->stream));
+    EVDB_CUDA(cudaGetLastError());
+    s->ingest_pending = 0;
+    s->ring_busy[0] = s->ring_busy[1] = 0;
+    s->ring_off = 0;
     return EVDB_OK;
 }
 
@@ -847,26 +957,16 @@ int evdb_store_delete(evdb_store *s, uint32_t slot, int64_t *moved_from) {
     uint64_t last = s->count - 1;
     cudaStream_t st = s->stream;
     if ((uint64_t)slot != last) {
-        EVDB_CUDA(cudaMemcpyAsync(s->rows + (size_t)slot * s->row_bytes, s->rows + last * s->row_bytes, s->row_bytes, cudaMemcpyDeviceToDevice, st));
-        EVDB_CUDA(cudaMemcpyAsync(s->norm64 + slot, s->norm64 + last, sizeof(double), cudaMemcpyDeviceToDevice, st));
-        EVDB_CUDA(cudaMemcpyAsync(s->inv_norm + slot, s->inv_norm + last, sizeof(float), cudaMemcpyDeviceToDevice, st));
-        EVDB_CUDA(cudaMemcpyAsync(s->norm_sq + slot, s->norm_sq + last, sizeof(float), cudaMemcpyDeviceToDevice, st));
-        if (is_quant(s)) {
-            EVDB_CUDA(cudaMemcpyAsync(s->qcoef + slot, s->qcoef + last, sizeof(float2), cudaMemcpyDeviceToDevice, st));
-            EVDB_CUDA(cudaMemcpyAsync(s->qms64 + slot, s->qms64 + last, sizeof(double2), cudaMemcpyDeviceToDevice, st));
-        }
-        if (s->shadow)
-            EVDB_CUDA(cudaMemcpyAsync(s->shadow + (size_t)slot * s->spitch, s->shadow + last * (size_t)s->spitch, (size_t)s->spitch * 2, cudaMemcpyDeviceToDevice, st));
-        if (s->shadow_l2 && (uint64_t)slot < s->l2_valid) {
-            if (last < s->l2_valid)
-            {
-                EVDB_CUDA(cudaMemcpyAsync(s->shadow_l2 + (size_t)slot * s->l2_pitch, s->shadow_l2 + last * (size_t)s->l2_pitch, (size_t)s->l2_pitch * 2, cudaMemcpyDeviceToDevice, st));
-                EVDB_CUDA(cudaMemcpyAsync(s->l2_tail + (size_t)slot * 16, s->l2_tail + last * 16, 32, cudaMemcpyDeviceToDevice, st));
-            }
-            else
-                s->l2_valid = slot;
-        }
-        EVDB_CUDA(cudaStreamSynchronize(st));
+        // the euclidean operand column follows only where both rows are current; otherwise the hole is rebuilt at the next search
+        const bool l2 = s->shadow_l2 && (uint64_t)slot < s->l2_valid && last < s->l2_valid;
+        if (s->shadow_l2 && (uint64_t)slot < s->l2_valid && !l2) s->l2_valid = slot;
+        delete_swap_kernel<<<1, 256, 0, st>>>(s->rows, s->row_bytes, s->norm64, s->inv_norm, s->norm_sq,
+                                             is_quant(s) ? s->qcoef : nullptr, s->qms64, s->shadow, s->spitch,
+                                             l2 ? s->shadow_l2 : nullptr, s->l2_tail, s->l2_pitch, (uint64_t)slot, last);
+        EVDB_CUDA(cudaGetLastError());
+        s->n_launches++;
+        if (!s->ev_ing) EVDB_CUDA(cudaEventCreateWithFlags(&s->ev_ing, cudaEventDisableTiming));
+        s->ingest_pending = 1;     // enqueued, not waited for: ordered before any later work on the store's stream
         if (moved_from) *moved_from = (int64_t)last;
     }
     s->count = last;
@@ -970,6 +1070,7 @@ int evdb_store_search_dev(evdb_store *s, const void *d_queries_f64, int B, int d
     if (d != s->dim) return EVDB_E_DIM_MISMATCH;
     EVDB_TRY(set_device(s));
     cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    EVDB_TRY(order_after_ingest(s, st));
     EVDB_TRY(search_core(s, (const double *)d_queries_f64, B, k, k, metric, 0, EVDB_PLAN_AUTO,
                          slot_base, (uint64_t *)d_out_ids_u64, (double *)d_out_dists_f64,
                          (int32_t *)d_out_counts_i32, (int32_t *)d_out_flags_i32, st));
@@ -988,6 +1089,7 @@ int evdb_store_search_dev_ex(evdb_store *s, const void *d_queries_f64, int B, in
     if (d != s->dim) return EVDB_E_DIM_MISMATCH;
     EVDB_TRY(set_device(s));
     cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    EVDB_TRY(order_after_ingest(s, st));
     const uint64_t keep_mul = s->slot_mul;
     s->slot_mul = o->slot_stride > 1 ? o->slot_stride : 1;
     const int rc = search_core(s, (const double *)d_queries_f64, B, k, k, metric, o->kp_min, o->plan, o->slot_base,
@@ -1047,6 +1149,7 @@ int evdb_store_search_sharded_phase1(evdb_store *s, evdb_exchange *xw, const voi
         return EVDB_E_UNSUPPORTED;
     EVDB_TRY(set_device(s));
     cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    EVDB_TRY(order_after_ingest(s, st));
     EVDB_TRY(ensure_bytes(&s->w_shard, &s->w_shard_cap, l.total));
     int lists = 0;
     const float *eps_q = nullptr;

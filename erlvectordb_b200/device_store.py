@@ -55,6 +55,10 @@ class DeviceStore:
         N.check(N.lib().evdb_store_stats(self._h, C.byref(st)), "evdb_store_stats")
         return {f: getattr(st, f) for f, _ in N.Stats._fields_}
 
+    def flush(self):
+        """Wait for every enqueued upsert / append / delete (they return before the device has run them)."""
+        N.check(N.lib().evdb_store_flush(self._h), "evdb_store_flush")
+
     def set_plan(self, plan):
         N.check(N.lib().evdb_store_set_plan(self._h, N.PLANS.get(plan, plan)), "evdb_store_set_plan")
 

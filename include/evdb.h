@@ -142,6 +142,10 @@ int evdb_store_upsert_f32(evdb_store *s, uint32_t slot, const float *vec, int d)
  * transfer and one finalize pass instead of n; same validation and error codes as upsert.      */
 int evdb_store_append_f64(evdb_store *s, const double *rows, uint64_t n, int d, uint64_t *first_slot);
 int evdb_store_append_f32(evdb_store *s, const float *rows, uint64_t n, int d, uint64_t *first_slot);
+/* upsert / append / delete only ENQUEUE their device work (the rows are staged through pinned memory, so
+ * the caller's buffer is free on return; searches are ordered behind them).  flush waits for everything
+ * enqueued so far and reports a device error that surfaced since -- terminate/2, sync/1 and tests call it. */
+int evdb_store_flush(evdb_store *s);
 /* Replace the whole content with n rows (vector_store:init/1 bulk load). */
 int evdb_store_bulk_load_f32(evdb_store *s, const float *rows, uint64_t n, int d);
 int evdb_store_bulk_load_f64(evdb_store *s, const double *rows, uint64_t n, int d);

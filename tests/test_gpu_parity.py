@@ -692,3 +692,78 @@ def test_vector_utils_pairwise_functions_are_bit_exact(native, oracle):
         assert sim[3] == 0.0 and sim[5] == 0.0
     # the documented fixture of SURVEY 8c: [2,3,4] against itself is 1 - (-2.2e-16) away from 1
     assert vu.cosine_similarity([2.0, 3.0, 4.0], [2.0, 3.0, 4.0]) == 1.0000000000000002
+
+
+@pytest.mark.parametrize("dtype", ["f32", "u8"])
+def test_enqueue_only_insert_delete_search_stream_equals_oracle(native, oracle, dtype):
+    """f-3 (reference src/vector_store.erl:113-141,152-164): upserts and deletes only enqueue their device
+    work (pinned staging ring, one delete kernel, no wait); a search issued right after must still see
+    exactly the store the reference would hold.  After EVERY step the device answer equals the oracle's
+    on a host-side model of the rows (swap-with-last slot discipline), without any flush in between."""
+    d, k = 40, 5
+    rng = np.random.default_rng(123)
+    pool = oracle.synth_f64(oracle.SEED_CORPUS, 0, 300, d)
+    qs = oracle.synth_f64(oracle.SEED_QUERY, 0, 3, d)
+    st = _store(native, dtype)
+    model = []     # model[slot] = the fp64 row the reference would search (decoded codes for u8)
+
+    def seen(v):
+        if dtype == "f32":
+            return v.astype(np.float32).astype(np.float64)
+        c, mn, mx, sc = oracle.quantize_8bit(v)
+        return oracle.dequantize_8bit(c, mn, sc)
+
+    try:
+        for step in range(220):
+            op = rng.integers(0, 10)
+            if not model or op < 5:
+                v = pool[rng.integers(0, 300)] * rng.uniform(0.5, 2.0)
+                assert st.upsert(len(model), v) == 0
+                model.append(seen(v))
+            elif op < 7:
+                slot = int(rng.integers(0, len(model)))
+                v = pool[rng.integers(0, 300)]
+                assert st.upsert(slot, v) == 0
+                model[slot] = seen(v)
+            else:
+                slot = int(rng.integers(0, len(model)))
+                moved = st.delete(slot)
+                last = len(model) - 1
+                assert moved == (last if slot != last else -1)
+                model[slot] = model[last]
+                model.pop()
+            if model:
+                rows = np.stack(model)
+                metric = ("cosine", "euclidean", "manhattan")[step % 3] if dtype == "f32" else "cosine"
+                slots, dists, counts = st.search(qs[step % 3], k, metric)
+                r, dd = oracle.search(rows, qs[step % 3], k, metric)
+                assert counts[0] == len(r) and slots[0, :len(r)].tolist() == r.tolist(), (step, op)
+                assert dists[0, :len(r)].tolist() == dd.tolist(), (step, op)
+        first = st.append(pool[:200])          # crosses several ring halves when rows are long; here one
+        assert first == len(model)
+        model.extend(seen(v) for v in pool[:200])
+        slots, dists, counts = st.search(qs, k, "cosine")
+        for b in range(3):
+            r, dd = oracle.search(np.stack(model), qs[b], k, "cosine")
+            assert slots[b].tolist() == r.tolist() and dists[b].tolist() == dd.tolist()
+        st.flush()
+        s = st.stats()
+        assert s["count"] == len(model) and s["upserts"] >= 200 and s["deletes"] > 0
+    finally:
+        st.close()
+
+
+def test_long_rows_wrap_the_staging_ring(native, oracle):
+    """Rows of 0.5 MB (d = 65536 fp64): eight fit a ring half, so a 40-row append reuses both halves
+    several times while earlier copies are still in flight."""
+    d, n = 65536, 40
+    rows = oracle.synth_f64(oracle.SEED_CORPUS, 0, n, d)
+    st = _store(native, "f32")
+    try:
+        assert st.append(rows) == 0
+        for slot in (0, 7, 8, 15, 16, 39):
+            assert np.array_equal(st.get(slot), rows[slot])
+        s, dd, c = st.search(rows[17], 3, "euclidean")
+        assert s[0, 0] == 17 and dd[0, 0] == 0.0
+    finally:
+        st.close()
