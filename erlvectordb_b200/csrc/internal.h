@@ -171,7 +171,7 @@ constexpr int kRawMaxLists = 640;  // NG * parts <= 148 * 4
 
 // ---- launchers (each returns EVDB_OK or an error; all async on `st`) ----
 int launch_prep_queries(evdb_store *s, const double *d_q64, int B, int metric, cudaStream_t st);
-int scan_grid_size(evdb_store *s, int metric, int KP, int *G_out);
+int scan_grid_size(evdb_store *s, int metric, int KP, int B, int *G_out);
 int debug_quant_dots(evdb_store *s, const double *d_q64, const uint32_t *d_slots, int n, long long *d_S, int *d_planes,
                      int *d_csum, float *h_fx, cudaStream_t st);
 int launch_scan(evdb_store *s, int metric, const ScanArgs &a, cudaStream_t st);

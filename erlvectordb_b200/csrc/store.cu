@@ -231,7 +231,7 @@ int search_core(evdb_store *s, const double *d_q64, int B, int k, int kstride, i
         EVDB_TRY(launch_prep_queries(s, d_q64, B, metric, st));
         s->last_plan = EVDB_PLAN_SCAN;
         int G = 0;
-        int rc = scan_grid_size(s, metric, KP, &G);
+        int rc = scan_grid_size(s, metric, KP, B, &G);
         if (rc == EVDB_E_UNSUPPORTED) {
             s->last_plan = EVDB_PLAN_EXACT;
             return exact_plan_search(s, d_q64, B, kk, kstride, metric, slot_base, d_ids, d_dists,

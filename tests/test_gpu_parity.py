@@ -767,3 +767,35 @@ def test_long_rows_wrap_the_staging_ring(native, oracle):
         assert s[0, 0] == 17 and dd[0, 0] == 0.0
     finally:
         st.close()
+
+
+@pytest.mark.parametrize("dtype,metric", [("f32", "manhattan"), ("f32", "euclidean"), ("f32", "cosine"),
+                                          ("bf16", "cosine"), ("bf16", "manhattan"), ("bf16", "euclidean")])
+def test_multi_query_scan_batches_equal_single_query_passes(native, oracle, dtype, metric):
+    """Batches on the plans without a GEMM form share every row load between up to 8 queries
+    (scan_float_mq_kernel).  The answers must not depend on how queries are grouped: every batch size,
+    ragged last groups included, returns what the one-query-per-pass kernel returns -- and for fp32
+    stores that is the oracle's result bit for bit."""
+    n, d, k = 30011, 200, 10
+    rows = oracle.synth_f64(oracle.SEED_CORPUS, 0, n, d)
+    st = _store(native, dtype)
+    try:
+        st.bulk_load(rows)
+        st.set_plan("scan")
+        qs = oracle.synth_f64(oracle.SEED_QUERY, 0, 19, d)
+        single = [st.search(qs[b], k, metric) for b in range(19)]       # B = 1: one query per pass
+        for B in (2, 3, 4, 5, 8, 9, 17, 19):
+            slots, dists, counts = st.search(qs[:B], k, metric)
+            for b in range(B):
+                assert slots[b].tolist() == single[b][0][0].tolist(), (B, b)
+                assert dists[b].tolist() == single[b][1][0].tolist(), (B, b)
+        if dtype == "f32":
+            for b in range(19):
+                r, dd = oracle.search(rows, qs[b], k, metric)
+                assert single[b][0][0].tolist() == r.tolist() and single[b][1][0].tolist() == dd.tolist()
+        slots, dists, counts = st.search(qs[:6], 100, metric)            # a 128-key window through the same kernel
+        for b in range(6):
+            s1, d1, _ = st.search(qs[b], 100, metric)
+            assert slots[b].tolist() == s1[0].tolist() and dists[b].tolist() == d1[0].tolist()
+    finally:
+        st.close()
