@@ -15,25 +15,25 @@
 // re-ranks them in exact fp64 and proves the window complete -- returned distances never see
 // fp16.
 //
-// Kernel anatomy (one persistent CTA per SM, 384 threads, no cluster):
+// Kernel anatomy (one persistent CTA per SM, 640 threads; d in [512, 1024]: CTA pairs as 2-CTA clusters):
 //   warp 0   TMA producer: cp.async.bulk.tensor 2D tiles (128B swizzle) of Q [128 x 64] and
-//            V [256 x 64] into a 4-stage shared-memory ring, mbarrier complete_tx
-//   warp 1   MMA issuer: one elected thread, tcgen05.mma cta_group::1 kind::f16, M=128 N=256
-//            K=16, up to 4 per stage; tcgen05.commit frees the stage / publishes the accumulator
+//            V [256 x 64] into a 4-stage shared-memory ring (6 stages of Q + half of V in the pair
+//            variant), mbarrier complete_tx
+//   warp 1   MMA issuer: one elected thread, tcgen05.mma kind::f16, M=128 (cta_group::1) or M=256
+//            (cta_group::2, issued by the pair's leader) x N=256 x K=16, up to 4 per stage;
+//            tcgen05.commit frees the stage / publishes the accumulator
 //   warp 2   TMEM allocator (512 columns = 2 accumulator stages x 256 fp32 columns)
-//   warps 4-11 epilogue: thread t owns TMEM lane t == query t of the CTA's 128-query block, two
-//            warps per lane quarter split the 256 columns; tcgen05.ld 32 columns at a time.
+//   warps 4-19 epilogue (16 warps): thread t owns TMEM lane t == query t of the CTA's 128-query block,
+//            four warps per lane quarter take 64 of the 256 columns each; tcgen05.ld 32 columns at a time.
 //            The score stream is filtered in the ACCUMULATOR domain: a 3-input-max tree over
-//            the 32 values (20 FMNMX3/FMNMX) against the query's admission threshold; only a
-//            chunk that beats it is expanded, and its hits are appended to the query's private
-//            candidate buffer (global memory, L2 resident).  A buffer that nears capacity is
-//            reduced to its KP best by value bisection with warp population counts (no sort),
-//            which also tightens the threshold.
+//            the 32 values against the query's admission threshold; only a chunk that beats it is
+//            expanded, and its hits are appended to the query's private candidate buffer (global
+//            memory, L2 resident).  A buffer that nears capacity is reduced to its KP best by value
+//            bisection with warp population counts (no sort), which also tightens the threshold.
 // A CTA keeps one query block for a whole sweep over its share of the corpus tiles; the 256-row
 // corpus tile is shared by the MB CTAs working on different query blocks at the same time (L2
 // hits).  Thresholds start from a sampled pre-pass (the same kernel in pooling mode over a strided
-// row sample).  A separate flush kernel (one warp per list) turns the buffers into the sorted
-// KP-key lists select.cu merges.
+// row sample).  The raw candidate buffers go to select.cu unsorted (select_warp_kernel gathers them).
 #include <cuda.h>
 #include <math.h>
 #include <stdlib.h>

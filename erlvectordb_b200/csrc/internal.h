@@ -29,6 +29,19 @@ constexpr int kProfMax = 512;
 
 namespace evdb { struct MStore; }
 
+namespace evdb {
+// what a captured search graph was built for: shape, store state, and the buffers baked into its nodes
+struct GraphKey {
+    int B = -1, k = 0, metric = 0, f64 = 0;
+    uint64_t count = 0, epoch = 0;
+    const void *q = nullptr, *out = nullptr, *pin = nullptr;
+    bool operator==(const GraphKey &o) const {
+        return B == o.B && k == o.k && metric == o.metric && f64 == o.f64 && count == o.count && epoch == o.epoch &&
+               q == o.q && out == o.out && pin == o.pin;
+    }
+};
+}  // namespace evdb
+
 // Device-resident store.  One owner thread at a time (the store's gen_server).
 struct evdb_store {
     evdb::MStore *multi = nullptr;   // n_shards > 1: this handle only fronts the shard stores (mstore.cu)
@@ -88,6 +101,12 @@ struct evdb_store {
     uint64_t ring_pos = 0;
     size_t ring_off = 0;        // bytes of the current half already handed to the stream
     int ingest_pending = 0;     // work enqueued on `stream` since the last flush
+    // small host searches replayed as one CUDA graph (store.cu search_host)
+    evdb::GraphKey gkey, last_key;
+    cudaGraphExec_t gexec = nullptr;
+    uint64_t graph_epoch = 0, graph_launches = 0;
+    int graph_plan = 0, graph_broken = 0;
+    void *h_gq = nullptr; size_t h_gq_cap = 0;   // pinned slot the graph copies its queries from
 
     // ---- dominant-kernel profiling (evdb_store_profile) ----
     int prof_on = 0, prof_n = 0;

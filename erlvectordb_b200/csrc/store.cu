@@ -132,6 +132,7 @@ static int ensure_capacity(evdb_store *s, uint64_t need) {
     if (s->dtype == EVDB_F32 && s->gemm_shadow)
         EVDB_TRY(regrow(&s->shadow, live, ncap, (size_t)s->spitch * sizeof(__half), s->stream));
     s->capacity = ncap;
+    s->graph_epoch++;
     return EVDB_OK;
 }
 
@@ -271,14 +272,6 @@ __global__ void widen_kernel(const float *__restrict__ in, double *__restrict__ 
         out[i] = (double)in[i];
 }
 
-static int ensure_out(evdb_store *s, int B, int kstride) {
-    size_t nk = (size_t)B * (kstride > 0 ? kstride : 1);
-    EVDB_TRY(ensure_bytes((void **)&s->w_ids, &s->w_ids_cap, nk * sizeof(uint64_t)));
-    EVDB_TRY(ensure_bytes((void **)&s->w_dists, &s->w_dists_cap, nk * sizeof(double)));
-    EVDB_TRY(ensure_bytes((void **)&s->w_counts, &s->w_counts_cap, sizeof(int32_t) * 2 * (size_t)B));
-    return EVDB_OK;
-}
-
 // exponent-field test on the raw words, accumulated without an early exit: the loop vectorises
 static bool all_finite(const void *v, bool is_f64, size_t n) {
     uint32_t bad = 0;
@@ -323,43 +316,115 @@ static int search_host(evdb_store *s, const void *queries, bool is_f64, int B, i
     cudaStream_t st = s->stream;
     const int kk = (uint64_t)k < s->count ? k : (int)s->count;
     const int kstride = kk;
+    const size_t esz = is_f64 ? sizeof(double) : sizeof(float);
+    const size_t nk = (size_t)B * kstride;
+    // one result blob on the device, one copy back: [ids u64][distances f64][counts i32][flags i32]
+    const size_t pin_need = nk * (sizeof(uint64_t) + sizeof(double)) + sizeof(int32_t) * 2 * (size_t)B;
     EVDB_TRY(ensure_bytes((void **)&s->w_q64, &s->w_q64_cap, nq * sizeof(double)));
-    EVDB_TRY(ensure_out(s, B, kstride));
-    EVDB_CUDA(cudaEventRecord(s->ev0, st));
-    if (is_f64) {
-        EVDB_CUDA(cudaMemcpyAsync(s->w_q64, queries, nq * sizeof(double), cudaMemcpyHostToDevice, st));
-    } else {
-        EVDB_TRY(ensure_bytes(&s->w_tmp, &s->w_tmp_cap, nq * sizeof(float)));
-        EVDB_CUDA(cudaMemcpyAsync(s->w_tmp, queries, nq * sizeof(float), cudaMemcpyHostToDevice, st));
-        widen_kernel<<<(int)((nq + 255) / 256 < 1024 ? (nq + 255) / 256 : 1024), 256, 0, st>>>(
-            (const float *)s->w_tmp, s->w_q64, nq);
-        s->n_launches++;
-        EVDB_CUDA(cudaGetLastError());
-    }
-    int32_t *d_counts = s->w_counts, *d_flags = s->w_counts + B;
-    EVDB_CUDA(cudaEventRecord(s->ev2, st));
-    EVDB_TRY(search_core(s, s->w_q64, B, k, kstride, metric, 0, EVDB_PLAN_AUTO, 0, s->w_ids,
-                         s->w_dists, d_counts, d_flags, st));
-    EVDB_CUDA(cudaEventRecord(s->ev3, st));
-    size_t nk = (size_t)B * kstride;
-    size_t pin_need = nk * (sizeof(uint64_t) + sizeof(double)) + sizeof(int32_t) * 2 * (size_t)B;
+    EVDB_TRY(ensure_bytes((void **)&s->w_ids, &s->w_ids_cap, pin_need));
     EVDB_TRY(ensure_bytes(&s->h_pin, &s->h_pin_cap, pin_need, true));
+    if (!is_f64) EVDB_TRY(ensure_bytes(&s->w_tmp, &s->w_tmp_cap, nq * sizeof(float)));
+    uint64_t *d_ids = s->w_ids;
+    double *d_dists = (double *)(d_ids + nk);
+    int32_t *d_counts = (int32_t *)(d_dists + nk), *d_flags = d_counts + B;
     uint64_t *h_ids = (uint64_t *)s->h_pin;
     double *h_d = (double *)(h_ids + nk);
     int32_t *h_c = (int32_t *)(h_d + nk);
-    EVDB_CUDA(cudaMemcpyAsync(h_ids, s->w_ids, nk * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    EVDB_CUDA(cudaMemcpyAsync(h_d, s->w_dists, nk * sizeof(double), cudaMemcpyDeviceToHost, st));
-    EVDB_CUDA(cudaMemcpyAsync(h_c, s->w_counts, sizeof(int32_t) * 2 * (size_t)B, cudaMemcpyDeviceToHost, st));
-    EVDB_CUDA(cudaEventRecord(s->ev1, st));
+
+    // ---- small batches: the whole call as ONE replayed CUDA graph ----------------------------------
+    // A lone query on a small store is bound by the host: a dozen driver calls (copies, launches, event
+    // records) cost more than the device work.  The second consecutive call of the same shape is
+    // captured -- query copy from a pinned slot, every kernel of the plan, result copy -- and later calls
+    // replay it with one cudaGraphLaunch.  Any ingest, delete, plan change or reallocation bumps
+    // graph_epoch and drops the graph; profiling (evdb_store_profile) and debug knobs bypass it.
+    GraphKey key;
+    key.B = B; key.k = k; key.metric = metric; key.f64 = is_f64 ? 1 : 0; key.count = s->count; key.epoch = s->graph_epoch;
+    key.q = s->w_q64; key.out = s->w_ids; key.pin = s->h_pin;
+    static int graphs_on = -1;
+    if (graphs_on < 0) { const char *e = getenv("EVDB_GRAPHS"); graphs_on = e ? atoi(e) : 1; }
+    const bool small = graphs_on && B <= 16 && !s->prof_on && !s->graph_broken && nq * esz <= (64u << 10);
+    bool replayed = false, capturing = false;
+    if (small && s->gexec && key == s->gkey) {
+        memcpy(s->h_gq, queries, nq * esz);
+        EVDB_CUDA(cudaEventRecord(s->ev0, st));
+        EVDB_CUDA(cudaGraphLaunch(s->gexec, st));
+        EVDB_CUDA(cudaEventRecord(s->ev1, st));
+        s->n_launches += s->graph_launches;
+        s->last_plan = s->graph_plan;
+        s->n_rows_scanned += (uint64_t)B * s->count;
+        replayed = true;
+    } else if (small && key == s->last_key) {
+        if (s->gexec) { cudaGraphExecDestroy(s->gexec); s->gexec = nullptr; }
+        EVDB_TRY(ensure_bytes(&s->h_gq, &s->h_gq_cap, 64u << 10, true));
+        key.pin = s->h_pin;
+        memcpy(s->h_gq, queries, nq * esz);
+        capturing = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (!capturing) { cudaGetLastError(); s->graph_broken = 1; }
+    }
+    s->last_key = key;
+    if (!replayed) {
+        const uint64_t launches0 = s->n_launches;
+        const void *src = capturing ? s->h_gq : queries;
+        int rc = EVDB_OK;
+        do {
+#define SH(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_cuda_error(_e, __FILE__, __LINE__); rc = _e == cudaErrorMemoryAllocation ? EVDB_E_OOM : EVDB_E_CUDA; } } while (0)
+            if (!capturing) SH(cudaEventRecord(s->ev0, st));
+            if (rc != EVDB_OK) break;
+            if (is_f64) {
+                SH(cudaMemcpyAsync(s->w_q64, src, nq * sizeof(double), cudaMemcpyHostToDevice, st));
+            } else {
+                SH(cudaMemcpyAsync(s->w_tmp, src, nq * sizeof(float), cudaMemcpyHostToDevice, st));
+                widen_kernel<<<(int)((nq + 255) / 256 < 1024 ? (nq + 255) / 256 : 1024), 256, 0, st>>>(
+                    (const float *)s->w_tmp, s->w_q64, nq);
+                s->n_launches++;
+                SH(cudaGetLastError());
+            }
+            if (rc != EVDB_OK) break;
+            if (!capturing) SH(cudaEventRecord(s->ev2, st));
+            rc = search_core(s, s->w_q64, B, k, kstride, metric, 0, EVDB_PLAN_AUTO, 0, d_ids, d_dists, d_counts, d_flags, st);
+            if (rc != EVDB_OK) break;
+            if (!capturing) SH(cudaEventRecord(s->ev3, st));
+            SH(cudaMemcpyAsync(s->h_pin, s->w_ids, pin_need, cudaMemcpyDeviceToHost, st));
+            if (!capturing) SH(cudaEventRecord(s->ev1, st));
+#undef SH
+        } while (0);
+        if (capturing) {
+            cudaGraph_t g = nullptr;
+            const cudaError_t ce = cudaStreamEndCapture(st, &g);
+            if (rc == EVDB_OK && ce == cudaSuccess && g && cudaGraphInstantiate(&s->gexec, g, 0) == cudaSuccess) {
+                s->gkey = key;
+                s->graph_launches = s->n_launches - launches0;
+                s->graph_plan = s->last_plan;
+                EVDB_CUDA(cudaEventRecord(s->ev0, st));
+                EVDB_CUDA(cudaGraphLaunch(s->gexec, st));
+                EVDB_CUDA(cudaEventRecord(s->ev1, st));
+                replayed = true;
+            } else {
+                // something in this plan cannot be captured (it allocates, synchronises or failed): never try again
+                cudaGetLastError();
+                s->gexec = nullptr;
+                s->graph_broken = 1;
+                if (g) cudaGraphDestroy(g);
+                return search_host(s, queries, is_f64, B, d, k, metric, out_slots, out_dists, out_counts);
+            }
+            if (g) cudaGraphDestroy(g);
+        } else if (rc != EVDB_OK) {
+            return rc;
+        }
+    }
     const bool bad_query = check_late && !all_finite(queries, is_f64, nq);
     EVDB_CUDA(cudaStreamSynchronize(st));
     if (bad_query) return EVDB_E_BAD_VECTOR;
     float ms = 0.f;
     cudaEventElapsedTime(&ms, s->ev0, s->ev1);
     s->last_search_ms = ms;
-    cudaEventElapsedTime(&ms, s->ev0, s->ev2); s->last_h2d_ms = ms;
-    cudaEventElapsedTime(&ms, s->ev2, s->ev3); s->last_device_ms = ms;
-    cudaEventElapsedTime(&ms, s->ev3, s->ev1); s->last_d2h_ms = ms;
+    if (!replayed) {
+        cudaEventElapsedTime(&ms, s->ev0, s->ev2); s->last_h2d_ms = ms;
+        cudaEventElapsedTime(&ms, s->ev2, s->ev3); s->last_device_ms = ms;
+        cudaEventElapsedTime(&ms, s->ev3, s->ev1); s->last_d2h_ms = ms;
+    } else {
+        s->last_h2d_ms = 0.0; s->last_device_ms = ms; s->last_d2h_ms = 0.0;   // one graph: copies included
+    }
     s->n_searches += (uint64_t)B;
 
     // escalate queries whose candidate window could not be proven complete
@@ -373,11 +438,11 @@ static int search_host(evdb_store *s, const void *queries, bool is_f64, int B, i
             if (attempt == 0 && (choose_kp(kk, kp_min) > kMaxKP)) continue;
             const double *dq = s->w_q64 + (size_t)b * d;
             EVDB_TRY(search_core(s, dq, 1, k, kstride, metric, kp_min, plan, 0,
-                                 s->w_ids + (size_t)b * kstride, s->w_dists + (size_t)b * kstride,
+                                 d_ids + (size_t)b * kstride, d_dists + (size_t)b * kstride,
                                  d_counts + b, d_flags + b, st));
-            EVDB_CUDA(cudaMemcpyAsync(h_ids + (size_t)b * kstride, s->w_ids + (size_t)b * kstride,
+            EVDB_CUDA(cudaMemcpyAsync(h_ids + (size_t)b * kstride, d_ids + (size_t)b * kstride,
                                       kstride * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-            EVDB_CUDA(cudaMemcpyAsync(h_d + (size_t)b * kstride, s->w_dists + (size_t)b * kstride,
+            EVDB_CUDA(cudaMemcpyAsync(h_d + (size_t)b * kstride, d_dists + (size_t)b * kstride,
                                       kstride * sizeof(double), cudaMemcpyDeviceToHost, st));
             EVDB_CUDA(cudaMemcpyAsync(h_c + b, d_counts + b, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
             EVDB_CUDA(cudaMemcpyAsync(h_c + B + b, d_flags + b, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -460,6 +525,7 @@ static int ingest_rows_big(evdb_store *s, uint64_t slot0, const void *rows, bool
         EVDB_CUDA(cudaStreamSynchronize(st));
     }
     s->max_norm_dirty = 1;
+    s->graph_epoch++;
     return EVDB_OK;
 }
 
@@ -521,6 +587,7 @@ static int ingest_rows(evdb_store *s, uint64_t slot0, const void *rows, bool is_
     }
     s->ingest_pending = 1;
     s->max_norm_dirty = 1;
+    s->graph_epoch++;
     return EVDB_OK;
 }
 
@@ -685,6 +752,7 @@ int store_load_codes(evdb_store *s, const uint8_t *codes, size_t code_pitch, con
     EVDB_CUDA(cudaStreamSynchronize(st));
     s->count = n;
     s->max_norm_dirty = 1;
+    s->graph_epoch++;
     return EVDB_OK;
 }
 
@@ -692,6 +760,7 @@ int store_load_codes(evdb_store *s, const uint8_t *codes, size_t code_pitch, con
 void store_drop_last(evdb_store *s) {
     if (s->count == 0) return;
     s->count--;
+    s->graph_epoch++;
     if (s->shadow_valid > s->count) s->shadow_valid = s->count;
     if (s->l2_valid > s->count) s->l2_valid = s->count;
 }
@@ -701,6 +770,7 @@ int store_refinalize(evdb_store *s, uint64_t slot0, uint64_t n, cudaStream_t st)
     EVDB_TRY(launch_finalize_rows(s, slot0, n, st));
     EVDB_TRY(launch_l2_shadow_rows(s, slot0, n, st));
     s->max_norm_dirty = 1;
+    s->graph_epoch++;
     return EVDB_OK;
 }
 
@@ -817,6 +887,8 @@ void evdb_store_destroy(evdb_store *s) {
     cudaFree(s->w_partial); cudaFree(s->w_ids); cudaFree(s->w_dists); cudaFree(s->w_counts);
     cudaFree(s->w_tmp); cudaFree(s->w_shard);
     if (s->h_pin) cudaFreeHost(s->h_pin);
+    if (s->gexec) cudaGraphExecDestroy(s->gexec);
+    if (s->h_gq) cudaFreeHost(s->h_gq);
     if (s->h_ring) cudaFreeHost(s->h_ring);
     cudaFree(s->d_ring);
     for (int i = 0; i < 2; ++i) if (s->ring_ev[i]) cudaEventDestroy(s->ring_ev[i]);
@@ -878,6 +950,7 @@ int evdb_store_set_plan(evdb_store *s, int plan) {
     if (!s || plan < EVDB_PLAN_AUTO || plan > EVDB_PLAN_EXACT) return EVDB_E_BAD_ARG;
     if (s->multi) return m_set_plan(s->multi, plan);
     s->plan = plan;
+    s->graph_epoch++;
     return EVDB_OK;
 }
 
@@ -970,6 +1043,7 @@ int evdb_store_delete(evdb_store *s, uint32_t slot, int64_t *moved_from) {
         if (moved_from) *moved_from = (int64_t)last;
     }
     s->count = last;
+    s->graph_epoch++;
     s->n_deletes++;
     if (s->shadow_valid > s->count) s->shadow_valid = s->count;
     if (s->l2_valid > s->count) s->l2_valid = s->count;
@@ -1042,6 +1116,7 @@ int store_fill_synthetic(evdb_store *s, uint64_t seed, uint64_t row0, uint64_t r
     s->shadow_valid = 0;
     s->l2_valid = 0;
     s->max_norm_dirty = 1;
+    s->graph_epoch++;
     EVDB_TRY(launch_fill_synthetic(s, seed, row0, row_stride, n, s->stream));
     EVDB_TRY(launch_finalize_rows(s, 0, n, s->stream));
     EVDB_CUDA(cudaStreamSynchronize(s->stream));
