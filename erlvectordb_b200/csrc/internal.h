@@ -76,6 +76,7 @@ struct evdb_store {
     double max_norm = 0.0;         // upper bound on the largest row norm (valid when !max_norm_dirty)
     int max_norm_dirty = 1;
     uint64_t slot_mul = 1;        // returned id = slot_base + slot * slot_mul (> 1: round-robin shard of a multi-device store)
+    unsigned int *d_arrive = nullptr;   // [8] arrival counters of the fused small-store kernel (zero between launches)
     int gemm_oom = 0;            // the GEMM plan ran out of device memory once: AUTO stays on the scan plan
     void *d_scalar = nullptr;      // 64-byte device scratch (reductions)
 
@@ -201,6 +202,11 @@ int launch_select(evdb_store *s, const double *d_q64, const uint64_t *partial, c
                   const float *eps_q, int squared, uint64_t slot_base, uint64_t *d_out_ids, double *d_out_dists,
                   int32_t *d_out_counts, int32_t *d_out_flags, cudaStream_t st);
 // d_src != NULL (float stores): rows [slot0, slot0+n) are first narrowed from the staged n x dim source (fused ingest)
+int launch_small_fused(evdb_store *s, const double *d_q64, int B, int KP, int kk, int kstride, int metric, int G, int tpr,
+                       uint64_t *partial, float *eps_q, unsigned int *arrive, float eps_abs, float eps_rel,
+                       uint64_t slot_base, uint64_t *d_out_ids, double *d_out_dists, int32_t *d_out_counts,
+                       int32_t *d_out_flags, cudaStream_t st);
+int scan_small_plan(evdb_store *s, int metric, int KP, int *G_out, int *tpr_out);   // grid / lane group the one-query float scan uses
 int launch_finalize_rows(evdb_store *s, uint64_t slot0, uint64_t n, cudaStream_t st, const void *d_src = nullptr, bool src_f64 = false);
 int launch_fill_synthetic(evdb_store *s, uint64_t seed, uint64_t row0, uint64_t rstride, uint64_t n, cudaStream_t st);
 int launch_quantize_rows(int dtype, const double *d_rows64, const float *d_rows32, uint64_t n,

@@ -20,6 +20,7 @@
 #include "exact.cuh"
 #include "internal.h"
 #include "topk.cuh"
+#include "scan_common.cuh"
 
 namespace evdb {
 
@@ -253,9 +254,8 @@ __device__ unsigned long long g_sel_dbg[10];
 
 // THREADS = 1024 for a lone query (latency), 256 for batches (more CTAs per SM, cheaper barriers).
 template <int DTYPE, int THREADS>
-__global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
+__device__ __forceinline__ void select_body(const SelectArgs &a, const int b, uint8_t *smem) {
     constexpr int kSelWarps = THREADS / 32;
-    extern __shared__ __align__(16) uint8_t smem[];
     uint64_t *buf = reinterpret_cast<uint64_t *>(smem);                       // [kSelSort]
     uint64_t *dkey = buf + kSelSort;                                          // [kMaxKP]
     uint64_t *dslot = dkey + kMaxKP;                                          // [kMaxKP]
@@ -263,7 +263,6 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
     __shared__ int s_ncand;
     __shared__ float s_bound;
 
-    const int b = blockIdx.x;
     const int KP = a.KP;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float eps_abs = a.eps_abs + (a.eps_q ? a.eps_q[b] : 0.f);
@@ -595,6 +594,143 @@ __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
         if (a.out_flags) a.out_flags[b] = flag;
     }
     SEL_MARK(6);
+}
+
+template <int DTYPE, int THREADS>
+__global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    select_body<DTYPE, THREADS>(a, blockIdx.x, smem);
+}
+
+// ============================================================================
+// Small stores, a handful of queries: query preparation + scan + selection in ONE launch.
+// The reference's everyday case (erlvectordb:search on ~10 k rows, BASELINE configs[0]) is bound by
+// launch latency, not by bytes: three dependent kernels cost more than their work.  Every CTA narrows
+// the query itself (d numbers: trivial), scans its rows exactly as scan_float_kernel does, publishes
+// its KP-key list, and the CTA that arrives LAST for a query (one atomic counter per query) runs the
+// whole selection -- merge, exact fp64 re-rank, order, proof (select_body) -- on the lists of all CTAs.
+// ============================================================================
+struct FusedArgs {
+    SelectArgs sel;            // partial = the per-CTA lists this kernel writes; eps_q = where the per-query bound goes
+    const float *inv_norm;     // row 1/norm (cosine)
+    uint64_t *partial;         // [B][G][KP]
+    float *eps_q;              // [B]
+    unsigned int *arrive;      // [B] zero between launches
+    int nch, tpr, G;
+};
+
+template <int METRIC, int DTYPE>
+__global__ void __launch_bounds__(256) small_fused_kernel(const FusedArgs f) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ double s_red[8];
+    __shared__ bool s_last;
+    constexpr int QPC = (DTYPE == EVDB_F32) ? 1 : 2;
+    constexpr int R = 4;
+    const SelectArgs &a = f.sel;
+    const int b = blockIdx.y, d = a.d, nch = f.nch, KP = a.KP, TPR = f.tpr, GPW = 32 / f.tpr;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *sqf = reinterpret_cast<float *>(smem);                                   // [nch*QPC*4] the query, fp32, zero padded
+    uint64_t *lists = reinterpret_cast<uint64_t *>(smem + (size_t)nch * QPC * 16);
+    // ---- 1. the query: fp32 copy, norm, and the narrowing residual that bounds the scan's score error ----
+    const double *q = a.q64 + (size_t)b * d;
+    double ss = 0.0, r2 = 0.0, r1 = 0.0;
+    for (int i = threadIdx.x; i < nch * QPC * 4; i += blockDim.x) {
+        const double v = i < d ? q[i] : 0.0;
+        const float fv = (float)v;
+        sqf[i] = fv;
+        ss += v * v;
+        const double df = fabs(v - (double)fv);
+        r2 += df * df;
+        r1 += df;
+    }
+    auto block_sum = [&](double v) -> double {
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        __syncthreads();
+        if (lane == 0) s_red[warp] = v;
+        __syncthreads();
+        double t = 0.0;
+        for (int i = 0; i < 8; ++i) t += s_red[i];
+        return t;
+    };
+    ss = block_sum(ss);
+    float eps_q = 0.f;
+    if (METRIC != EVDB_COSINE) {
+        r2 = block_sum(r2);
+        r1 = block_sum(r1);
+        eps_q = METRIC == EVDB_EUCLIDEAN ? (float)(sqrt(r2) * 1.0000002) : (float)(r1 * 1.0000002);
+        if (eps_q > 0.f) eps_q = nextafterf(eps_q, __int_as_float(0x7f800000));
+    }
+    if (threadIdx.x == 0) f.eps_q[b] = eps_q;      // every CTA writes the same value
+    const float q_inv = ss > 0.0 ? (float)(1.0 / sqrt(ss)) : 0.0f;
+    __syncthreads();
+    // ---- 2. the scan (scan_float_kernel with a run-time lane group) ----
+    const float4 *sq = reinterpret_cast<const float4 *>(sqf);
+    WarpCands wc;
+    wc.init(lists, KP, warp);
+    const int g = lane / TPR, gl = lane % TPR;
+    const uint64_t rows_per_wi = (uint64_t)GPW * R;
+    const uint64_t total_wi = (a.n + rows_per_wi - 1) / rows_per_wi;
+    for (uint64_t wi = (uint64_t)blockIdx.x * kScanWarps + warp; wi < total_wi; wi += (uint64_t)gridDim.x * kScanWarps) {
+        const uint64_t base = wi * rows_per_wi;
+        const uint4 *rp[R];
+        uint64_t rix[R];
+        bool valid[R];
+        float inv[R];
+        float4 acc[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            const uint64_t r = base + (uint64_t)j * GPW + g;
+            valid[j] = r < a.n;
+            rix[j] = r;
+            rp[j] = reinterpret_cast<const uint4 *>(a.rows + (valid[j] ? r : a.n - 1) * a.row_bytes);
+            inv[j] = (METRIC == EVDB_COSINE && valid[j] && gl == 0) ? __ldg(f.inv_norm + rix[j]) : 0.f;
+            acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll 2
+        for (int c = gl; c < nch; c += TPR) {
+            uint4 v[R];
+#pragma unroll
+            for (int j = 0; j < R; ++j) v[j] = ldg_stream_u4(rp[j] + c);
+            if (DTYPE == EVDB_F32) {
+                const float4 q0 = sq[c];
+#pragma unroll
+                for (int j = 0; j < R; ++j)
+                    acc_f4<METRIC>(acc[j], make_float4(__uint_as_float(v[j].x), __uint_as_float(v[j].y),
+                                                       __uint_as_float(v[j].z), __uint_as_float(v[j].w)), q0);
+            } else {
+                const float4 q0 = sq[2 * c], q1 = sq[2 * c + 1];
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    acc_f4<METRIC>(acc[j], bf16x4_lo(v[j]), q0);
+                    acc_f4<METRIC>(acc[j], bf16x4_hi(v[j]), q1);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            float sacc = (acc[j].x + acc[j].y) + (acc[j].z + acc[j].w);
+            for (int o = TPR >> 1; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+            float score;
+            if (METRIC == EVDB_COSINE) score = (inv[j] == 0.f || q_inv == 0.f) ? 1.0f : 1.0f - sacc * inv[j] * q_inv;
+            else if (METRIC == EVDB_EUCLIDEAN) score = sqrtf(sacc);
+            else score = sacc;
+            const uint64_t key = (valid[j] && gl == 0) ? make_key(score, (uint32_t)rix[j]) : kKeyMax;
+            wc.offer(key, lane);
+        }
+    }
+    wc.finish(lists, warp, lane);
+    cta_merge_and_store(lists, KP, f.partial + ((size_t)b * f.G + blockIdx.x) * KP);
+    // ---- 3. the last CTA of this query selects ----
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s_last = atomicAdd(f.arrive + b, 1u) == (unsigned)f.G - 1u;
+        if (s_last) f.arrive[b] = 0;       // ready for the next launch (every CTA of this query has arrived)
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    select_body<DTYPE, 256>(a, b, smem);
 }
 
 // ============================================================================
@@ -1611,6 +1747,41 @@ int launch_select(evdb_store *s, const double *d_q64, const uint64_t *partial, c
                 (double)h[0] / B, (double)h[1] / B, (double)h[2] / B, (double)h[3] / B, (double)h[4] / B, (double)h[5] / B,
                 (double)h[6] / B, (double)h[7] / B, (double)h[8] / B);
     }
+    return EVDB_OK;
+}
+
+// One launch for query prep + scan + selection (small float stores, B <= 8).  G = CTAs per query, partial /
+// eps_q / arrive = the store's workspaces.  EVDB_E_UNSUPPORTED when the shape does not fit (caller falls back).
+int launch_small_fused(evdb_store *s, const double *d_q64, int B, int KP, int kk, int kstride, int metric, int G, int tpr,
+                       uint64_t *partial, float *eps_q, unsigned int *arrive, float eps_abs, float eps_rel,
+                       uint64_t slot_base, uint64_t *d_out_ids, double *d_out_dists, int32_t *d_out_counts,
+                       int32_t *d_out_flags, cudaStream_t st) {
+    if ((s->dtype != EVDB_F32 && s->dtype != EVDB_BF16) || B > 8 || KP > kAppendMaxKP) return EVDB_E_UNSUPPORTED;
+    FusedArgs f;
+    memset(&f, 0, sizeof(f));
+    SelectArgs &a = f.sel;
+    a.rows = s->rows; a.row_bytes = s->row_bytes; a.norm64 = s->norm64; a.qms64 = s->qms64;
+    a.n = s->count; a.d = s->dim; a.q64 = d_q64; a.partial = partial; a.L = G; a.KP = KP;
+    a.kk = kk; a.kstride = kstride; a.metric = metric; a.eps_abs = eps_abs; a.eps_rel = eps_rel;
+    a.eps_q = eps_q; a.squared = 0; a.win_mode = 0; a.variant = 0;
+    a.slot_base = slot_base; a.slot_mul = s->slot_mul; a.out_ids = d_out_ids; a.out_dists = d_out_dists;
+    a.out_counts = d_out_counts; a.out_flags = d_out_flags;
+    f.inv_norm = s->inv_norm; f.partial = partial; f.eps_q = eps_q; f.arrive = arrive;
+    f.nch = s->nch; f.tpr = tpr; f.G = G;
+    const size_t scan_smem = (size_t)s->nch * (s->dtype == EVDB_F32 ? 16 : 32) + scan_list_bytes(KP);
+    size_t smem = select_smem(256);
+    if (scan_smem > smem) smem = scan_smem;
+    if (smem > 100 * 1024) return EVDB_E_UNSUPPORTED;
+    void (*fn)(const FusedArgs) = nullptr;
+#define EVDB_FUSED(DT)                                                                             \
+    fn = metric == EVDB_COSINE ? small_fused_kernel<EVDB_COSINE, DT>                                 \
+       : metric == EVDB_EUCLIDEAN ? small_fused_kernel<EVDB_EUCLIDEAN, DT> : small_fused_kernel<EVDB_MANHATTAN, DT>
+    if (s->dtype == EVDB_F32) { EVDB_FUSED(EVDB_F32); } else { EVDB_FUSED(EVDB_BF16); }
+#undef EVDB_FUSED
+    EVDB_TRY(ensure_func_smem((const void *)fn, smem));
+    fn<<<dim3(G, B), 256, smem, st>>>(f);
+    s->n_launches++;
+    EVDB_CUDA(cudaGetLastError());
     return EVDB_OK;
 }
 

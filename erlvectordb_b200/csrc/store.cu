@@ -229,6 +229,39 @@ int search_core(evdb_store *s, const double *d_q64, int B, int k, int kstride, i
         }
     }
     if (!use_gemm) {
+        // Small float stores, a lone query: prep + scan + selection in ONE launch (select.cu small_fused_kernel)
+        // -- three dependent kernels cost more than their work.
+        static int fused_on = -1;
+        if (fused_on < 0) { const char *e = getenv("EVDB_FUSED_SMALL"); fused_on = e ? atoi(e) : 1; }
+        // (measured on B200, tools/sweep.py, device-timed step: 10 k x 128 B = 1: 29.9 us fused against 36.1; 100 k x 128:
+        //  48.3 against 48.4; 20 k x 768 B = 4: 131 against 75 -- with long rows or several queries the one CTA that
+        //  selects is slower than the 1024-thread select kernel, so the fused launch is kept for short rows and lone queries)
+        if (fused_on && (s->dtype == EVDB_F32 || s->dtype == EVDB_BF16) && B <= 2 && KP <= 128 && s->dim <= 256 &&
+            (double)s->count * (double)s->row_bytes <= 32e6) {
+            int G = 0, tpr = 0;
+            if (scan_small_plan(s, metric, KP, &G, &tpr) == EVDB_OK) {
+                EVDB_TRY(ensure_bytes((void **)&s->w_partial, &s->w_partial_cap, sizeof(uint64_t) * (size_t)B * G * KP));
+                EVDB_TRY(ensure_bytes((void **)&s->w_qeps, &s->w_qeps_cap, sizeof(float) * (size_t)B));
+                if (!s->d_arrive) {
+                    EVDB_CUDA(cudaMalloc((void **)&s->d_arrive, 8 * sizeof(unsigned int)));
+                    EVDB_CUDA(cudaMemsetAsync(s->d_arrive, 0, 8 * sizeof(unsigned int), st));
+                }
+                const double depth = (double)s->dim / 64.0 + 24.0;
+                const float ea = metric == EVDB_COSINE ? (float)(depth * u) : 1e-37f;
+                const float er = metric == EVDB_COSINE ? 0.f : (float)(depth * u);
+                prof_begin(s, st);
+                const int rc = launch_small_fused(s, d_q64, B, KP, kk, kstride, metric, G, tpr, s->w_partial, s->w_qeps,
+                                                  s->d_arrive, ea, er, slot_base, d_ids, d_dists, d_counts, d_flags, st);
+                prof_end(s, st);
+                if (rc == EVDB_OK) {
+                    s->last_plan = EVDB_PLAN_SCAN;
+                    s->n_rows_scanned += (uint64_t)B * s->count;
+                    return EVDB_OK;
+                }
+                if (rc != EVDB_E_UNSUPPORTED) return rc;
+                if (s->prof_on && s->prof_n > 0) s->prof_n--;   // the bracket measured nothing
+            }
+        }
         EVDB_TRY(launch_prep_queries(s, d_q64, B, metric, st));
         s->last_plan = EVDB_PLAN_SCAN;
         int G = 0;
@@ -882,6 +915,7 @@ void evdb_store_destroy(evdb_store *s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     cudaFree(s->rows); cudaFree(s->norm64); cudaFree(s->inv_norm); cudaFree(s->norm_sq);
+    cudaFree(s->d_arrive);
     cudaFree(s->qcoef); cudaFree(s->qms64); cudaFree(s->shadow); cudaFree(s->shadow_l2); cudaFree(s->l2_tail); cudaFree(s->d_scalar);
     cudaFree(s->w_q64); cudaFree(s->w_q32); cudaFree(s->w_qdig); cudaFree(s->w_qh); cudaFree(s->w_seed); cudaFree(s->w_qstat); cudaFree(s->w_qeps);
     cudaFree(s->w_partial); cudaFree(s->w_ids); cudaFree(s->w_dists); cudaFree(s->w_counts);

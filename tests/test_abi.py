@@ -89,3 +89,64 @@ def test_erlang_nif_shim_compiles_against_the_abi(tmp_path):
                         f"-I{tmp_path}", f"-I{os.path.join(root, 'include')}",
                         os.path.join(root, "erlang", "c_src", "evdb_nif.c")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """The ctypes mirrors of evdb_opts / evdb_stats / evdb_search_opts (and therefore the NIF, which uses the
+    C structs directly) must agree with include/evdb.h field by field: a C program prints the sizes and
+    offsets the compiler assigns, ctypes must assign the same."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    from erlvectordb_b200 import _native as N
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    structs = {"evdb_opts": N.Opts, "evdb_stats": N.Stats, "evdb_search_opts": N.SearchOpts}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "evdb.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  printf("EVDB_MAX_SHARDS %d\\n", EVDB_MAX_SHARDS);', '  printf("EVDB_ABI_VERSION %d\\n", EVDB_ABI_VERSION);',
+              '  return 0; }']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    r = subprocess.run([gcc, "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = dict(ln.split() for ln in subprocess.run([str(exe)], capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
+    assert int(got["EVDB_MAX_SHARDS"]) == 16 == len(N.Opts().devices)
+    assert int(got["EVDB_ABI_VERSION"]) == N.lib().evdb_abi_version()
+
+
+def test_multi_device_slot_arithmetic():
+    """Host arithmetic of the one-handle multi-device store (csrc/mstore.cu): global slot g lives on shard
+    g mod S at local slot g div S; appends and swap-with-last deletes keep every shard dense and within one
+    row of the others.  Replayed here on plain lists against a flat model."""
+    import random
+    rnd = random.Random(5)
+    for S in (2, 3, 8):
+        shards = [[] for _ in range(S)]
+        flat = []
+        for step in range(2000):
+            if not flat or rnd.random() < 0.6:
+                g = len(flat)
+                assert len(shards[g % S]) == g // S          # an append lands at the end of its shard
+                shards[g % S].append(step)
+                flat.append(step)
+            else:
+                g, last = rnd.randrange(len(flat)), len(flat) - 1
+                assert len(shards[last % S]) - 1 == last // S   # the global last row is the last row of its shard
+                shards[g % S][g // S] = shards[last % S][last // S]
+                shards[last % S].pop()
+                flat[g] = flat[last]
+                flat.pop()
+            n = len(flat)
+            assert [len(sh) for sh in shards] == [(n - j + S - 1) // S if n > j else 0 for j in range(S)]
+            assert max(map(len, shards)) - min(map(len, shards)) <= 1
+        assert all(shards[g % S][g // S] == flat[g] for g in range(len(flat)))

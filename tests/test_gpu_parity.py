@@ -799,3 +799,30 @@ def test_multi_query_scan_batches_equal_single_query_passes(native, oracle, dtyp
             assert slots[b].tolist() == s1[0].tolist() and dists[b].tolist() == d1[0].tolist()
     finally:
         st.close()
+
+
+@pytest.mark.parametrize("metric", METRICS)
+def test_bf16_store_scores_stay_within_1e_2_of_the_unnarrowed_reference(native, oracle, metric):
+    """north_star: scores within 1e-2 relative of the Erlang fp64 result for bf16 stores.  Checked for
+    every returned neighbour of 40 queries (not one top-1): the device distance of the id it returns
+    is within 1e-2 of the fp64 distance of the UN-narrowed row, and the returned set agrees with the
+    reference's top-k wherever the reference's own distances are more than 2e-2 apart."""
+    n, d, k = 6000, 192, 10
+    rng = np.random.default_rng(17)
+    rows = rng.standard_normal((n, d))
+    qs = rng.standard_normal((40, d))
+    st = _store(native, "bf16")
+    try:
+        st.bulk_load(rows)
+        slots, dists, counts = st.search(qs, k, metric)
+        for b in range(40):
+            full = oracle.distances(rows, qs[b], metric)
+            for j in range(k):
+                ref = full[slots[b, j]]
+                assert abs(dists[b, j] - ref) <= REL_TOL_BF16 * max(abs(ref), 1e-300), (b, j, dists[b, j], ref)
+            order = np.argsort(full, kind="stable")
+            kth = full[order[k - 1]]
+            sure = [i for i in order[:k] if full[i] < kth * (1 - 2 * REL_TOL_BF16)]   # clearly inside the top k
+            assert set(sure) <= set(slots[b].tolist())
+    finally:
+        st.close()
