@@ -754,18 +754,6 @@ struct SwLayout {
     static constexpr int kPerWarp = kUnion + kSwMaxKP * 8 * 3;  // + ckeys/dkey/dslot
 };
 
-// Exact f32 -> f64 widening with integer instructions (the fp64 pipe of this part issues one warp
-// instruction per ~16 cycles whatever the number of active lanes: conversions do not belong there).
-__device__ __forceinline__ double widen_f32(uint32_t u) {
-    const uint32_t e = (u >> 23) & 0xFFu;
-    if (e == 0u) {
-        if ((u << 1) == 0u) return __hiloint2double((int)(u & 0x80000000u), 0);  // +-0
-        return (double)__uint_as_float(u);                                        // subnormal: rare
-    }
-    const uint32_t hi = (u & 0x80000000u) | ((e + 896u) << 20) | ((u >> 3) & 0xFFFFFu);
-    return __hiloint2double((int)hi, (int)(u << 29));
-}
-
 // ascending bitonic sort of n (power of two) u64 keys in shared memory by one warp
 __device__ __forceinline__ void warp_bitonic_smem(uint64_t *k, int n, int lane) {
     for (int k2 = 2; k2 <= n; k2 <<= 1)
@@ -905,77 +893,8 @@ __device__ __forceinline__ void warp_select_inplace(uint64_t *keys, int T, int n
     }
 }
 
-// One chain of the exact re-rank (F32 rows): lane r < nr passes the slot of the row it folds; with
-// `qrow`, lane nr folds q*q.  The independent terms (q*v, (q-v)^2, |q-v|) are formed by all 32 lanes
-// in parallel -- 32 useful fp64 multiplies per instruction -- and staged as fp64 in shared memory;
-// then every lane folds its row strictly left to right.  Returns the lane's sum.
-__device__ __forceinline__ double sw_fold_chain(const uint8_t *__restrict__ rows, size_t row_bytes,
-                                                const double *__restrict__ q, int d, int metric, uint8_t *stage,
-                                                uint32_t my_slot, int nr, bool qrow, int lane) {
-    // The fold itself is cheap (a dependent DADD is ~9 cycles here, tools/micro/fp64_bench.cu); what
-    // a chain waits for is its operands: rows scattered over the store.  So the raw rows and the query
-    // values of chunk c+1 are loaded into registers BEFORE chunk c is folded.
-    const int nrows = nr + (qrow ? 1 : 0);
-    const int unit = lane & 15, rsub = lane >> 4;   // a row chunk is 16 units of 4 elements: half a warp per row
-    constexpr int kIt = kSwRows / 2;                // row pairs per chunk
-    uint4 raw[kIt];
-    double qd[4];
-    auto load_chunk = [&](int kb) {
-        const int e0 = kb + 4 * unit;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) qd[i] = e0 + i < d ? __ldg(q + e0 + i) : 0.0;
-#pragma unroll
-        for (int it = 0; it < kIt; ++it) {
-            const int r = 2 * it + rsub;
-            const uint32_t rslot = __shfl_sync(0xffffffffu, my_slot, r < nr ? r : 0);
-            raw[it] = make_uint4(0u, 0u, 0u, 0u);
-            if (2 * it < nrows && r < nr && (size_t)e0 * 4 < row_bytes)
-                raw[it] = __ldg(reinterpret_cast<const uint4 *>(rows + (size_t)rslot * row_bytes) + (e0 >> 2));
-        }
-    };
-    double s = 0.0;
-    load_chunk(0);
-    for (int kb = 0; kb < d; kb += kSwKC) {
-        const int cnt = d - kb < kSwKC ? d - kb : kSwKC;
-        __syncwarp();
-#pragma unroll
-        for (int it = 0; it < kIt; ++it) {
-            const int r = 2 * it + rsub;
-            if (2 * it >= nrows || r >= nrows) continue;
-            const uint32_t w[4] = {raw[it].x, raw[it].y, raw[it].z, raw[it].w};
-            double t[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const double x = r < nr ? widen_f32(w[i]) : qd[i];     // the last row: the query's own squares
-                if (metric == EVDB_COSINE) t[i] = __dmul_rn(qd[i], x);
-                else {
-                    const double df = __dsub_rn(qd[i], x);
-                    t[i] = metric == EVDB_EUCLIDEAN ? __dmul_rn(df, df) : fabs(df);
-                }
-            }
-            double2 *dst = reinterpret_cast<double2 *>(stage + (size_t)r * kSwProdStride) + 2 * unit;
-            dst[0] = make_double2(t[0], t[1]);
-            dst[1] = make_double2(t[2], t[3]);
-        }
-        if (kb + kSwKC < d) load_chunk(kb + kSwKC);   // in flight during the fold below
-        __syncwarp();
-        if (lane < nrows) {
-            const double2 *p = reinterpret_cast<const double2 *>(stage + (size_t)lane * kSwProdStride);
-            const int pairs = cnt >> 1;
-#pragma unroll 4
-            for (int i = 0; i < pairs; ++i) {
-                const double2 v = p[i];
-                s = __dadd_rn(s, v.x);
-                s = __dadd_rn(s, v.y);
-            }
-            if (cnt & 1) s = __dadd_rn(s, reinterpret_cast<const double *>(p)[cnt - 1]);
-        }
-    }
-    return s;
-}
-
-// ---- the same fold by a GROUP of warps (one query): a leader and kMwProducers producer warps --------
-// One warp per query is bound by its own instruction latency: ~500 instructions per 64-element chunk,
+// ---- the exact fp64 fold by a GROUP of warps (one query): a leader and kMwProducers producer warps ----
+// One warp per query (round 1) is bound by its own instruction latency: ~500 instructions per 64-element chunk,
 // each waiting ~5 cycles for the previous one, 12 chunks at d = 768 -- 89 k cycles for a chain whose
 // dependent DADDs need 6.6 k (r02 EVDB_SEL_VARIANT=16 counters).  Here the producer warps form the
 // products of chunk c (two rows per warp instruction, row pairs dealt round-robin) into one half of

@@ -63,7 +63,7 @@ enum {
     EVDB_E_BAD_ARG = -6,
     EVDB_E_NO_DEVICE = -7,
     EVDB_E_UNSUPPORTED = -8,
-    EVDB_E_BADARITH = -9 /* Max == Min in a quantizer (reference: badarith) */
+    EVDB_E_BADARITH = -9 /* Max == Min in a quantizer (reference: badarith); reserved: see upsert */
 };
 
 typedef struct evdb_opts {
@@ -134,7 +134,13 @@ int evdb_store_profile_read(evdb_store *s, int32_t *n_samples, double *total_ms)
  * First vector fixes the dimension; d != dimension -> EVDB_E_DIM_MISMATCH.
  * Non-finite elements -> EVDB_E_BAD_VECTOR (Erlang floats are always finite).
  * For U8/U4 stores the row is quantized on the device exactly as
- * compress_{8,4}bit_quantization does (fp64); Max == Min -> EVDB_E_BADARITH. */
+ * compress_{8,4}bit_quantization does (fp64).  A row with Max == Min (the reference raises badarith and
+ * keeps the RAW constant vector, src/vector_compression.erl:62-64, src/vector_persistence.erl:114-116)
+ * is stored as {min, scale = 0} with all-zero codes, which decodes to exactly that vector: the insert
+ * succeeds, as it does in the reference.  (EVDB_E_BADARITH is reported by the standalone codecs through
+ * their ok[] output, not by a store.)
+ * The dimension is fixed only by a vector that passed every check (:128-131): a rejected first vector
+ * leaves it undefined.                                                          */
 int evdb_store_upsert_f64(evdb_store *s, uint32_t slot, const double *vec, int d);
 int evdb_store_upsert_f32(evdb_store *s, uint32_t slot, const float *vec, int d);
 /* Batched insert of NEW ids (a run of handle_call({insert,..}) with fresh keys, or a reload in
