@@ -308,7 +308,9 @@ def run_ours(args):
             assert int(out[3].sum().item()) == 0
         return {"ms_per_step": ms / steps, "qps": batch * steps / (ms / 1e3),
                 "kernel_ms": (kms / nsamp) if nsamp else None, "plan": stt["last_plan"], "launches": launches,
-                "clocks": clocks, "phases": ph, "escalated": st.n_escalations - esc0, "qd": qd}
+                "clocks": clocks, "phases": ph, "escalated": st.n_escalations - esc0, "qd": qd,
+                "exchange": ("peer-memory mailboxes (CUDA IPC, NVLink stores, on-device flag wait)" if st.exchange == "p2p"
+                             else "NCCL all_gather_into_tensor + merge kernel") if world > 1 else "none"}
 
     def e2e_timed(store: DeviceStore, d, k, metric, batch, steps, warmup):
         """The C-ABI host call with pageable numpy buffers, wall clock, rank 0's process."""
@@ -522,6 +524,7 @@ def run_ours(args):
             "config": {"workload": "1Mx768 fp32 cosine k=10 (BASELINE.json configs[1])", "rows": N_ROWS,
                        "dim": DIM, "k": K, "batch": args.batch, "plan": {1: "scan", 2: "gemm", 3: "exact"}.get(main["plan"]),
                        "sharding": f"rows/{world}" if world > 1 else "none",
+                       "exchange": main["exchange"],
                        "queries": f"{POOL} distinct batches rotated through the steps",
                        "cache": "inputs larger than L2 (3.07 GB fp32 corpus, 126 MB L2)",
                        "result_check": chk_main},

@@ -155,6 +155,10 @@ class ShardedStore:
                 if x is not None:
                     x.close()
                 x = None
+                if self.exchange != "nccl" and self.rank == 0:
+                    import sys
+                    print("[erlvectordb_b200] peer mailboxes could not be mapped (no CUDA IPC / P2P between the ranks): "
+                          "the sharded search exchanges through NCCL all_gather instead", file=sys.stderr)
                 self.exchange = "nccl"
             self._xchg[key] = x
         return self._xchg[key]
