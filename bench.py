@@ -288,16 +288,19 @@ def run_ours(args):
         st._dev.profile(False)
         ph = None
         if phases and st.phase_events:
-            acc = [0.0, 0.0, 0.0]
+            nph = len(st.phase_events[0]) - 1
+            acc = [0.0] * nph
             for ev in st.phase_events:
-                for j in range(3):
+                for j in range(nph):
                     acc[j] += ev[j].elapsed_time(ev[j + 1])
             n = len(st.phase_events)
-            ph = {"phase1_prep_seed_gemm_window_push_us": max_over_ranks(acc[0] / n * 1e3),
-                  "phase2_merge_rerank_push_us": max_over_ranks(acc[1] / n * 1e3),
-                  "phase3_final_us": max_over_ranks(acc[2] / n * 1e3),
-                  "gemm_kernel_us": max_over_ranks((kms / nsamp) * 1e3 if nsamp else 0.0),
-                  "how": "CUDA events between the phases on the real GPUs, mean over the timed steps, max over ranks"}
+            names = (["phase1_prep_seed_gemm_window_push_us", "phase2_merge_rerank_push_us", "phase3_final_us"] if nph == 3
+                     else ["local_search_prep_seed_gemm_select_rerank_us", "push_wait_merge_us"])
+            ph = {nm: max_over_ranks(acc[j] / n * 1e3) for j, nm in enumerate(names)}
+            ph["gemm_kernel_us"] = max_over_ranks((kms / nsamp) * 1e3 if nsamp else 0.0)
+            ph["scheme"] = ("two-phase: approximate windows travel, owners re-rank" if nph == 3
+                            else "one exchange: every rank re-ranks its local window, finished results travel")
+            ph["how"] = "CUDA events between the phases on the real GPUs, mean over the timed steps, max over ranks"
         st.phase_events = None
         stt = st._dev.stats()
         launches = stt["kernel_launches"] - l0 + (steps if (world > 1 and ph is None) else 0)  # + the merge kernel

@@ -20,6 +20,7 @@
 // Queries whose window could not be proven complete are re-issued on every shard (256-key scan
 // window, then the exhaustive fp64 plan): no unproven result leaves the handle.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -608,7 +609,12 @@ static int search_pass(MStore *m, const void *queries, bool is_f64, int B, int d
     // most 128 keys, every shard at least one corpus tile.
     const int KP = gemm_window_of(k, o->count);
     const uint64_t smallest = shard_count(o->count, S, S - 1);
-    jb.two_phase = S > 1 && S <= 32 && plan == EVDB_PLAN_AUTO && kp_min == 0 && o->plan == EVDB_PLAN_AUTO &&
+    // (one exchange of finished per-shard results is the default since the group-of-warps fold: re-ranking a
+    //  whole local window costs a shard little more than its share of the global one, and it saves a cross-GPU
+    //  wait; EVDB_SHARD_TWO_PHASE=1 selects the window / owner scheme, which stays tested)
+    const char *tp_env = getenv("EVDB_SHARD_TWO_PHASE");   // read per call: tests flip it
+    const bool two_phase_on = tp_env && atoi(tp_env) == 1;
+    jb.two_phase = two_phase_on && S > 1 && S <= 32 && plan == EVDB_PLAN_AUTO && kp_min == 0 && o->plan == EVDB_PLAN_AUTO &&
                    o->dtype == EVDB_F32 && o->gemm_shadow && (metric == EVDB_COSINE || metric == EVDB_EUCLIDEAN) &&
                    B >= 16 && B <= gemm_max_batch() && KP <= 128 && (size_t)S * KP <= 2048 && smallest >= 256;
     if (jb.two_phase)

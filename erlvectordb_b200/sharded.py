@@ -18,6 +18,8 @@ re-rank and merge are the library's CUDA kernels.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -174,6 +176,12 @@ class ShardedStore:
         shard at least one corpus tile)."""
         if self._merge is not None or self._local_search is not None or self.exchange != "p2p" or self.world < 2:
             return False
+        # Since the exact fold runs on a group of warps per query (select.cu mw_fold) re-ranking a whole local
+        # window costs a rank little more than re-ranking its eighth of the global one, and ONE exchange
+        # (finished per-shard results + merge) beats the two of the window/owner scheme: N = 4, batch 1024:
+        # 0.478 against 0.495 ms.  The two-phase search stays available (EVDB_SHARD_TWO_PHASE=1) and tested.
+        if os.environ.get("EVDB_SHARD_TWO_PHASE", "0") != "1":
+            return False
         per = (self.n_total + self.world - 1) // self.world
         smallest = self.n_total - per * (self.world - 1)
         return (self.dtype == "f32" and metric in ("cosine", "euclidean") and 16 <= B <= 8192 and
@@ -244,6 +252,10 @@ class ShardedStore:
             if r is not None:
                 return r
         local, gathered, merged, lv, mv, lptrs = self._buffers(B, k, q.device)
+        ev = None
+        if self.phase_events is not None and q.is_cuda:   # measurement aid (bench.py)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
         if self._local_search is not None:      # injected (CPU tests): tensors in, packed here
             if forced:
                 ids, dists, counts, flags = self._local_search(q, k, metric, plan=plan, kp_min=kp_min)
@@ -254,12 +266,17 @@ class ShardedStore:
             self._cuda_local_search(q, k, metric, lptrs, plan, kp_min)
         if self.world == 1:
             return lv
+        if ev:
+            ev[1].record()
         if self._merge is None and self.exchange == "p2p":
             x = self._p2p(B, k, q.device)
             if x is not None:
                 stream = _stream_handle(q.device)
                 x.push(local.data_ptr(), B, k, stream)      # my blob -> every rank's mailbox, then the epoch flag
                 x.merge(B, k, merged.data_ptr(), stream)    # waits on the device for all ranks' flags
+                if ev:
+                    ev[2].record()
+                    self.phase_events.append(ev)
                 return mv
         gather_blobs(local, self.world, self.group, out=gathered)
         if self._merge is not None:             # injected (CPU tests)

@@ -66,9 +66,12 @@ def test_bulk_load_and_lone_queries_equal_single_store(native, oracle, devices, 
         m.close(); s.close()
 
 
+@pytest.mark.parametrize("scheme", ["one-exchange", "two-phase"])
 @pytest.mark.parametrize("metric,k,B", [("cosine", 10, 64), ("euclidean", 100, 130), ("cosine", 10, 1024)])
-def test_tcgen05_batches_two_phase_equal_single_store(native, oracle, devices, metric, k, B):
-    """Batches take the two-phase sharded search (windows travel, owners re-rank) inside the handle."""
+def test_tcgen05_batches_two_phase_equal_single_store(native, oracle, devices, metric, k, B, scheme, monkeypatch):
+    """tcgen05 batches inside the handle, under both cross-shard schemes: finished per-shard results travel
+    once (the default), or approximate windows travel and owners re-rank (EVDB_SHARD_TWO_PHASE=1)."""
+    monkeypatch.setenv("EVDB_SHARD_TWO_PHASE", "1" if scheme == "two-phase" else "0")
     n, d = 6000 * len(devices), 128
     m, s = _pair(native, devices)
     try:

@@ -55,8 +55,15 @@ for dtype, metric, n, d, B, k, cluster in CASES:
         st.fill_synthetic(synth.SEED_CORPUS, n, d)
         one.fill_synthetic(synth.SEED_CORPUS, n, d)
     q = torch.from_numpy(qh).cuda()
+    if B >= 16:          # tcgen05 batches: the window / owner two-phase scheme must agree with the default one-exchange scheme
+        os.environ["EVDB_SHARD_TWO_PHASE"] = "1"
+        t_ids, t_dd, _, t_fl = st.search(q, k, metric)
+        t_ids, t_dd = t_ids.clone(), t_dd.clone()
+        os.environ["EVDB_SHARD_TWO_PHASE"] = "0"
     for _ in range(4):   # repeated searches: epoch/parity reuse of the peer mailboxes
         ids, dd, cnt, flags = st.search(q, k, metric)
+    if B >= 16:
+        assert torch.equal(t_ids, ids) and torch.equal(t_dd, dd), "two-phase and one-exchange schemes disagree"
     assert int(flags.sum()) == 0, "an unproven result left ShardedStore.search"
     if not cluster:
         st2 = ShardedStore(dtype=dtype, device=local, rank=rank, world=world, exchange="nccl")
