@@ -154,3 +154,38 @@ def test_two_phase_sharded_search_equals_single_store(native, oracle, metric, n,
     for st, _ in stores:
         st.close()
     one.close()
+
+
+@pytest.mark.parametrize("metric,B", [("cosine", 40), ("manhattan", 5)])
+def test_replica_group_and_sharded_store_classes_on_one_gpu(native, oracle, metric, B):
+    """SURVEY 8f-4 (cluster_manager.erl:148-171: whole-store replicas) and the row-sharded class with a world
+    of one: the CUDA paths behind ReplicaGroup.search / ShardedStore.search (escalating API, device-resident
+    queries) return what the host entry point returns for the same store -- including a near-duplicate
+    cluster that the first pass cannot prove."""
+    import torch
+    from erlvectordb_b200.device_store import DeviceStore
+    from erlvectordb_b200.sharded import ReplicaGroup, ShardedStore
+    n, d, k = 30_000, 64, 10
+    rows = oracle.synth_f64(oracle.SEED_CORPUS, 0, n, d).astype(np.float32)
+    qh = oracle.synth_f64(oracle.SEED_QUERY, 0, B, d)
+    rng = np.random.default_rng(9)
+    for i in range(300):
+        rows[5 + 61 * i] = (qh[2] * (1.0 + 2e-7 * rng.standard_normal(d))).astype(np.float32)
+    one = DeviceStore(dtype="f32", device=0)
+    one.bulk_load(rows)
+    want = one.search(qh, k, metric)
+    q = torch.from_numpy(qh).cuda()
+    rg = ReplicaGroup(dtype="f32", device=0, rank=0, world=1)
+    rg.bulk_load(rows)
+    ss = ShardedStore(dtype="f32", device=0, rank=0, world=1)
+    ss.bulk_load_shard(rows, n)
+    try:
+        for st in (rg, ss):
+            ids, dd, cnt, flags = st.search(q, k, metric)
+            assert int(flags.sum()) == 0
+            assert np.array_equal(ids.cpu().numpy().astype(np.uint32), want[0])
+            assert np.array_equal(dd.cpu().numpy(), want[1])
+        if metric == "cosine":
+            assert rg.n_escalations + ss.n_escalations >= 2      # the cluster forced the ladder in both classes
+    finally:
+        rg.close(); ss.close(); one.close()
