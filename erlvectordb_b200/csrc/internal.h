@@ -35,9 +35,10 @@ struct GraphKey {
     int B = -1, k = 0, metric = 0, f64 = 0;
     uint64_t count = 0, epoch = 0;
     const void *q = nullptr, *out = nullptr, *pin = nullptr;
+    uint64_t ws = 0;     // signature of every workspace / column pointer the plan's kernels were given
     bool operator==(const GraphKey &o) const {
         return B == o.B && k == o.k && metric == o.metric && f64 == o.f64 && count == o.count && epoch == o.epoch &&
-               q == o.q && out == o.out && pin == o.pin;
+               q == o.q && out == o.out && pin == o.pin && ws == o.ws;
     }
 };
 }  // namespace evdb

@@ -373,6 +373,13 @@ static int search_host(evdb_store *s, const void *queries, bool is_f64, int B, i
     GraphKey key;
     key.B = B; key.k = k; key.metric = metric; key.f64 = is_f64 ? 1 : 0; key.count = s->count; key.epoch = s->graph_epoch;
     key.q = s->w_q64; key.out = s->w_ids; key.pin = s->h_pin;
+    {   // a call of another shape may have regrown (= moved) a workspace since the capture: the graph must not outlive it
+        const void *ws[] = {s->rows, s->norm64, s->inv_norm, s->qcoef, s->qms64, s->shadow, s->shadow_l2, s->l2_tail, s->w_q32,
+                            s->w_qdig, s->w_seed, s->w_qh, s->w_qstat, s->w_qeps, s->w_partial, s->w_tmp, s->d_arrive, s->d_scalar};
+        uint64_t h = 1469598103934665603ull;
+        for (const void *p : ws) h = (h ^ (uint64_t)(uintptr_t)p) * 1099511628211ull;
+        key.ws = h;
+    }
     static int graphs_on = -1;
     if (graphs_on < 0) { const char *e = getenv("EVDB_GRAPHS"); graphs_on = e ? atoi(e) : 1; }
     const bool small = graphs_on && B <= 16 && !s->prof_on && !s->graph_broken && nq * esz <= (64u << 10);

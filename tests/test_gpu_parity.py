@@ -826,3 +826,43 @@ def test_bf16_store_scores_stay_within_1e_2_of_the_unnarrowed_reference(native, 
             assert set(sure) <= set(slots[b].tolist())
     finally:
         st.close()
+
+
+def test_replayed_graphs_survive_interleaved_shapes_and_ingest(native, oracle):
+    """Small host searches replay as a CUDA graph from their third identical call on.  Calls of OTHER shapes
+    in between regrow (move) workspaces, ingest changes the rows, a plan change reroutes: a stale graph must
+    never be replayed.  Every answer is checked against the oracle."""
+    n, d, k = 20000, 96, 10
+    rows = oracle.synth_f64(oracle.SEED_CORPUS, 0, n, d).astype(np.float32).astype(np.float64)
+    qs = oracle.synth_f64(oracle.SEED_QUERY, 0, 300, d)
+    st = _store(native, "f32")
+    model = rows.copy()
+
+    def check(q, kk, metric="cosine"):
+        s, dd, c = st.search(q, kk, metric)
+        for b in range(np.atleast_2d(q).shape[0]):
+            r, ref = oracle.search(model, np.atleast_2d(q)[b], kk, metric)
+            assert s[b, :len(r)].tolist() == r.tolist() and dd[b, :len(r)].tolist() == ref.tolist()
+
+    try:
+        st.bulk_load(rows)
+        for rep in range(4):
+            check(qs[rep], k)                       # same shape four times: normal, normal, capture, replay
+        check(qs[:256], k)                          # a batch: grows the candidate workspaces
+        check(qs[:3], 100, "euclidean")             # a wider window, another metric
+        for rep in range(4):
+            check(qs[10 + rep], k)                  # the B = 1 shape again: must re-capture, not replay a stale graph
+        v = qs[13] * 1.0000001
+        assert st.upsert(77, v) == 0                # overwrite in place: count unchanged, rows changed
+        model[77] = v.astype(np.float32).astype(np.float64)
+        for rep in range(4):
+            check(qs[13], k)                        # row 77 is now the nearest neighbour of this query
+        assert st.delete(5) == n - 1
+        model[5] = model[n - 1]; model = model[:n - 1]
+        for rep in range(3):
+            check(qs[20 + rep], k, "manhattan")
+        st.set_plan("exact")
+        for rep in range(3):
+            check(qs[30], k)
+    finally:
+        st.close()
