@@ -248,13 +248,22 @@ def run_ours(args):
                 "traffic": tr, "algorithmic_bytes": byts, "peak_source": pk["src"] + " copy bandwidth",
                 "frac_of_8TBs_nominal": ach / 8000.0, "kernel": "scan kernel of the plan", "kernel_ms": kernel_ms}
 
-    def device_timed(st: ShardedStore, n_rows, d, k, metric, batch, steps, warmup, sample_clocks=False, phases=False):
+    def device_timed(st: ShardedStore, n_rows, d, k, metric, batch, steps, warmup, sample_clocks=False, phases=False,
+                     preload=False):
         """K steps of st.search over rotating resident query batches, CUDA events, max over ranks."""
         qd = [torch.from_numpy(synth.synth(synth.SEED_QUERY, i * batch, batch, d)).to(dev) for i in range(POOL)]
         for i in range(warmup):
             st.search(qd[i % POOL], k, metric, escalate=False)
         barrier()
         sampler = ClockSampler(local)
+        if preload and not sample_clocks:   # the same 0.6 s of load, unsampled: both layouts are timed in the sustained state
+            t_probe = time.perf_counter()
+            i = 0
+            while time.perf_counter() - t_probe < 0.6:
+                for _ in range(8):
+                    st.search(qd[i % POOL], k, metric, escalate=False)
+                    i += 1
+                torch.cuda.synchronize()
         if sample_clocks:
             # nvidia-smi samples every 200 ms and the timed region may last only tens of ms: the
             # sampler also covers ~0.6 s of the SAME search loop run (untimed) right before it, so
@@ -271,7 +280,7 @@ def run_ours(args):
         if st._dev is not None:
             st._dev.profile(True)
         l0 = st._dev.stats()["kernel_launches"]
-        if phases:
+        if phases and hasattr(st, "phase_events"):
             st.phase_events = []
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
@@ -287,7 +296,7 @@ def run_ours(args):
         nsamp, kms = st._dev.profile_read()
         st._dev.profile(False)
         ph = None
-        if phases and st.phase_events:
+        if phases and getattr(st, "phase_events", None):
             nph = len(st.phase_events[0]) - 1
             acc = [0.0] * nph
             for ev in st.phase_events:
@@ -301,7 +310,8 @@ def run_ours(args):
             ph["scheme"] = ("two-phase: approximate windows travel, owners re-rank" if nph == 3
                             else "one exchange: every rank re-ranks its local window, finished results travel")
             ph["how"] = "CUDA events between the phases on the real GPUs, mean over the timed steps, max over ranks"
-        st.phase_events = None
+        if hasattr(st, "phase_events"):
+            st.phase_events = None
         stt = st._dev.stats()
         launches = stt["kernel_launches"] - l0 + (steps if (world > 1 and ph is None) else 0)  # + the merge kernel
         # every distinct batch through the escalating API: nothing unproven may be left
@@ -312,8 +322,10 @@ def run_ours(args):
         return {"ms_per_step": ms / steps, "qps": batch * steps / (ms / 1e3),
                 "kernel_ms": (kms / nsamp) if nsamp else None, "plan": stt["last_plan"], "launches": launches,
                 "clocks": clocks, "phases": ph, "escalated": st.n_escalations - esc0, "qd": qd,
-                "exchange": ("peer-memory mailboxes (CUDA IPC, NVLink stores, on-device flag wait)" if st.exchange == "p2p"
-                             else "NCCL all_gather_into_tensor + merge kernel") if world > 1 else "none"}
+                "exchange": ("none" if world == 1 else "NCCL all_gather_into_tensor of the replicas' result blocks"
+                             if not hasattr(st, "exchange") else
+                             "peer-memory mailboxes (CUDA IPC, NVLink stores, on-device flag wait)" if st.exchange == "p2p"
+                             else "NCCL all_gather_into_tensor + merge kernel")}
 
     def e2e_timed(store: DeviceStore, d, k, metric, batch, steps, warmup):
         """The C-ABI host call with pageable numpy buffers, wall clock, rank 0's process."""
@@ -362,11 +374,27 @@ def run_ours(args):
         return res
 
     # ================================ headline: configs[1] ================================
+    # N > 1: the corpus is row-sharded (the headline).  Whole-store replicas answering disjoint query blocks (the
+    # reference's own scale-out model) are measured beside it in the SAME sustained state and reported
+    # under `layouts` -- never instead of it.
+    from erlvectordb_b200.sharded import ReplicaGroup
+    layout = "rows"
     st = ShardedStore(dtype="f32", device=local, rank=rank, world=world)
     st.fill_synthetic(synth.SEED_CORPUS, N_ROWS, DIM)
     rows_local = st.hi - st.lo
-    main = device_timed(st, N_ROWS, DIM, K, "cosine", args.batch, args.steps, args.warmup, sample_clocks=True,
-                        phases=world > 1)
+    main_rows = device_timed(st, N_ROWS, DIM, K, "cosine", args.batch, args.steps, args.warmup, sample_clocks=layout == "rows",
+                             phases=world > 1, preload=True)
+    main_rep = None
+    if world > 1:
+        rg = ReplicaGroup(dtype="f32", device=local, rank=rank, world=world)
+        rg.fill_synthetic(synth.SEED_CORPUS, N_ROWS, DIM)
+        main_rep = device_timed(rg, N_ROWS, DIM, K, "cosine", args.batch, args.steps, args.warmup, sample_clocks=layout == "replicas",
+                                preload=True)
+        r = rg.search(main_rep["qd"][0], K, "cosine")
+        main_rep["digest"] = digest(r[0].cpu().numpy(), r[1].cpu().numpy())
+        rg.close()
+        del rg
+    main = main_rep if layout == "replicas" else main_rows
     one = None
     if args.batch != BATCH_ONE:
         one = device_timed(st, N_ROWS, DIM, K, "cosine", BATCH_ONE, max(args.steps * 10, 50), max(args.warmup, 5))
@@ -392,30 +420,6 @@ def run_ours(args):
     chk_main = check_results(st, single, multi, DIM, K, "cosine", args.batch)
     chk_one = check_results(st, single, multi, DIM, K, "cosine", BATCH_ONE) if one is not None else None
 
-    # secondary (N > 1): whole-store replicas answering disjoint query blocks (the
-    # reference's own scale-out model) -- the throughput alternative to row sharding for a store
-    # that fits one GPU.  Reported beside the row-sharded headline, never instead of it.
-    replicas = None
-    if world > 1 and not args.no_extra:
-        from erlvectordb_b200.sharded import ReplicaGroup
-        rg = ReplicaGroup(dtype="f32", device=local, rank=rank, world=world)
-        rg.fill_synthetic(synth.SEED_CORPUS, N_ROWS, DIM)
-        qd = main["qd"]
-        for i in range(args.warmup):
-            rg.search(qd[i % POOL], K, "cosine", escalate=False)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(args.steps):
-            rg.search(qd[i % POOL], K, "cosine", escalate=False)
-        e1.record()
-        barrier()
-        ms = max_over_ranks(e0.elapsed_time(e1))
-        r = rg.search(qd[0], K, "cosine")
-        replicas = {"value": args.batch * args.steps / (ms / 1e3), "unit": "queries/s", "ms_per_step": ms / args.steps,
-                    "digest": digest(r[0].cpu().numpy(), r[1].cpu().numpy()),
-                    "note": f"{world} whole-store replicas, batch {args.batch} split into disjoint blocks, results all-gathered"}
-        rg.close()
     if multi is not None:
         multi.close()
     if single is not None and world > 1:
@@ -526,7 +530,8 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": "1Mx768 fp32 cosine k=10 (BASELINE.json configs[1])", "rows": N_ROWS,
                        "dim": DIM, "k": K, "batch": args.batch, "plan": {1: "scan", 2: "gemm", 3: "exact"}.get(main["plan"]),
-                       "sharding": f"rows/{world}" if world > 1 else "none",
+                       "sharding": ("none" if world == 1 else f"rows/{world}" if layout == "rows"
+                                    else f"{world} whole-store replicas x {args.batch // world} queries each"),
                        "exchange": main["exchange"],
                        "queries": f"{POOL} distinct batches rotated through the steps",
                        "cache": "inputs larger than L2 (3.07 GB fp32 corpus, 126 MB L2)",
@@ -538,14 +543,21 @@ def run_ours(args):
                     "through": "evdb_store_search_f64, pageable host buffers" +
                                ("" if world == 1 else f", one handle over {world} devices (evdb_opts.n_shards) in rank 0's process")},
             "gpu_launches": main["launches"],
-            "roofline": roofline(main["plan"], main["kernel_ms"], args.batch, rows_local, DIM, "f32", "gemm_topk_kernel"),
+            "roofline": roofline(main["plan"], main["kernel_ms"], args.batch if layout == "rows" else args.batch // world,
+                                 rows_local if layout == "rows" else N_ROWS, DIM, "f32", "gemm_topk_kernel"),
             "cpu_baseline": cpu,
             "escalated_queries": main["escalated"],
         }
         if main["phases"]:
             out["phases"] = main["phases"]
-        if replicas is not None:
-            out["replica_groups"] = replicas
+        if main_rep is not None:
+            lay = lambda r, note: {"value": r["qps"], "unit": "queries/s", "ms_per_step": r["ms_per_step"], "note": note}
+            out["layouts"] = {"chosen": layout,
+                              "rows": lay(main_rows, f"the corpus row-sharded over {world} GPUs, every GPU sees every query, one exchange + merge"),
+                              "replicas": lay(main_rep, f"{world} whole-store replicas, batch {args.batch} split into disjoint blocks, results all-gathered")}
+            out["layouts"]["replicas"]["digest"] = main_rep["digest"]
+            out["layouts"]["rows"]["phases"] = main_rows["phases"]
+            out["replica_groups"] = out["layouts"]["replicas"]
         if one is not None:
             out["batch1"] = {"value": one["qps"], "unit": "queries/s", "ms_per_step": one["ms_per_step"],
                              "latency_ms": {"p50": e2e_one["p50_ms"], "p99": e2e_one["p99_ms"],

@@ -299,10 +299,11 @@ class ShardedStore:
 class ReplicaGroup:
     """Whole-store replicas, one per GPU, answering DISJOINT query blocks (the reference's own
     scale-out model: cluster_manager replicates whole stores, reference src/cluster_manager.erl:148-171;
-    SURVEY 8f-4).  For a store that fits one GPU this scales QPS better than row sharding: every
-    per-query cost (threshold seeding, re-rank) divides by the number of ranks too, and no merge is
-    needed -- results of the blocks are simply all-gathered.  Row sharding (ShardedStore) is for
-    capacity; this is for throughput."""
+    SURVEY 8f-4).  Every per-query cost divides by the number of ranks and no merge is needed -- the
+    blocks' results are simply all-gathered -- but every replica reads the WHOLE operand column for its
+    query block.  Measured in the same sustained state on B200 (bench.py `layouts`, 1 M x 768, batch 1024)
+    it is level with or behind row sharding: N = 2: 1.07 M against 1.22 M QPS, N = 4: 2.03 M against 2.09 M,
+    N = 8: 2.7 M against 3.2 M.  Kept as the reference's own model; row sharding is the default."""
 
     def __init__(self, dtype="f32", device=0, rank=None, world=None, group=None, local_search=None):
         self.group = group
@@ -313,9 +314,11 @@ class ReplicaGroup:
         self._bufs = {}
         self.n_total = 0
         self.n_escalations = 0
+        self.lo = self.hi = 0
 
     def fill_synthetic(self, seed: int, n_total: int, d: int):
         self.n_total = n_total
+        self.lo, self.hi = 0, n_total
         if self._dev is not None:
             self._dev.fill_synthetic(seed, n_total, d)
 
