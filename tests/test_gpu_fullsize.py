@@ -102,3 +102,44 @@ def test_config5_1m_x_1536_manhattan_and_4bit(native, oracle):
     e_s, e_d, e_c = s4.search(qs, k, "cosine")
     assert np.array_equal(a_s, e_s) and np.array_equal(a_d, e_d)
     s4.close()
+
+
+def test_config5_manhattan_batch_shares_row_loads_and_stays_exact(native, oracle):
+    """BASELINE configs[4] at full size, a BATCH: the multi-query scan (8 queries per pass over the 6 GB of
+    rows) must return, for every query, exactly what the one-query pass returns, and the winners' distances
+    are the strict oracle's."""
+    from erlvectordb_b200.device_store import DeviceStore
+    n, d, k, B = 1_000_000, 1536, 10, 11
+    qs = oracle.synth_f64(oracle.SEED_QUERY, 0, B, d)
+    st = DeviceStore(dtype="f32", device=0)
+    st.fill_synthetic(oracle.SEED_CORPUS, n, d)
+    bs, bd, bc = st.search(qs, k, "manhattan")             # 8 + 3 queries: a full and a ragged pass
+    assert st.stats()["last_plan"] == native.PLAN_SCAN and (bc == k).all()
+    for b in (0, 7, 8, 10):
+        s1, d1, _ = st.search(qs[b], k, "manhattan")
+        assert bs[b].tolist() == s1[0].tolist() and bd[b].tolist() == d1[0].tolist()
+    _winners_are_exact(oracle, st, bs, bd, qs, d, "manhattan", nq=2)
+    st.close()
+
+
+def test_config2_one_handle_three_shards_equals_single_store(native, oracle):
+    """BASELINE configs[1] at full size behind ONE multi-shard handle (three shards sharing this GPU): batch
+    1024 and a lone query, under the default one-exchange scheme, bit-equal to the single-device store."""
+    from erlvectordb_b200.device_store import DeviceStore
+    n, d, k = 1_000_000, 768, 10
+    qs = oracle.synth_f64(oracle.SEED_QUERY, 0, 1024, d)
+    one = DeviceStore(dtype="f32", device=0)
+    one.fill_synthetic(oracle.SEED_CORPUS, n, d)
+    want = one.search(qs, k, "cosine")
+    w1 = one.search(qs[5], k, "cosine")
+    one.close()
+    m = DeviceStore(dtype="f32", devices=[0, 0, 0])
+    m.fill_synthetic(oracle.SEED_CORPUS, n, d)
+    got = m.search(qs, k, "cosine")
+    g1 = m.search(qs[5], k, "cosine")
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    for a, b in zip(g1, w1):
+        assert np.array_equal(a, b)
+    _winners_are_exact(oracle, m, got[0], got[1], qs, d, "cosine", nq=2)
+    m.close()
