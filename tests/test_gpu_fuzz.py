@@ -46,3 +46,46 @@ def test_gemm_scan_oracle_agree(native, oracle, n, d, B, k, metric, seed):
         assert gc[b] == kk
         assert gs[b, :kk].tolist() == r.tolist() and gd[b, :kk].tolist() == dd.tolist(), (b,)
     st.close()
+
+
+def _small_cases():
+    rng = np.random.default_rng(77)
+    out = []
+    for i in range(18):
+        n = int(rng.choice([1, 2, 9, 31, 100, 257, 1000, 4097, 20_000]))
+        d = int(rng.choice([1, 2, 5, 16, 33, 96, 128, 255, 256, 257, 400]))
+        B = int(rng.choice([1, 1, 2, 3, 5, 8, 9, 13]))
+        k = int(rng.choice([1, 3, 10, 40, 100]))
+        out.append((n, d, B, k, ["cosine", "euclidean", "manhattan"][i % 3], ["f32", "bf16"][(i // 3) % 2], int(rng.integers(1, 1 << 30))))
+    return out
+
+
+@pytest.mark.parametrize("n,d,B,k,metric,dtype,seed", _small_cases())
+def test_small_store_and_multi_query_paths_agree_with_the_exhaustive_plan(native, oracle, n, d, B, k, metric, dtype, seed):
+    """The one-launch small-store search (B <= 2, d <= 256) and the multi-query float scan (B >= 2) over odd
+    shapes -- fewer rows than k, one-element vectors, ragged query groups, duplicates, a zero row -- against
+    the exhaustive fp64 plan of the same store, and for fp32 stores against the strict oracle."""
+    from erlvectordb_b200.device_store import DeviceStore
+    rng = np.random.default_rng(seed)
+    rows = rng.standard_normal((n, d)).astype(np.float32)
+    if n > 3:
+        rows[1] = rows[3]            # exact duplicate: tie broken by slot
+        rows[2] = 0.0                # zero norm: cosine distance 1.0
+    qs = rng.standard_normal((B, d))
+    st = DeviceStore(dtype=dtype, device=0)
+    try:
+        st.bulk_load(rows)
+        got = st.search(qs, k, metric)
+        assert st.stats()["last_plan"] in (native.PLAN_SCAN, native.PLAN_GEMM, native.PLAN_EXACT)
+        st.set_plan("exact")
+        want = st.search(qs, k, metric)
+        for a, b in zip(got, want):
+            assert np.array_equal(a, b)
+        if dtype == "f32":
+            ref = rows.astype(np.float64)
+            kk = min(k, n)
+            for b in range(B):
+                r, dd = oracle.search(ref, qs[b], k, metric)
+                assert got[2][b] == kk and got[0][b, :kk].tolist() == r.tolist() and got[1][b, :kk].tolist() == dd.tolist()
+    finally:
+        st.close()
