@@ -5,6 +5,7 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/evdb.h"
 
@@ -105,6 +106,36 @@ __device__ __forceinline__ uint32_t dp4a_uu(uint32_t a, uint32_t b, uint32_t c) 
     uint32_t d;
     asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
+}
+
+// ---- programmatic dependent launch (the kernel chain of one search) -----------------------------
+// A kernel launched with launch_chained() may be scheduled while its predecessor in the stream still
+// runs; it must call pdl_wait() before it touches anything the predecessor wrote (or still reads), and
+// a predecessor lets its dependent in with pdl_launch_dependents().  The launch latency of the next link
+// then overlaps the tail of the previous one.  EVDB_PDL=0 launches every link the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_chained(void (*fn)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                         int cluster_x, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (pdl_enabled()) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (cluster_x > 1) {
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = cluster_x; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    cfg.attrs = at; cfg.numAttrs = na;
+    return cudaLaunchKernelEx(&cfg, fn, args...);
 }
 
 __host__ __device__ __forceinline__ int round_up(int x, int m) { return (x + m - 1) / m * m; }

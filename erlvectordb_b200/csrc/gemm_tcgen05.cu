@@ -388,6 +388,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // barriers and TMEM are set up: everything below reads what earlier kernels of the chain wrote
+    pdl_wait();
+    pdl_launch_dependents();
 
     const int cta = blockIdx.x;
     const int nCTA = a.MB * a.NG;
@@ -590,6 +593,7 @@ __global__ void __launch_bounds__(256) prep_queries_gemm_kernel(const double *__
                                                                 float *__restrict__ eps_q) {
     __shared__ double red[8];
     __shared__ double redm[8];
+    pdl_launch_dependents();   // first link of the chain (launched the ordinary way): the next one may queue up
     const int b = blockIdx.x;
     __half *o = qh + (size_t)b * kpitch;
     // the norm K-step multiplies the three fp16 pieces of -sigma^2*||v||^2/2 by exactly 1
@@ -693,6 +697,8 @@ __global__ void __launch_bounds__(kSeedThreads) seed_threshold_kernel(const floa
                                                                       int S, int need, uint32_t *__restrict__ thr0) {
     __shared__ int s_cnt[6];
     __shared__ uint32_t s_lo, s_hi;
+    pdl_wait();                // the pooled scores come from the pre-pass
+    pdl_launch_dependents();
     // blockIdx.y = group of <= 8192 pooled values: the `need`-th smallest of each group, maximum over
     // the groups (atomicMax, thr0 zeroed before) -- with need = ceil(KP / groups) at least KP values
     // of the whole sample are at or below that maximum, so it still bounds the KP-th best
@@ -788,26 +794,12 @@ static int launch_gemm_kernel(bool pair, int grid, cudaStream_t st, const CUtens
     if (!pair) {
         const size_t smem = GemmCfg<false>::kSmem;
         EVDB_TRY(ensure_func_smem((const void *)gemm_topk_kernel<false>, smem));
-        gemm_topk_kernel<false><<<grid, kGemmThreads, smem, st>>>(tmQ, tmV, tmQt, tmVt, a);
-        EVDB_CUDA(cudaGetLastError());
+        EVDB_CUDA(launch_chained(gemm_topk_kernel<false>, dim3(grid), dim3(kGemmThreads), smem, st, 1, tmQ, tmV, tmQt, tmVt, a));
         return EVDB_OK;
     }
     const size_t smem = GemmCfg<true>::kSmem;
     EVDB_TRY(ensure_func_smem((const void *)gemm_topk_kernel<true>, smem));
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kGemmThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    EVDB_CUDA(cudaLaunchKernelEx(&cfg, gemm_topk_kernel<true>, tmQ, tmV, tmQt, tmVt, a));
+    EVDB_CUDA(launch_chained(gemm_topk_kernel<true>, dim3(grid), dim3(kGemmThreads), smem, st, 2, tmQ, tmV, tmQt, tmVt, a));
     return EVDB_OK;
 }
 
@@ -938,6 +930,7 @@ int launch_gemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int metr
     int *cand_cnt = (int *)wp; wp += cnt_bytes;
     uint64_t *cand = (uint64_t *)wp;
 
+    EVDB_CUDA(cudaMemsetAsync(thr, 0, sizeof(uint32_t) * (size_t)Bpad, st));   // seeded thresholds accumulate by atomicMax
     prep_queries_gemm_kernel<<<Bpad, 256, 0, st>>>(d_q64, B, s->dim, metric, sigma, s->max_norm, qh, kpitch,
                                                    l2 ? qtail : nullptr, qc0, eps_q);
     EVDB_CUDA(cudaGetLastError());
@@ -992,12 +985,12 @@ int launch_gemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int metr
         const int groups = (pooled + kSeedThreads * kSeedMaxVpt - 1) / (kSeedThreads * kSeedMaxVpt);
         const int need = (KP + groups - 1) / groups;
         const dim3 sgrid(Bpad, groups);
-        EVDB_CUDA(cudaMemsetAsync(thr, 0, sizeof(uint32_t) * (size_t)Bpad, st));
-        if (vpt <= 4) seed_threshold_kernel<4><<<sgrid, kSeedThreads, 0, st>>>(dump, pooled, pooled, need, thr);
-        else if (vpt <= 8) seed_threshold_kernel<8><<<sgrid, kSeedThreads, 0, st>>>(dump, pooled, pooled, need, thr);
-        else if (vpt <= 16) seed_threshold_kernel<16><<<sgrid, kSeedThreads, 0, st>>>(dump, pooled, pooled, need, thr);
-        else seed_threshold_kernel<kSeedMaxVpt><<<sgrid, kSeedThreads, 0, st>>>(dump, pooled, pooled, need, thr);
-        EVDB_CUDA(cudaGetLastError());
+        // (thr was zeroed before the query prep: nothing but kernels between the links of the chain)
+        const int pooled_i = pooled;
+        if (vpt <= 4) EVDB_CUDA(launch_chained(seed_threshold_kernel<4>, sgrid, dim3(kSeedThreads), 0, st, 1, (const float *)dump, pooled_i, pooled_i, need, thr));
+        else if (vpt <= 8) EVDB_CUDA(launch_chained(seed_threshold_kernel<8>, sgrid, dim3(kSeedThreads), 0, st, 1, (const float *)dump, pooled_i, pooled_i, need, thr));
+        else if (vpt <= 16) EVDB_CUDA(launch_chained(seed_threshold_kernel<16>, sgrid, dim3(kSeedThreads), 0, st, 1, (const float *)dump, pooled_i, pooled_i, need, thr));
+        else EVDB_CUDA(launch_chained(seed_threshold_kernel<kSeedMaxVpt>, sgrid, dim3(kSeedThreads), 0, st, 1, (const float *)dump, pooled_i, pooled_i, need, thr));
         s->n_launches += 2;
         thr0 = thr;
     }

@@ -599,6 +599,7 @@ __device__ __forceinline__ void select_body(const SelectArgs &a, const int b, ui
 template <int DTYPE, int THREADS>
 __global__ void __launch_bounds__(THREADS) select_kernel(const SelectArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
+    pdl_wait();   // last link of a search's kernel chain (common.cuh): the candidates come from the scan / GEMM before it
     select_body<DTYPE, THREADS>(a, blockIdx.x, smem);
 }
 
@@ -1036,6 +1037,7 @@ __device__ __forceinline__ void mw_produce(const uint8_t *rows, size_t row_bytes
 __global__ void __launch_bounds__(kSwWarps * kMwGroup * 32) select_warp_kernel(const SelectArgs a, int B) {
     using LY = SwLayout;
     extern __shared__ __align__(16) uint8_t smem[];
+    pdl_wait();   // the candidate buffers come from gemm_topk_kernel
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int role = wid < kSwWarps ? 0 : 1 + (wid - kSwWarps) % kMwProducers;
     const int warp = wid < kSwWarps ? wid : (wid - kSwWarps) / kMwProducers;   // the query of the CTA this warp works for
@@ -1294,8 +1296,7 @@ static int launch_select_warp(const SelectArgs &a, int B, cudaStream_t st) {
     const size_t smem = (size_t)kSwWarps * SwLayout::kPerWarp + (size_t)(a.L + 1) * kSwWarps * 6 + (size_t)(a.L + 1) * 4 + 16;
     if (smem > 220 * 1024) return EVDB_E_UNSUPPORTED;
     EVDB_TRY(ensure_func_smem((const void *)select_warp_kernel, smem));
-    select_warp_kernel<<<(B + kSwWarps - 1) / kSwWarps, kSwWarps * kMwGroup * 32, smem, st>>>(a, B);
-    EVDB_CUDA(cudaGetLastError());
+    EVDB_CUDA(launch_chained(select_warp_kernel, dim3((B + kSwWarps - 1) / kSwWarps), dim3(kSwWarps * kMwGroup * 32), smem, st, 1, a, B));
     if (a.variant & 16) {
         cudaStreamSynchronize(st);
         unsigned long long h[10], z[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -1654,9 +1655,8 @@ int launch_select(evdb_store *s, const double *d_q64, const uint64_t *partial, c
     }
 #undef EVDB_SEL
     EVDB_TRY(ensure_func_smem((const void *)fn, smem));
-    fn<<<B, threads, smem, st>>>(a);
+    EVDB_CUDA(launch_chained(fn, dim3(B), dim3(threads), smem, st, 1, a));
     s->n_launches++;
-    EVDB_CUDA(cudaGetLastError());
     if (a.variant & 16) {
         cudaStreamSynchronize(st);
         unsigned long long h[10], z[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};

@@ -85,6 +85,12 @@ int cached_occupancy(const void *fn, int threads, size_t smem, int *occ) {
     return EVDB_OK;
 }
 
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("EVDB_PDL"); on = e ? (atoi(e) != 0) : 1; }
+    return on != 0;
+}
+
 static bool is_quant(const evdb_store *s) { return s->dtype == EVDB_U8 || s->dtype == EVDB_U4; }
 
 static int set_device(const evdb_store *s) {
