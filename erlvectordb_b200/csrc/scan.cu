@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const double *__restr
                                                            QStat *__restrict__ qstat, float *__restrict__ qeps) {
     __shared__ double redd[8];
     __shared__ long long redl[8];
+    pdl_launch_dependents();   // first link of a scan plan's chain (common.cuh)
     const int b = blockIdx.x;
     const double *q = q64 + (size_t)b * d;
     double ss = 0.0, sm = 0.0, mx = 0.0;
@@ -162,6 +163,8 @@ template <int METRIC, int DTYPE, int TPR, int R>
 __global__ void __launch_bounds__(kScanWarps * 32, DTYPE == EVDB_F32 ? 4 : 3)   // F32: 4 CTAs (32 warps) per SM -- the loads in flight are what hides HBM latency
 scan_float_kernel(const ScanArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
+    pdl_wait();                // the prepared query comes from prep_queries_kernel
+    pdl_launch_dependents();
     constexpr int QPC = (DTYPE == EVDB_F32) ? 1 : 2;  // query float4s per 16-byte row chunk
     constexpr int GPW = 32 / TPR;                      // row groups per warp
     const int nch = a.nch, KP = a.KP;
@@ -259,6 +262,8 @@ template <int METRIC, int DTYPE, int TPR, int Q>
 __global__ void __launch_bounds__(kScanWarps * 32, (DTYPE == EVDB_BF16 && Q > 2) ? 1 : 2)
 scan_float_mq_kernel(const ScanArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
+    pdl_wait();                // the prepared query comes from prep_queries_kernel
+    pdl_launch_dependents();
     // rows in flight per group.  F32: R * Q = 8 accumulators, two CTAs per SM (measured on B200, 1 M x 1536 manhattan:
     // 3.5 k QPS against 2.6 k with 16 accumulators and one CTA per SM); BF16 (two query float4s per chunk: twice the
     // shared-memory reads per row byte) gains from reusing every query value for more rows: 16 accumulators, one CTA
@@ -508,6 +513,8 @@ template <int DTYPE, int TPR, int R>
 __global__ void __launch_bounds__(kScanWarps * 32, 2)
 scan_quant_kernel(const ScanArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
+    pdl_wait();                // the prepared query comes from prep_queries_kernel
+    pdl_launch_dependents();
     constexpr int GPW = 32 / TPR;
     constexpr int UPC = (DTYPE == EVDB_U8) ? 1 : 2;  // uint4 of digits per plane per row chunk
     const int nch = a.nch, KP = a.KP;
@@ -622,6 +629,8 @@ template <int DTYPE, int TPR, int R>
 __global__ void __launch_bounds__((kScanWarps + 1) * 32, 2)
 scan_quant_tma_kernel(const ScanArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];   // (the runtime places dynamic shared memory on a >= 128-byte boundary; stages are multiples of 128 B)
+    pdl_wait();                // the prepared query comes from prep_queries_kernel
+    pdl_launch_dependents();
     constexpr int GPW = 32 / TPR;
     constexpr int UPC = (DTYPE == EVDB_U8) ? 1 : 2;
     const int WT = a.tma_wt, NG = kScanWarps / WT;     // warps per tile, consumer groups
@@ -1046,9 +1055,8 @@ int launch_scan(evdb_store *s, int metric, const ScanArgs &a0, cudaStream_t st) 
     a.tma_wt = p.wt;
     if (p.smem > 48 * 1024) EVDB_TRY(ensure_func_smem((const void *)p.fn, p.smem));
     dim3 grid(a.G, p.mq ? (a.B + p.mq - 1) / p.mq : a.B);
-    p.fn<<<grid, p.threads, p.smem, st>>>(a);
+    EVDB_CUDA(launch_chained(p.fn, grid, dim3(p.threads), p.smem, st, 1, a));
     s->n_launches++;
-    EVDB_CUDA(cudaGetLastError());
     return EVDB_OK;
 }
 
