@@ -817,8 +817,8 @@ __device__ __forceinline__ uint32_t warp_nth_of_regs(const uint32_t (&v)[VPL], i
 // strided SUBSET bounds the need-th smallest overall, so only keys at or below it can matter --
 // about T * need / subset of them.  The subset lives in registers (no shared-memory passes per
 // bisection round); one compaction pass, then the exact selection runs on what is left.
+template <int VPL>                               // 32 * VPL-key subset
 __device__ __forceinline__ int warp_precut_inplace(uint64_t *keys, int T, int need, int lane) {
-    constexpr int VPL = 8;                       // 256-key subset
     const uint32_t *hi32 = reinterpret_cast<const uint32_t *>(keys) + 1;
     const int stride = T / (32 * VPL);
     uint32_t v[VPL];
@@ -842,7 +842,10 @@ __device__ __forceinline__ int warp_precut_inplace(uint64_t *keys, int T, int ne
 
 __device__ __forceinline__ void warp_select_inplace(uint64_t *keys, int T, int need, int lane) {
     if (need <= 64 && T >= 8 * need && T >= 512) {
-        T = warp_precut_inplace(keys, T, need, lane);
+        T = warp_precut_inplace<8>(keys, T, need, lane);
+        if (T == need) return;
+    } else if (need <= 128 && T >= 8 * need && T >= 1024) {      // k = 100 windows: a 512-key subset (stride >= 2)
+        T = warp_precut_inplace<16>(keys, T, need, lane);
         if (T == need) return;
     }
     const uint32_t *hi32 = reinterpret_cast<const uint32_t *>(keys) + 1;  // score word of key i at hi32[2*i]
