@@ -19,7 +19,8 @@ CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(ROOT, "build", "evdb")
 LIB = os.path.join(PKG, "libevdb_b200.so")
 
-SOURCES = ["store.cu", "mstore.cu", "scan.cu", "select.cu", "ingest.cu", "gemm_tcgen05.cu", "exchange.cu"]
+SOURCES = ["store.cu", "mstore.cu", "scan.cu", "scan_mq_f32.cu", "scan_mq_bf16.cu", "select.cu", "ingest.cu",
+           "gemm_tcgen05.cu", "exchange.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

@@ -192,6 +192,9 @@ constexpr int kRawMaxLists = 640;  // NG * parts <= 148 * 4
 
 // ---- launchers (each returns EVDB_OK or an error; all async on `st`) ----
 int launch_prep_queries(evdb_store *s, const double *d_q64, int B, int metric, cudaStream_t st);
+typedef void (*scan_fn_t)(const ScanArgs);
+scan_fn_t pick_float_mq_f32(int metric, int tpr, int Q);    // scan_mq_f32.cu
+scan_fn_t pick_float_mq_bf16(int metric, int tpr, int Q);   // scan_mq_bf16.cu
 int scan_grid_size(evdb_store *s, int metric, int KP, int B, int *G_out);
 int debug_quant_dots(evdb_store *s, const double *d_q64, const uint32_t *d_slots, int n, long long *d_S, int *d_planes,
                      int *d_csum, float *h_fx, cudaStream_t st);
