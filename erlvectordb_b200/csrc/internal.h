@@ -55,7 +55,7 @@ struct evdb_store {
     int sm_count = 148;
     int plan = EVDB_PLAN_AUTO;
     int gemm_shadow = 0;
-    uint64_t count = 0, capacity = 0;
+    uint64_t count = 0, capacity = 0, capacity_hint = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;   // host search: start, end, after H2D, before D2H
 

@@ -126,6 +126,7 @@ static int ensure_capacity(evdb_store *s, uint64_t need) {
     if (need <= s->capacity) return EVDB_OK;
     uint64_t ncap = s->capacity ? s->capacity * 2 : 1024;
     if (ncap < need) ncap = need;
+    if (s->capacity == 0 && ncap < s->capacity_hint) ncap = s->capacity_hint;   // evdb_opts.capacity_hint, also when the dimension came later
     uint64_t live = s->count;
     EVDB_TRY(regrow(&s->rows, live, ncap, s->row_bytes, s->stream));
     EVDB_TRY(regrow(&s->norm64, live, ncap, sizeof(double), s->stream));
@@ -903,6 +904,7 @@ int evdb_store_create(const evdb_opts *opts, evdb_store **out) {
     s->device = opts->device;
     s->dtype = opts->dtype;
     s->gemm_shadow = opts->gemm_shadow;
+    s->capacity_hint = opts->capacity_hint;
     int rc = EVDB_OK;
     do {
         if (cudaSetDevice(s->device) != cudaSuccess) { rc = EVDB_E_CUDA; break; }
