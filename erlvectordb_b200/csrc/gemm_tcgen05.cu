@@ -93,7 +93,7 @@ struct GemmArgs {
     const uint32_t *thr0;  // mode 0: per-query starting threshold, orderable key score (NULL = none)
     const float *qc0;    // [Bpad] key score = fma(acc, c1, qc0[q])
     float c1;            // < 0
-    int debug;           // EVDB_GEMM_DEBUG (measurement only): 1 = no appends, 2 = no TMEM loads, 8 = cycle breakdown
+    int debug;           // EVDB_GEMM_DEBUG (measurement only): 1 = no appends, 2 = no TMEM loads, 8 = cycle breakdown, 16 = no Q reloads (pair variant)
     unsigned long long *dbg;  // [CTAs][epilogue warps][8]
 };
 
@@ -414,8 +414,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                         if (PAIR) {
                             // both CTAs' tiles complete on the LEADER's barrier; it alone posts the byte count
                             const uint32_t fb = mapa_u32(full0 + 8 * stage, 0);
-                            if (leader) mbar_arrive_expect_tx(full0 + 8 * stage, 2 * kStageBytes);
-                            tma_load_2d_pair(sa, &tmQ, fb, kb * GK, qrow);
+                            const bool skipq = (a.debug & 16) && t > 0;   // measurement only: stale Q operand, V traffic alone
+                            if (leader) mbar_arrive_expect_tx(full0 + 8 * stage, skipq ? 2 * Cfg::kStageBBytes : 2 * kStageBytes);
+                            if (!skipq) tma_load_2d_pair(sa, &tmQ, fb, kb * GK, qrow);
                             tma_load_2d_pair(sa + kStageABytes, &tmV, fb, kb * GK, vrow + (int)(crank * Cfg::kBRows));
                         } else {
                             mbar_arrive_expect_tx(full0 + 8 * stage, kStageBytes);
