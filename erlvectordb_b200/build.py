@@ -20,7 +20,7 @@ OBJ = os.path.join(ROOT, "build", "evdb")
 LIB = os.path.join(PKG, "libevdb_b200.so")
 
 SOURCES = ["store.cu", "mstore.cu", "scan.cu", "scan_mq_f32.cu", "scan_mq_bf16.cu", "select.cu", "ingest.cu",
-           "gemm_tcgen05.cu", "exchange.cu"]
+           "gemm_tcgen05.cu", "gemm_i8.cu", "exchange.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

@@ -199,6 +199,10 @@ int scan_grid_size(evdb_store *s, int metric, int KP, int B, int *G_out);
 int debug_quant_dots(evdb_store *s, const double *d_q64, const uint32_t *d_slots, int n, long long *d_S, int *d_planes,
                      int *d_csum, float *h_fx, cudaStream_t st);
 int launch_scan(evdb_store *s, int metric, const ScanArgs &a, cudaStream_t st);
+// gemm_i8.cu: query batches against a U8 store as a tcgen05 kind::i8 GEMM over the codes
+bool qgemm_plan_supported(evdb_store *s, int metric, int B, int KP);
+int launch_qgemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int *lists_per_query,
+                      const float **d_eps_q, RawCands *raw, cudaStream_t st);
 // eps_q: optional per-query absolute bound added to eps_abs; squared: key scores are squared
 // distances (euclidean GEMM plan)
 int launch_select(evdb_store *s, const double *d_q64, const uint64_t *partial, const RawCands *raw, int lists_per_query,

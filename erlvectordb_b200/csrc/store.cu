@@ -195,9 +195,17 @@ int search_core(evdb_store *s, const double *d_q64, int B, int k, int kstride, i
         (plan == EVDB_PLAN_AUTO && !s->gemm_oom &&
          (B >= 16 || (double)B * (double)s->count * (double)s->row_bytes >= gemm_min_bytes)))
         use_gemm = gemm_plan_supported(s, metric, B, gemm_kp(KP));
-    if (plan == EVDB_PLAN_GEMM && !use_gemm) return EVDB_E_UNSUPPORTED;
+    // quantization_8bit stores: batches run as a kind::i8 GEMM over the codes themselves (gemm_i8.cu); a scan
+    // pass serves one query, so the crossover is a handful of queries (EVDB_QGEMM_MIN_BATCH overrides it)
+    bool use_qgemm = false;
+    static int qgemm_min_batch = -1;
+    if (qgemm_min_batch < 0) { const char *e = getenv("EVDB_QGEMM_MIN_BATCH"); qgemm_min_batch = e ? atoi(e) : 4; }
+    if (s->dtype == EVDB_U8 && metric == EVDB_COSINE &&
+        (plan == EVDB_PLAN_GEMM || (plan == EVDB_PLAN_AUTO && !s->gemm_oom && B >= qgemm_min_batch)))
+        use_qgemm = qgemm_plan_supported(s, metric, B, gemm_kp(KP));
+    if (plan == EVDB_PLAN_GEMM && !use_gemm && !use_qgemm) return EVDB_E_UNSUPPORTED;
 
-    if (use_gemm && B > gemm_max_batch()) {
+    if ((use_gemm || use_qgemm) && B > gemm_max_batch()) {
         // the candidate buffers are sized per sweep: larger batches go through in slices
         const int slice = gemm_max_batch();
         for (int b0 = 0; b0 < B; b0 += slice) {
@@ -235,7 +243,24 @@ int search_core(evdb_store *s, const double *d_q64, int B, int k, int kstride, i
             squared = metric == EVDB_EUCLIDEAN;
         }
     }
-    if (!use_gemm) {
+    if (use_qgemm) {
+        const int rc = launch_qgemm_topk(s, d_q64, B, gemm_kp(KP), &lists, &eps_q, &raw, st);
+        if (rc == EVDB_E_OOM && plan == EVDB_PLAN_AUTO) {
+            (void)cudaGetLastError();
+            s->gemm_oom = 1;
+            use_qgemm = false;
+            eps_q = nullptr;
+        } else {
+            EVDB_TRY(rc);
+            s->last_plan = EVDB_PLAN_GEMM;
+            KP = gemm_kp(KP);
+            have_raw = true;
+            // exact integer digit sums; fp32 from there on: two int->float, the combine, cy*sum(Q), two fmas
+            // (48 u leaves the same head-room over the count as the scan's 24 u); + the query-grid bound in eps_q
+            eps_abs = (float)(48.0 * u);
+        }
+    }
+    if (!use_gemm && !use_qgemm) {
         // Small float stores, a lone query: prep + scan + selection in ONE launch (select.cu small_fused_kernel)
         // -- three dependent kernels cost more than their work.
         static int fused_on = -1;

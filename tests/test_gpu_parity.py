@@ -543,11 +543,12 @@ def test_tma_staged_quantized_scan_equals_exhaustive_plan(native, oracle, n, d, 
 
 def test_scan_batch_larger_than_the_grid_limit_is_sliced(native, oracle):
     """The scan kernels carry the query index in gridDim.y: more than 32768 queries on a store
-    without a GEMM plan (here: quantized) go through in slices, every slice in its own rows."""
+    on the scan plan (here: a quantized store pinned to it) go through in slices, every slice in its own rows."""
     n, d, B, k = 3000, 32, 32768 + 700, 5
     st = _store(native, "u8")
     st.fill_synthetic(oracle.SEED_CORPUS, n, d)
     qs = oracle.synth_f64(oracle.SEED_QUERY, 0, B, d)
+    st.set_plan("scan")
     slots, dists, counts = st.search(qs, k, "cosine")
     assert st.stats()["last_plan"] == native.PLAN_SCAN
     assert (counts == k).all()

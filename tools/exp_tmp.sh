@@ -1,0 +1,1 @@
+timeout 900 python -m pytest tests/test_gpu_qgemm.py -x -q 2>&1 | tail -30
