@@ -224,6 +224,19 @@ def run_ours(args):
         if kernel_ms is None or kernel_ms <= 0:
             return None
         tr = traffic.get(tkey) if (tkey and world == 1) else None
+        if plan == N.PLAN_GEMM and dtype == "u8":
+            # quantization_8bit batches: tcgen05 kind::i8 over the codes x two query digit planes (gemm_i8.cu).  One logical
+            # dot product = 2*d integer ops per (query, row); the kernel issues two MMAs (high and low digit) for it.  There is
+            # no measured int8 peak in MEASURED_PEAKS.json: the bf16 figure is the denominator, and says so.
+            ops = 2.0 * rows_local * d * batch
+            ach = ops / (kernel_ms * 1e-3) / 1e12
+            return {"bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                    "frac": ach / pk["tf_sustained"], "traffic": tr, "algorithmic_flops": ops,
+                    "peak_source": pk["src"] + " bf16 sustained (no measured int8 peak; the kernel runs 2 digit-plane MMAs per logical dot)",
+                    "frac_of_burst": ach / pk["tf_burst"],
+                    "kernel": "gemm_i8_topk_kernel (tcgen05 kind::i8, int32 accumulate in TMEM, exact digit-plane sums)",
+                    "kernel_ms": kernel_ms,
+                    "code_bytes_equivalent_gbs": float(rows_local) * BPR[dtype](d) * batch / (kernel_ms * 1e-3) / 1e9}
         if plan == N.PLAN_GEMM and batch < 128:
             # a handful of queries: 2*B flop per operand byte is far below the machine balance, the
             # tcgen05 candidate pass is bound by reading its 2-byte operand column once
@@ -473,6 +486,11 @@ def run_ours(args):
                                12_500_000 * world, 96, "u8", "cosine", 10, 1, 100,
                                "int8 dp4a scan on TMA-staged tiles + peer-memory exchange + merge; weak scaling: north_star's 100M point is N = 8",
                                weak=True),
+            "cfg4_batch": extra(f"configs[3] row shape, query batch: {12.5 * world:g}M x96 quantization_8bit over {world} GPU(s), batch 1024",
+                                12_500_000 * world, 96, "u8", "cosine", 10, 1024, max(3, min(args.steps, 5)),
+                                "tcgen05 kind::i8 over the stored codes x the query's two 8-bit digit planes (exact integer sums), "
+                                "fused top-k epilogue, fp64 re-rank from the codes; the dp4a scan serves one query per pass",
+                                weak=True),
             "cfg5_manhattan": extra("configs[4]: 1M x1536 manhattan k=10, batch 1", 1_000_000, 1536, "f32", "manhattan", 10, 1, 50,
                                     "bandwidth-bound fp32 scan"),
             "cfg5_u4": extra("configs[4]: 1M x1536 quantization_4bit cosine k=10, batch 1", 1_000_000, 1536, "u4", "cosine", 10, 1, 100,

@@ -16,7 +16,9 @@
 //
 // Kernel anatomy (one persistent CTA per SM, 640 threads, no shadow column -- the codes ARE the operand):
 //   warp 0   TMA producer: per 128-byte K block a [128 x 128 B] tile of each digit plane of the CTA's
-//            query block and a [128 rows x 128 B] tile of codes (128B swizzle) -> 4-stage ring
+//            query block and a [128 rows x 128 B] tile of codes (128B swizzle) -> 4-stage ring; for
+//            d <= 384 the query planes are loaded ONCE per sweep and stay resident, the ring (6-10
+//            stages) carries codes only
 //   warp 1   MMA issuer: per K block up to 4 K-steps (K = 32) x 2 planes, M = 128, N = 128
 //   warp 2   TMEM allocator (512 columns = 2 accumulator stages x {Sa[128], Sb[128]})
 //   warps 4-19  epilogue: thread <-> TMEM lane <-> query; the 4 warps of a lane quarter take 32 of the
@@ -38,13 +40,17 @@ namespace evdb {
 constexpr int QN = 128;        // corpus rows per tile (UMMA N)
 constexpr int QKB = 128;       // K bytes per stage (one 128-byte swizzle row of codes)
 constexpr int QUK = 32;        // UMMA K of kind::i8
-constexpr int kQStages = 4;
-constexpr uint32_t kQPlaneBytes = GM * QKB;            // 16 KB: one digit plane of the query block
-constexpr uint32_t kQCodeBytes = QN * QKB;             // 16 KB: 128 rows of codes
-constexpr uint32_t kQStageBytes = 2 * kQPlaneBytes + kQCodeBytes;
-constexpr int kQBars = 2 * kQStages + 4;               // full[S] empty[S] tfull[2] tempty[2]
-constexpr size_t kQCoefBytes = (size_t)kEpiWarps * 32 * sizeof(float2);
-constexpr size_t kQSmem = 1024 + (size_t)kQStages * kQStageBytes + kQCoefBytes + kQBars * 8 + 16;
+constexpr uint32_t kQPlaneBytes = GM * QKB;            // 16 KB: one digit plane of the query block, one K block
+constexpr uint32_t kQCodeBytes = QN * QKB;             // 16 KB: 128 rows of codes, one K block
+constexpr uint32_t kQRingBytes = 192 * 1024;           // operand shared memory: resident query planes + the ring
+// RES (d <= 384): the CTA's query block stays in shared memory for a whole sweep -- both digit planes, all K
+// blocks, loaded once -- and the ring carries codes only (16 KB stages): a third of the L2 -> shared-memory
+// traffic of streaming {Qa, Qb, codes} per K block, which is what paces a one-K-block tile otherwise.
+constexpr int kQResMaxKBlocks = 3;
+constexpr int kQMaxStages = 10;
+constexpr int kQBars = 2 * kQMaxStages + 6;            // full[S] empty[S] tfull[2] tempty[2] qfull qempty
+constexpr size_t kQCoefBytes = (size_t)kEpiWarps * 32 * sizeof(float4);   // per epilogue warp: 32 rows x {256 cx, cy, K', cx}
+constexpr size_t kQSmem = 1024 + (size_t)kQRingBytes + kQCoefBytes + kQBars * 8 + 16;
 constexpr int kQMaxDim = 16384;                        // d * 255 * 255 < 2^31
 
 struct QGemmArgs {
@@ -55,10 +61,18 @@ struct QGemmArgs {
     int cap;             // candidate buffer capacity in use
     int nt;              // corpus tiles = ceil(n / 128)
     int MB, NG, nchunks, KP;
+    int stages;          // ring depth: 4 x {Qa, Qb, codes} streamed, or (192 KB - resident planes) / 16 KB of codes
     uint64_t *cand;      // [sweep][CTA][part][cap][128]
     int *cand_cnt;       // [sweep][CTA][part][128]
     const QStat *qstat;  // [B]
-    const float2 *qcoef; // [n] {scale, min}/||y||
+    const float2 *qcoef; // [n * coef_step] {scale, min}/||y|| (the sampled pre-pass reads every coef_step-th row's)
+    uint64_t coef_step;
+    int mode;            // 0 = fused top-k, 1 = pooled key scores of a strided row sample (threshold seeding)
+    float *dump;         // mode 1: [Bpad][dump_ld] best key score of every 32-row chunk
+    int dump_ld;
+    const uint32_t *thr0;  // mode 0: per-query starting threshold, orderable key score (NULL = none)
+    float sb_max;        // FAST: upper bound of the low-digit sum, 255 * 255 * d, plus the slack of the coarse filter
+    int debug;           // EVDB_QGEMM_DEBUG (measurement only): 1 = no epilogue arithmetic, 2 = one MMA per tile, 4 = no TMEM loads, 8 = no code TMA after the first tile, 16 = no coarse filter
 };
 
 // kind::i8 instruction descriptor: (u8|s8) x u8 -> s32, both K-major
@@ -78,24 +92,28 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
 
 // FAST: |Sa| < 2^22 and 0 <= Sb < 2^23 (d <= 128): int -> float by the mantissa trick (two full-rate
 // instructions instead of a quarter-rate I2F); exact either way below 2^24.
-template <bool FAST>
+template <bool FAST, bool RES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_i8_topk_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb,
                     const __grid_constant__ CUtensorMap tmV, const QGemmArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t *stage_base = smem;                                                // [stages][Qa | Qb | codes]
-    float2 *coef_base = reinterpret_cast<float2 *>(smem + kQStages * kQStageBytes);   // [epilogue warp][32]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kQStages * kQStageBytes + kQCoefBytes);
+    const int kStages = a.stages;
+    const uint32_t kStageBytes = RES ? kQCodeBytes : 2 * kQPlaneBytes + kQCodeBytes;
+    uint8_t *qres_base = smem;                                                 // RES: [K block][Qa | Qb]
+    uint8_t *stage_base = smem + (RES ? (size_t)a.kblocks * 2 * kQPlaneBytes : 0);   // [stages][codes] or [stages][Qa | Qb | codes]
+    float4 *coef_base = reinterpret_cast<float4 *>(smem + kQRingBytes);        // [epilogue warp][32]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kQRingBytes + kQCoefBytes);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + kQBars);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int KP = a.KP;
-    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kQStages);
-    const uint32_t tfull0 = smem_u32(bars + 2 * kQStages), tempty0 = smem_u32(bars + 2 * kQStages + 2);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kQMaxStages);
+    const uint32_t tfull0 = smem_u32(bars + 2 * kQMaxStages), tempty0 = smem_u32(bars + 2 * kQMaxStages + 2);
+    const uint32_t qfull = smem_u32(bars + 2 * kQMaxStages + 4), qempty = smem_u32(bars + 2 * kQMaxStages + 5);
 
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < kQStages; ++i) {
+        for (int i = 0; i < kStages; ++i) {
             mbar_init(full0 + 8 * i, 1);
             mbar_init(empty0 + 8 * i, 1);
         }
@@ -103,6 +121,8 @@ gemm_i8_topk_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
             mbar_init(tfull0 + 8 * i, 1);
             mbar_init(tempty0 + 8 * i, kEpiWarps);
         }
+        mbar_init(qfull, 1);
+        mbar_init(qempty, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -131,16 +151,35 @@ gemm_i8_topk_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
             for (int c = 0; c < a.nchunks; ++c) {
                 int qrow = (c * a.MB + mb_local) * GM;
                 if (qrow >= a.B) qrow = 0;   // a padding block of the last sweep: any rows will do, nothing is admitted
+                if (RES) {
+                    // the sweep's query planes: once the previous sweep's MMAs have retired
+                    mbar_wait(qempty, (uint32_t)(c & 1) ^ 1);
+                    mbar_arrive_expect_tx(qfull, (uint32_t)a.kblocks * 2 * kQPlaneBytes);
+                    for (int kb = 0; kb < a.kblocks; ++kb) {
+                        const uint32_t qa = smem_u32(qres_base + (size_t)kb * 2 * kQPlaneBytes);
+                        tma_load_2d(qa, &tmQa, qfull, kb * QKB, qrow);
+                        tma_load_2d(qa + kQPlaneBytes, &tmQb, qfull, kb * QKB, qrow);
+                    }
+                }
                 for (int t = 0; t < my_tiles; ++t) {
                     const int vrow = (ng + t * a.NG) * QN;
                     for (int kb = 0; kb < a.kblocks; ++kb) {
                         mbar_wait(empty0 + 8 * stage, phase ^ 1);
-                        const uint32_t sa = smem_u32(stage_base + stage * kQStageBytes);
-                        mbar_arrive_expect_tx(full0 + 8 * stage, kQStageBytes);
-                        tma_load_2d(sa, &tmQa, full0 + 8 * stage, kb * QKB, qrow);
-                        tma_load_2d(sa + kQPlaneBytes, &tmQb, full0 + 8 * stage, kb * QKB, qrow);
-                        tma_load_2d(sa + 2 * kQPlaneBytes, &tmV, full0 + 8 * stage, kb * QKB, vrow);
-                        if (++stage == kQStages) { stage = 0; phase ^= 1; }
+                        const uint32_t sa = smem_u32(stage_base + (size_t)stage * kStageBytes);
+                        if (RES && (a.debug & 8) && t > 0) {   // measurement only: stale codes, no TMA traffic
+                            mbar_arrive(full0 + 8 * stage);
+                            if (++stage == kStages) { stage = 0; phase ^= 1; }
+                            continue;
+                        }
+                        mbar_arrive_expect_tx(full0 + 8 * stage, kStageBytes);
+                        if (RES) {
+                            tma_load_2d(sa, &tmV, full0 + 8 * stage, kb * QKB, vrow);
+                        } else {
+                            tma_load_2d(sa, &tmQa, full0 + 8 * stage, kb * QKB, qrow);
+                            tma_load_2d(sa + kQPlaneBytes, &tmQb, full0 + 8 * stage, kb * QKB, qrow);
+                            tma_load_2d(sa + 2 * kQPlaneBytes, &tmV, full0 + 8 * stage, kb * QKB, vrow);
+                        }
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
@@ -155,6 +194,10 @@ gemm_i8_topk_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int c = 0; c < a.nchunks; ++c) {
+                if (RES) {
+                    mbar_wait(qfull, (uint32_t)(c & 1));
+                    tc_fence_after();
+                }
                 for (int t = 0; t < my_tiles; ++t) {
                     mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);  // epilogue drained this accumulator pair
                     tc_fence_after();
@@ -163,26 +206,28 @@ gemm_i8_topk_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
                     for (int kb = 0; kb < a.kblocks; ++kb) {
                         mbar_wait(full0 + 8 * stage, phase);
                         tc_fence_after();
-                        const uint32_t sa = smem_u32(stage_base + stage * kQStageBytes);
-                        const uint64_t adesc = make_sw128_kmajor_desc(sa);
-                        const uint64_t bdesc = make_sw128_kmajor_desc(sa + kQPlaneBytes);
-                        const uint64_t vdesc = make_sw128_kmajor_desc(sa + 2 * kQPlaneBytes);
+                        const uint32_t sa = smem_u32(stage_base + (size_t)stage * kStageBytes);
+                        const uint32_t qa = RES ? smem_u32(qres_base + (size_t)kb * 2 * kQPlaneBytes) : sa;
+                        const uint64_t adesc = make_sw128_kmajor_desc(qa);
+                        const uint64_t bdesc = make_sw128_kmajor_desc(qa + kQPlaneBytes);
+                        const uint64_t vdesc = make_sw128_kmajor_desc(RES ? sa : sa + 2 * kQPlaneBytes);
                         const int ksteps = kb + 1 == a.kblocks ? a.last_ksteps : QKB / QUK;
 #pragma unroll
                         for (int k = 0; k < QKB / QUK; ++k) {
                             // advance 32 codes = 32 bytes along K inside the swizzled row: +2 in >>4 units
-                            if (k < ksteps) {
+                            if (k < ksteps && !((a.debug & 2) && (kb | k) != 0)) {
                                 const uint32_t accum = (uint32_t)((kb | k) != 0);
                                 umma_i8(tmem_a, adesc + (uint64_t)(2 * k), vdesc + (uint64_t)(2 * k), idesc_a, accum);
                                 umma_i8(tmem_b, bdesc + (uint64_t)(2 * k), vdesc + (uint64_t)(2 * k), idesc_b, accum);
                             }
                         }
                         umma_commit(empty0 + 8 * stage);   // stage reusable once these MMAs retire
-                        if (++stage == kQStages) { stage = 0; phase ^= 1; }
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
                     umma_commit(tfull0 + 8 * acc);         // both accumulators complete
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
+                if (RES) umma_commit(qempty);              // the resident planes may be replaced
             }
         }
     } else if (active && warp >= 4) {
@@ -192,7 +237,7 @@ gemm_i8_topk_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
         const int part = ew >> 2;                // rows [32*part, 32*part+32) of every tile
         const int et = lg * 32 + lane;           // query within the CTA's block
         const float kInf = __int_as_float(0x7f800000);
-        float2 *wcoef = coef_base + ew * 32;
+        const uint32_t wcoef = smem_u32(coef_base + ew * 32);   // [32] float4; explicit shared-space accesses (the realigned base pointer is generic)
         int acc = 0;
         uint32_t acc_phase = 0;
         const uint32_t nrows = (uint32_t)a.n;
@@ -212,49 +257,95 @@ gemm_i8_topk_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
                 if (!(c1 < 0.f)) c1 = -1e-30f;             // zero query: every key is 1.0
             }
             const float c0 = 1.0f;
-            float tau = kInf;
-            float thrS = -kInf;
+            const bool admit = live && a.mode == 0;
+            // admission threshold: seeded by the sampled pre-pass, tightened by every prune; held in the x domain
+            float tau = (a.thr0 && live) ? f32_from_orderable(a.thr0[qglob]) : kInf;
+            float thrS = acc_threshold(tau, c0, c1);
+            // this warp's 32 rows' coefficients, fetched one tile ahead (a dependent global load per tile
+            // would put its whole latency on every tile of the warp)
+            auto load_coef = [&](int t) -> float2 {
+                const uint32_t r = (uint32_t)(ng + t * a.NG) * QN + (uint32_t)part * 32 + lane;
+                return (t < my_tiles && r < nrows) ? __ldg(a.qcoef + (size_t)r * a.coef_step) : make_float2(0.f, 0.f);
+            };
+            float2 co_next = load_coef(0), co_next2 = load_coef(1);   // two tiles ahead: a tile is shorter than a DRAM round trip
+            const bool coarse = FAST && a.mode == 0 && !(a.debug & 16);
             for (int t = 0; t < my_tiles; ++t) {
                 const int tile = ng + t * a.NG;
                 const uint32_t row0 = (uint32_t)tile * QN + (uint32_t)part * 32;
-                // this warp's 32 rows' coefficients: fetched before the accumulator is awaited
                 {
-                    const uint32_t r = row0 + lane;
-                    wcoef[lane] = r < nrows ? __ldg(a.qcoef + r) : make_float2(0.f, 0.f);
+                    // row constants of the coarse filter (FAST): with F = float bits of (Sa + 0x4B400000) = 12582912 + Sa,
+                    //   x <= cx*(256 Sa + SbMax) + cy*Cq = (256 cx)*F + (cy*Cq + K'),  K' = cx*SbMax' - 256 cx * 12582912
+                    // K' is formed in fp64 and rounded UP; SbMax' carries the slack that covers every fp32 rounding of
+                    // both evaluations (2048 units of S per cx, 1.5 |cy| for the cy*Cq products, |Cq| <= 2^22)
+                    const double cx = (double)co_next.x, cy = (double)co_next.y;
+                    const double kp = cx * (double)a.sb_max + 1.5 * fabs(cy) - cx * 256.0 * 12582912.0;
+                    float kpf = (float)kp;
+                    if ((double)kpf < kp) kpf = __int_as_float(__float_as_int(kpf) + (kpf >= 0.f ? 1 : -1));
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(wcoef + lane * 16), "f"(co_next.x * 256.0f),
+                                 "f"(co_next.y), "f"(kpf), "f"(co_next.x) : "memory");
                 }
                 __syncwarp();
+                co_next = co_next2;
+                co_next2 = load_coef(t + 2);
                 mbar_wait(tfull0 + 8 * acc, acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)acc * (2 * QN) + part * 32;
-                uint32_t va[32], vb[32];
-                tmem_ld_32x32b_x32(taddr, va);
-                tmem_ld_32x32b_x32(taddr + QN, vb);
-                tmem_ld_wait();
-                // both accumulators are in registers: hand the TMEM stage back before the arithmetic
+                uint32_t va[32];
+                if (!(a.debug & 4)) {
+                    tmem_ld_32x32b_x32(taddr, va);
+                    tmem_ld_wait();
+                }
+                bool exact = !coarse;
+                if (coarse && !(a.debug & 1)) {
+                    // high digit only: an upper bound of every x of the chunk, three instructions per row
+                    float g[8];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float c256, cy, kp, cx;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c256), "=f"(cy), "=f"(kp), "=f"(cx) : "r"(wcoef + j * 16));
+                        const float F = __int_as_float((int)va[j] + 0x4B400000);
+                        const float xu = fmaf(c256, F, fmaf(cy, Cq, kp));
+                        g[j >> 2] = (j & 3) ? fmaxf(g[j >> 2], xu) : xu;
+                    }
+                    const float mu = fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])), fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])));
+                    exact = __any_sync(0xffffffffu, mu > thrS);
+                }
+                float m = 0.f;
+                if (exact && !(a.debug & 1)) {
+                    uint32_t vb[32];
+                    tmem_ld_32x32b_x32(taddr + QN, vb);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float fa, fb, c256, cy, kp, cx;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c256), "=f"(cy), "=f"(kp), "=f"(cx) : "r"(wcoef + j * 16));
+                        if (FAST) {
+                            fa = __int_as_float((int)va[j] + 0x4B400000) - 12582912.0f;   // |Sa| < 2^22
+                            fb = __int_as_float((int)vb[j] + 0x4B000000) - 8388608.0f;    // 0 <= Sb < 2^23
+                        } else {
+                            fa = __int2float_rn((int)va[j]);
+                            fb = __int2float_rn((int)vb[j]);
+                        }
+                        const float S = fmaf(fa, 256.0f, fb);
+                        vb[j] = __float_as_uint(fmaf(cx, S, cy * Cq));
+                    }
+                    m = epi_chunk(vb, thrS, row0, nrows, c0, c1, mybuf, cnt, admit);
+                }
+                // hand the TMEM stage back
                 tc_fence_before();
-                __syncwarp();
+                __syncwarp();   // (also: wcoef is rewritten at the top of the next tile)
                 if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float fa, fb;
-                    if (FAST) {
-                        fa = __int_as_float((int)va[j] + 0x4B400000) - 12582912.0f;   // |Sa| < 2^22
-                        fb = __int_as_float((int)vb[j] + 0x4B000000) - 8388608.0f;    // 0 <= Sb < 2^23
-                    } else {
-                        fa = __int2float_rn((int)va[j]);
-                        fb = __int2float_rn((int)vb[j]);
-                    }
-                    const float2 co = wcoef[j];
-                    const float S = fmaf(fa, 256.0f, fb);
-                    va[j] = __float_as_uint(fmaf(co.x, S, co.y * Cq));
+                if (a.mode == 1) {   // sampled pre-pass: best key score of the chunk
+                    a.dump[qglob * a.dump_ld + (size_t)tile * kEpiParts + part] = fmaf(m, c1, c0);
+                    continue;
                 }
-                __syncwarp();   // wcoef is rewritten at the top of the next tile
-                (void)epi_chunk(va, thrS, row0, nrows, c0, c1, mybuf, cnt, live);
-                const unsigned need = __ballot_sync(0xffffffffu, cnt > a.cap - 32);
-                if (need) prune_buffers(cbase + lg * 32, need, KP, lane, c0, c1, cnt, tau, thrS);
+                if (exact) {
+                    const unsigned need = __ballot_sync(0xffffffffu, cnt > a.cap - 32);
+                    if (need) prune_buffers(cbase + lg * 32, need, KP, lane, c0, c1, cnt, tau, thrS);
+                }
             }
-            a.cand_cnt[lbase * GM + et] = cnt;
+            if (a.mode == 0) a.cand_cnt[lbase * GM + et] = cnt;
         }
     }
 
@@ -305,18 +396,28 @@ int launch_qgemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int *li
     const int nCTA = MB * NG;
     const int cap = KP <= 32 ? 128 : kCandCapMax;
 
+    const int Bpad = nchunks * MB * GM;
+    const size_t thr_bytes = round_up64((size_t)Bpad * sizeof(uint32_t), 256);
     const size_t cnt_bytes = round_up64((size_t)nchunks * nCTA * kEpiParts * GM * sizeof(int), 256);
     const size_t cand_bytes = (size_t)nchunks * nCTA * kEpiParts * cap * GM * sizeof(uint64_t);
-    EVDB_TRY(ensure_bytes((void **)&s->w_qh, &s->w_qh_cap, cnt_bytes + cand_bytes));
-    int *cand_cnt = (int *)s->w_qh;
-    uint64_t *cand = (uint64_t *)((uint8_t *)s->w_qh + cnt_bytes);
+    EVDB_TRY(ensure_bytes((void **)&s->w_qh, &s->w_qh_cap, thr_bytes + cnt_bytes + cand_bytes));
+    uint32_t *thr = (uint32_t *)s->w_qh;
+    int *cand_cnt = (int *)((uint8_t *)s->w_qh + thr_bytes);
+    uint64_t *cand = (uint64_t *)((uint8_t *)s->w_qh + thr_bytes + cnt_bytes);
+    EVDB_CUDA(cudaMemsetAsync(thr, 0, sizeof(uint32_t) * (size_t)Bpad, st));   // seeded thresholds accumulate by atomicMax
 
     EVDB_TRY(launch_prep_queries(s, d_q64, B, EVDB_COSINE, st));   // [B][2][dpad] digits, QStat, grid bound
     CUtensorMap tmQa, tmQb, tmV;
     const uint64_t dp = (uint64_t)s->dpad;
     EVDB_TRY(make_map_u8(&tmQa, s->w_qdig, (uint64_t)B, dp, (uint64_t)kQPlanes * dp));
     EVDB_TRY(make_map_u8(&tmQb, s->w_qdig + dp, (uint64_t)B, dp, (uint64_t)kQPlanes * dp));
-    EVDB_TRY(make_map_u8(&tmV, s->rows, s->count, dp, (uint64_t)s->row_bytes));
+    // the code tiles may run past a row's end (into the next row; the allocation carries slack for the last one):
+    // the digit planes are zero there.  Rows shorter than the 128-byte box are otherwise filled by TMA's
+    // out-of-bounds path, which is several times slower for a store of 96-byte rows.
+    static int vext = -1;
+    if (vext < 0) { const char *e = getenv("EVDB_QGEMM_VEXT"); vext = e ? atoi(e) : 1; }
+    const uint64_t vcols = vext ? (dp + QKB - 1) / QKB * QKB : dp;
+    EVDB_TRY(make_map_u8(&tmV, s->rows, s->count, vcols, (uint64_t)s->row_bytes));
 
     QGemmArgs a;
     memset(&a, 0, sizeof(a));
@@ -330,12 +431,40 @@ int launch_qgemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int *li
     a.cand = cand; a.cand_cnt = cand_cnt;
     a.qstat = s->w_qstat;
     a.qcoef = s->qcoef;
+    a.coef_step = 1;
+    a.sb_max = 65025.0f * (float)s->dim + 2048.0f;
+    { const char *e = getenv("EVDB_QGEMM_DEBUG"); a.debug = e ? atoi(e) : 0; }
     const bool fast = s->dim <= 128;
-    const void *fn = fast ? (const void *)gemm_i8_topk_kernel<true> : (const void *)gemm_i8_topk_kernel<false>;
-    EVDB_TRY(ensure_func_smem(fn, kQSmem));
+    bool use_res = a.kblocks <= kQResMaxKBlocks;
+    { const char *e = getenv("EVDB_QGEMM_RES"); if (e) use_res = use_res && atoi(e) != 0; }   // A/B: 0 = always stream the planes
+    a.stages = use_res ? (int)((kQRingBytes - (size_t)a.kblocks * 2 * kQPlaneBytes) / kQCodeBytes) : 4;
+    if (a.stages > kQMaxStages) a.stages = kQMaxStages;
+    void (*fn)(CUtensorMap, CUtensorMap, CUtensorMap, QGemmArgs) =
+        use_res ? (fast ? gemm_i8_topk_kernel<true, true> : gemm_i8_topk_kernel<false, true>)
+                : (fast ? gemm_i8_topk_kernel<true, false> : gemm_i8_topk_kernel<false, false>);
+    EVDB_TRY(ensure_func_smem((const void *)fn, kQSmem));
+    // ---- sampled pre-pass (as in gemm_tcgen05.cu): S strided rows pooled per 32-row chunk seed every query's threshold ----
+    const char *noseed = getenv("EVDB_GEMM_NOSEED");
+    uint64_t S = (uint64_t)8192 * KP;
+    while (S * 16 > s->count && S > 1024) S >>= 1;
+    if (S >= (uint64_t)64 * KP && S * 16 <= s->count && !(noseed && atoi(noseed))) {
+        const uint64_t step = s->count / S;
+        const int snt = (int)(S / QN);
+        int sNG = s->sm_count / MB;
+        if (sNG > snt) sNG = snt;
+        const int pooled = (int)(S / 32);
+        EVDB_TRY(ensure_bytes((void **)&s->w_seed, &s->w_seed_cap, (size_t)Bpad * pooled * sizeof(float)));
+        CUtensorMap tmVs;
+        EVDB_TRY(make_map_u8(&tmVs, s->rows, S, vcols, (uint64_t)s->row_bytes * step));
+        QGemmArgs p = a;
+        p.n = S; p.nt = snt; p.NG = sNG; p.mode = 1; p.dump = (float *)s->w_seed; p.dump_ld = pooled; p.coef_step = step;
+        EVDB_CUDA(launch_chained(fn, dim3(MB * sNG), dim3(kGemmThreads), kQSmem, st, 1, tmQa, tmQb, tmVs, p));
+        EVDB_TRY(launch_seed_thresholds((const float *)s->w_seed, pooled, Bpad, KP, thr, st));
+        s->n_launches += 2;
+        a.thr0 = thr;
+    }
     prof_begin(s, st);
-    if (fast) EVDB_CUDA(launch_chained(gemm_i8_topk_kernel<true>, dim3(nCTA), dim3(kGemmThreads), kQSmem, st, 1, tmQa, tmQb, tmV, a));
-    else EVDB_CUDA(launch_chained(gemm_i8_topk_kernel<false>, dim3(nCTA), dim3(kGemmThreads), kQSmem, st, 1, tmQa, tmQb, tmV, a));
+    EVDB_CUDA(launch_chained(fn, dim3(nCTA), dim3(kGemmThreads), kQSmem, st, 1, tmQa, tmQb, tmV, a));
     prof_end(s, st);
     s->n_launches += 1;
     raw->cand = cand; raw->cnt = cand_cnt; raw->cap = cap; raw->nCTA = nCTA; raw->MB = MB; raw->NG = NG;

@@ -628,6 +628,21 @@ int launch_l2_shadow_rows(evdb_store *s, uint64_t slot0, uint64_t n, cudaStream_
     return EVDB_OK;
 }
 
+// thr[q] (zeroed by the caller, combined by atomicMax) <- an upper bound on query q's KP-th best key score, from
+// the [Bpad][pooled] best-of-32-rows key scores a pooling pass left in `dump` (also used by gemm_i8.cu)
+int launch_seed_thresholds(const float *dump, int pooled, int Bpad, int KP, uint32_t *thr, cudaStream_t st) {
+    const int vpt = (pooled + kSeedThreads - 1) / kSeedThreads;
+    const int groups = (pooled + kSeedThreads * kSeedMaxVpt - 1) / (kSeedThreads * kSeedMaxVpt);
+    const int need = (KP + groups - 1) / groups;
+    const dim3 sgrid(Bpad, groups);
+    const int pooled_i = pooled;
+    if (vpt <= 4) EVDB_CUDA(launch_chained(seed_threshold_kernel<4>, sgrid, dim3(kSeedThreads), 0, st, 1, dump, pooled_i, pooled_i, need, thr));
+    else if (vpt <= 8) EVDB_CUDA(launch_chained(seed_threshold_kernel<8>, sgrid, dim3(kSeedThreads), 0, st, 1, dump, pooled_i, pooled_i, need, thr));
+    else if (vpt <= 16) EVDB_CUDA(launch_chained(seed_threshold_kernel<16>, sgrid, dim3(kSeedThreads), 0, st, 1, dump, pooled_i, pooled_i, need, thr));
+    else EVDB_CUDA(launch_chained(seed_threshold_kernel<kSeedMaxVpt>, sgrid, dim3(kSeedThreads), 0, st, 1, dump, pooled_i, pooled_i, need, thr));
+    return EVDB_OK;
+}
+
 int launch_gemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int metric, int *lists_per_query,
                      const float **d_eps_q, RawCands *raw, cudaStream_t st) {
     const bool l2 = metric == EVDB_EUCLIDEAN;
@@ -722,16 +737,7 @@ int launch_gemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int metr
         GemmArgs p = a;
         p.n = S; p.nt = snt; p.NG = sNG; p.mode = 1; p.dump = dump; p.dump_ld = pooled;
         EVDB_TRY(launch_gemm_kernel(pair, MB * sNG, st, tmQ, tmVs, tmQt, tmVts, p));
-        const int vpt = (pooled + kSeedThreads - 1) / kSeedThreads;
-        const int groups = (pooled + kSeedThreads * kSeedMaxVpt - 1) / (kSeedThreads * kSeedMaxVpt);
-        const int need = (KP + groups - 1) / groups;
-        const dim3 sgrid(Bpad, groups);
-        // (thr was zeroed before the query prep: nothing but kernels between the links of the chain)
-        const int pooled_i = pooled;
-        if (vpt <= 4) EVDB_CUDA(launch_chained(seed_threshold_kernel<4>, sgrid, dim3(kSeedThreads), 0, st, 1, (const float *)dump, pooled_i, pooled_i, need, thr));
-        else if (vpt <= 8) EVDB_CUDA(launch_chained(seed_threshold_kernel<8>, sgrid, dim3(kSeedThreads), 0, st, 1, (const float *)dump, pooled_i, pooled_i, need, thr));
-        else if (vpt <= 16) EVDB_CUDA(launch_chained(seed_threshold_kernel<16>, sgrid, dim3(kSeedThreads), 0, st, 1, (const float *)dump, pooled_i, pooled_i, need, thr));
-        else EVDB_CUDA(launch_chained(seed_threshold_kernel<kSeedMaxVpt>, sgrid, dim3(kSeedThreads), 0, st, 1, (const float *)dump, pooled_i, pooled_i, need, thr));
+        EVDB_TRY(launch_seed_thresholds(dump, pooled, Bpad, KP, thr, st));   // (thr was zeroed before the query prep)
         s->n_launches += 2;
         thr0 = thr;
     }

@@ -201,6 +201,7 @@ int debug_quant_dots(evdb_store *s, const double *d_q64, const uint32_t *d_slots
 int launch_scan(evdb_store *s, int metric, const ScanArgs &a, cudaStream_t st);
 // gemm_i8.cu: query batches against a U8 store as a tcgen05 kind::i8 GEMM over the codes
 bool qgemm_plan_supported(evdb_store *s, int metric, int B, int KP);
+int launch_seed_thresholds(const float *dump, int pooled, int Bpad, int KP, uint32_t *thr, cudaStream_t st);   // gemm_tcgen05.cu
 int launch_qgemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int *lists_per_query,
                       const float **d_eps_q, RawCands *raw, cudaStream_t st);
 // eps_q: optional per-query absolute bound added to eps_abs; squared: key scores are squared

@@ -112,7 +112,7 @@ static void set_dim(evdb_store *s, int d) {
 template <typename T>
 static int regrow(T **p, uint64_t old_rows, uint64_t new_rows, size_t per_row, cudaStream_t st) {
     T *np = nullptr;
-    EVDB_CUDA(cudaMalloc((void **)&np, new_rows * per_row));
+    EVDB_CUDA(cudaMalloc((void **)&np, new_rows * per_row + 256));   // slack: the i8 plan's code tiles may read up to 127 bytes past the last row
     if (*p && old_rows) EVDB_CUDA(cudaMemcpyAsync(np, *p, old_rows * per_row, cudaMemcpyDeviceToDevice, st));
     if (*p) {
         EVDB_CUDA(cudaStreamSynchronize(st));
