@@ -49,7 +49,7 @@ constexpr uint32_t kQRingBytes = 192 * 1024;           // operand shared memory:
 constexpr int kQResMaxKBlocks = 3;
 constexpr int kQMaxStages = 10;
 constexpr int kQBars = 2 * kQMaxStages + 6;            // full[S] empty[S] tfull[2] tempty[2] qfull qempty
-constexpr size_t kQCoefBytes = (size_t)kEpiWarps * 32 * sizeof(float4);   // per epilogue warp: 32 rows x {256 cx, cy, K', cx}
+constexpr size_t kQCoefBytes = (size_t)kEpiWarps * 32 * sizeof(float4);   // per epilogue warp: 32 rows x {256 cx, K', cy, cx}
 constexpr size_t kQSmem = 1024 + (size_t)kQRingBytes + kQCoefBytes + kQBars * 8 + 16;
 constexpr int kQMaxDim = 16384;                        // d * 255 * 255 < 2^31
 
@@ -282,7 +282,7 @@ gemm_i8_topk_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
                     float kpf = (float)kp;
                     if ((double)kpf < kp) kpf = __int_as_float(__float_as_int(kpf) + (kpf >= 0.f ? 1 : -1));
                     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(wcoef + lane * 16), "f"(co_next.x * 256.0f),
-                                 "f"(co_next.y), "f"(kpf), "f"(co_next.x) : "memory");
+                                 "f"(kpf), "f"(co_next.y), "f"(co_next.x) : "memory");   // {256 cx, K', cy, cx}
                 }
                 __syncwarp();
                 co_next = co_next2;
@@ -302,7 +302,7 @@ gemm_i8_topk_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         float c256, cy, kp, cx;
-                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c256), "=f"(cy), "=f"(kp), "=f"(cx) : "r"(wcoef + j * 16));
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c256), "=f"(kp), "=f"(cy), "=f"(cx) : "r"(wcoef + j * 16));
                         const float F = __int_as_float((int)va[j] + 0x4B400000);
                         const float xu = fmaf(c256, F, fmaf(cy, Cq, kp));
                         g[j >> 2] = (j & 3) ? fmaxf(g[j >> 2], xu) : xu;
@@ -317,8 +317,8 @@ gemm_i8_topk_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        float fa, fb, c256, cy, kp, cx;
-                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c256), "=f"(cy), "=f"(kp), "=f"(cx) : "r"(wcoef + j * 16));
+                        float fa, fb, cy, cx;
+                        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(cy), "=f"(cx) : "r"(wcoef + j * 16 + 8));
                         if (FAST) {
                             fa = __int_as_float((int)va[j] + 0x4B400000) - 12582912.0f;   // |Sa| < 2^22
                             fb = __int_as_float((int)vb[j] + 0x4B000000) - 8388608.0f;    // 0 <= Sb < 2^23

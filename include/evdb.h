@@ -50,7 +50,9 @@ typedef struct evdb_store evdb_store;
 enum { EVDB_F32 = 0, EVDB_BF16 = 1, EVDB_U8 = 2, EVDB_U4 = 3 };
 /* distance (src/vector_store.erl:238-246, src/vector_utils.erl:38-43) */
 enum { EVDB_COSINE = 0, EVDB_EUCLIDEAN = 1, EVDB_MANHATTAN = 2 };
-/* search plan override (evdb_store_set_plan); AUTO picks by batch size */
+/* search plan override (evdb_store_set_plan); AUTO picks by batch size.  GEMM = tensor cores: tcgen05 kind::f16
+ * over the fp16 operand column of an F32 store (cosine, euclidean), kind::i8 over the codes of a U8 store
+ * (cosine); EVDB_E_UNSUPPORTED for other dtype / metric pairs when forced. */
 enum { EVDB_PLAN_AUTO = 0, EVDB_PLAN_SCAN = 1, EVDB_PLAN_GEMM = 2, EVDB_PLAN_EXACT = 3 };
 
 enum {

@@ -143,3 +143,26 @@ def test_config2_one_handle_three_shards_equals_single_store(native, oracle):
         assert np.array_equal(a, b)
     _winners_are_exact(oracle, m, got[0], got[1], qs, d, "cosine", nq=2)
     m.close()
+
+
+def test_config4_shard_query_batch_on_the_i8_plan(native, oracle):
+    """One GPU's share of BASELINE configs[3] (12.5M x 96 quantization_8bit) answering a 256-query batch
+    on the tcgen05 kind::i8 plan: every query equals the dp4a scan plan's answer, two of them the
+    exhaustive fp64 plan's."""
+    from erlvectordb_b200.device_store import DeviceStore
+    n, d, k, B = 12_500_000, 96, 10, 256
+    st = DeviceStore(dtype="u8", device=0)
+    try:
+        st.fill_synthetic(oracle.SEED_CORPUS, n, d)
+        qs = oracle.synth_f64(oracle.SEED_QUERY, 0, B, d)
+        gs, gd, gc = st.search(qs, k, "cosine")
+        assert st.stats()["last_plan"] == native.PLAN_GEMM and (gc == k).all()
+        st.set_plan("scan")
+        ss, sd, sc = st.search(qs, k, "cosine")
+        assert st.stats()["last_plan"] == native.PLAN_SCAN
+        assert np.array_equal(gs, ss) and np.array_equal(gd, sd)
+        st.set_plan("exact")
+        es, ed, ec = st.search(qs[:2], k, "cosine")
+        assert np.array_equal(gs[:2], es) and np.array_equal(gd[:2], ed)
+    finally:
+        st.close()

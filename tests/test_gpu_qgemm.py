@@ -137,7 +137,7 @@ def test_i8_plan_escalates_what_it_cannot_prove(native, oracle):
 def test_i8_plan_follows_inserts_and_deletes(native, oracle):
     """The codes ARE the operand (no shadow column to keep current): after every change of the
     store the batch result equals the exhaustive plan's."""
-    d, B, k = 32, 8, 5
+    d, B, k = 32, 16, 5
     pool = oracle.synth_f64(oracle.SEED_CORPUS, 0, 600, d)
     qs = oracle.synth_f64(oracle.SEED_QUERY, 0, B, d)
     st = _store(native)
@@ -175,3 +175,38 @@ def test_multi_device_handle_uses_the_i8_plan_per_shard(native, oracle):
             assert np.array_equal(x, y)
     finally:
         m.close(); s.close()
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_i8_plan_fuzz_against_exhaustive_plan(native, oracle, seed):
+    """Random shapes, windows and data (duplicated rows = exact ties, integer-valued rows, skewed scales):
+    the forced i8 plan through the escalating host entry equals the exhaustive fp64 plan bit for bit."""
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(128, 30_000))
+    d = int(rng.choice([4, 17, 64, 96, 100, 128, 129, 300, 520, 700]))
+    B = int(rng.integers(1, 300))
+    k = int(rng.choice([1, 10, 50, 100]))
+    kind = seed % 3
+    if kind == 0:
+        rows = rng.standard_normal((n, d))
+    elif kind == 1:
+        rows = rng.integers(-6, 7, size=(n, d)).astype(np.float64)
+        rows[rows.max(axis=1) == rows.min(axis=1), 0] += 1.0     # Max == Min is badarith in the reference codec
+    else:
+        rows = rng.standard_normal((n, d)) * np.exp(rng.uniform(-6, 6, size=(n, 1))) + rng.uniform(-3, 3, size=(n, 1))
+    dup = rng.integers(0, n, size=n // 10)
+    rows[dup] = rows[rng.integers(0, n, size=n // 10)]           # exact ties, broken by slot order
+    qs = rng.standard_normal((B, d))
+    qs[0] = rows[int(rng.integers(0, n))]
+    st = _store(native)
+    try:
+        st.bulk_load(rows)
+        st.set_plan("gemm")
+        a = st.search(qs, k, "cosine")
+        assert st.stats()["last_plan"] == native.PLAN_GEMM
+        st.set_plan("exact")
+        e = st.search(qs, k, "cosine")
+        for x, y in zip(a, e):
+            assert np.array_equal(x, y)
+    finally:
+        st.close()

@@ -57,6 +57,18 @@ def test_gemm_kernel_uses_tcgen05_tmem_and_tma(sass):
         assert "UTCHMMA.2CTA" not in body
 
 
+def test_i8_kernel_uses_integer_tcgen05_and_shared_space_loads(sass):
+    ks = _pick(sass, "gemm_i8_topk_kernel")
+    assert len(ks) == 4                   # {mantissa-trick, I2F} x {resident, streamed query planes}
+    for name, body in ks.items():
+        assert "UTCIMMA" in body, name    # tcgen05.mma.kind::i8
+        assert "LDTM.x32" in body and "UTMALDG.2D" in body and "UTCBAR" in body, name
+        assert "LDS.64" in body, name     # row coefficients: shared-space loads, not generic ones
+        if "ILb1E" in name:
+            assert "LDS.128" in body, name  # the coarse filter's {256 cx, K', cy, cx}
+        assert "UTCHMMA" not in body, name
+
+
 def test_tma_staged_scan_uses_bulk_copies_mbarriers_and_dp4a(sass):
     ks = _pick(sass, "scan_quant_tma_kernel")
     assert len(ks) == 12                  # {u8, u4} x six lanes-per-row variants
