@@ -36,7 +36,8 @@ def digest(ids, dd):
 CASES = [("f32", "cosine", 200_000, 128, 4, 10, False), ("f32", "cosine", 300_000, 256, 256, 10, False),
          ("f32", "euclidean", 200_000, 128, 128, 100, False), ("u8", "cosine", 400_000, 96, 1, 10, False),
          ("f32", "manhattan", 100_000, 64, 3, 10, False), ("u4", "cosine", 200_000, 64, 2, 10, False),
-         ("f32", "cosine", 160_000, 64, 64, 10, True), ("f32", "euclidean", 160_000, 64, 3, 10, True)]
+         ("f32", "cosine", 160_000, 64, 64, 10, True), ("f32", "euclidean", 160_000, 64, 3, 10, True),
+         ("u8", "cosine", 400_000, 96, 64, 10, False)]   # quantization_8bit batch: tcgen05 kind::i8 plan on every shard
 for dtype, metric, n, d, B, k, cluster in CASES:
     qh = synth.synth(synth.SEED_QUERY, 0, B, d)
     st = ShardedStore(dtype=dtype, device=local, rank=rank, world=world)
