@@ -308,7 +308,7 @@ gemm_i8_topk_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
                         g[j >> 2] = (j & 3) ? fmaxf(g[j >> 2], xu) : xu;
                     }
                     const float mu = fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])), fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])));
-                    exact = __any_sync(0xffffffffu, mu > thrS);
+                    exact = __any_sync(0xffffffffu, admit && mu > thrS);   // (padding lanes of a ragged batch hold no threshold)
                 }
                 float m = 0.f;
                 if (exact && !(a.debug & 1)) {
