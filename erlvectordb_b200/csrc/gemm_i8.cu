@@ -14,18 +14,20 @@
 // them with the row's {scale, min}/||y|| into the candidate key in fp32.  The keys only GENERATE
 // CANDIDATES: select.cu re-ranks them in exact fp64 from the codes and proves the window complete.
 //
-// Kernel anatomy (one persistent CTA per SM, 640 threads, no shadow column -- the codes ARE the operand):
+// Kernel anatomy (one persistent CTA per SM, 384 threads, no shadow column -- the codes ARE the operand):
 //   warp 0   TMA producer: per 128-byte K block a [128 x 128 B] tile of each digit plane of the CTA's
 //            query block and a [128 rows x 128 B] tile of codes (128B swizzle) -> 4-stage ring; for
 //            d <= 384 the query planes are loaded ONCE per sweep and stay resident, the ring (6-10
 //            stages) carries codes only
 //   warp 1   MMA issuer: per K block up to 4 K-steps (K = 32) x 2 planes, M = 128, N = 128
 //   warp 2   TMEM allocator (512 columns = 2 accumulator stages x {Sa[128], Sb[128]})
-//   warps 4-19  epilogue: thread <-> TMEM lane <-> query; the 4 warps of a lane quarter take 32 of the
-//            tile's 128 rows each: two tcgen05.ld (Sa, Sb), per column S = 256*Sa + Sb in fp32,
-//            x = cx*S + cy*sum(Q) with the row's coefficients (staged per warp in shared memory),
-//            then the shared accumulator-domain filter / append / prune (tc05.cuh) with the per-query
-//            key = 1 - x * fx/||q||.
+//   warps 4-11  epilogue (8 warps, 168 registers): thread <-> TMEM lane <-> query; the 2 warps of a lane quarter
+//            take 64 of the tile's 128 rows each, as two 32-row chunks whose high-digit sums are fetched together
+//            (a 16-warp, one-chunk variant is kept for A/B).  Per chunk: a coarse filter on Sa alone (d <= 128),
+//            then -- only if some lane's bound beats its threshold -- tcgen05.ld of Sb, per column
+//            S = 256*Sa + Sb in fp32, x = cx*S + cy*sum(Q) with the row's coefficients (staged per warp in
+//            shared memory), and the shared accumulator-domain filter / append / prune (tc05.cuh) with the
+//            per-query key = 1 - x * fx/||q||.
 #include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
@@ -92,8 +94,8 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
 
 // FAST: |Sa| < 2^22 and 0 <= Sb < 2^23 (d <= 128): int -> float by the mantissa trick (two full-rate
 // instructions instead of a quarter-rate I2F); exact either way below 2^24.
-template <bool FAST, bool RES>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <bool FAST, bool RES, int EW>
+__global__ void __launch_bounds__(128 + 32 * EW, 1)
 gemm_i8_topk_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb,
                     const __grid_constant__ CUtensorMap tmV, const QGemmArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -119,7 +121,7 @@ gemm_i8_topk_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(tfull0 + 8 * i, 1);
-            mbar_init(tempty0 + 8 * i, kEpiWarps);
+            mbar_init(tempty0 + 8 * i, EW);
         }
         mbar_init(qfull, 1);
         mbar_init(qempty, 1);
@@ -232,9 +234,12 @@ gemm_i8_topk_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
         }
     } else if (active && warp >= 4) {
         // ===== epilogue =====
-        const int ew = warp - 4;                 // 0..15
+        // EW epilogue warps: 16 (one 32-row chunk of every tile per warp) or 8 (two chunks per warp, 168 registers per thread)
+        constexpr int kParts = EW / 4;           // candidate lists per query and CTA
+        constexpr int kCpw = 4 / kParts;         // 32-row chunks per warp and tile
+        const int ew = warp - 4;                 // 0..EW-1
         const int lg = ew & 3;                   // == warp % 4: TMEM lanes [32*lg, 32*lg+32)
-        const int part = ew >> 2;                // rows [32*part, 32*part+32) of every tile
+        const int part = ew >> 2;                // rows [32*kCpw*part, 32*kCpw*(part+1)) of every tile
         const int et = lg * 32 + lane;           // query within the CTA's block
         const float kInf = __int_as_float(0x7f800000);
         const uint32_t wcoef = smem_u32(coef_base + ew * 32);   // [32] float4; explicit shared-space accesses (the realigned base pointer is generic)
@@ -242,7 +247,7 @@ gemm_i8_topk_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
         uint32_t acc_phase = 0;
         const uint32_t nrows = (uint32_t)a.n;
         for (int c = 0; c < a.nchunks; ++c) {
-            const size_t lbase = ((size_t)c * nCTA + cta) * kEpiParts + part;
+            const size_t lbase = ((size_t)c * nCTA + cta) * kParts + part;
             uint64_t *cbase = a.cand + lbase * a.cap * GM;
             uint64_t *mybuf = cbase + et;
             int cnt = 0;
@@ -263,15 +268,21 @@ gemm_i8_topk_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
             float thrS = acc_threshold(tau, c0, c1);
             // this warp's 32 rows' coefficients, fetched one tile ahead (a dependent global load per tile
             // would put its whole latency on every tile of the warp)
-            auto load_coef = [&](int t) -> float2 {
-                const uint32_t r = (uint32_t)(ng + t * a.NG) * QN + (uint32_t)part * 32 + lane;
+            auto load_coef = [&](int st) -> float2 {   // step st = chunk st % kCpw of the warp's tile st / kCpw
+                const int t = st / kCpw;
+                const uint32_t r = (uint32_t)(ng + t * a.NG) * QN + (uint32_t)(part * kCpw + st % kCpw) * 32 + lane;
                 return (t < my_tiles && r < nrows) ? __ldg(a.qcoef + (size_t)r * a.coef_step) : make_float2(0.f, 0.f);
             };
             float2 co_next = load_coef(0), co_next2 = load_coef(1);   // two tiles ahead: a tile is shorter than a DRAM round trip
             const bool coarse = FAST && a.mode == 0 && !(a.debug & 16);
             for (int t = 0; t < my_tiles; ++t) {
                 const int tile = ng + t * a.NG;
-                const uint32_t row0 = (uint32_t)tile * QN + (uint32_t)part * 32;
+                mbar_wait(tfull0 + 8 * acc, acc_phase);
+                tc_fence_after();
+                // one 32-row chunk; PRE: its high-digit sums were fetched before the loop (both chunks' loads in flight together)
+                auto do_chunk = [&](const int cb, uint32_t (&va)[32], const bool pre) {
+                const int chunk = part * kCpw + cb;      // 32-row chunk of the tile
+                const uint32_t row0 = (uint32_t)tile * QN + (uint32_t)chunk * 32;
                 {
                     // row constants of the coarse filter (FAST): with F = float bits of (Sa + 0x4B400000) = 12582912 + Sa,
                     //   x <= cx*(256 Sa + SbMax) + cy*Cq = (256 cx)*F + (cy*Cq + K'),  K' = cx*SbMax' - 256 cx * 12582912
@@ -286,12 +297,9 @@ gemm_i8_topk_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
                 }
                 __syncwarp();
                 co_next = co_next2;
-                co_next2 = load_coef(t + 2);
-                mbar_wait(tfull0 + 8 * acc, acc_phase);
-                tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)acc * (2 * QN) + part * 32;
-                uint32_t va[32];
-                if (!(a.debug & 4)) {
+                co_next2 = load_coef(t * kCpw + cb + 2);
+                const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)acc * (2 * QN) + chunk * 32;
+                if (!pre && !(a.debug & 4)) {
                     tmem_ld_32x32b_x32(taddr, va);
                     tmem_ld_wait();
                 }
@@ -331,18 +339,37 @@ gemm_i8_topk_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
                     }
                     m = epi_chunk(vb, thrS, row0, nrows, c0, c1, mybuf, cnt, admit);
                 }
-                // hand the TMEM stage back
-                tc_fence_before();
-                __syncwarp();   // (also: wcoef is rewritten at the top of the next tile)
-                if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                __syncwarp();   // wcoef is rewritten at the top of the next chunk
+                if (cb == kCpw - 1) {
+                    // hand the TMEM stage back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
                 if (a.mode == 1) {   // sampled pre-pass: best key score of the chunk
-                    a.dump[qglob * a.dump_ld + (size_t)tile * kEpiParts + part] = fmaf(m, c1, c0);
-                    continue;
+                    a.dump[qglob * a.dump_ld + (size_t)tile * 4 + chunk] = fmaf(m, c1, c0);
+                    return;
                 }
                 if (exact) {
                     const unsigned need = __ballot_sync(0xffffffffu, cnt > a.cap - 32);
                     if (need) prune_buffers(cbase + lg * 32, need, KP, lane, c0, c1, cnt, tau, thrS);
+                }
+                };
+                if constexpr (kCpw == 2) {
+                    uint32_t v0[32], v1[32];
+                    const uint32_t t0 = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)acc * (2 * QN) + part * kCpw * 32;
+                    tmem_ld_32x32b_x32(t0, v0);
+                    tmem_ld_32x32b_x32(t0 + 32, v1);
+                    tmem_ld_wait();
+                    do_chunk(0, v0, true);
+                    do_chunk(1, v1, true);
+                } else {
+#pragma unroll 1
+                    for (int cb = 0; cb < kCpw; ++cb) {
+                        uint32_t va[32];
+                        do_chunk(cb, va, false);
+                    }
                 }
             }
             if (a.mode == 0) a.cand_cnt[lbase * GM + et] = cnt;
@@ -439,9 +466,20 @@ int launch_qgemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int *li
     { const char *e = getenv("EVDB_QGEMM_RES"); if (e) use_res = use_res && atoi(e) != 0; }   // A/B: 0 = always stream the planes
     a.stages = use_res ? (int)((kQRingBytes - (size_t)a.kblocks * 2 * kQPlaneBytes) / kQCodeBytes) : 4;
     if (a.stages > kQMaxStages) a.stages = kQMaxStages;
-    void (*fn)(CUtensorMap, CUtensorMap, CUtensorMap, QGemmArgs) =
-        use_res ? (fast ? gemm_i8_topk_kernel<true, true> : gemm_i8_topk_kernel<false, true>)
-                : (fast ? gemm_i8_topk_kernel<true, false> : gemm_i8_topk_kernel<false, false>);
+    // epilogue warps: 8 x 168 registers, two 32-row chunks of every tile per warp with both TMEM loads in flight together
+    // (no spills, room for instruction-level parallelism), or 16 x 96 registers, one chunk each (EVDB_QGEMM_EW=16).
+    // Same-box A/B, kernel ms at 16 / 8 warps: 12.5 M x 96 B = 1024 10.6 / 8.35, B = 64 1.45 / 1.02; 4 M x 256 4.31 / 2.68;
+    // 1 M x 768 1.57 / 1.46 (4 warps x 221 registers: 13.0 at 12.5 M x 96)
+    static int ew = -1;
+    if (ew < 0) { const char *e = getenv("EVDB_QGEMM_EW"); ew = (e && atoi(e) == 16) ? 16 : 8; }
+    const int parts = ew / 4;
+    void (*fn)(CUtensorMap, CUtensorMap, CUtensorMap, QGemmArgs) = nullptr;
+#define EVDB_QSEL(EWN)                                                                                             \
+    fn = use_res ? (fast ? gemm_i8_topk_kernel<true, true, EWN> : gemm_i8_topk_kernel<false, true, EWN>)           \
+                 : (fast ? gemm_i8_topk_kernel<true, false, EWN> : gemm_i8_topk_kernel<false, false, EWN>)
+    if (ew == 8) { EVDB_QSEL(8); } else { EVDB_QSEL(16); }
+#undef EVDB_QSEL
+    const int threads = 128 + 32 * ew;
     EVDB_TRY(ensure_func_smem((const void *)fn, kQSmem));
     // ---- sampled pre-pass (as in gemm_tcgen05.cu): S strided rows pooled per 32-row chunk seed every query's threshold ----
     const char *noseed = getenv("EVDB_GEMM_NOSEED");
@@ -458,18 +496,18 @@ int launch_qgemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int *li
         EVDB_TRY(make_map_u8(&tmVs, s->rows, S, vcols, (uint64_t)s->row_bytes * step));
         QGemmArgs p = a;
         p.n = S; p.nt = snt; p.NG = sNG; p.mode = 1; p.dump = (float *)s->w_seed; p.dump_ld = pooled; p.coef_step = step;
-        EVDB_CUDA(launch_chained(fn, dim3(MB * sNG), dim3(kGemmThreads), kQSmem, st, 1, tmQa, tmQb, tmVs, p));
+        EVDB_CUDA(launch_chained(fn, dim3(MB * sNG), dim3(threads), kQSmem, st, 1, tmQa, tmQb, tmVs, p));
         EVDB_TRY(launch_seed_thresholds((const float *)s->w_seed, pooled, Bpad, KP, thr, st));
         s->n_launches += 2;
         a.thr0 = thr;
     }
     prof_begin(s, st);
-    EVDB_CUDA(launch_chained(fn, dim3(nCTA), dim3(kGemmThreads), kQSmem, st, 1, tmQa, tmQb, tmV, a));
+    EVDB_CUDA(launch_chained(fn, dim3(nCTA), dim3(threads), kQSmem, st, 1, tmQa, tmQb, tmV, a));
     prof_end(s, st);
     s->n_launches += 1;
     raw->cand = cand; raw->cnt = cand_cnt; raw->cap = cap; raw->nCTA = nCTA; raw->MB = MB; raw->NG = NG;
-    raw->parts = kEpiParts; raw->gm = GM;
-    *lists_per_query = kEpiParts * NG;
+    raw->parts = parts; raw->gm = GM;
+    *lists_per_query = parts * NG;
     *d_eps_q = s->w_qeps;
     return EVDB_OK;
 }

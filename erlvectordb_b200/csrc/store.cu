@@ -197,12 +197,13 @@ int search_core(evdb_store *s, const double *d_q64, int B, int k, int kstride, i
         use_gemm = gemm_plan_supported(s, metric, B, gemm_kp(KP));
     // quantization_8bit stores: batches run as a kind::i8 GEMM over the codes themselves (gemm_i8.cu).  A scan pass
     // serves one query; one GEMM sweep serves up to 128 per CTA at a fixed cost of several scan passes (measured on
-    // B200, tools/sweep.py, step time gemm / scan: 12.5 M x 96: B = 8 1.28 / 1.54 ms, B = 16 1.35 / 2.94 ms;
-    // 1 M x 768: B = 4 0.57 / 0.51 ms, B = 8 0.60 / 0.96 ms).  EVDB_QGEMM_MIN_BATCH overrides the crossover.
+    // B200, tools/sweep.py, step time gemm / scan: 12.5 M x 96: B = 4 0.89 / 0.81 ms, B = 6 0.91 / 1.17 ms;
+    // 4 M x 256: B = 4 0.41 / 0.66 ms; 1 M x 768: B = 3 0.41 / 0.40 ms, B = 4 0.44 / 0.50 ms).
+    // EVDB_QGEMM_MIN_BATCH overrides the crossover.
     bool use_qgemm = false;
     static int qgemm_min_env = -2;
     if (qgemm_min_env == -2) { const char *e = getenv("EVDB_QGEMM_MIN_BATCH"); qgemm_min_env = e ? atoi(e) : -1; }
-    const int qgemm_min_batch = qgemm_min_env >= 0 ? qgemm_min_env : (s->dpad <= 128 ? 7 : (s->dpad <= 384 ? 6 : 5));
+    const int qgemm_min_batch = qgemm_min_env >= 0 ? qgemm_min_env : (s->dpad <= 128 ? 5 : 4);
     if (s->dtype == EVDB_U8 && metric == EVDB_COSINE &&
         (plan == EVDB_PLAN_GEMM || (plan == EVDB_PLAN_AUTO && !s->gemm_oom && B >= qgemm_min_batch)))
         use_qgemm = qgemm_plan_supported(s, metric, B, gemm_kp(KP));

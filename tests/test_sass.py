@@ -59,7 +59,7 @@ def test_gemm_kernel_uses_tcgen05_tmem_and_tma(sass):
 
 def test_i8_kernel_uses_integer_tcgen05_and_shared_space_loads(sass):
     ks = _pick(sass, "gemm_i8_topk_kernel")
-    assert len(ks) == 4                   # {mantissa-trick, I2F} x {resident, streamed query planes}
+    assert len(ks) == 8                   # {mantissa-trick, I2F} x {resident, streamed query planes} x {8, 16 epilogue warps}
     for name, body in ks.items():
         assert "UTCIMMA" in body, name    # tcgen05.mma.kind::i8
         assert "LDTM.x32" in body and "UTMALDG.2D" in body and "UTCBAR" in body, name
