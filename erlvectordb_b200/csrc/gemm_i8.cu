@@ -73,6 +73,7 @@ struct QGemmArgs {
     float *dump;         // mode 1: [Bpad][dump_ld] best key score of every 32-row chunk
     int dump_ld;
     const uint32_t *thr0;  // mode 0: per-query starting threshold, orderable key score (NULL = none)
+    int coarse;          // FAST: run the high-digit coarse filter before fetching the low-digit sums
     float sb_max;        // FAST: upper bound of the low-digit sum, 255 * 255 * d, plus the slack of the coarse filter
     int debug;           // EVDB_QGEMM_DEBUG (measurement only): 1 = no epilogue arithmetic, 2 = one MMA per tile, 4 = no TMEM loads, 8 = no code TMA after the first tile, 16 = no coarse filter
 };
@@ -274,7 +275,7 @@ gemm_i8_topk_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
                 return (t < my_tiles && r < nrows) ? __ldg(a.qcoef + (size_t)r * a.coef_step) : make_float2(0.f, 0.f);
             };
             float2 co_next = load_coef(0), co_next2 = load_coef(1);   // two tiles ahead: a tile is shorter than a DRAM round trip
-            const bool coarse = FAST && a.mode == 0 && !(a.debug & 16);
+            const bool coarse = FAST && a.mode == 0 && a.coarse && !(a.debug & 16);
             for (int t = 0; t < my_tiles; ++t) {
                 const int tile = ng + t * a.NG;
                 mbar_wait(tfull0 + 8 * acc, acc_phase);
@@ -288,10 +289,13 @@ gemm_i8_topk_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
                     //   x <= cx*(256 Sa + SbMax) + cy*Cq = (256 cx)*F + (cy*Cq + K'),  K' = cx*SbMax' - 256 cx * 12582912
                     // K' is formed in fp64 and rounded UP; SbMax' carries the slack that covers every fp32 rounding of
                     // both evaluations (2048 units of S per cx, 1.5 |cy| for the cy*Cq products, |Cq| <= 2^22)
-                    const double cx = (double)co_next.x, cy = (double)co_next.y;
-                    const double kp = cx * (double)a.sb_max + 1.5 * fabs(cy) - cx * 256.0 * 12582912.0;
-                    float kpf = (float)kp;
-                    if ((double)kpf < kp) kpf = __int_as_float(__float_as_int(kpf) + (kpf >= 0.f ? 1 : -1));
+                    float kpf = 0.f;
+                    if (coarse) {
+                        const double cx = (double)co_next.x, cy = (double)co_next.y;
+                        const double kp = cx * (double)a.sb_max + 1.5 * fabs(cy) - cx * 256.0 * 12582912.0;
+                        kpf = (float)kp;
+                        if ((double)kpf < kp) kpf = __int_as_float(__float_as_int(kpf) + (kpf >= 0.f ? 1 : -1));
+                    }
                     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(wcoef + lane * 16), "f"(co_next.x * 256.0f),
                                  "f"(kpf), "f"(co_next.y), "f"(co_next.x) : "memory");   // {256 cx, K', cy, cx}
                 }
@@ -473,6 +477,12 @@ int launch_qgemm_topk(evdb_store *s, const double *d_q64, int B, int KP, int *li
     static int ew = -1;
     if (ew < 0) { const char *e = getenv("EVDB_QGEMM_EW"); ew = (e && atoi(e) == 16) ? 16 : 8; }
     const int parts = ew / 4;
+    // the coarse filter pays when registers are short (16 warps: 11.5 -> 10.5 ms at 12.5 M x 96) and when few lanes of a
+    // warp hold a live query (8 warps, B = 8: 0.97 -> 0.85 ms); with 168 registers and full warps the exact path straight
+    // away is faster (B = 1024: 8.59 -> 8.18 ms, k = 100: 9.85 -> 8.51, 4 M x 128: 3.28 -> 2.79)
+    static int coarse_env = -2;
+    if (coarse_env == -2) { const char *e = getenv("EVDB_QGEMM_COARSE"); coarse_env = e ? atoi(e) : -1; }
+    a.coarse = coarse_env >= 0 ? coarse_env : ((ew == 16 || B < 64) ? 1 : 0);
     void (*fn)(CUtensorMap, CUtensorMap, CUtensorMap, QGemmArgs) = nullptr;
 #define EVDB_QSEL(EWN)                                                                                             \
     fn = use_res ? (fast ? gemm_i8_topk_kernel<true, true, EWN> : gemm_i8_topk_kernel<false, true, EWN>)           \
