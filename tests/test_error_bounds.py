@@ -117,3 +117,76 @@ def test_scan_fp32_bound():
         eps = (d / 64.0 + 24.0) * U
         assert np.max(np.abs(score_t - exact)) <= eps, (d, np.max(np.abs(score_t - exact)), eps)
         assert np.max(np.abs(score - exact)) <= 40 * eps     # sanity of the emulation itself
+
+
+def _f32(x):
+    return np.asarray(x, dtype=np.float32)
+
+
+def _fma32(a, b, c):
+    """fp32 fma: the exact product and sum in fp64 (both fit: 24 + 24 + alignment < 2^-53 relative here), rounded once."""
+    return _f32(np.float64(a) * np.float64(b) + np.float64(c))
+
+
+@pytest.mark.parametrize("d", [16, 96, 128])
+def test_i8_plan_digit_sums_keys_and_coarse_filter(d):
+    """csrc/gemm_i8.cu restated in numpy (d <= 128, the mantissa-trick variant):
+    (1) the two MMA accumulators Sa = sum a_k c_k (signed high digit) and Sb = sum b_k c_k (unsigned low digit)
+        reassemble the exact integer sum(Q_k c_k) the dp4a scan forms;
+    (2) the fp32 key 1 - x*fx/||q||, x = cx*S + cy*sum(Q), is within 48*2^-24 of the exact score of the grid
+        query (the arithmetic part of the bound the window proof consumes; the grid part is tested above);
+    (3) the coarse filter's bound, evaluated in fp32 exactly as the kernel does -- F = float_bits(Sa + 0x4B400000),
+        xu = fma(256cx, F, fma(cy, Cq, K')) with K' formed in fp64 and rounded up -- is never below the x the exact
+        path computes: a row the exact path would admit always passes the coarse test."""
+    rng = np.random.default_rng(d)
+    n = 3000
+    codes = rng.integers(0, 256, size=(n, d)).astype(np.int64)
+    codes[0] = 255
+    codes[1] = 0
+    codes[2, ::2] = 255
+    mins = rng.standard_normal(n) * np.exp(rng.uniform(-3, 3, n))
+    scales = np.abs(rng.standard_normal(n)) * np.exp(rng.uniform(-6, 1, n)) + 1e-9
+    mins[3], scales[3] = 100.0, 1e-6 / 255                      # nearly constant row: |min| sqrt(d) / ||y|| ~ 1
+    y = mins[:, None] + codes * scales[:, None]
+    ynorm = np.sqrt((y * y).sum(1))
+    cx, cy = _f32(scales / ynorm), _f32(mins / ynorm)           # ingest: {scale, min}/||y|| as fp32
+    sb_max = np.float32(65025.0 * d + 2048.0)
+    worst = 0.0
+    for q in _queries(rng, d):
+        qn = np.sqrt((q * q).sum())
+        mx = np.abs(q).max()
+        _, xe = np.frexp(mx)
+        e = 15 - int(xe)
+        Q = np.clip(np.rint(q * 2.0 ** e), -32768, 32767).astype(np.int64)
+        lo = Q & 0xFF
+        hi = (Q - lo) >> 8                                      # signed high digit
+        assert np.all((hi >= -128) & (hi <= 127))
+        Sa, Sb = codes @ hi, codes @ lo
+        assert np.array_equal(256 * Sa + Sb, codes @ Q)         # (1)
+        assert np.all(np.abs(Sa) < 2 ** 22) and np.all((Sb >= 0) & (Sb < 2 ** 23))
+        fx = np.float32(2.0 ** -e)
+        inv_norm = np.float32(1.0 / qn)
+        Cq = np.float32(np.float32(Q.sum() * 2.0 ** -e) / fx)   # QStat.sum / QStat.fx
+        c1 = -(inv_norm * fx)
+        # exact path of the kernel
+        fa = _f32(_f32(Sa + 12582912) - np.float32(12582912.0))
+        fb = _f32(_f32(Sb + 8388608) - np.float32(8388608.0))
+        assert np.array_equal(fa, Sa) and np.array_equal(fb, Sb)
+        S = _fma32(fa, np.float32(256.0), fb)
+        x = _fma32(cx, S, _f32(cy * Cq))
+        key = _fma32(x, c1, np.float32(1.0))
+        # the same score in fp64 from the same fp32 inputs
+        ref = 1.0 - (np.float64(cx) * (256.0 * Sa + Sb) + np.float64(cy) * np.float64(Cq)) * np.float64(inv_norm) * np.float64(fx)
+        err = np.max(np.abs(np.float64(key) - ref))
+        worst = max(worst, err)
+        assert err <= 48 * U, (err / U, d)                     # (2)
+        # coarse filter
+        kp = np.float64(cx) * np.float64(sb_max) + 1.5 * np.abs(np.float64(cy)) - np.float64(cx) * 256.0 * 12582912.0
+        kpf = _f32(kp)
+        up = np.float64(kpf) < kp
+        kpf = np.where(up, np.nextafter(kpf, np.float32(np.inf)), kpf).astype(np.float32)
+        assert np.all(np.float64(kpf) >= kp)
+        F = _f32(Sa + 12582912)                                 # float_bits(Sa + 0x4B400000): exact below 2^24
+        xu = _fma32(_f32(cx * np.float32(256.0)), F, _fma32(cy, Cq, kpf))
+        assert np.all(xu >= x), (np.min(np.float64(xu) - np.float64(x)), d)   # (3)
+    assert worst > 0.0
