@@ -47,7 +47,8 @@ constexpr uint32_t kQCodeBytes = QN * QKB;             // 16 KB: 128 rows of cod
 constexpr uint32_t kQRingBytes = 192 * 1024;           // operand shared memory: resident query planes + the ring
 // RES (d <= 384): the CTA's query block stays in shared memory for a whole sweep -- both digit planes, all K
 // blocks, loaded once -- and the ring carries codes only (16 KB stages): a third of the L2 -> shared-memory
-// traffic of streaming {Qa, Qb, codes} per K block, which is what paces a one-K-block tile otherwise.
+// traffic of streaming {Qa, Qb, codes} per K block.  Measured +-0 at d = 96, where the epilogue paces the
+// kernel (EVDB_QGEMM_RES=0 for the A/B); kept because the traffic it removes is what bounds the long-row shapes.
 constexpr int kQResMaxKBlocks = 3;
 constexpr int kQMaxStages = 10;
 constexpr int kQBars = 2 * kQMaxStages + 6;            // full[S] empty[S] tfull[2] tempty[2] qfull qempty
@@ -75,7 +76,8 @@ struct QGemmArgs {
     const uint32_t *thr0;  // mode 0: per-query starting threshold, orderable key score (NULL = none)
     int coarse;          // FAST: run the high-digit coarse filter before fetching the low-digit sums
     float sb_max;        // FAST: upper bound of the low-digit sum, 255 * 255 * d, plus the slack of the coarse filter
-    int debug;           // EVDB_QGEMM_DEBUG (measurement only): 1 = no epilogue arithmetic, 2 = one MMA per tile, 4 = no TMEM loads, 8 = no code TMA after the first tile, 16 = no coarse filter
+    int debug;           // EVDB_QGEMM_DEBUG (measurement only): 1 = no epilogue arithmetic, 2 = one MMA per tile,
+                         // 4 = no TMEM loads, 8 = no code TMA after the first tile, 16 = no coarse filter
 };
 
 // kind::i8 instruction descriptor: (u8|s8) x u8 -> s32, both K-major
@@ -267,14 +269,14 @@ gemm_i8_topk_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_const
             // admission threshold: seeded by the sampled pre-pass, tightened by every prune; held in the x domain
             float tau = (a.thr0 && live) ? f32_from_orderable(a.thr0[qglob]) : kInf;
             float thrS = acc_threshold(tau, c0, c1);
-            // this warp's 32 rows' coefficients, fetched one tile ahead (a dependent global load per tile
-            // would put its whole latency on every tile of the warp)
+            // the coefficients of the warp's next 32-row chunks, fetched two chunks ahead (a dependent global load
+            // per chunk would put its whole latency on every chunk of the warp)
             auto load_coef = [&](int st) -> float2 {   // step st = chunk st % kCpw of the warp's tile st / kCpw
                 const int t = st / kCpw;
                 const uint32_t r = (uint32_t)(ng + t * a.NG) * QN + (uint32_t)(part * kCpw + st % kCpw) * 32 + lane;
                 return (t < my_tiles && r < nrows) ? __ldg(a.qcoef + (size_t)r * a.coef_step) : make_float2(0.f, 0.f);
             };
-            float2 co_next = load_coef(0), co_next2 = load_coef(1);   // two tiles ahead: a tile is shorter than a DRAM round trip
+            float2 co_next = load_coef(0), co_next2 = load_coef(1);
             const bool coarse = FAST && a.mode == 0 && a.coarse && !(a.debug & 16);
             for (int t = 0; t < my_tiles; ++t) {
                 const int tile = ng + t * a.NG;
