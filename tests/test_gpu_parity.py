@@ -867,3 +867,45 @@ def test_replayed_graphs_survive_interleaved_shapes_and_ingest(native, oracle):
             check(qs[30], k)
     finally:
         st.close()
+
+
+@pytest.mark.parametrize("dtype", ["f32", "quantization_8bit"])
+def test_facade_search_batch_equals_single_searches_with_ties_and_options(native, oracle, fresh_name, dtype):
+    """erlvectordb:search_batch/3,4 (additive; the reference's Options map of src/erlvectordb.erl:91-92 honoured):
+    ONE device call for the batch -- the tcgen05 plans for 40 queries (kind::f16 on the fp32 store, kind::i8 on the
+    quantization_8bit store) -- must give, per query, exactly what search/3,4 gives, with exact-distance ties ordered by
+    Id term order although slot order differs (lists:sort/1, src/vector_store.erl:233)."""
+    from erlvectordb_b200 import erlvectordb as db
+    from erlvectordb_b200 import vector_store as vs
+    rng = np.random.default_rng(17)
+    d, n, B = 16, 600, 40
+    base = rng.integers(-3, 4, size=(40, d)).astype(np.float64)
+    base[base.max(axis=1) == base.min(axis=1), 0] += 1.0
+    rows = base[rng.integers(0, 40, size=n)]                     # every vector ~15 times: large exact tie groups
+    ids = [bytes([97 + (i * 11) % 26, 97 + (i * 7) % 26]) + str(i).encode() for i in range(n)]
+    name = fresh_name
+    old = db.env["gpu_dtype"]
+    db.env["gpu_dtype"] = dtype                                  # application env, as the gen_server's init/1 reads it
+    try:
+        assert db.create_store(name)[0] == "ok"
+        assert db.insert_batch(name, [(i, v.tolist(), {"n": j}) for j, (i, v) in enumerate(zip(ids, rows))]) == "ok"
+        qs = rng.integers(-3, 4, size=(B, d)).astype(np.float64)
+        qs[0] = rows[5]
+        metrics = ("cosine",) if dtype != "f32" else ("cosine", "euclidean", "manhattan")
+        for metric in metrics:
+            for k in (1, 10, 33):
+                ok, batch = db.search_batch(name, qs.tolist(), k, {"metric": metric})
+                assert ok == "ok" and len(batch) == B
+                for b in (0, 1, 7, B - 1):
+                    ok1, one = db.search(name, qs[b].tolist(), k, {"metric": metric})
+                    assert ok1 == "ok" and one == batch[b], (metric, k, b)
+                if dtype == "f32":
+                    for b in (0, 3):
+                        r, dd = oracle.search(rows, qs[b], k, metric, ranks=oracle.id_ranks(ids))
+                        assert [x[0] for x in batch[b]] == [ids[i] for i in r], (metric, k, b)
+                        assert [x[2] for x in batch[b]] == dd.tolist()
+        assert db.search_batch(name, qs.tolist(), 5) == db.search_batch(name, qs.tolist(), 5, {})   # default metric: cosine
+        assert db.search_batch(name, [[1.0] * (d - 1)], 3) == ("error", "dimension_mismatch")
+    finally:
+        db.env["gpu_dtype"] = old
+        vs.stop(name)
